@@ -1,0 +1,202 @@
+/*
+ * mvdseg.h -- C ABI of libmvdseg.so: the hand-written sm_100a kernels behind the nnU-Net v2 3d_fullres
+ * training step of JaronTu/Multimodal_MVD_Seg (PlainConvUNet fwd/bwd, deep-supervision Dice+CE, mutual-distillation
+ * KL, soft-skeleton clDice, clip + SGD-nesterov).
+ *
+ * The reference has no FFI of its own: it reaches the GPU through torch.nn modules / ATen.  Each
+ * entry point below therefore names the reference call (file:line under nnUNet/nnunetv2/) whose device work it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, floats; no torch / C++ types.  The caller owns every buffer (outputs and
+ *     workspaces included); the library allocates nothing persistent.
+ *   - activations are bf16 "NDHWC": logical [B][D][H][W][C], channel contiguous, voxel pitch `ld` elements
+ *     (ld >= C; ld > C addresses a channel slice of a wider buffer, which is how the decoder's torch.cat,
+ *     training/my_network/UNetDecoder.py:107, is made copy-free).  Voxels are dense: sample pitch = D*H*W*ld.
+ *   - every call is asynchronous on `stream`, performs no host synchronisation and no allocation, and is CUDA-graph
+ *     capturable.  Device is taken from the current context of the calling thread (one process per GPU).
+ *   - return 0 on success, a negative mvd_status otherwise; text via mvd_last_error() (thread-local).
+ */
+#ifndef MVDSEG_H_
+#define MVDSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mvd_stream_t; /* cudaStream_t */
+
+enum mvd_status {
+  MVD_OK = 0,
+  MVD_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  MVD_ERR_CUDA = -2,        /* CUDA runtime / driver error      */
+  MVD_ERR_UNSUPPORTED = -3  /* no kernel for this case          */
+};
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int mvd_version(void);
+const char* mvd_last_error(void);
+/* number of kernels this library has launched since load / last reset (bench.py's gpu_launches) */
+unsigned long long mvd_launch_count(void);
+void mvd_reset_launch_count(void);
+int mvd_shutdown(void);
+
+/* ---- layout at the module edge ---------------------------------------------------------------------------- */
+/* data.to(device) then network(data): fp32 NCDHW batch -> bf16 NDHWC (nnUNetTrainer.py:895,907) */
+int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int B, int C, long long V, int ld_dst,
+                                mvd_stream_t stream);
+/* logits back to fp32 NCDHW for callers that want the reference's memory format */
+int mvd_ndhwc_bf16_to_ncdhw_f32(const void* src, int ld_src, float* dst, int B, int C, long long V,
+                                mvd_stream_t stream);
+
+/* ---- convolution ------------------------------------------------------------------------------------------ */
+/* Replaces torch.nn.Conv3d / ConvTranspose3d fprop, dgrad, wgrad as instantiated at
+ * utilities/get_network_from_plans.py:70-83 and training/my_network/UNetDecoder.py:55-65.
+ * One geometry struct serves all six entry points; (Di,Hi,Wi,Cin) is always the conv INPUT side
+ * (for a transposed conv the "conv" is its adjoint, i.e. Cin = the ConvTranspose3d's out_channels). */
+typedef struct {
+  int B;
+  int Di, Hi, Wi, Cin;   /* conv input  [B,Di,Hi,Wi,Cin]  */
+  int Do, Ho, Wo, Cout;  /* conv output [B,Do,Ho,Wo,Cout] */
+  int kd, kh, kw;        /* kernel                                   */
+  int sd, sh, sw;        /* stride                                   */
+  int pd, ph, pw;        /* zero padding                             */
+  const void* x;   int ldx;   /* bf16 conv-input-side activation (fprop in, dgrad out, wgrad in)            */
+  const void* y;   int ldy;   /* bf16 conv-output-side activation (fprop out, dgrad in, wgrad in)           */
+  const void* w;              /* bf16 packed weights, see mvd_pack_conv_weights                             */
+  const float* bias;          /* fp32 [Cout] (fprop) / [Cin] (transposed fprop); may be NULL                */
+  double* stats;              /* optional [B][C][2] running (sum, sum of squares) of the bf16-rounded output,
+                                 accumulated (caller zeroes); InstanceNorm statistics, fprop only           */
+  float* dw;                  /* wgrad out, fp32 in torch layout [Cout][Cin][kd][kh][kw]                    */
+  float* dbias;               /* wgrad out, fp32 [Cout]; may be NULL                                        */
+  void* workspace; size_t workspace_bytes; /* scratch (wgrad split-K partials); see mvd_conv3d_workspace_bytes */
+  int algo;                   /* 0 auto, 1 CUDA-core tiles, 2 tcgen05 implicit GEMM                          */
+  int accumulate;             /* dgrad: add into the output instead of overwriting it                       */
+} mvd_conv3d_args;
+
+/* pack fp32 torch-layout weights [Cout][Cin][kd][kh][kw] into the two bf16 GEMM layouts:
+ *   w_fprop [tap][Cout][Cin]  (B operand of fprop:  N = Cout rows, K = Cin contiguous)
+ *   w_dgrad [tap][Cin][Cout]  (B operand of dgrad:  N = Cin rows,  K = Cout contiguous)
+ * either output may be NULL. tap = (kd*KH + kh)*KW + kw. */
+int mvd_pack_conv_weights(const float* w, int Cout, int Cin, int taps, void* w_fprop, void* w_dgrad,
+                          mvd_stream_t stream);
+size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass /*0 fprop,1 dgrad,2 wgrad*/);
+int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream); /* y = conv(x, w) + bias  (w = w_fprop) */
+int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* x = conv^T(y, w)       (w = w_dgrad) */
+int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* dw = x (*) y, dbias = sum y          */
+
+/* ---- InstanceNorm3d(affine, eps) + LeakyReLU -------------------------------------------------------------- */
+/* Replaces nn.InstanceNorm3d + nn.LeakyReLU(inplace) of every ConvDropoutNormReLU block
+ * (get_network_from_plans.py:41-44).  stats = [B][C][2] doubles (sum, sumsq) over the V voxels of each (b,c). */
+int mvd_inorm_stats(const void* y, int ldy, int B, long long V, int C, double* stats, mvd_stream_t stream);
+int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* stats, const float* gamma,
+                        const float* beta, int B, long long V, int C, float eps, float slope, mvd_stream_t stream);
+/* bstats = [B][C][2] doubles: sum g', sum g'*xhat with g' = dz * lrelu'(.) ; caller zeroes */
+int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, const double* stats,
+                              const float* gamma, const float* beta, int B, long long V, int C, float eps,
+                              float slope, double* bstats, mvd_stream_t stream);
+/* dy = gamma*rstd*(g' - mean(g') - xhat*mean(g' xhat)); dgamma/dbeta (fp32 [C]) written when non-NULL */
+int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, void* dy, int lddy,
+                              const double* stats, const double* bstats, const float* gamma, const float* beta,
+                              int B, long long V, int C, float eps, float slope, float* dgamma, float* dbeta,
+                              mvd_stream_t stream);
+
+/* ---- 1x1x1 segmentation heads (UNetDecoder.py:67-70) ------------------------------------------------------- */
+int mvd_head_fwd(const void* z, int ldz, const float* w /*[K][C] fp32*/, const float* bias /*[K]*/, void* logits,
+                 int ldl, long long NV /*B*V*/, int C, int K, mvd_stream_t stream);
+/* dz (bf16) = dlogits * w ; dw [K][C], dbias [K] fp32 accumulated (caller zeroes) */
+int mvd_head_bwd(const void* dlogits, int ldl, const void* z, int ldz, const float* w, void* dz, int lddz,
+                 float* dw, float* dbias, long long NV, int C, int K, mvd_stream_t stream);
+
+/* ---- deep-supervision Dice + CE (nnUNetTrainer.py:359-374; robust_ce_loss.py:12-16) ----------------------- */
+/* acc = [B][C][3] doubles (intersect, sum_pred, sum_gt) followed by 1 double (sum of -log p[target]); caller zeroes.
+ * logits bf16 NDHWC [B][V][C] pitch ld; target fp32 [B][V] holding class ids (the reference's float targets,
+ * MVDTrainer.py:765).  C <= 8. */
+int mvd_dice_ce_fwd(const void* logits, int ld, const float* target, int B, long long V, int C, double* acc,
+                    mvd_stream_t stream);
+/* loss_out[0] += weight * (w_ce*CE + w_dice*Dice); coef = [B][C][2] floats (a, e) kept for the backward.
+ * batch_dice: sums over b first (MemoryEfficientSoftDiceLoss batch_dice=True). do_bg as in the reference. */
+int mvd_dice_ce_finalize(const double* acc, int B, long long V, int C, float smooth, int do_bg, int batch_dice,
+                         float w_ce, float w_dice, float weight, float* coef, float* loss_out, mvd_stream_t stream);
+/* dlogits (bf16, pitch ldd) = gout[0] * weight * d(w_ce*CE + w_dice*Dice)/dlogits */
+int mvd_dice_ce_bwd(const void* logits, int ld, const float* target, int B, long long V, int C, const float* coef,
+                    float w_ce, float weight, const float* gout, void* dlogits, int ldd, mvd_stream_t stream);
+/* validation_step's online tp/fp/fn of the argmax segmentation (nnUNetTrainer.py:973-1004): out = [C][3] doubles */
+int mvd_argmax_tp_fp_fn(const void* logits, int ld, const float* target, int B, long long V, int C, double* out,
+                        mvd_stream_t stream);
+
+/* ---- mutual-distillation KL (training/loss/other_loss.py:51-64; call site MVDTrainer.py:897-899) ---------- */
+/* C == 1 selects the reference's shape[1]==1 branch (the single logit against a constant zero logit, 2 classes).
+ * loss_sum[0] (double, caller zeroes) accumulates sum p_t*(log p_t - log p_s); the host scales by T^2/numel. */
+int mvd_kl_fwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, double* loss_sum,
+               mvd_stream_t stream);
+/* dys/dyt (bf16) = gout[0]*scale * dKL/dy ; scale = T^2/numel supplied by the caller; either may be NULL */
+int mvd_kl_bwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, float scale,
+               const float* gout, void* dys, int ldds, void* dyt, int lddt, mvd_stream_t stream);
+
+/* ---- soft skeleton / clDice (training/loss/soft_skeleton.py:6-37) ------------------------------------------ */
+/* fp32 volumes [B][D][H][W] */
+int mvd_soft_erode(const float* in, float* out, int B, int D, int H, int W, mvd_stream_t stream);
+int mvd_soft_dilate(const float* in, float* out, int B, int D, int H, int W, mvd_stream_t stream);
+/* PyTorch tie rules: max_pool3d -> first maximum in scan order; torch.min -> 0.5/0.5 */
+int mvd_soft_erode_bwd(const float* in, const float* gout, float* gin /*accumulated*/, int B, int D, int H, int W,
+                       mvd_stream_t stream);
+int mvd_soft_dilate_bwd(const float* in, const float* gout, float gscale, float* gin /*accumulated*/, int B, int D,
+                        int H, int W, mvd_stream_t stream);
+/* one skeleton level: delta = relu(E_j - dilate(E_j1)); skel_out = first ? delta : skel_in + relu(delta - skel_in*delta) */
+int mvd_skel_update(const float* Ej, const float* Ej1, const float* skel_in, float* delta_out, float* skel_out,
+                    int first, int B, int D, int H, int W, mvd_stream_t stream);
+/* pointwise backward of the skeleton recursion for all levels: E/delta/skel are [L][N] stacks (L = iter+1),
+ * g_skel [N] in, g_delta [L][N] out */
+int mvd_skel_chain_bwd(const float* delta, const float* skel, const float* g_skel, float* g_delta, int L,
+                       long long N, mvd_stream_t stream);
+/* gE_j += g_delta_j * [delta_j > 0];  gE_j1 (via dilate backward) -= same   (one level) */
+int mvd_skel_level_bwd(const float* Ej1, const float* delta_j, const float* g_delta_j, float* gEj, float* gEj1,
+                       int B, int D, int H, int W, mvd_stream_t stream);
+/* sums[0..3] (double, caller zeroes) += sum(a*b), sum(a) , used for clDice's tprec / tsens */
+int mvd_dot_sum(const float* a, const float* b, long long N, double* sums2, mvd_stream_t stream);
+/* prob = softmax(logits)[:, channel] (fp32) and onehot = (target == channel) (fp32) */
+int mvd_softmax_channel_fwd(const void* logits, int ld, const float* target, long long NV, int C, int channel,
+                            float* prob, float* onehot, mvd_stream_t stream);
+/* dlogits (bf16) = dprob * d softmax_channel / d logits */
+int mvd_softmax_channel_bwd(const void* logits, int ld, const float* dprob, long long NV, int C, int channel,
+                            void* dlogits, int ldd, mvd_stream_t stream);
+/* clDice chain rule, device scalars only (no host sync): out4 from mvd_cldice_finalize, gout may be NULL (=1)
+ *   seed:    g_skel[i] = gout * (out4[1]*y[i] + out4[2])
+ *   combine: dprob[i]  = gE0[i] + gout * out4[3] * skel_y[i] */
+int mvd_cldice_seed(const float* y, const float* out4, const float* gout, float* g_skel, long long N,
+                    mvd_stream_t stream);
+int mvd_cldice_combine(const float* gE0, const float* skel_y, const float* out4, const float* gout, float* dprob,
+                       long long N, mvd_stream_t stream);
+/* clDice scalar + chain-rule coefficients from the four sums: sums = [S(skel_p*y), S(skel_p), S(skel_y*p), S(skel_y)]
+ * out[0] = loss; out[1] = dL/dS1, out[2] = dL/dS2, out[3] = dL/dS3   (fp32) */
+int mvd_cldice_finalize(const double* sums4, float smooth, float* out4, mvd_stream_t stream);
+
+/* ---- optimiser tail (MVDTrainer.py:978-979, 482-486) ------------------------------------------------------- */
+/* multi-tensor tables live in device memory: ptrs = [n][3] (param, grad, momentum_buf) as uint64, numel = [n] int64,
+ * chunk_tensor / chunk_offset = [n_chunks] (int32 tensor id, int64 element offset), chunk elements = 4096 */
+int mvd_grad_sqnorm(const uint64_t* ptrs, const long long* numel, const int* chunk_tensor,
+                    const long long* chunk_offset, int n_chunks, double* sqnorm /*caller zeroes*/,
+                    mvd_stream_t stream);
+/* clip coef = min(1, max_norm / (sqrt(sqnorm*gscale^2) + 1e-6)); g = grad*gscale*coef + wd*p; buf = mom*buf + g;
+ * p -= lr * (g + mom*buf)   (torch.optim.SGD nesterov; gscale folds the DDP 1/world mean) */
+int mvd_sgd_nesterov_clip(const uint64_t* ptrs, const long long* numel, const int* chunk_tensor,
+                          const long long* chunk_offset, int n_chunks, const double* sqnorm, float gscale,
+                          float max_norm, float lr, float weight_decay, float momentum, mvd_stream_t stream);
+
+/* ---- utility ----------------------------------------------------------------------------------------------- */
+/* out[c] = sum over NV voxels of g[v][c] (fp32; bias gradient of ConvTranspose3d) */
+int mvd_channel_sum(const void* g, int ld, long long NV, int C, float* out, mvd_stream_t stream);
+/* out[0] (+)= scale * in[0]: device-side double -> float scalar algebra (keeps the step free of host syncs) */
+int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream);
+int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int C, mvd_stream_t stream); /* dst += src */
+/* hardware probe used by tests/bench: runs the tcgen05 self-test (descriptor semantics); fills out[0..n) */
+int mvd_tc_selftest(float* out_dev, int n, mvd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVDSEG_H_ */

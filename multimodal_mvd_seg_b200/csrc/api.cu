@@ -1,0 +1,38 @@
+// api.cu -- library bookkeeping: error text, launch counter, device properties.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include "common.cuh"
+
+namespace mvd {
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+static int g_num_sms = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+}  // namespace mvd
+
+extern "C" {
+int mvd_version(void) { return 100; }
+const char* mvd_last_error(void) { return mvd::g_err; }
+unsigned long long mvd_launch_count(void) { return mvd::g_launches.load(); }
+void mvd_reset_launch_count(void) { mvd::g_launches.store(0); }
+int mvd_shutdown(void) { return MVD_OK; }
+}

@@ -1,0 +1,84 @@
+// common.cuh -- shared helpers for libmvdseg.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mvdseg.h"
+
+namespace mvd {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+
+typedef __nv_bfloat16 bf16;
+
+#define MVD_REQUIRE(cond, ...)                \
+  do {                                        \
+    if (!(cond)) {                            \
+      mvd::set_error(__VA_ARGS__);            \
+      return MVD_ERR_INVALID;                 \
+    }                                         \
+  } while (0)
+
+#define MVD_LAUNCH_CHECK(name)                                                   \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      mvd::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return MVD_ERR_CUDA;                                                       \
+    }                                                                            \
+    mvd::count_launch();                                                         \
+  } while (0)
+
+#define MVD_CUDA(call)                                                           \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      mvd::set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return MVD_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float round_bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// 8 bf16 <-> 8 floats through one 16-byte vector
+struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int grid_for(long long work_items, int per_block, int max_blocks) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace mvd

@@ -1,0 +1,62 @@
+// conv_api.cu -- argument validation and algorithm choice for the convolution entry points.
+#include "conv_common.cuh"
+
+using namespace mvd;
+
+static int check_geom(const mvd_conv3d_args* a, const char* who) {
+  MVD_REQUIRE(a != nullptr, "%s: null args", who);
+  MVD_REQUIRE(a->B > 0 && a->Di > 0 && a->Hi > 0 && a->Wi > 0 && a->Cin > 0 && a->Do > 0 && a->Ho > 0 && a->Wo > 0 &&
+                  a->Cout > 0, "%s: non-positive dimension", who);
+  MVD_REQUIRE(a->kd > 0 && a->kh > 0 && a->kw > 0 && a->sd > 0 && a->sh > 0 && a->sw > 0 && a->pd >= 0 && a->ph >= 0 &&
+                  a->pw >= 0, "%s: bad kernel/stride/padding", who);
+  MVD_REQUIRE(a->Do == (a->Di + 2 * a->pd - a->kd) / a->sd + 1 && a->Ho == (a->Hi + 2 * a->ph - a->kh) / a->sh + 1 &&
+                  a->Wo == (a->Wi + 2 * a->pw - a->kw) / a->sw + 1,
+              "%s: output extent does not match floor((in + 2p - k)/s) + 1", who);
+  MVD_REQUIRE(a->x && a->y && a->ldx >= a->Cin && a->ldy >= a->Cout, "%s: bad activation pointers / pitches", who);
+  MVD_REQUIRE(a->algo >= 0 && a->algo <= 2, "%s: algo must be 0, 1 or 2", who);
+  return MVD_OK;
+}
+
+extern "C" {
+
+size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass) {
+  if (!a) return 0;
+  if (pass == 2 && a->algo != 1 && tc_wgrad_supported(a)) return tc_wgrad_workspace_bytes(a);
+  return 0;
+}
+
+int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream) {
+  int rc = check_geom(a, "conv3d_fprop");
+  if (rc) return rc;
+  MVD_REQUIRE(a->w, "conv3d_fprop: null weights");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = tc_fprop_supported(a);
+  if (a->algo == 2 && !tc) { set_error("conv3d_fprop: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
+  rc = (a->algo != 1 && tc) ? tc_fprop(a, st) : generic_fprop(a, st);
+  if (rc) return rc;
+  if (a->stats)
+    return mvd_inorm_stats(a->y, a->ldy, a->B, (long long)a->Do * a->Ho * a->Wo, a->Cout, a->stats, stream);
+  return MVD_OK;
+}
+
+int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
+  int rc = check_geom(a, "conv3d_dgrad");
+  if (rc) return rc;
+  MVD_REQUIRE(a->w, "conv3d_dgrad: null weights");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = tc_dgrad_supported(a);
+  if (a->algo == 2 && !tc) { set_error("conv3d_dgrad: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
+  return (a->algo != 1 && tc) ? tc_dgrad(a, st) : generic_dgrad(a, st);
+}
+
+int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
+  int rc = check_geom(a, "conv3d_wgrad");
+  if (rc) return rc;
+  MVD_REQUIRE(a->dw, "conv3d_wgrad: null dw");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = tc_wgrad_supported(a);
+  if (a->algo == 2 && !tc) { set_error("conv3d_wgrad: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
+  return (a->algo != 1 && tc) ? tc_wgrad(a, st) : generic_wgrad(a, st);
+}
+
+}  // extern "C"

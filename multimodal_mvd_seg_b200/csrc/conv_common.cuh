@@ -1,0 +1,18 @@
+// conv_common.cuh -- internal interface between the conv entry points and their two implementations.
+#pragma once
+#include "common.cuh"
+
+namespace mvd {
+// CUDA-core tiles (conv_generic.cu)
+int generic_fprop(const mvd_conv3d_args* a, cudaStream_t st);
+int generic_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
+int generic_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
+// tcgen05 implicit GEMM (conv_tc.cu); *_supported() says whether the shape is covered
+bool tc_fprop_supported(const mvd_conv3d_args* a);
+bool tc_dgrad_supported(const mvd_conv3d_args* a);
+bool tc_wgrad_supported(const mvd_conv3d_args* a);
+int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st);
+int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
+int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
+size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);
+}  // namespace mvd

@@ -1,0 +1,558 @@
+// losses.cu -- fused loss kernels on the bf16 NDHWC logits (HBM-bound, one thread per voxel, C <= 8 classes in
+// registers, fp32 math, double accumulation of the global sums).
+//
+//   dice_ce_*      : softmax + MemoryEfficientSoftDiceLoss + RobustCrossEntropyLoss of one deep-supervision scale
+//                    (nnUNetTrainer.py:359-374; robust_ce_loss.py:12-16).  fwd = one pass producing the per-(b,c)
+//                    sums; bwd = one pass producing dlogits; the scalar algebra in between is a 1-block kernel.
+//   kl_*           : temperature KL of other_loss.py:51-64 (distill_kl), both gradients in one pass.
+//   softmax_channel: softmax(logits)[:, ch] and its backward (input of the clDice term, MVDTrainer.py:904-908).
+#include "common.cuh"
+
+namespace mvd {
+
+template <int C>
+__device__ __forceinline__ void load_logits(const bf16* __restrict__ p, float* z) {
+  if constexpr (C == 4) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+      uint2 raw = *reinterpret_cast<const uint2*>(p);
+      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+      __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+      float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+      z[0] = fa.x; z[1] = fa.y; z[2] = fb.x; z[3] = fb.y;
+      return;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) z[c] = bf2f(p[c]);
+}
+
+template <int C>
+__device__ __forceinline__ void store_bf16(bf16* __restrict__ p, const float* z) {
+  if constexpr (C == 4) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(z[0], z[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(z[2], z[3]);
+      uint2 raw;
+      raw.x = *reinterpret_cast<uint32_t*>(&a);
+      raw.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p) = raw;
+      return;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) p[c] = f2bf(z[c]);
+}
+
+// softmax in place; returns log-sum-exp offset so that log p_c = z_c_in - lse
+template <int C>
+__device__ __forceinline__ float softmax_inplace(float* z) {
+  float m = z[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    z[c] = expf(z[c] - m);
+    s += z[c];
+  }
+  float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < C; ++c) z[c] *= inv;
+  return m + logf(s);
+}
+
+// block-wide sum of NVAL per-thread floats into double atomics
+template <int NVAL>
+__device__ __forceinline__ void block_accumulate(const float* vals, double* __restrict__ dst) {
+  __shared__ float red[8][NVAL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NVAL; ++i) {
+    float v = warp_sum(vals[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NVAL) {
+    double a = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) a += (double)red[w][threadIdx.x];
+    atomicAdd(&dst[threadIdx.x], a);
+  }
+}
+
+// acc layout: [B][C][3] (intersect, sum_pred, sum_gt) then acc[B*C*3] = CE sum
+template <int C>
+__global__ void __launch_bounds__(256) dice_ce_fwd_kernel(const bf16* __restrict__ logits, int ld,
+                                                          const float* __restrict__ target, long long V,
+                                                          double* __restrict__ acc, int B) {
+  const int b = blockIdx.y;
+  const bf16* lb = logits + (long long)b * V * ld;
+  const float* tb = target + (long long)b * V;
+  float vals[3 * C + 1];
+#pragma unroll
+  for (int i = 0; i < 3 * C + 1; ++i) vals[i] = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    float z[C];
+    load_logits<C>(lb + v * ld, z);
+    const int t = (int)__ldg(tb + v);
+    float zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) zt = (c == t) ? z[c] : zt;
+    float lse = softmax_inplace<C>(z);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float y = (c == t) ? 1.f : 0.f;
+      vals[3 * c + 0] += z[c] * y;
+      vals[3 * c + 1] += z[c];
+      vals[3 * c + 2] += y;
+    }
+    vals[3 * C] += (t >= 0 && t < C) ? (lse - zt) : 0.f;
+  }
+  // per-(b,c) sums go to acc[b], the CE sum to the tail slot; two accumulate calls share the shared buffer
+  __shared__ float red[8][3 * C + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 3 * C + 1; ++i) {
+    float s = warp_sum(vals[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C + 1) {
+    double a = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) a += (double)red[w][threadIdx.x];
+    if (threadIdx.x < 3 * C) atomicAdd(&acc[(long long)b * C * 3 + threadIdx.x], a);
+    else atomicAdd(&acc[(long long)B * C * 3], a);
+  }
+}
+
+// one block: dc, loss, backward coefficients.  coef[b][c] = (A, E): d(w_dice*Dice)/dp_vc = A*y_vc - E
+__global__ void dice_ce_finalize_kernel(const double* __restrict__ acc, int B, long long V, int C, float smooth,
+                                        int do_bg, int batch_dice, float w_ce, float w_dice, float weight,
+                                        float* __restrict__ coef, float* __restrict__ loss_out) {
+  if (threadIdx.x != 0) return;
+  const int c0 = do_bg ? 0 : 1;
+  const int nC = C - c0;
+  double dc_sum = 0.0;
+  if (batch_dice) {
+    const double nterms = (double)nC;
+    for (int c = 0; c < C; ++c) {
+      double I = 0, P = 0, G = 0;
+      for (int b = 0; b < B; ++b) {
+        I += acc[((long long)b * C + c) * 3 + 0];
+        P += acc[((long long)b * C + c) * 3 + 1];
+        G += acc[((long long)b * C + c) * 3 + 2];
+      }
+      double num = 2.0 * I + smooth, den = G + P + smooth;
+      if (den < 1e-8) den = 1e-8;
+      float A = 0.f, E = 0.f;
+      if (c >= c0) {
+        dc_sum += num / den;
+        A = (float)(-(double)w_dice * (2.0 / den) / nterms);
+        E = (float)(-(double)w_dice * (num / (den * den)) / nterms);
+      }
+      for (int b = 0; b < B; ++b) {
+        coef[((long long)b * C + c) * 2 + 0] = A;
+        coef[((long long)b * C + c) * 2 + 1] = E;
+      }
+    }
+    dc_sum /= nterms;
+  } else {
+    const double nterms = (double)B * nC;
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < C; ++c) {
+        double I = acc[((long long)b * C + c) * 3 + 0];
+        double P = acc[((long long)b * C + c) * 3 + 1];
+        double G = acc[((long long)b * C + c) * 3 + 2];
+        double num = 2.0 * I + smooth, den = G + P + smooth;
+        if (den < 1e-8) den = 1e-8;
+        float A = 0.f, E = 0.f;
+        if (c >= c0) {
+          dc_sum += num / den;
+          A = (float)(-(double)w_dice * (2.0 / den) / nterms);
+          E = (float)(-(double)w_dice * (num / (den * den)) / nterms);
+        }
+        coef[((long long)b * C + c) * 2 + 0] = A;
+        coef[((long long)b * C + c) * 2 + 1] = E;
+      }
+    dc_sum /= nterms;
+  }
+  double ce = acc[(long long)B * C * 3] / ((double)B * (double)V);
+  double l = (double)w_ce * ce + (double)w_dice * (-dc_sum);
+  loss_out[0] += (float)((double)weight * l);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) dice_ce_bwd_kernel(const bf16* __restrict__ logits, int ld,
+                                                          const float* __restrict__ target, long long V,
+                                                          const float* __restrict__ coef, float ce_scale,
+                                                          float weight, const float* __restrict__ gout,
+                                                          bf16* __restrict__ dlogits, int ldd) {
+  const int b = blockIdx.y;
+  const bf16* lb = logits + (long long)b * V * ld;
+  const float* tb = target + (long long)b * V;
+  bf16* db = dlogits + (long long)b * V * ldd;
+  float A[C], E[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    A[c] = coef[((long long)b * C + c) * 2 + 0];
+    E[c] = coef[((long long)b * C + c) * 2 + 1];
+  }
+  const float g = (gout ? gout[0] : 1.f) * weight;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    float p[C];
+    load_logits<C>(lb + v * ld, p);
+    const int t = (int)__ldg(tb + v);
+    softmax_inplace<C>(p);
+    float q[C], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      q[c] = ((c == t) ? A[c] : 0.f) - E[c];
+      dot = fmaf(p[c], q[c], dot);
+    }
+    float o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float dce = (p[c] - ((c == t) ? 1.f : 0.f)) * ce_scale;
+      o[c] = g * (dce + p[c] * (q[c] - dot));
+    }
+    store_bf16<C>(db + v * ldd, o);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) argmax_tp_fp_fn_kernel(const bf16* __restrict__ logits, int ld,
+                                                              const float* __restrict__ target, long long NV,
+                                                              double* __restrict__ out) {
+  float vals[3 * C];
+#pragma unroll
+  for (int i = 0; i < 3 * C; ++i) vals[i] = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
+    float z[C];
+    load_logits<C>(logits + v * ld, z);
+    const int t = (int)__ldg(target + v);
+    int pred = 0;
+    float m = z[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+      if (z[c] > m) { m = z[c]; pred = c; }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      vals[3 * c + 0] += (pred == c && t == c) ? 1.f : 0.f;
+      vals[3 * c + 1] += (pred == c && t != c) ? 1.f : 0.f;
+      vals[3 * c + 2] += (pred != c && t == c) ? 1.f : 0.f;
+    }
+  }
+  block_accumulate<3 * C>(vals, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KL.  C == 1 is the reference's shape[1]==1 branch: the single logit against a constant zero logit (2 classes).
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+struct KLWidth { static constexpr int W = (C == 1) ? 2 : C; };
+
+template <int C>
+__device__ __forceinline__ void kl_load(const bf16* __restrict__ p, float invT, float* u) {
+  if constexpr (C == 1) {
+    u[0] = bf2f(p[0]) * invT;
+    u[1] = 0.f;
+  } else {
+    load_logits<C>(p, u);
+#pragma unroll
+    for (int c = 0; c < C; ++c) u[c] *= invT;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) kl_fwd_kernel(const bf16* __restrict__ ys, int lds,
+                                                     const bf16* __restrict__ yt, int ldt, long long NV, float invT,
+                                                     double* __restrict__ loss_sum) {
+  constexpr int W = KLWidth<C>::W;
+  float acc = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
+    float us[W], ut[W], ps[W], pt[W];
+    kl_load<C>(ys + v * lds, invT, us);
+    kl_load<C>(yt + v * ldt, invT, ut);
+#pragma unroll
+    for (int c = 0; c < W; ++c) { ps[c] = us[c]; pt[c] = ut[c]; }
+    float lse_s = softmax_inplace<W>(ps);
+    float lse_t = softmax_inplace<W>(pt);
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+      float d = (ut[c] - lse_t) - (us[c] - lse_s);
+      acc += pt[c] > 0.f ? pt[c] * d : 0.f;
+    }
+  }
+  float vals[1] = {acc};
+  block_accumulate<1>(vals, loss_sum);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) kl_bwd_kernel(const bf16* __restrict__ ys, int lds,
+                                                     const bf16* __restrict__ yt, int ldt, long long NV, float invT,
+                                                     float scale, const float* __restrict__ gout,
+                                                     bf16* __restrict__ dys, int ldds, bf16* __restrict__ dyt,
+                                                     int lddt) {
+  constexpr int W = KLWidth<C>::W;
+  const float g = (gout ? gout[0] : 1.f) * scale * invT;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
+    float us[W], ut[W], ps[W], pt[W];
+    kl_load<C>(ys + v * lds, invT, us);
+    kl_load<C>(yt + v * ldt, invT, ut);
+#pragma unroll
+    for (int c = 0; c < W; ++c) { ps[c] = us[c]; pt[c] = ut[c]; }
+    float lse_s = softmax_inplace<W>(ps);
+    float lse_t = softmax_inplace<W>(pt);
+    float d[W], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+      d[c] = (ut[c] - lse_t) - (us[c] - lse_s);
+      dot = fmaf(pt[c], d[c], dot);
+    }
+    if (dys) {
+      float o[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = g * (ps[c] - pt[c]);
+      store_bf16<C>(dys + v * ldds, o);
+    }
+    if (dyt) {
+      float o[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = g * pt[c] * (d[c] - dot);
+      store_bf16<C>(dyt + v * lddt, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) softmax_channel_fwd_kernel(const bf16* __restrict__ logits, int ld,
+                                                                  const float* __restrict__ target, long long NV,
+                                                                  int ch, float* __restrict__ prob,
+                                                                  float* __restrict__ onehot) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
+    float z[C];
+    load_logits<C>(logits + v * ld, z);
+    softmax_inplace<C>(z);
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = (c == ch) ? z[c] : p;
+    prob[v] = p;
+    if (onehot) onehot[v] = ((int)__ldg(target + v) == ch) ? 1.f : 0.f;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) softmax_channel_bwd_kernel(const bf16* __restrict__ logits, int ld,
+                                                                  const float* __restrict__ dprob, long long NV,
+                                                                  int ch, bf16* __restrict__ dlogits, int ldd) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += (long long)gridDim.x * blockDim.x) {
+    float z[C];
+    load_logits<C>(logits + v * ld, z);
+    softmax_inplace<C>(z);
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = (c == ch) ? z[c] : p;
+    const float g = dprob[v] * p;
+    float o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = g * (((c == ch) ? 1.f : 0.f) - z[c]);
+    store_bf16<C>(dlogits + v * ldd, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      long long N, double* __restrict__ sums2) {
+  float vals[2] = {0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    float x = a[i];
+    vals[0] = fmaf(x, b[i], vals[0]);
+    vals[1] += x;
+  }
+  block_accumulate<2>(vals, sums2);
+}
+
+__global__ void __launch_bounds__(256) cldice_seed_kernel(const float* __restrict__ y, const float* __restrict__ out4,
+                                                          const float* __restrict__ gout, float* __restrict__ g,
+                                                          long long N) {
+  const float go = gout ? gout[0] : 1.f;
+  const float c1 = go * out4[1], c2 = go * out4[2];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    g[i] = fmaf(c1, y[i], c2);
+}
+
+__global__ void __launch_bounds__(256) cldice_combine_kernel(const float* __restrict__ gE0,
+                                                             const float* __restrict__ sy,
+                                                             const float* __restrict__ out4,
+                                                             const float* __restrict__ gout,
+                                                             float* __restrict__ dp, long long N) {
+  const float c3 = (gout ? gout[0] : 1.f) * out4[3];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    dp[i] = fmaf(c3, sy[i], gE0[i]);
+}
+
+// sums = [S1 = sum(skel_p*y), S2 = sum(skel_p), S3 = sum(skel_y*p), S4 = sum(skel_y)]
+__global__ void cldice_finalize_kernel(const double* __restrict__ s, float smooth, float* __restrict__ out4) {
+  if (threadIdx.x != 0) return;
+  double sm = smooth;
+  double tprec = (s[0] + sm) / (s[1] + sm);
+  double tsens = (s[2] + sm) / (s[3] + sm);
+  double sum = tprec + tsens;
+  double loss = 1.0 - 2.0 * tprec * tsens / sum;
+  // dL/dtprec = -2 tsens^2/sum^2 ; dL/dtsens = -2 tprec^2/sum^2
+  double dLp = -2.0 * tsens * tsens / (sum * sum);
+  double dLs = -2.0 * tprec * tprec / (sum * sum);
+  out4[0] = (float)loss;
+  out4[1] = (float)(dLp / (s[1] + sm));                              // dL/dS1
+  out4[2] = (float)(-dLp * (s[0] + sm) / ((s[1] + sm) * (s[1] + sm)));  // dL/dS2
+  out4[3] = (float)(dLs / (s[3] + sm));                              // dL/dS3
+}
+
+}  // namespace mvd
+
+using namespace mvd;
+
+#define C_DISPATCH(C, CALL)   \
+  switch (C) {                \
+    case 1: CALL(1); break;   \
+    case 2: CALL(2); break;   \
+    case 3: CALL(3); break;   \
+    case 4: CALL(4); break;   \
+    case 5: CALL(5); break;   \
+    case 6: CALL(6); break;   \
+    case 7: CALL(7); break;   \
+    case 8: CALL(8); break;   \
+    default: mvd::set_error("number of classes must be in 1..8 (got %d)", C); return MVD_ERR_UNSUPPORTED; \
+  }
+
+extern "C" {
+
+int mvd_dice_ce_fwd(const void* logits, int ld, const float* target, int B, long long V, int C, double* acc,
+                    mvd_stream_t stream) {
+  MVD_REQUIRE(logits && target && acc && B > 0 && V > 0 && ld >= C, "dice_ce_fwd: bad arguments");
+  dim3 grid(grid_for(V, 256 * 4, num_sms() * 4), B);
+#define CALL(CC) dice_ce_fwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, target, V, acc, B)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("dice_ce_fwd");
+  return MVD_OK;
+}
+
+int mvd_dice_ce_finalize(const double* acc, int B, long long V, int C, float smooth, int do_bg, int batch_dice,
+                         float w_ce, float w_dice, float weight, float* coef, float* loss_out, mvd_stream_t stream) {
+  MVD_REQUIRE(acc && coef && loss_out && B > 0 && V > 0 && C >= 1 && C <= 8, "dice_ce_finalize: bad arguments");
+  dice_ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, B, V, C, smooth, do_bg, batch_dice, w_ce, w_dice,
+                                                               weight, coef, loss_out);
+  MVD_LAUNCH_CHECK("dice_ce_finalize");
+  return MVD_OK;
+}
+
+int mvd_dice_ce_bwd(const void* logits, int ld, const float* target, int B, long long V, int C, const float* coef,
+                    float w_ce, float weight, const float* gout, void* dlogits, int ldd, mvd_stream_t stream) {
+  MVD_REQUIRE(logits && target && coef && dlogits && B > 0 && V > 0 && ld >= C && ldd >= C, "dice_ce_bwd: bad arguments");
+  dim3 grid(grid_for(V, 256 * 2, num_sms() * 8), B);
+  const float ce_scale = w_ce / ((float)B * (float)V);
+#define CALL(CC)                                                                                                   \
+  dice_ce_bwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, target, V, coef, ce_scale, \
+                                                                 weight, gout, (bf16*)dlogits, ldd)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("dice_ce_bwd");
+  return MVD_OK;
+}
+
+int mvd_argmax_tp_fp_fn(const void* logits, int ld, const float* target, int B, long long V, int C, double* out,
+                        mvd_stream_t stream) {
+  MVD_REQUIRE(logits && target && out && B > 0 && V > 0 && ld >= C, "argmax_tp_fp_fn: bad arguments");
+  const long long NV = (long long)B * V;
+  int grid = grid_for(NV, 256 * 4, num_sms() * 4);
+#define CALL(CC) argmax_tp_fp_fn_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, target, NV, out)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("argmax_tp_fp_fn");
+  return MVD_OK;
+}
+
+int mvd_kl_fwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, double* loss_sum,
+               mvd_stream_t stream) {
+  MVD_REQUIRE(ys && yt && loss_sum && NV > 0 && lds >= C && ldt >= C && T > 0.f, "kl_fwd: bad arguments");
+  int grid = grid_for(NV, 256 * 4, num_sms() * 4);
+#define CALL(CC) kl_fwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)ys, lds, (const bf16*)yt, ldt, NV, 1.f / T, loss_sum)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("kl_fwd");
+  return MVD_OK;
+}
+
+int mvd_kl_bwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, float scale,
+               const float* gout, void* dys, int ldds, void* dyt, int lddt, mvd_stream_t stream) {
+  MVD_REQUIRE(ys && yt && NV > 0 && lds >= C && ldt >= C && T > 0.f && (dys || dyt), "kl_bwd: bad arguments");
+  int grid = grid_for(NV, 256 * 2, num_sms() * 8);
+#define CALL(CC)                                                                                                 \
+  kl_bwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)ys, lds, (const bf16*)yt, ldt, NV, 1.f / T, \
+                                                            scale, gout, (bf16*)dys, ldds, (bf16*)dyt, lddt)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("kl_bwd");
+  return MVD_OK;
+}
+
+int mvd_softmax_channel_fwd(const void* logits, int ld, const float* target, long long NV, int C, int channel,
+                            float* prob, float* onehot, mvd_stream_t stream) {
+  MVD_REQUIRE(logits && prob && NV > 0 && ld >= C && channel >= 0 && channel < C && (target || !onehot),
+              "softmax_channel_fwd: bad arguments");
+  int grid = grid_for(NV, 256 * 2, num_sms() * 8);
+#define CALL(CC) softmax_channel_fwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, target, NV, channel, prob, onehot)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("softmax_channel_fwd");
+  return MVD_OK;
+}
+
+int mvd_softmax_channel_bwd(const void* logits, int ld, const float* dprob, long long NV, int C, int channel,
+                            void* dlogits, int ldd, mvd_stream_t stream) {
+  MVD_REQUIRE(logits && dprob && dlogits && NV > 0 && ld >= C && ldd >= C && channel >= 0 && channel < C,
+              "softmax_channel_bwd: bad arguments");
+  int grid = grid_for(NV, 256 * 2, num_sms() * 8);
+#define CALL(CC) softmax_channel_bwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, dprob, NV, channel, (bf16*)dlogits, ldd)
+  C_DISPATCH(C, CALL)
+#undef CALL
+  MVD_LAUNCH_CHECK("softmax_channel_bwd");
+  return MVD_OK;
+}
+
+int mvd_dot_sum(const float* a, const float* b, long long N, double* sums2, mvd_stream_t stream) {
+  MVD_REQUIRE(a && b && sums2 && N > 0, "dot_sum: bad arguments");
+  int grid = grid_for(N, 256 * 8, num_sms() * 4);
+  dot_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, N, sums2);
+  MVD_LAUNCH_CHECK("dot_sum");
+  return MVD_OK;
+}
+
+int mvd_cldice_seed(const float* y, const float* out4, const float* gout, float* g_skel, long long N,
+                    mvd_stream_t stream) {
+  MVD_REQUIRE(y && out4 && g_skel && N > 0, "cldice_seed: bad arguments");
+  int grid = grid_for(N, 256 * 4, num_sms() * 8);
+  cldice_seed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, out4, gout, g_skel, N);
+  MVD_LAUNCH_CHECK("cldice_seed");
+  return MVD_OK;
+}
+
+int mvd_cldice_combine(const float* gE0, const float* skel_y, const float* out4, const float* gout, float* dprob,
+                       long long N, mvd_stream_t stream) {
+  MVD_REQUIRE(gE0 && skel_y && out4 && dprob && N > 0, "cldice_combine: bad arguments");
+  int grid = grid_for(N, 256 * 4, num_sms() * 8);
+  cldice_combine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gE0, skel_y, out4, gout, dprob, N);
+  MVD_LAUNCH_CHECK("cldice_combine");
+  return MVD_OK;
+}
+
+int mvd_cldice_finalize(const double* sums4, float smooth, float* out4, mvd_stream_t stream) {
+  MVD_REQUIRE(sums4 && out4, "cldice_finalize: bad arguments");
+  cldice_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums4, smooth, out4);
+  MVD_LAUNCH_CHECK("cldice_finalize");
+  return MVD_OK;
+}
+
+}  // extern "C"

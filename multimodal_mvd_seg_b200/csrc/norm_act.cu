@@ -1,0 +1,402 @@
+// norm_act.cu -- layout conversion at the module edge, InstanceNorm3d(affine)+LeakyReLU forward/backward,
+// bf16 accumulate.  All kernels are HBM-bound streaming kernels: 16-byte vector accesses along the contiguous
+// channel axis, grids sized in multiples of the SM count, fp32 math, double accumulation of the per-(b,c) sums.
+//
+// Reference ops replaced: nn.InstanceNorm3d(eps=1e-5, affine=True) + nn.LeakyReLU(inplace=True)
+// (nnunetv2/utilities/get_network_from_plans.py:41-44) and their autograd.
+#include "common.cuh"
+
+namespace mvd {
+
+// ------------------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void ncdhw_to_ndhwc_small_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long V,
+                                            int ld) {
+  const int b = blockIdx.y;
+  const float* s = src + (long long)b * C * V;
+  bf16* d = dst + (long long)b * V * ld;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[v * ld + c] = f2bf(__ldg(s + (long long)c * V + v));
+  }
+}
+
+__global__ void ncdhw_to_ndhwc_generic_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C,
+                                              long long V, int ld) {
+  const int b = blockIdx.y;
+  const float* s = src + (long long)b * C * V;
+  bf16* d = dst + (long long)b * V * ld;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) d[v * ld + c] = f2bf(__ldg(s + (long long)c * V + v));
+}
+
+__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, int ld, float* __restrict__ dst, int C,
+                                      long long V) {
+  const int b = blockIdx.y;
+  const bf16* s = src + (long long)b * V * ld;
+  float* d = dst + (long long)b * C * V;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) d[(long long)c * V + v] = bf2f(s[v * ld + c]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// InstanceNorm statistics: per (b,c) sum and sum of squares over V voxels.
+// Thread layout: CG = C/8 channel groups (one 16-byte vector each); a block of 256 threads covers 256/CG voxel rows
+// per step.  Per-thread fp32 partials over a bounded run (<= 4096 rows), block tree in shared memory, then one double
+// atomicAdd per (channel, block) -- contention is B*C addresses x gridDim.x adds, negligible.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kStatThreads = 256;
+
+__global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* __restrict__ y, int ld, long long V,
+                                                                   int C, double* __restrict__ stats,
+                                                                   long long rows_per_block) {
+  extern __shared__ float sm[];  // [rows][CG*8][2]
+  const int b = blockIdx.y;
+  const int CG = C >> 3;
+  const int rows = kStatThreads / CG;  // voxel rows handled in parallel
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, r = tid / CG;
+  const bf16* base = y + (long long)b * V * ld;
+  long long v0 = (long long)blockIdx.x * rows_per_block;
+  long long v1 = v0 + rows_per_block;
+  if (v1 > V) v1 = V;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < rows) {
+    for (long long v = v0 + r; v < v1; v += rows) {
+      bf16x8 p = *reinterpret_cast<const bf16x8*>(base + v * ld + cg * 8);
+      float f[8];
+      unpack8(p, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+  // reduce across the `rows` threads that share a channel group
+  float* ss = sm;                       // [rows][C]
+  float* qq = sm + rows * C;            // [rows][C]
+  if (r < rows) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ss[r * C + cg * 8 + i] = s[i];
+      qq[r * C + cg * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kStatThreads) {
+    double a = 0.0, d = 0.0;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += (double)ss[rr * C + c];
+      d += (double)qq[rr * C + c];
+    }
+    atomicAdd(&stats[((long long)b * C + c) * 2 + 0], a);
+    atomicAdd(&stats[((long long)b * C + c) * 2 + 1], d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward apply:  t = bf16(gamma*(y-mean)*rstd + beta);  z = t > 0 ? t : bf16(slope*t)
+// (two roundings, as the reference's bf16 InstanceNorm followed by an in-place bf16 LeakyReLU produces)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_scale_shift(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, int b, int C, long long V, float eps,
+                                                 float* sc, float* sh, float* mean_out, float* rstd_out) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = stats[((long long)b * C + c) * 2 + 0];
+    double s2 = stats[((long long)b * C + c) * 2 + 1];
+    double m = s1 / (double)V;
+    double var = s2 / (double)V - m * m;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f;
+    float be = beta ? beta[c] : 0.f;
+    sc[c] = g * rstd;
+    sh[c] = be - (float)m * g * rstd;
+    if (mean_out) mean_out[c] = (float)m;
+    if (rstd_out) rstd_out[c] = rstd;
+  }
+}
+
+__global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __restrict__ y, int ldy,
+                                                              bf16* __restrict__ z, int ldz,
+                                                              const double* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, long long V, int C,
+                                                              float eps, float slope) {
+  extern __shared__ float sm[];
+  float* sc = sm;
+  float* sh = sm + C;
+  const int b = blockIdx.y;
+  load_scale_shift(stats, gamma, beta, b, C, V, eps, sc, sh, nullptr, nullptr);
+  __syncthreads();
+  const int CG = C >> 3;
+  const long long nvec = V * CG;
+  const bf16* yb = y + (long long)b * V * ldy;
+  bf16* zb = z + (long long)b * V * ldz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / CG;
+    int cg = (int)(i - v * CG);
+    bf16x8 p = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+    float f[8];
+    unpack8(p, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = round_bf(fmaf(f[k], sc[cg * 8 + k], sh[cg * 8 + k]));
+      f[k] = t > 0.f ? t : slope * t;
+    }
+    *reinterpret_cast<bf16x8*>(zb + v * ldz + cg * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward statistics: g' = dz * (pre > 0 ? 1 : slope);  S1 = sum g',  S2 = sum g' * xhat   per (b,c)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_stats_kernel(
+    const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, const double* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, long long V, int C, float eps, float slope,
+    double* __restrict__ bstats, long long rows_per_block) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y;
+  const int CG = C >> 3;
+  const int rows = kStatThreads / CG;
+  float* sc = sm;            // gamma*rstd
+  float* sh = sm + C;        // beta - mean*gamma*rstd
+  float* mean = sm + 2 * C;
+  float* rstd = sm + 3 * C;
+  float* red = sm + 4 * C;   // [rows][C][2]
+  load_scale_shift(stats, gamma, beta, b, C, V, eps, sc, sh, mean, rstd);
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, r = tid / CG;
+  const bf16* yb = y + (long long)b * V * ldy;
+  const bf16* gb = dz + (long long)b * V * lddz;
+  long long v0 = (long long)blockIdx.x * rows_per_block;
+  long long v1 = v0 + rows_per_block;
+  if (v1 > V) v1 = V;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (r < rows) {
+    for (long long v = v0 + r; v < v1; v += rows) {
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      float fy[8], fg[8];
+      unpack8(py, fy);
+      unpack8(pg, fg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        float pre = round_bf(fmaf(fy[k], sc[c], sh[c]));
+        float gp = pre > 0.f ? fg[k] : slope * fg[k];
+        float xh = (fy[k] - mean[c]) * rstd[c];
+        s1[k] += gp;
+        s2[k] = fmaf(gp, xh, s2[k]);
+      }
+    }
+  }
+  if (r < rows) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[(r * C + cg * 8 + k) * 2 + 0] = s1[k];
+      red[(r * C + cg * 8 + k) * 2 + 1] = s2[k];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kStatThreads) {
+    double a = 0.0, d = 0.0;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += (double)red[(rr * C + c) * 2 + 0];
+      d += (double)red[(rr * C + c) * 2 + 1];
+    }
+    atomicAdd(&bstats[((long long)b * C + c) * 2 + 0], a);
+    atomicAdd(&bstats[((long long)b * C + c) * 2 + 1], d);
+  }
+}
+
+// dy = gamma*rstd*(g' - S1/V - xhat*S2/V)
+__global__ void __launch_bounds__(256) inorm_lrelu_bwd_apply_kernel(
+    const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, bf16* __restrict__ dy, int lddy,
+    const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
+    float* __restrict__ dbeta) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y;
+  float* sc = sm;
+  float* sh = sm + C;
+  float* mean = sm + 2 * C;
+  float* rstd = sm + 3 * C;
+  float* m1 = sm + 4 * C;  // S1/V
+  float* m2 = sm + 5 * C;  // S2/V
+  load_scale_shift(stats, gamma, beta, b, C, V, eps, sc, sh, mean, rstd);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    m1[c] = (float)(bstats[((long long)b * C + c) * 2 + 0] / (double)V);
+    m2[c] = (float)(bstats[((long long)b * C + c) * 2 + 1] / (double)V);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma || dbeta)) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double a = 0.0, d = 0.0;
+      for (int bb = 0; bb < B; ++bb) {
+        a += bstats[((long long)bb * C + c) * 2 + 0];
+        d += bstats[((long long)bb * C + c) * 2 + 1];
+      }
+      if (dbeta) dbeta[c] = (float)a;
+      if (dgamma) dgamma[c] = (float)d;
+    }
+  }
+  __syncthreads();
+  const int CG = C >> 3;
+  const long long nvec = V * CG;
+  const bf16* yb = y + (long long)b * V * ldy;
+  const bf16* gb = dz + (long long)b * V * lddz;
+  bf16* ob = dy + (long long)b * V * lddy;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / CG;
+    int cg = (int)(i - v * CG);
+    bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+    bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+    float fy[8], fg[8], o[8];
+    unpack8(py, fy);
+    unpack8(pg, fg);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      float pre = round_bf(fmaf(fy[k], sc[c], sh[c]));
+      float gp = pre > 0.f ? fg[k] : slope * fg[k];
+      float xh = (fy[k] - mean[c]) * rstd[c];
+      o[k] = sc[c] * (gp - m1[c] - xh * m2[c]);
+    }
+    *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pack8(o);
+  }
+}
+
+// dst += src (bf16, pitched)
+__global__ void __launch_bounds__(256) add_bf16_kernel(bf16* __restrict__ dst, int ldd, const bf16* __restrict__ src,
+                                                       int lds, long long NV, int C) {
+  const int CG = C >> 3;
+  const long long nvec = NV * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / CG;
+    int cg = (int)(i - v * CG);
+    bf16x8 a = *reinterpret_cast<const bf16x8*>(dst + v * ldd + cg * 8);
+    bf16x8 s = *reinterpret_cast<const bf16x8*>(src + v * lds + cg * 8);
+    float fa[8], fs[8];
+    unpack8(a, fa);
+    unpack8(s, fs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fa[k] += fs[k];
+    *reinterpret_cast<bf16x8*>(dst + v * ldd + cg * 8) = pack8(fa);
+  }
+}
+
+static bool vec_ok(const void* p, int ld, int C) {
+  return (C % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" {
+
+int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int B, int C, long long V, int ld_dst,
+                                mvd_stream_t stream) {
+  MVD_REQUIRE(src && dst && B > 0 && C > 0 && V > 0 && ld_dst >= C, "ncdhw_to_ndhwc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(grid_for(V, 256, num_sms() * 8), B);
+  bf16* d = (bf16*)dst;
+  if (C == 1) ncdhw_to_ndhwc_small_kernel<1><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
+  else if (C == 2) ncdhw_to_ndhwc_small_kernel<2><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
+  else if (C == 4) ncdhw_to_ndhwc_small_kernel<4><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
+  else ncdhw_to_ndhwc_generic_kernel<<<grid, 256, 0, st>>>(src, d, C, V, ld_dst);
+  MVD_LAUNCH_CHECK("ncdhw_to_ndhwc");
+  return MVD_OK;
+}
+
+int mvd_ndhwc_bf16_to_ncdhw_f32(const void* src, int ld_src, float* dst, int B, int C, long long V,
+                                mvd_stream_t stream) {
+  MVD_REQUIRE(src && dst && B > 0 && C > 0 && V > 0 && ld_src >= C, "ndhwc_to_ncdhw: bad arguments");
+  dim3 grid(grid_for(V, 256, num_sms() * 8), B);
+  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, dst, C, V);
+  MVD_LAUNCH_CHECK("ndhwc_to_ncdhw");
+  return MVD_OK;
+}
+
+int mvd_inorm_stats(const void* y, int ldy, int B, long long V, int C, double* stats, mvd_stream_t stream) {
+  MVD_REQUIRE(y && stats && B > 0 && V > 0, "inorm_stats: bad arguments");
+  MVD_REQUIRE(vec_ok(y, ldy, C) && C <= 2048 && (kStatThreads / (C / 8)) >= 1,
+              "inorm_stats: need C %% 8 == 0, ld %% 8 == 0, 16B-aligned pointer, C <= 2048 (C=%d ld=%d)", C, ldy);
+  const int rows = kStatThreads / (C / 8);
+  long long rpb = 4096;  // bounded fp32 run per thread: 4096/rows terms
+  long long nblk = (V + rpb - 1) / rpb;
+  // aim for >= 4 blocks per SM when the volume allows it
+  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
+    rpb >>= 1;
+    nblk = (V + rpb - 1) / rpb;
+  }
+  dim3 grid((unsigned)nblk, B);
+  size_t smem = (size_t)rows * C * 2 * sizeof(float);
+  inorm_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, V, C, stats, rpb);
+  MVD_LAUNCH_CHECK("inorm_stats");
+  return MVD_OK;
+}
+
+int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* stats, const float* gamma,
+                        const float* beta, int B, long long V, int C, float eps, float slope, mvd_stream_t stream) {
+  MVD_REQUIRE(y && z && stats && B > 0 && V > 0, "inorm_lrelu_fwd: bad arguments");
+  MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(z, ldz, C), "inorm_lrelu_fwd: need C %% 8 == 0 and 16B-aligned pitched rows");
+  dim3 grid(grid_for(V * (C / 8), 256 * 4, num_sms() * 8), B);
+  inorm_lrelu_fwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)y, ldy, (bf16*)z, ldz, stats, gamma, beta, V, C, eps, slope);
+  MVD_LAUNCH_CHECK("inorm_lrelu_fwd");
+  return MVD_OK;
+}
+
+int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, const double* stats,
+                              const float* gamma, const float* beta, int B, long long V, int C, float eps,
+                              float slope, double* bstats, mvd_stream_t stream) {
+  MVD_REQUIRE(dz && y && stats && bstats && B > 0 && V > 0, "inorm_lrelu_bwd_stats: bad arguments");
+  MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && C <= 2048, "inorm_lrelu_bwd_stats: alignment/C");
+  const int rows = kStatThreads / (C / 8);
+  long long rpb = 4096;
+  long long nblk = (V + rpb - 1) / rpb;
+  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
+    rpb >>= 1;
+    nblk = (V + rpb - 1) / rpb;
+  }
+  dim3 grid((unsigned)nblk, B);
+  size_t smem = (size_t)(4 * C + rows * C * 2) * sizeof(float);
+  inorm_lrelu_bwd_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(
+      (const bf16*)dz, lddz, (const bf16*)y, ldy, stats, gamma, beta, V, C, eps, slope, bstats, rpb);
+  MVD_LAUNCH_CHECK("inorm_lrelu_bwd_stats");
+  return MVD_OK;
+}
+
+int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, void* dy, int lddy,
+                              const double* stats, const double* bstats, const float* gamma, const float* beta,
+                              int B, long long V, int C, float eps, float slope, float* dgamma, float* dbeta,
+                              mvd_stream_t stream) {
+  MVD_REQUIRE(dz && y && dy && stats && bstats && B > 0 && V > 0, "inorm_lrelu_bwd_apply: bad arguments");
+  MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && vec_ok(dy, lddy, C), "inorm_lrelu_bwd_apply: alignment/C");
+  dim3 grid(grid_for(V * (C / 8), 256 * 4, num_sms() * 8), B);
+  inorm_lrelu_bwd_apply_kernel<<<grid, 256, 6 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)dz, lddz, (const bf16*)y, ldy, (bf16*)dy, lddy, stats, bstats, gamma, beta, B, V, C, eps, slope,
+      dgamma, dbeta);
+  MVD_LAUNCH_CHECK("inorm_lrelu_bwd_apply");
+  return MVD_OK;
+}
+
+int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int C, mvd_stream_t stream) {
+  MVD_REQUIRE(dst && src && NV > 0, "add_bf16: bad arguments");
+  MVD_REQUIRE(vec_ok(dst, ldd, C) && vec_ok(src, lds, C), "add_bf16: alignment/C");
+  int grid = grid_for(NV * (C / 8), 256 * 4, num_sms() * 8);
+  add_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)dst, ldd, (const bf16*)src, lds, NV, C);
+  MVD_LAUNCH_CHECK("add_bf16");
+  return MVD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,727 @@
+"""torch.autograd Functions over the C ABI of libmvdseg.so.
+
+PyTorch is plumbing here (device memory, streams, the autograd tape); every device computation below is a call into
+the hand-written sm_100a library.  Activations travel as bf16 tensors of logical shape [B, D, H, W, C] ("NDHWC"),
+possibly a channel slice of a wider buffer (voxel pitch ld > C), see include/mvdseg.h.
+"""
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import ConvArgs, MvdError, lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, who: str):
+    if not t.is_cuda:
+        raise MvdError(f'{who}: tensors must live on a CUDA device (got {t.device}); libmvdseg has no CPU path')
+
+
+def cl_pitch(t: torch.Tensor) -> int:
+    """voxel pitch (elements) of an NDHWC tensor; raises if the voxels are not dense."""
+    assert t.dim() == 5, t.shape
+    B, D, H, W, C = t.shape
+    st = t.stride()
+    if C > 1 and st[4] != 1:
+        raise MvdError('NDHWC tensor must have unit channel stride')
+    if W > 1:
+        ld = st[3]
+    elif H > 1:
+        ld = st[2]
+    elif D > 1:
+        ld = st[1]
+    elif B > 1:
+        ld = st[0]
+    else:
+        ld = C
+    exp = (D * H * W * ld, H * W * ld, W * ld, ld)
+    for i, n in enumerate((B, D, H, W)):
+        if n > 1 and st[i] != exp[i]:
+            raise MvdError(f'NDHWC tensor has non-dense voxels: shape {tuple(t.shape)} strides {st}')
+    if ld < C:
+        raise MvdError('bad pitch')
+    return ld
+
+
+def as_cl(t: torch.Tensor) -> torch.Tensor:
+    """returns t if it is a valid pitched NDHWC bf16 tensor, else a dense copy."""
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    try:
+        cl_pitch(t)
+        return t
+    except MvdError:
+        return t.contiguous()
+
+
+def ncdhw_view(t_cl: torch.Tensor) -> torch.Tensor:
+    """[B,D,H,W,C] -> logical [B,C,D,H,W] view (channels-last-3d memory format)."""
+    return t_cl.permute(0, 4, 1, 2, 3)
+
+
+def to_cl_view(t: torch.Tensor) -> torch.Tensor:
+    """logical [B,C,D,H,W] (any strides) -> NDHWC bf16 tensor usable by the kernels (view when possible)."""
+    return as_cl(t.permute(0, 2, 3, 4, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# layout at the module edge
+# ---------------------------------------------------------------------------------------------------------------
+def input_to_cl(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCDHW batch -> bf16 NDHWC (no gradient: the network input is data)."""
+    require_cuda(x, 'input_to_cl')
+    x = x.contiguous().float()
+    B, C, D, H, W = x.shape
+    out = torch.empty((B, D, H, W, C), dtype=BF16, device=x.device)
+    lib.ncdhw_f32_to_ndhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, D * H * W, C, _stream())
+    return out
+
+
+def cl_to_ncdhw_f32(t_cl: torch.Tensor) -> torch.Tensor:
+    B, D, H, W, C = t_cl.shape
+    ld = cl_pitch(t_cl)
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=t_cl.device)
+    lib.ndhwc_bf16_to_ncdhw_f32(t_cl.data_ptr(), ld, out.data_ptr(), B, C, D * H * W, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution plumbing
+# ---------------------------------------------------------------------------------------------------------------
+class Slot:
+    """holds a preallocated output tensor; passed to Functions as a non-tensor argument so that autograd does not
+    treat the destination buffer as an input."""
+    __slots__ = ('t',)
+
+    def __init__(self, t):
+        self.t = t
+
+
+class ConvGeom:
+    """geometry of a conv (or of the conv a transposed conv is the adjoint of)."""
+    __slots__ = ('k', 's', 'p')
+
+    def __init__(self, k, s, p):
+        self.k, self.s, self.p = tuple(k), tuple(s), tuple(p)
+
+    def out_size(self, in_size):
+        return tuple((i + 2 * p - k) // s + 1 for i, k, s, p in zip(in_size, self.k, self.s, self.p))
+
+
+_ALGO = {'auto': 0, 'generic': 1, 'tc': 2}
+_default_algo = 0
+
+
+def set_conv_algo(name: str):
+    """'auto' (tcgen05 where covered), 'generic' (CUDA-core tiles), 'tc' (tcgen05 or error). Test hook."""
+    global _default_algo
+    _default_algo = _ALGO[name]
+
+
+def _conv_args(geom: ConvGeom, x_cl: torch.Tensor, y_cl: torch.Tensor, w_packed=None, bias=None, stats=None, dw=None,
+               dbias=None, accumulate=False, workspace=None) -> ConvArgs:
+    B, Di, Hi, Wi, Cin = x_cl.shape
+    Bo, Do, Ho, Wo, Cout = y_cl.shape
+    assert B == Bo
+    a = ConvArgs()
+    a.B, a.Di, a.Hi, a.Wi, a.Cin = B, Di, Hi, Wi, Cin
+    a.Do, a.Ho, a.Wo, a.Cout = Do, Ho, Wo, Cout
+    a.kd, a.kh, a.kw = geom.k
+    a.sd, a.sh, a.sw = geom.s
+    a.pd, a.ph, a.pw = geom.p
+    a.x, a.ldx = x_cl.data_ptr(), cl_pitch(x_cl)
+    a.y, a.ldy = y_cl.data_ptr(), cl_pitch(y_cl)
+    a.w = _ptr(w_packed)
+    a.bias = _ptr(bias)
+    a.stats = _ptr(stats)
+    a.dw = _ptr(dw)
+    a.dbias = _ptr(dbias)
+    a.workspace = _ptr(workspace)
+    a.workspace_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    a.algo = _default_algo
+    a.accumulate = 1 if accumulate else 0
+    return a
+
+
+def pack_weights(w: torch.Tensor, want_fprop=True, want_dgrad=True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """fp32 [Cout][Cin][kd][kh][kw] -> bf16 [tap][Cout][Cin] and [tap][Cin][Cout]."""
+    require_cuda(w, 'pack_weights')
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    wf = torch.empty((taps, Cout, Cin), dtype=BF16, device=w.device) if want_fprop else None
+    wd = torch.empty((taps, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
+    lib.pack_conv_weights(w.data_ptr(), Cout, Cin, taps, _ptr(wf), _ptr(wd), _stream())
+    return wf, wd
+
+
+class ConvTimer:
+    """optional CUDA-event bracket around every conv launch (bench.py's live roofline measurement): per pass
+    ('fprop' | 'dgrad' | 'wgrad') the algorithmic FLOPs 2*B*Vout*Cout*Cin*taps and the event-timed duration."""
+
+    def __init__(self):
+        self.records = []   # (pass, flops, start_event, end_event, tag)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, e0, e1, tag in self.records:
+            d = out.setdefault(kind, dict(flops=0.0, ms=0.0, launches=0))
+            d['flops'] += flops
+            d['ms'] += e0.elapsed_time(e1)
+            d['launches'] += 1
+        return out
+
+    def per_layer(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, e0, e1, tag in self.records:
+            d = out.setdefault((kind, tag), dict(flops=0.0, ms=0.0, launches=0))
+            d['flops'] += flops
+            d['ms'] += e0.elapsed_time(e1)
+            d['launches'] += 1
+        return out
+
+
+_conv_timer: Optional[ConvTimer] = None
+
+
+def set_conv_timer(t: Optional[ConvTimer]):
+    global _conv_timer
+    _conv_timer = t
+
+
+def _timed(kind, a: ConvArgs, fn):
+    if _conv_timer is None:
+        fn(ctypes.byref(a), _stream())
+        return
+    flops = 2.0 * a.B * a.Do * a.Ho * a.Wo * a.Cout * a.Cin * a.kd * a.kh * a.kw
+    tag = f'{a.Cin}->{a.Cout} k{a.kd}{a.kh}{a.kw} s{a.sd}{a.sh}{a.sw} out{a.Do}x{a.Ho}x{a.Wo}'
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(ctypes.byref(a), _stream())
+    e1.record()
+    _conv_timer.records.append((kind, flops, e0, e1, tag))
+
+
+def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None):
+    a = _conv_args(geom, x_cl, y_cl, w_packed=wf, bias=bias, stats=stats)
+    _timed('fprop', a, lib.conv3d_fprop)
+
+
+def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False):
+    a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd, bias=bias, accumulate=accumulate)
+    _timed('dgrad', a, lib.conv3d_dgrad)
+
+
+def conv_wgrad(geom, x_cl, y_cl, dw, dbias=None):
+    a = _conv_args(geom, x_cl, y_cl, dw=dw, dbias=dbias)
+    nbytes = lib.conv3d_workspace_bytes(ctypes.byref(a), 2)
+    ws = None
+    if nbytes:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x_cl.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    _timed('wgrad', a, lib.conv3d_wgrad)
+
+
+_grad_alloc = None
+
+
+def set_grad_allocator(fn):
+    """fn(param) -> fp32 tensor view (same shape) the weight gradient is written into (DDP bucket arena), or None."""
+    global _grad_alloc
+    _grad_alloc = fn
+
+
+def _grad_like(p: torch.Tensor) -> torch.Tensor:
+    if _grad_alloc is not None:
+        g = _grad_alloc(p)
+        if g is not None:
+            return g
+    return torch.empty(p.shape, dtype=torch.float32, device=p.device)
+
+
+_backward_hooks = []
+
+
+def add_param_grad_ready_hook(fn):
+    """fn(list_of_params) is called from backward as soon as those parameters' gradients have been written."""
+    _backward_hooks.append(fn)
+    return fn
+
+
+def clear_param_grad_ready_hooks():
+    _backward_hooks.clear()
+
+
+def _notify(params):
+    for fn in _backward_hooks:
+        fn(params)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Conv3d -> InstanceNorm3d(affine) -> LeakyReLU   (one ConvDropoutNormReLU block)
+# ---------------------------------------------------------------------------------------------------------------
+class ConvNormActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, weight, bias, gamma, beta, geom: ConvGeom, eps: float, slope: float,
+                out_slot: Optional['Slot'], params_for_hook):
+        require_cuda(x_cl, 'ConvNormAct')
+        out = out_slot.t if out_slot is not None else None
+        x_cl = as_cl(x_cl)
+        B, Di, Hi, Wi, Cin = x_cl.shape
+        Cout = weight.shape[0]
+        Do, Ho, Wo = geom.out_size((Di, Hi, Wi))
+        dev = x_cl.device
+        need_dx = ctx.needs_input_grad[0]
+        wf, wd = pack_weights(weight, True, need_dx)
+        y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
+        stats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev)
+        V = Do * Ho * Wo
+        conv_fprop(geom, x_cl, y, wf, bias=bias)
+        lib.inorm_stats(y.data_ptr(), cl_pitch(y), B, V, Cout, stats.data_ptr(), _stream())
+        z = out if out is not None else torch.empty_like(y)
+        lib.inorm_lrelu_fwd(y.data_ptr(), cl_pitch(y), z.data_ptr(), cl_pitch(z), stats.data_ptr(), _ptr(gamma),
+                            _ptr(beta), B, V, Cout, eps, slope, _stream())
+        ctx.geom, ctx.eps, ctx.slope = geom, eps, slope
+        ctx.params_for_hook = params_for_hook
+        ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x_cl, y, stats, wd, weight, bias, gamma, beta = ctx.saved_tensors
+        geom, eps, slope = ctx.geom, ctx.eps, ctx.slope
+        dz = as_cl(dz)
+        B, Do, Ho, Wo, Cout = y.shape
+        V = Do * Ho * Wo
+        dev = y.device
+        st = _stream()
+        bstats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev)
+        lib.inorm_lrelu_bwd_stats(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), stats.data_ptr(),
+                                  _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, bstats.data_ptr(), st)
+        dy = torch.empty_like(y)
+        dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
+        dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
+        lib.inorm_lrelu_bwd_apply(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy),
+                                  stats.data_ptr(), bstats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
+                                  _ptr(dgamma), _ptr(dbeta), st)
+        dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
+        db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
+        if dw is not None:
+            conv_wgrad(geom, x_cl, dy, dw, db)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
+            conv_dgrad(geom, dx, dy, wd)
+        if ctx.params_for_hook:
+            _notify(ctx.params_for_hook)
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ConvTranspose3d with kernel == stride (the decoder's upsampling), expressed through the adjoint conv
+# ---------------------------------------------------------------------------------------------------------------
+class ConvTransposeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, weight, bias, stride, out_slot: Optional['Slot'], params_for_hook):
+        require_cuda(x_cl, 'ConvTranspose')
+        out = out_slot.t if out_slot is not None else None
+        x_cl = as_cl(x_cl)
+        B, d, h, w, CinT = x_cl.shape
+        CoutT = weight.shape[1]
+        s = tuple(stride)
+        geom = ConvGeom(s, s, (0, 0, 0))  # adjoint conv: hi-res (CoutT) -> lo-res (CinT)
+        dev = x_cl.device
+        wf, wd = pack_weights(weight, True, True)
+        up = out if out is not None else torch.empty((B, d * s[0], h * s[1], w * s[2], CoutT), dtype=BF16, device=dev)
+        conv_dgrad(geom, up, x_cl, wd, bias=bias)
+        ctx.geom = geom
+        ctx.params_for_hook = params_for_hook
+        ctx.save_for_backward(x_cl, wf, weight, bias)
+        return up
+
+    @staticmethod
+    def backward(ctx, dup):
+        x_cl, wf, weight, bias = ctx.saved_tensors
+        geom = ctx.geom
+        dup = as_cl(dup)
+        dev = dup.device
+        dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
+        db = None
+        if dw is not None:
+            conv_wgrad(geom, dup, x_cl, dw, None)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _grad_like(bias)
+            B, D, H, W, C = dup.shape
+            lib.channel_sum(dup.data_ptr(), cl_pitch(dup), B * D * H * W, C, db.data_ptr(), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
+            conv_fprop(geom, dup, dx, wf)
+        if ctx.params_for_hook:
+            _notify(ctx.params_for_hook)
+        return dx, dw, db, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# zero-copy concat: `up` and `skip` are the two channel slices of one buffer
+# ---------------------------------------------------------------------------------------------------------------
+class ConcatViewFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, up, skip, buf_slot: 'Slot'):
+        buf = buf_slot.t
+        c1 = up.shape[-1]
+        assert up.data_ptr() == buf.data_ptr() and skip.data_ptr() == buf.data_ptr() + c1 * buf.element_size()
+        assert buf.shape[-1] == c1 + skip.shape[-1]
+        ctx.c1 = c1
+        return buf.view(buf.shape)  # a fresh tensor object aliasing the buffer
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.c1], g[..., ctx.c1:], None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 1x1x1 segmentation head
+# ---------------------------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_cl, weight, bias, params_for_hook):
+        require_cuda(z_cl, 'Head')
+        z_cl = as_cl(z_cl)
+        B, D, H, W, C = z_cl.shape
+        K = weight.shape[0]
+        logits = torch.empty((B, D, H, W, K), dtype=BF16, device=z_cl.device)
+        w2 = weight.detach().reshape(K, C)
+        if w2.dtype != torch.float32 or not w2.is_contiguous():
+            w2 = w2.float().contiguous()
+        lib.head_fwd(z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(bias), logits.data_ptr(), K,
+                     B * D * H * W, C, K, _stream())
+        ctx.params_for_hook = params_for_hook
+        ctx.save_for_backward(z_cl, weight, bias)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        z_cl, weight, bias = ctx.saved_tensors
+        dl = as_cl(dl)
+        B, D, H, W, C = z_cl.shape
+        K = weight.shape[0]
+        dev = z_cl.device
+        w2 = weight.detach().reshape(K, C)
+        if w2.dtype != torch.float32 or not w2.is_contiguous():
+            w2 = w2.float().contiguous()
+        dz = torch.empty((B, D, H, W, C), dtype=BF16, device=dev) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = _grad_like(weight)
+            dw.zero_()
+            db = _grad_like(bias) if bias is not None else None
+            if db is not None:
+                db.zero_()
+        lib.head_bwd(dl.data_ptr(), cl_pitch(dl), z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(dz),
+                     C if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, _stream())
+        if ctx.params_for_hook:
+            _notify(ctx.params_for_hook)
+        return dz, dw, db, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------------------
+def _target_f32(t: torch.Tensor) -> torch.Tensor:
+    """(B,1,D,H,W) or (B,D,H,W) class ids -> contiguous fp32 [B][V]."""
+    if t.dim() == 5:
+        assert t.shape[1] == 1
+        t = t[:, 0]
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class DiceCEMultiScaleFn(torch.autograd.Function):
+    """sum_i weight_i * (w_ce*CE + w_dice*SoftDice)(logits_i, target_i) -- DeepSupervisionWrapper(DC_and_CE_loss)."""
+
+    @staticmethod
+    def forward(ctx, cfg: dict, *tensors):
+        n = len(tensors) // 2
+        logits, targets = tensors[:n], tensors[n:]
+        weights = cfg['weights']
+        dev = logits[0].device
+        require_cuda(logits[0], 'DC_and_CE_loss')
+        st = _stream()
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        saved, meta = [], []
+        for i in range(n):
+            if weights[i] == 0:
+                meta.append(None)
+                continue
+            lg = to_cl_view(logits[i])
+            B, D, H, W, C = lg.shape
+            V = D * H * W
+            tg = _target_f32(targets[i])
+            acc = torch.zeros((B * C * 3 + 1,), dtype=torch.float64, device=dev)
+            lib.dice_ce_fwd(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, V, C, acc.data_ptr(), st)
+            gscale = 1.0
+            if cfg['batch_dice'] and cfg['ddp'] and torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(acc[:B * C * 3])  # AllGatherGrad(...).sum(0), ddp_allgather.py:35-48
+                gscale = float(torch.distributed.get_world_size())
+            coef = torch.empty((B, C, 2), dtype=torch.float32, device=dev)
+            lib.dice_ce_finalize(acc.data_ptr(), B, V, C, cfg['smooth'], int(cfg['do_bg']), int(cfg['batch_dice']),
+                                 cfg['weight_ce'], cfg['weight_dice'], float(weights[i]), coef.data_ptr(),
+                                 loss.data_ptr(), st)
+            if gscale != 1.0:
+                coef.mul_(gscale)
+            saved += [lg, tg, coef]
+            meta.append((B, V, C, tuple(logits[i].shape)))
+        ctx.cfg, ctx.meta, ctx.n = cfg, meta, n
+        ctx.save_for_backward(*saved)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg, meta, n = ctx.cfg, ctx.meta, ctx.n
+        saved = ctx.saved_tensors
+        st = _stream()
+        gout = gout.contiguous().float()
+        grads, j = [], 0
+        for i in range(n):
+            if meta[i] is None or not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                if meta[i] is not None:
+                    j += 3
+                continue
+            lg, tg, coef = saved[j:j + 3]
+            j += 3
+            B, V, C, shp = meta[i]
+            dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
+            lib.dice_ce_bwd(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, V, C, coef.data_ptr(), cfg['weight_ce'],
+                            float(cfg['weights'][i]), gout.data_ptr(), dl.data_ptr(), C, st)
+            grads.append(ncdhw_view(dl))
+        return (None, *grads, *([None] * n))
+
+
+class KLFn(torch.autograd.Function):
+    """distill_kl(y_s, y_t, T) of other_loss.py:51-64 on logits of logical shape [B,C,...]."""
+
+    @staticmethod
+    def forward(ctx, ys, yt, T: float):
+        require_cuda(ys, 'distill_kl')
+        a, b = to_cl_view(ys), to_cl_view(yt)
+        assert a.shape == b.shape
+        B, D, H, W, C = a.shape
+        NV = B * D * H * W
+        width = 2 if C == 1 else C
+        st = _stream()
+        acc = torch.zeros((1,), dtype=torch.float64, device=a.device)
+        lib.kl_fwd(a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, float(T), acc.data_ptr(), st)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        scale = float(T) ** 2 / float(NV * width)
+        lib.scalar_axpy(acc.data_ptr(), scale, loss.data_ptr(), 0, st)
+        ctx.T, ctx.scale = float(T), scale
+        ctx.save_for_backward(a, b)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        B, D, H, W, C = a.shape
+        NV = B * D * H * W
+        gout = gout.contiguous().float()
+        da = torch.empty(a.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[0] else None
+        db = torch.empty(b.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[1] else None
+        if da is not None or db is not None:
+            lib.kl_bwd(a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, ctx.T, ctx.scale, gout.data_ptr(),
+                       _ptr(da), C, _ptr(db), C, _stream())
+        return (None if da is None else ncdhw_view(da)), (None if db is None else ncdhw_view(db)), None
+
+
+class SoftmaxChannelFn(torch.autograd.Function):
+    """softmax(logits, 1)[:, ch:ch+1] as fp32 [B,1,D,H,W] (the clDice term's prediction, MVDTrainer.py:904-908)."""
+
+    @staticmethod
+    def forward(ctx, logits, channel: int):
+        require_cuda(logits, 'softmax_channel')
+        lg = to_cl_view(logits)
+        B, D, H, W, C = lg.shape
+        prob = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=lg.device)
+        lib.softmax_channel_fwd(lg.data_ptr(), cl_pitch(lg), None, B * D * H * W, C, channel, prob.data_ptr(), None,
+                                _stream())
+        ctx.channel = channel
+        ctx.save_for_backward(lg)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        (lg,) = ctx.saved_tensors
+        B, D, H, W, C = lg.shape
+        dprob = dprob.contiguous().float()
+        dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
+        lib.softmax_channel_bwd(lg.data_ptr(), cl_pitch(lg), dprob.data_ptr(), B * D * H * W, C, ctx.channel,
+                                dl.data_ptr(), C, _stream())
+        return ncdhw_view(dl), None
+
+
+def _vol_dims(t: torch.Tensor):
+    """(B,1,D,H,W) / (B,C,D,H,W) fp32 -> (B*C, D, H, W)."""
+    assert t.dim() == 5
+    return t.shape[0] * t.shape[1], t.shape[2], t.shape[3], t.shape[4]
+
+
+def _f32c(t):
+    return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+
+class SoftErodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        require_cuda(img, 'soft_erode')
+        img = _f32c(img)
+        out = torch.empty_like(img)
+        lib.soft_erode(img.data_ptr(), out.data_ptr(), *_vol_dims(img), _stream())
+        ctx.save_for_backward(img)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (img,) = ctx.saved_tensors
+        g = _f32c(g)
+        gin = torch.zeros_like(img)
+        lib.soft_erode_bwd(img.data_ptr(), g.data_ptr(), gin.data_ptr(), *_vol_dims(img), _stream())
+        return gin
+
+
+class SoftDilateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        require_cuda(img, 'soft_dilate')
+        img = _f32c(img)
+        out = torch.empty_like(img)
+        lib.soft_dilate(img.data_ptr(), out.data_ptr(), *_vol_dims(img), _stream())
+        ctx.save_for_backward(img)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (img,) = ctx.saved_tensors
+        g = _f32c(g)
+        gin = torch.zeros_like(img)
+        lib.soft_dilate_bwd(img.data_ptr(), g.data_ptr(), 1.0, gin.data_ptr(), *_vol_dims(img), _stream())
+        return gin
+
+
+def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
+    """runs soft_skel's levels; returns (skel, E stack [L+1], delta stack [L], skel stack [L]) (stacks None if !keep)."""
+    dims = _vol_dims(img)
+    N = img.numel()
+    L = iters + 1
+    st = _stream()
+    dev = img.device
+    E = torch.empty((L + 1, N), dtype=torch.float32, device=dev)
+    E[0].copy_(img.reshape(-1))
+    delta = torch.empty((L, N), dtype=torch.float32, device=dev) if keep else None
+    skel = torch.empty((L, N), dtype=torch.float32, device=dev)
+    for j in range(L):
+        lib.soft_erode(E[j].data_ptr(), E[j + 1].data_ptr(), *dims, st)
+        lib.skel_update(E[j].data_ptr(), E[j + 1].data_ptr(), skel[j - 1].data_ptr() if j > 0 else None,
+                        delta[j].data_ptr() if keep else None, skel[j].data_ptr(), 1 if j == 0 else 0, *dims, st)
+    return skel[L - 1].view(img.shape), (E if keep else None), delta, (skel if keep else None)
+
+
+def _skel_backward(g_skel: torch.Tensor, E, delta, skel, dims):
+    """gradient of soft_skel w.r.t. its input, given d/d(skel)."""
+    L, N = delta.shape
+    st = _stream()
+    dev = g_skel.device
+    g_delta = torch.empty((L, N), dtype=torch.float32, device=dev)
+    lib.skel_chain_bwd(delta.data_ptr(), skel.data_ptr(), g_skel.data_ptr(), g_delta.data_ptr(), L, N, st)
+    gE = torch.zeros((L + 1, N), dtype=torch.float32, device=dev)
+    for j in range(L):
+        lib.skel_level_bwd(E[j + 1].data_ptr(), delta[j].data_ptr(), g_delta[j].data_ptr(), gE[j].data_ptr(),
+                           gE[j + 1].data_ptr(), *dims, st)
+    for lvl in range(L, 0, -1):
+        lib.soft_erode_bwd(E[lvl - 1].data_ptr(), gE[lvl].data_ptr(), gE[lvl - 1].data_ptr(), *dims, st)
+    return gE[0]
+
+
+class SoftSkelFn(torch.autograd.Function):
+    """soft_skel(img, iter_) of soft_skeleton.py:29-37."""
+
+    @staticmethod
+    def forward(ctx, img, iters: int):
+        require_cuda(img, 'soft_skel')
+        img = _f32c(img)
+        need = ctx.needs_input_grad[0]
+        sk, E, delta, skel = _skel_forward(img, iters, need)
+        ctx.dims, ctx.shape = _vol_dims(img), img.shape
+        if need:
+            ctx.save_for_backward(E, delta, skel)
+        return sk.clone() if need else sk
+
+    @staticmethod
+    def backward(ctx, g):
+        E, delta, skel = ctx.saved_tensors
+        g = _f32c(g).reshape(-1)
+        return _skel_backward(g, E, delta, skel, ctx.dims).view(ctx.shape), None
+
+
+class SoftClDiceFn(torch.autograd.Function):
+    """soft_cldice(iter_, smooth)(y_true, y_pred) -- fused: both skeletons, the four sums, the scalar and (in
+    backward) the whole chain down to d/d(y_pred)."""
+
+    @staticmethod
+    def forward(ctx, y_true, y_pred, iters: int, smooth: float):
+        require_cuda(y_pred, 'soft_cldice')
+        y_true, y_pred = _f32c(y_true), _f32c(y_pred)
+        assert y_true.shape == y_pred.shape
+        dev = y_pred.device
+        st = _stream()
+        N = y_pred.numel()
+        need = ctx.needs_input_grad[1]
+        sp, E, delta, skel = _skel_forward(y_pred, iters, need)
+        stv, _, _, _ = _skel_forward(y_true, iters, False)
+        sums = torch.zeros((4,), dtype=torch.float64, device=dev)
+        lib.dot_sum(sp.data_ptr(), y_true.data_ptr(), N, sums.data_ptr(), st)
+        lib.dot_sum(stv.data_ptr(), y_pred.data_ptr(), N, sums[2:].data_ptr(), st)
+        out4 = torch.empty((4,), dtype=torch.float32, device=dev)
+        lib.cldice_finalize(sums.data_ptr(), float(smooth), out4.data_ptr(), st)
+        ctx.dims, ctx.shape = _vol_dims(y_pred), y_pred.shape
+        if need:
+            ctx.save_for_backward(E, delta, skel, y_true, stv.reshape(-1).clone(), out4)
+        return out4[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        E, delta, skel, y_true, stv, out4 = ctx.saved_tensors
+        st = _stream()
+        N = y_true.numel()
+        gout = gout.contiguous().float()
+        g_skel = torch.empty((N,), dtype=torch.float32, device=y_true.device)
+        lib.cldice_seed(y_true.data_ptr(), out4.data_ptr(), gout.data_ptr(), g_skel.data_ptr(), N, st)
+        gE0 = _skel_backward(g_skel, E, delta, skel, ctx.dims)
+        dp = torch.empty((N,), dtype=torch.float32, device=y_true.device)
+        lib.cldice_combine(gE0.data_ptr(), stv.data_ptr(), out4.data_ptr(), gout.data_ptr(), dp.data_ptr(), N, st)
+        return None, dp.view(ctx.shape), None, None
+
+
+def argmax_tp_fp_fn(logits: torch.Tensor, target: torch.Tensor):
+    """validation_step's hard tp/fp/fn over axes [0,2,3,4] (nnUNetTrainer.py:973-1004). Returns three [C] tensors."""
+    lg = to_cl_view(logits)
+    B, D, H, W, C = lg.shape
+    tg = _target_f32(target)
+    out = torch.zeros((C, 3), dtype=torch.float64, device=lg.device)
+    lib.argmax_tp_fp_fn(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, D * H * W, C, out.data_ptr(), _stream())
+    return out[:, 0], out[:, 1], out[:, 2]

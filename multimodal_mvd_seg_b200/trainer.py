@@ -1,0 +1,397 @@
+"""nnUNetTrainer-style trainers for the built hot path.
+
+``nnUNetTrainer`` keeps the hook names, signatures and return conventions of the reference base trainer
+(nnunetv2/training/nnUNetTrainer/nnUNetTrainer.py:68-1004) for the path north_star names: ``initialize``,
+``build_network_architecture`` (static), ``_build_loss``, ``_get_deep_supervision_scales``, ``configure_optimizers``,
+``set_deep_supervision_enabled``, ``train_step(batch) -> {'loss': np.ndarray}``,
+``validation_step(batch) -> {'loss','tp_hard','fp_hard','fn_hard'}``, ``save_checkpoint`` / ``load_checkpoint`` keys.
+``MVDTrainer`` (the reference's ``ContrastiveTrainer``, MVDTrainer.py:76-985) adds the second modality network, the
+mutual-distillation KL and the topological term with the canonical decisions of SURVEY.md section 8c.
+
+Everything outside the step (dataset unpacking, batchgenerators augmentation, logging, plotting, sliding-window
+validation export) is out of scope; ``plans`` / ``dataset_json`` are read through the two small accessors below, which
+expose the same property names as the reference's ConfigurationManager / LabelManager
+(utilities/plans_handling/plans_handler.py:32-291, utilities/label_handling/label_handling.py:21-234).
+"""
+import os
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from .ddp import GradArena, split_batch_for_rank
+from .losses import (DC_and_CE_loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss, distill_kl, soft_cldice,
+                     softmax_channel)
+from .network import get_network_from_plans
+from .optim import PolyLRScheduler, SGDNesterovClip
+
+
+class ConfigurationManager(object):
+    """property names of plans_handler.py:32-176 (the subset the hot path reads)."""
+
+    def __init__(self, configuration_dict: dict):
+        self.configuration = configuration_dict
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__['configuration'][name]
+        except KeyError:
+            raise AttributeError(name)
+
+    @property
+    def batch_dice(self) -> bool:
+        return self.configuration.get('batch_dice', False)
+
+    @property
+    def UNet_class_name(self) -> str:
+        return self.configuration.get('UNet_class_name', 'PlainConvUNet')
+
+    @property
+    def previous_stage_name(self):
+        return self.configuration.get('previous_stage')
+
+
+class LabelManager(object):
+    """label_handling.py:21-234, classes-only subset (no regions, no ignore label on this path)."""
+
+    def __init__(self, label_dict: dict):
+        self.label_dict = label_dict
+        vals = []
+        for v in label_dict.values():
+            if isinstance(v, (tuple, list)):
+                raise NotImplementedError('region-based training is outside the built hot path')
+            vals.append(int(v))
+        if 'ignore' in label_dict:
+            raise NotImplementedError('the ignore label is outside the built hot path')
+        self.all_labels = sorted(vals)
+        self.has_regions = False
+        self.ignore_label = None
+        self.has_ignore_label = False
+
+    @property
+    def foreground_labels(self):
+        return [i for i in self.all_labels if i != 0]
+
+    @property
+    def num_segmentation_heads(self) -> int:
+        return len(self.all_labels)
+
+
+class PlansManager(object):
+    def __init__(self, plans: dict):
+        self.plans = plans
+
+    def get_configuration(self, name: str) -> ConfigurationManager:
+        cfg = dict(self.plans['configurations'][name])
+        while 'inherits_from' in cfg:   # plans_handler.py:197-228
+            parent = dict(self.plans['configurations'][cfg.pop('inherits_from')])
+            parent.update(cfg)
+            cfg = parent
+        return ConfigurationManager(cfg)
+
+    def get_label_manager(self, dataset_json: dict) -> LabelManager:
+        return LabelManager(dataset_json['labels'])
+
+
+def determine_num_input_channels(plans_manager, configuration_manager, dataset_json) -> int:
+    """label_handling.py:283-300 (no cascade on this path)."""
+    return len(dataset_json['modality']) if 'modality' in dataset_json else len(dataset_json['channel_names'])
+
+
+def make_plans(patch_size, batch_size: int = 2, n_modalities: int = 2, n_classes: int = 4, batch_dice: bool = False,
+               base_features: int = 32, max_features: int = 320, min_edge: int = 4) -> Tuple[dict, dict]:
+    """synthetic plans.json / dataset.json for a 3d_fullres configuration with the reference's topology rule
+    (network_topology.py:30-105 for isotropic spacing; default_experiment_planner.py:50-66 constants)."""
+    cur = list(patch_size)
+    pool = [[1, 1, 1]]
+    while True:
+        valid = [i for i in range(3) if cur[i] >= 2 * min_edge]
+        if len(valid) < 1:
+            break
+        if len(valid) == 1 and cur[valid[0]] < 3 * min_edge:
+            break
+        pool.append([2 if i in valid else 1 for i in range(3)])
+        cur = [int(np.ceil(c / 2)) if i in valid else c for i, c in enumerate(cur)]
+    n = len(pool)
+    cfg = {'patch_size': list(patch_size), 'batch_size': batch_size, 'UNet_class_name': 'PlainConvUNet',
+           'UNet_base_num_features': base_features, 'unet_max_num_features': max_features,
+           'n_conv_per_stage_encoder': [2] * n, 'n_conv_per_stage_decoder': [2] * (n - 1),
+           'pool_op_kernel_sizes': pool, 'conv_kernel_sizes': [[3, 3, 3]] * n, 'batch_dice': batch_dice,
+           'spacing': [1.0, 1.0, 1.0]}
+    plans = {'plans_name': 'syntheticPlans', 'dataset_name': 'Dataset000_Synthetic',
+             'configurations': {'3d_fullres': cfg}}
+    dataset_json = {'channel_names': {str(i): f'mod{i}' for i in range(n_modalities)},
+                    'labels': {'background': 0, **{f'class{i}': i for i in range(1, n_classes)}}}
+    return plans, dataset_json
+
+
+class nnUNetTrainer(object):
+    def __init__(self, plans: dict, configuration: str, fold: int, dataset_json: dict, unpack_dataset: bool = True,
+                 device: torch.device = torch.device('cuda'), specified_cfg: str = ''):
+        self.is_ddp = dist.is_available() and dist.is_initialized()
+        self.local_rank = 0 if not self.is_ddp else dist.get_rank()
+        self.device = device
+        if self.device.type != 'cuda':
+            raise RuntimeError('this trainer drives hand-written sm_100a kernels: device must be CUDA '
+                               '(the reference\'s CPU path is timed by bench.py --impl reference)')
+        self.plans_manager = PlansManager(plans)
+        self.configuration_manager = self.plans_manager.get_configuration(configuration)
+        self.configuration_name = configuration
+        self.dataset_json = dataset_json
+        self.fold = fold
+        self.label_manager = self.plans_manager.get_label_manager(dataset_json)
+        # hyper-parameters: MVDTrainer.py:161-166
+        self.initial_lr = 1e-2
+        self.weight_decay = 3e-5
+        self.oversample_foreground_percent = 0.33
+        self.num_iterations_per_epoch = 250
+        self.num_val_iterations_per_epoch = 50
+        self.num_epochs = 1000
+        self.current_epoch = 0
+        self.enable_deep_supervision = True
+        self.num_input_channels = None
+        self.network = None
+        self.optimizer = self.lr_scheduler = None
+        self.grad_scaler = None  # bf16 path: the reference's no-scaler branch (nnUNetTrainer.py:921-924)
+        self.loss = None
+        self.was_initialized = False
+        self._arenas: List[GradArena] = []
+        self._set_batch_size_and_oversample()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _set_batch_size_and_oversample(self):
+        if not self.is_ddp:
+            self.batch_size = self.configuration_manager.batch_size
+        else:
+            self.batch_size, self.oversample_foreground_percent = split_batch_for_rank(
+                self.configuration_manager.batch_size, dist.get_world_size(), dist.get_rank(),
+                self.oversample_foreground_percent)
+
+    def initialize(self):
+        if self.was_initialized:
+            raise RuntimeError('You have called self.initialize even though the trainer was already initialized.')
+        self.num_input_channels = determine_num_input_channels(self.plans_manager, self.configuration_manager,
+                                                               self.dataset_json)
+        self.network = self.build_network_architecture(self.plans_manager, self.dataset_json,
+                                                       self.configuration_manager, self.num_input_channels,
+                                                       enable_deep_supervision=True).to(self.device)
+        self.optimizer, self.lr_scheduler = self.configure_optimizers()
+        self._setup_grad_arenas()
+        self.loss = self._build_loss()
+        self.was_initialized = True
+
+    def _networks(self) -> List[nn.Module]:
+        return [self.network]
+
+    def _setup_grad_arenas(self):
+        """replaces DDP(self.network, device_ids=[local_rank]) (nnUNetTrainer.py:236-238): gradients live in flat
+        arenas, buckets are all-reduced as backward produces them."""
+        self._arenas = [GradArena(list(n.parameters())) for n in self._networks()]
+        lookup = {}
+        for a in self._arenas:
+            for p in a.params:
+                lookup[id(p)] = a
+
+        def alloc(p):
+            a = lookup.get(id(p))
+            return None if a is None else a.view_for(p)
+
+        def ready(params):
+            for p in params:
+                a = lookup.get(id(p))
+                if a is not None:
+                    a.on_params_ready([p])
+
+        ops.set_grad_allocator(alloc)
+        ops.clear_param_grad_ready_hooks()
+        ops.add_param_grad_ready_hook(ready)
+
+    @staticmethod
+    def build_network_architecture(plans_manager, dataset_json, configuration_manager, num_input_channels,
+                                   enable_deep_supervision: bool = True) -> nn.Module:
+        return get_network_from_plans(plans_manager, dataset_json, configuration_manager, num_input_channels,
+                                      deep_supervision=enable_deep_supervision)
+
+    def _get_deep_supervision_scales(self):
+        return list(list(i) for i in 1 / np.cumprod(np.vstack(self.configuration_manager.pool_op_kernel_sizes),
+                                                     axis=0))[:-1]
+
+    def _build_loss(self):
+        if self.label_manager.has_regions:
+            raise NotImplementedError('region-based training (DC_and_BCE_loss) is outside the built hot path')
+        loss = DC_and_CE_loss({'batch_dice': self.configuration_manager.batch_dice, 'smooth': 1e-5, 'do_bg': False,
+                               'ddp': self.is_ddp}, {}, weight_ce=1, weight_dice=1,
+                              ignore_label=self.label_manager.ignore_label, dice_class=MemoryEfficientSoftDiceLoss)
+        if self.enable_deep_supervision:
+            deep_supervision_scales = self._get_deep_supervision_scales()
+            weights = np.array([1 / (2 ** i) for i in range(len(deep_supervision_scales))])
+            weights[-1] = 0
+            weights = weights / weights.sum()
+            loss = DeepSupervisionWrapper(loss, weights)
+        return loss
+
+    def configure_optimizers(self):
+        params = [p for n in self._networks() for p in n.parameters()]
+        optimizer = SGDNesterovClip(params, self.initial_lr, weight_decay=self.weight_decay, momentum=0.99,
+                                    nesterov=True, max_norm=12.0)
+        lr_scheduler = PolyLRScheduler(optimizer, self.initial_lr, self.num_epochs)
+        return optimizer, lr_scheduler
+
+    def set_deep_supervision_enabled(self, enabled: bool):
+        for n in self._networks():
+            n.decoder.deep_supervision = enabled
+
+    def on_train_epoch_start(self):
+        for n in self._networks():
+            n.train()
+        self.lr_scheduler.step(self.current_epoch)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _forward_loss(self, data, target):
+        output = self.network(data)
+        return self.loss(output, target), output
+
+    def _to_device(self, batch):
+        data = batch['data'].to(self.device, non_blocking=True)
+        target = batch['target']
+        if isinstance(target, list):
+            target = [i.to(self.device, non_blocking=True) for i in target]
+        else:
+            target = target.to(self.device, non_blocking=True)
+        return data, target
+
+    def train_step(self, batch: dict) -> dict:
+        l = self.train_step_async(batch)
+        return {'loss': l.detach().cpu().numpy()}
+
+    def train_step_async(self, batch: dict) -> torch.Tensor:
+        """the step without the device->host read of the loss (returned as a device scalar)."""
+        data, target = self._to_device(batch)
+        self.optimizer.zero_grad(set_to_none=True)
+        for a in self._arenas:
+            a.begin_step()
+        l, _ = self._forward_loss(data, target)
+        l.backward()
+        world = 1
+        for a in self._arenas:
+            a.finish()
+            a.attach_grads()
+            world = a.world_size
+        self.optimizer.step(grad_scale=1.0 / world)
+        return l
+
+    def validation_step(self, batch: dict) -> dict:
+        data, target = self._to_device(batch)
+        with torch.no_grad():
+            l, output = self._forward_loss(data, target)
+        if self.enable_deep_supervision:
+            output, target = output[0], target[0]
+        tp, fp, fn = ops.argmax_tp_fp_fn(output, target)
+        tp_hard, fp_hard, fn_hard = (t.detach().cpu().numpy()[1:] for t in (tp, fp, fn))
+        return {'loss': l.detach().cpu().numpy(), 'tp_hard': tp_hard, 'fp_hard': fp_hard, 'fn_hard': fn_hard}
+
+    # ------------------------------------------------------------------------------------------------------------
+    def save_checkpoint(self, filename: str) -> None:
+        """keys of MVDTrainer.py:1129-1152."""
+        if self.local_rank != 0:
+            return
+        checkpoint = {
+            'network_weights': self.network.state_dict(),
+            'optimizer_state': self.optimizer.state_dict(),
+            'grad_scaler_state': None,
+            'logging': {},
+            '_best_ema': None,
+            'current_epoch': self.current_epoch + 1,
+            'init_args': {'configuration': self.configuration_name, 'fold': self.fold},
+            'trainer_name': self.__class__.__name__,
+            'inference_allowed_mirroring_axes': None,
+        }
+        torch.save(checkpoint, filename)
+
+    def load_checkpoint(self, filename_or_checkpoint: Union[dict, str]) -> None:
+        """MVDTrainer.py:1154-1190: strips the DDP 'module.' prefix."""
+        if not self.was_initialized:
+            self.initialize()
+        ck = filename_or_checkpoint
+        if isinstance(ck, str):
+            ck = torch.load(ck, map_location=self.device, weights_only=False)
+        new_state_dict = {}
+        for k, value in ck['network_weights'].items():
+            key = k
+            if key not in self.network.state_dict().keys() and key.startswith('module.'):
+                key = key[7:]
+            new_state_dict[key] = value
+        self.current_epoch = ck['current_epoch']
+        self.network.load_state_dict(new_state_dict)
+        self.optimizer.load_state_dict(ck['optimizer_state'])
+
+
+class MVDTrainer(nnUNetTrainer):
+    """canonical mutual-distillation step (the reference's ContrastiveTrainer.train_step, MVDTrainer.py:879-985;
+    decisions of SURVEY.md section 8c): net1 sees modality 0, net2 modality 1 (split selfattnNet.py:588-589);
+    total = L(out1,tgt) + L(out2,tgt) + lambda3 * topo + lambda1 * KL  (MVDTrainer.py:925, lambdas :132-134).
+    The memory-bank contrastive branch (:927-972) depends on modules missing from the reference tree and is not built."""
+
+    def __init__(self, *a, topo_iter: Optional[int] = 3, kl_T: float = 1.0, kl_vessel_only: bool = False, **kw):
+        super().__init__(*a, **kw)
+        self.lambda1, self.lambda2, self.lambda3 = 0.5, 0.1, 1.0
+        self.vessel_class = 2
+        self.topo_iter = topo_iter
+        self.kl_T = kl_T
+        self.kl_vessel_only = kl_vessel_only
+        self.network2 = None
+
+    def initialize(self):
+        if self.was_initialized:
+            raise RuntimeError('You have called self.initialize even though the trainer was already initialized.')
+        n_mod = determine_num_input_channels(self.plans_manager, self.configuration_manager, self.dataset_json)
+        assert n_mod == 2, 'the mutual-distillation step needs exactly two modalities'
+        self.num_input_channels = n_mod
+        self.network = self.build_network_architecture(self.plans_manager, self.dataset_json,
+                                                       self.configuration_manager, 1, True).to(self.device)
+        self.network2 = self.build_network_architecture(self.plans_manager, self.dataset_json,
+                                                        self.configuration_manager, 1, True).to(self.device)
+        self.optimizer, self.lr_scheduler = self.configure_optimizers()
+        self._setup_grad_arenas()
+        self.loss = self._build_loss()
+        self.topo = soft_cldice(iter_=self.topo_iter, smooth=1.) if self.topo_iter is not None else None
+        self.was_initialized = True
+
+    def _networks(self):
+        return [self.network, self.network2]
+
+    def _forward_loss(self, data, target):
+        out1 = self.network(data[:, 0:1])
+        out2 = self.network2(data[:, 1:2])
+        l = self.loss(out1, target) + self.loss(out2, target)
+        c = self.vessel_class
+        if self.kl_vessel_only:
+            mutual = distill_kl(out1[0][:, c:c + 1], out2[0][:, c:c + 1], self.kl_T)
+        else:
+            mutual = distill_kl(out1[0], out2[0], self.kl_T)
+        l = l + self.lambda1 * mutual
+        if self.topo is not None:
+            prob = softmax_channel(out1[0], c)
+            gt = (target[0] == c).float()
+            l = l + self.lambda3 * self.topo(gt, prob)
+        self.last_terms = dict(mutual=mutual.detach())
+        return l, out1
+
+    def save_checkpoint(self, filename: str) -> None:
+        if self.local_rank != 0:
+            return
+        super().save_checkpoint(filename)
+        ck = torch.load(filename, weights_only=False)
+        ck['network2_weights'] = self.network2.state_dict()
+        torch.save(ck, filename)
+
+    def load_checkpoint(self, filename_or_checkpoint):
+        ck = filename_or_checkpoint
+        if isinstance(ck, str):
+            ck = torch.load(ck, map_location=self.device, weights_only=False)
+        super().load_checkpoint(ck)
+        if 'network2_weights' in ck:
+            self.network2.load_state_dict(ck['network2_weights'])

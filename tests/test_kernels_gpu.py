@@ -1,0 +1,358 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the oracle / PyTorch fp32 math on the same
+bf16-rounded inputs.  Tolerances (BASELINE.json north_star): fp32 loss reductions 1e-5 relative, bf16 tensors 2e-2
+relative (norm-wise: ||got - want||_2 <= 2e-2 * ||want||_2), integer/morphology outputs bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def rel_err(got, want):
+    got, want = got.double().flatten(), want.double().flatten()
+    return float((got - want).norm() / want.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope='module')
+def m():
+    import multimodal_mvd_seg_b200 as mod
+    assert torch.cuda.is_available()
+    return mod
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def rand_cl(shape, seed, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(BF).to(dev())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_layout_roundtrip(m):
+    x = torch.randn(2, 2, 5, 6, 7, device=dev())
+    cl = m.ops.input_to_cl(x)
+    assert cl.shape == (2, 5, 6, 7, 2) and cl.dtype == BF
+    assert torch.equal(cl, x.permute(0, 2, 3, 4, 1).to(BF))
+    back = m.ops.cl_to_ncdhw_f32(cl)
+    assert torch.equal(back, x.to(BF).float())
+
+
+CONV_CASES = [
+    # (B, Cin, Cout, (D,H,W), k, s)
+    (2, 32, 32, (8, 8, 8), 3, (1, 1, 1)),
+    (1, 32, 64, (8, 12, 16), 3, (2, 2, 2)),
+    (1, 64, 32, (6, 10, 12), 3, (2, 2, 1)),
+    (2, 2, 32, (9, 8, 10), 3, (1, 1, 1)),     # stem: Cin = 2
+    (1, 1, 32, (8, 8, 8), 3, (1, 1, 1)),      # MVD stem: Cin = 1
+    (1, 96, 40, (5, 5, 6), 3, (1, 1, 1)),     # odd extents, channels not multiples of 32
+    (1, 16, 24, (4, 4, 4), 1, (1, 1, 1)),
+]
+
+
+def _conv_ref(x_cl, w, b, k, s):
+    x = x_cl.float().permute(0, 4, 1, 2, 3)
+    y = F.conv3d(x, w.to(BF).float(), None if b is None else b.to(BF).float(), stride=s, padding=(k - 1) // 2)
+    return y
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('algo', ['generic', 'auto'])
+def test_conv_fprop_dgrad_wgrad(m, case, algo):
+    B, Cin, Cout, (D, H, W), k, s = case
+    ops = m.ops
+    ops.set_conv_algo(algo)
+    try:
+        torch.manual_seed(1)
+        x = rand_cl((B, D, H, W, Cin), 3)
+        w = (torch.randn(Cout, Cin, k, k, k) * (1.0 / np.sqrt(Cin * k ** 3))).to(dev())
+        b = torch.randn(Cout).to(dev()) * 0.1
+        geom = ops.ConvGeom((k,) * 3, s, ((k - 1) // 2,) * 3)
+        Do, Ho, Wo = geom.out_size((D, H, W))
+        wf, wd = ops.pack_weights(w)
+        # fprop (pitched output: channel slice of a wider buffer)
+        ybuf = torch.zeros((B, Do, Ho, Wo, Cout + 8), dtype=BF, device=dev())
+        y = ybuf[..., 8:]
+        ops.conv_fprop(geom, x, y, wf, bias=b)
+        xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+        wr = w.to(BF).float().requires_grad_(True)
+        yr = F.conv3d(xr, wr, b.to(BF).float(), stride=s, padding=(k - 1) // 2)
+        assert rel_err(y.float().permute(0, 4, 1, 2, 3), yr) < 1e-2
+        assert float(ybuf[..., :8].abs().max()) == 0.0
+        # backward operands
+        dy = rand_cl((B, Do, Ho, Wo, Cout), 5)
+        yr.backward(dy.float().permute(0, 4, 1, 2, 3))
+        dx = torch.empty_like(x)
+        ops.conv_dgrad(geom, dx, dy, wd)
+        assert rel_err(dx.float().permute(0, 4, 1, 2, 3), xr.grad) < 1e-2
+        # accumulate mode
+        dx2 = dx.clone()
+        ops.conv_dgrad(geom, dx2, dy, wd, accumulate=True)
+        assert rel_err(dx2.float(), 2 * dx.float()) < 1e-2
+        dw = torch.empty_like(w)
+        db = torch.empty_like(b)
+        ops.conv_wgrad(geom, x, dy, dw, db)
+        assert rel_err(dw, wr.grad) < 1e-2
+        assert rel_err(db, dy.float().sum((0, 1, 2, 3))) < 1e-3
+    finally:
+        ops.set_conv_algo('auto')
+
+
+@pytest.mark.parametrize('stride', [(2, 2, 2), (2, 2, 1)])
+@pytest.mark.parametrize('cin,cout', [(64, 32), (320, 320), (48, 24)])
+def test_conv_transpose(m, stride, cin, cout):
+    ops = m.ops
+    x = rand_cl((2, 3, 4, 5, cin), 11)
+    w = (torch.randn(cin, cout, *stride) * (1.0 / np.sqrt(cin))).to(dev()).requires_grad_(True)
+    b = (torch.randn(cout) * 0.1).to(dev()).requires_grad_(True)
+    xin = x.clone().requires_grad_(True)
+    up = ops.ConvTransposeFn.apply(xin, w, b, stride, None, None)
+    xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wr = w.detach().to(BF).float().requires_grad_(True)
+    br = b.detach().to(BF).float().requires_grad_(True)
+    ur = F.conv_transpose3d(xr, wr, br, stride=stride)
+    assert rel_err(up.float().permute(0, 4, 1, 2, 3), ur) < 1e-2
+    g = rand_cl(tuple(up.shape), 12)
+    up.backward(g)
+    ur.backward(g.float().permute(0, 4, 1, 2, 3))
+    assert rel_err(xin.grad.float().permute(0, 4, 1, 2, 3), xr.grad) < 1e-2
+    assert rel_err(w.grad, wr.grad) < 1e-2
+    assert rel_err(b.grad, br.grad) < 1e-3
+
+
+@pytest.mark.parametrize('C,shape', [(32, (2, 8, 9, 10)), (320, (2, 4, 4, 4)), (64, (1, 16, 16, 8))])
+def test_instance_norm_lrelu_fwd_bwd(m, C, shape):
+    lib, ops = m.lib, m.ops
+    B, D, H, W = shape
+    V = D * H * W
+    y = rand_cl((B, D, H, W, C), 21, scale=2.0) + 0.5
+    gamma = (torch.rand(C) + 0.5).to(dev())
+    beta = (torch.randn(C) * 0.2).to(dev())
+    st = torch.cuda.current_stream().cuda_stream
+    stats = torch.zeros((B, C, 2), dtype=torch.float64, device=dev())
+    lib.inorm_stats(y.data_ptr(), C, B, V, C, stats.data_ptr(), st)
+    yf = y.double().reshape(B, V, C)
+    np.testing.assert_allclose(stats[..., 0].cpu(), yf.sum(1).cpu(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(stats[..., 1].cpu(), (yf * yf).sum(1).cpu(), rtol=1e-6)
+    zbuf = torch.zeros((B, D, H, W, 2 * C), dtype=BF, device=dev())
+    z = zbuf[..., C:]
+    lib.inorm_lrelu_fwd(y.data_ptr(), C, z.data_ptr(), 2 * C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                        B, V, C, 1e-5, 0.01, st)
+    # reference: fp32 instance norm -> bf16 -> leaky relu -> bf16, with autograd for the backward
+    yr = y.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    t = F.instance_norm(yr, weight=gr, bias=br, eps=1e-5)
+    zr = F.leaky_relu(t, 0.01)
+    assert rel_err(z.float().permute(0, 4, 1, 2, 3), zr) < 6e-3   # two bf16 roundings
+    assert float(zbuf[..., :C].abs().max()) == 0.0
+    dz = rand_cl((B, D, H, W, C), 22)
+    zr.backward(dz.float().permute(0, 4, 1, 2, 3))
+    bstats = torch.zeros((B, C, 2), dtype=torch.float64, device=dev())
+    lib.inorm_lrelu_bwd_stats(dz.data_ptr(), C, y.data_ptr(), C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                              B, V, C, 1e-5, 0.01, bstats.data_ptr(), st)
+    dy = torch.empty_like(y)
+    dg, db = torch.empty_like(gamma), torch.empty_like(beta)
+    lib.inorm_lrelu_bwd_apply(dz.data_ptr(), C, y.data_ptr(), C, dy.data_ptr(), C, stats.data_ptr(),
+                              bstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, V, C, 1e-5, 0.01,
+                              dg.data_ptr(), db.data_ptr(), st)
+    assert rel_err(dy.float().permute(0, 4, 1, 2, 3), yr.grad) < 1e-2
+    assert rel_err(dg, gr.grad) < 5e-3
+    assert rel_err(db, br.grad) < 5e-3
+
+
+@pytest.mark.parametrize('C,K', [(32, 4), (320, 4), (64, 3)])
+def test_head(m, C, K):
+    ops = m.ops
+    z = rand_cl((2, 5, 6, 7, C), 31)
+    w = (torch.randn(K, C, 1, 1, 1) / np.sqrt(C)).to(dev()).requires_grad_(True)
+    b = (torch.randn(K) * 0.1).to(dev()).requires_grad_(True)
+    zin = z.clone().requires_grad_(True)
+    out = ops.HeadFn.apply(zin, w, b, None)
+    zr = z.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wr = w.detach().to(BF).float().requires_grad_(True)
+    br = b.detach().to(BF).float().requires_grad_(True)
+    outr = F.conv3d(zr, wr, br)
+    assert rel_err(out.float().permute(0, 4, 1, 2, 3), outr) < 5e-3
+    g = rand_cl(tuple(out.shape), 32)
+    out.backward(g)
+    outr.backward(g.float().permute(0, 4, 1, 2, 3))
+    assert rel_err(zin.grad.float().permute(0, 4, 1, 2, 3), zr.grad) < 5e-3
+    assert rel_err(w.grad, wr.grad) < 1e-3
+    assert rel_err(b.grad, br.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _logits_targets(B, C, shape, seed, scales=1):
+    g = torch.Generator().manual_seed(seed)
+    outs, tgts = [], []
+    cur = list(shape)
+    for _ in range(scales):
+        lg = (torch.randn((B, *cur, C), generator=g) * 2).to(BF).to(dev())
+        tg = torch.randint(0, C, (B, 1, *cur), generator=g).float().to(dev())
+        outs.append(lg)
+        tgts.append(tg)
+        cur = [max(1, c // 2) for c in cur]
+    return outs, tgts
+
+
+@pytest.mark.parametrize('batch_dice', [False, True])
+@pytest.mark.parametrize('C', [4, 3])
+def test_dc_and_ce_matches_oracle(m, batch_dice, C):
+    import oracle
+    (lg,), (tg,) = _logits_targets(2, C, (9, 10, 11), 41)
+    mine = m.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {},
+                            weight_ce=1, weight_dice=1, ignore_label=None, dice_class=m.MemoryEfficientSoftDiceLoss)
+    ref = oracle.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {},
+                                weight_ce=1, weight_dice=1, ignore_label=None,
+                                dice_class=oracle.MemoryEfficientSoftDiceLoss)
+    x = m.ops.ncdhw_view(lg).requires_grad_(True)
+    l = mine(x, tg)
+    xr = lg.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    lr = ref(xr, tg)
+    assert abs(float(l) - float(lr)) <= 1e-5 * max(1.0, abs(float(lr)))
+    (l * 3.0).backward()
+    (lr * 3.0).backward()
+    assert rel_err(x.grad.float(), xr.grad) < 6e-3     # bf16 rounding of the gradient
+    # individual members
+    dc = m.MemoryEfficientSoftDiceLoss(apply_nonlin=m.softmax_helper_dim1, batch_dice=batch_dice, do_bg=False,
+                                       smooth=1e-5, ddp=False)(m.ops.ncdhw_view(lg), tg)
+    dcr = oracle.MemoryEfficientSoftDiceLoss(apply_nonlin=oracle.softmax_helper_dim1, batch_dice=batch_dice,
+                                             do_bg=False, smooth=1e-5, ddp=False)(lg.float().permute(0, 4, 1, 2, 3), tg)
+    assert abs(float(dc) - float(dcr)) <= 1e-5
+    ce = m.RobustCrossEntropyLoss()(m.ops.ncdhw_view(lg), tg)
+    cer = oracle.RobustCrossEntropyLoss()(lg.float().permute(0, 4, 1, 2, 3), tg)
+    assert abs(float(ce) - float(cer)) <= 1e-5 * float(cer)
+
+
+def test_deep_supervision_wrapper_matches_oracle(m):
+    import oracle
+    outs, tgts = _logits_targets(2, 4, (16, 16, 12), 43, scales=4)
+    w = m.deep_supervision_weights(4)
+    mk = lambda mod: mod.DeepSupervisionWrapper(
+        mod.DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, weight_ce=1,
+                           weight_dice=1, ignore_label=None, dice_class=mod.MemoryEfficientSoftDiceLoss), w)
+    xs = [m.ops.ncdhw_view(o).requires_grad_(True) for o in outs]
+    l = mk(m)(xs, tgts)
+    xr = [o.float().permute(0, 4, 1, 2, 3).requires_grad_(True) for o in outs]
+    lr = mk(oracle)(xr, tgts)
+    assert abs(float(l) - float(lr)) <= 1e-5 * max(1.0, abs(float(lr)))
+    l.backward()
+    lr.backward()
+    for i in range(3):
+        assert rel_err(xs[i].grad.float(), xr[i].grad) < 6e-3
+    assert xs[3].grad is None and float(xr[3].grad.abs().max()) == 0.0   # zero-weighted scale
+
+
+def test_argmax_tp_fp_fn(m):
+    import oracle
+    (lg,), (tg,) = _logits_targets(2, 4, (7, 8, 9), 44)
+    tp, fp, fn = m.ops.argmax_tp_fp_fn(m.ops.ncdhw_view(lg), tg)
+    x = lg.float().permute(0, 4, 1, 2, 3)
+    onehot = torch.zeros_like(x).scatter_(1, x.argmax(1)[:, None], 1)
+    tpr, fpr, fnr, _ = oracle.get_tp_fp_fn_tn(onehot, tg, axes=[0, 2, 3, 4])
+    assert torch.equal(tp.float(), tpr) and torch.equal(fp.float(), fpr) and torch.equal(fn.float(), fnr)
+
+
+@pytest.mark.parametrize('C,T', [(4, 1.0), (4, 2.0), (1, 1.0)])
+def test_distill_kl_matches_oracle(m, C, T):
+    import oracle
+    (a,), _ = _logits_targets(2, 4, (8, 9, 10), 51)
+    (b,), _ = _logits_targets(2, 4, (8, 9, 10), 52)
+    av, bv = m.ops.ncdhw_view(a), m.ops.ncdhw_view(b)
+    ar, br = a.float().permute(0, 4, 1, 2, 3), b.float().permute(0, 4, 1, 2, 3)
+    if C == 1:   # the vessel-channel call site (MVDTrainer.py:897-899): a strided one-channel view
+        av, bv, ar, br = av[:, 2:3], bv[:, 2:3], ar[:, 2:3], br[:, 2:3]
+    av, bv = av.detach().requires_grad_(True), bv.detach().requires_grad_(True)
+    ar, br = ar.detach().clone().requires_grad_(True), br.detach().clone().requires_grad_(True)
+    l = m.distill_kl(av, bv, T)
+    lr = oracle.distill_kl(ar, br, T)
+    assert abs(float(l) - float(lr)) <= 1e-5 * max(abs(float(lr)), 1e-3)
+    l.backward()
+    lr.backward()
+    assert rel_err(av.grad.float(), ar.grad) < 6e-3
+    assert rel_err(bv.grad.float(), br.grad) < 6e-3
+
+
+def test_distill_kl_golden(m, golden_misc):
+    g = golden_misc
+    for tag in ('c4_T1', 'c4_T2', 'c1_T1'):
+        ys = torch.from_numpy(g[f'kl.{tag}.ys']).to(BF)
+        yt = torch.from_numpy(g[f'kl.{tag}.yt']).to(BF)
+        # the fixture inputs are fp32; compare on their bf16 roundings via the oracle (pinned to the same fixture)
+        import oracle
+        want = oracle.distill_kl(ys.float(), yt.float(), float(g[f'kl.{tag}.T']))
+        got = m.distill_kl(ys.to(dev()), yt.to(dev()), float(g[f'kl.{tag}.T']))
+        assert abs(float(got) - float(want)) <= 1e-5 * max(abs(float(want)), 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('vol', ['smooth', 'ties'])
+@pytest.mark.parametrize('fn', ['soft_erode', 'soft_dilate', 'soft_open'])
+def test_morphology_golden_bit_exact(m, golden_skel, vol, fn):
+    g = golden_skel
+    x = torch.from_numpy(g[f'{vol}.{fn}.in']).to(dev()).requires_grad_(True)
+    y = getattr(m, fn)(x)
+    assert np.array_equal(y.detach().cpu().numpy(), g[f'{vol}.{fn}.out'])
+    (y * torch.from_numpy(g[f'{vol}.{fn}.w']).to(dev())).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.{fn}.grad'], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('vol', ['smooth', 'ties'])
+@pytest.mark.parametrize('it', [0, 1, 3])
+def test_soft_skel_golden(m, golden_skel, vol, it):
+    g = golden_skel
+    x = torch.from_numpy(g[f'{vol}.soft_erode.in']).to(dev()).requires_grad_(True)
+    y = m.soft_skel(x, it)
+    assert np.array_equal(y.detach().cpu().numpy(), g[f'{vol}.soft_skel{it}.out'])
+    (y * torch.from_numpy(g[f'{vol}.soft_skel{it}.w']).to(dev())).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.soft_skel{it}.grad'], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize('it', [3, 10])
+def test_soft_cldice_matches_oracle(m, it):
+    import oracle
+    lab = oracle.structured_labels(2, (24, 28, 20), seed=5)
+    gt = (lab == 2).float().to(dev())
+    g = torch.Generator().manual_seed(9)
+    logits = (torch.randn((2, 24, 28, 20, 4), generator=g) * 1.5).to(BF).to(dev())
+    logits[..., 2] += (gt[:, 0] * 3).to(BF)
+    x = m.ops.ncdhw_view(logits).detach().requires_grad_(True)
+    prob = m.softmax_channel(x, 2)
+    l = m.soft_cldice(iter_=it, smooth=1.)(gt, prob)
+    xr = logits.float().permute(0, 4, 1, 2, 3).detach().clone().requires_grad_(True)
+    pr = torch.softmax(xr, 1)[:, 2:3]
+    lr = oracle.soft_cldice(iter_=it, smooth=1.)(gt, pr)
+    assert torch.equal(prob.detach(), pr.detach()) or rel_err(prob.detach(), pr.detach()) < 1e-6
+    assert abs(float(l) - float(lr)) <= 1e-5
+    l.backward()
+    lr.backward()
+    assert rel_err(x.grad.float(), xr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_sgd_nesterov_clip_matches_torch(m):
+    torch.manual_seed(3)
+    shapes = [(32, 2, 3, 3, 3), (32,), (64, 32, 3, 3, 3), (5000,), (4, 32, 1, 1, 1)]
+    p_ref = [torch.nn.Parameter(torch.randn(s, device=dev())) for s in shapes]
+    p_mine = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    ref = torch.optim.SGD(p_ref, 1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    mine = m.SGDNesterovClip(p_mine, 1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True, max_norm=12.0)
+    for it in range(4):
+        scale = 30.0 if it % 2 == 0 else 0.01     # clipped and unclipped steps
+        grads = [torch.randn_like(p) * scale for p in p_ref]
+        for a, b, g in zip(p_ref, p_mine, grads):
+            a.grad, b.grad = g.clone(), g.clone()
+        if it == 2:
+            p_ref[3].grad = torch.zeros_like(p_ref[3])
+            p_mine[3].grad = None                  # missing gradient behaves like a zero gradient
+        total = torch.nn.utils.clip_grad_norm_(p_ref, 12)
+        ref.step()
+        mine.step()
+        assert float(mine.last_sqnorm.sqrt()) == pytest.approx(float(total), rel=1e-5)
+        for a, b in zip(p_ref, p_mine):
+            assert rel_err(b.detach(), a.detach()) < 1e-6
+        ref.param_groups[0]['lr'] = mine.param_groups[0]['lr'] = 5e-3
