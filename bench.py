@@ -131,7 +131,7 @@ def reference_step_time(steps, warmup, dual, topo_iter, threads=None):
         l.backward()
         torch.nn.utils.clip_grad_norm_(params, 12)
         opt.step()
-        float(l)
+        float(l.detach())
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     frac = (crop[0] * crop[1] * crop[2]) / float(full_patch[0] * full_patch[1] * full_patch[2])

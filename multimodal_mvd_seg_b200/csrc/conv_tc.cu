@@ -1,12 +1,463 @@
-// placeholder until the tcgen05 kernels land
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (fprop and dgrad of Conv3d, and through the
+// adjoint formulation ConvTranspose3d fprop / dgrad).
+//
+// GEMM view:  D[m, n] = sum_{tap} sum_{k} A_tap[m, k] * W[tap][n][k]
+//   m  : 128 voxels of the produced tensor = an 8 (w) x 16 (h) x 1 (d) brick of one sample (UMMA M = 128)
+//   n  : produced channels, tile = UMMA N (<= 256, multiple of 32)
+//   k  : gathered channels, KC = 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B) per pipeline stage
+//   tap: a (tensor-map, dz, dy, dx) shift of the gathered tensor.  Strided convolutions are expressed on the s^3
+//        parity sub-lattices of the strided side (each a plain strided 5-D tensor map), so every tap is an ordinary
+//        box load; out-of-volume rows are zero-filled by TMA, which implements the conv padding.
+// Pipeline (one persistent CTA per SM, 192 threads):
+//   warp 0 lane 0 : TMA producer    -- per stage one 5-D box load of A (128 x KC) and one 2-D box load of W (N x KC)
+//   warp 1 lane 0 : MMA issuer      -- KC/16 tcgen05.mma per stage into one of two TMEM accumulators; tcgen05.commit
+//                                      releases the stage and, after the last stage, publishes the accumulator
+//   warps 2..5    : epilogue        -- tcgen05.ld 32 columns at a time, + bias, bf16, 16-byte global stores
+// smem full/empty mbarriers between producer and issuer, tmem full/empty mbarriers between issuer and epilogue.
+#include <mutex>
 #include "conv_common.cuh"
+#include "tc_common.cuh"
+
 namespace mvd {
-bool tc_fprop_supported(const mvd_conv3d_args*) { return false; }
-bool tc_dgrad_supported(const mvd_conv3d_args*) { return false; }
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+namespace {
+
+using namespace tc;
+
+constexpr int kMaxTaps = 27;
+constexpr int kMaxMaps = 8;
+constexpr int TILE_W = 8, TILE_H = 16;
+constexpr int kThreads = 192;
+
+struct TcTap {
+  int map;          // which A tensor map
+  int dz, dy, dx;   // shift (in that map's lattice coordinates) relative to the tile origin
+  int wrow;         // first row of this tap's [N][K] weight block in the 2-D weight map
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap a[kMaxMaps];
+  CUtensorMap b;
+};
+
+struct TcParams {
+  int B, Dt, Ht, Wt;             // lattice of produced voxels this launch covers
+  int tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles;
+  int n_tile;                    // UMMA N
+  int ntaps, kchunks;
+  int stages;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  bf16* out;                     // element (b,d,h,w,n) at out + b*sb + d*sd + h*sh + w*sw + n
+  long long sb, sd, sh, sw;
+  const float* bias;             // per produced channel, may be null
+  int accumulate;
+  TcTap taps[kMaxTaps];
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps,
+                                                              const __grid_constant__ TcParams P) {
+  constexpr int A_BYTES = 128 * KC * 2;
+  constexpr uint64_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
+  constexpr uint32_t SBO = 8 * KC * 2;  // 8 rows of KC bf16
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+
+  // dynamic smem may only be 16-byte aligned by the runtime: align by hand (host adds 1 KB of slack)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = P.n_tile * KC * 2;
+  const int stage_bytes = A_BYTES + b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = P.stages;
+  const int kiters = P.ntaps * P.kchunks;
+  const int total_tiles = P.num_m_tiles * P.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bar_tfull[a], 1);
+      mbar_init(&bar_tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  auto decode_tile = [&](int tile, int& n0, int& b, int& d, int& h0, int& w0) {
+    const int nt = tile % P.num_n_tiles;
+    int m = tile / P.num_n_tiles;
+    n0 = nt * P.n_tile;
+    w0 = (m % P.tiles_w) * TILE_W;
+    m /= P.tiles_w;
+    h0 = (m % P.tiles_h) * TILE_H;
+    m /= P.tiles_h;
+    d = m % P.Dt;
+    b = m / P.Dt;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      tma_prefetch_desc(&maps.b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, b, d, h0, w0;
+        decode_tile(tile, n0, b, d, h0, w0);
+        for (int t = 0; t < P.ntaps; ++t) {
+          const TcTap tap = P.taps[t];
+          for (int kc = 0; kc < P.kchunks; ++kc) {
+            mbar_wait(&bar_empty[stage], phase ^ 1, 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)stage_bytes);
+            tma_load_5d(&maps.a[tap.map], sa, &bar_full[stage], kc * KC, w0 + tap.dx, h0 + tap.dy, d + tap.dz, b);
+            tma_load_2d(&maps.b, sa + A_BYTES, &bar_full[stage], kc * KC, tap.wrow + n0);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, accphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&bar_tempty[acc], accphase ^ 1, 2);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.n_tile);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&bar_full[stage], phase, 3);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa, 16, SBO, LAYOUT);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, SBO, LAYOUT);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)  // advance 32 bytes (16 bf16) along K inside the swizzle atom
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (it | k) ? 1u : 0u);
+          umma_commit(&bar_empty[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // the TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n0, b, d, h0, w0;
+      decode_tile(tile, n0, b, d, h0, w0);
+      mbar_wait(&bar_tfull[acc], accphase, 4);
+      tcgen05_fence_after();
+      const int r = q * 32 + lane;
+      const int h = h0 + (r >> 3), w = w0 + (r & 7);
+      const bool valid = (h < P.Ht) && (w < P.Wt);
+      bf16* orow = P.out + (long long)b * P.sb + (long long)d * P.sd + (long long)h * P.sh + (long long)w * P.sw + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
+      for (int c = 0; c < P.n_tile; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __uint_as_float(v[g * 8 + j]);
+              if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + g * 8 + j));
+            }
+            bf16x8* dst = reinterpret_cast<bf16x8*>(orow + c + g * 8);
+            if (P.accumulate) {
+              float o[8];
+              unpack8(*dst, o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += o[j];
+            }
+            *dst = pack8(f);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------------------------------------
+int pick_n_tile(int N) {
+  if (N % 32) return 0;
+  if (N <= 256) return N;
+  for (int t = 256; t >= 32; t -= 32)
+    if (N % t == 0) return t;
+  return 0;
+}
+
+bool encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4] /*W,H,D,B extents*/,
+                    const long long strides_el[4] /*W,H,D,B strides in elements*/, int kc) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2], (cuuint64_t)dims[3]};
+  cuuint64_t gstr[4] = {(cuuint64_t)strides_el[0] * 2, (cuuint64_t)strides_el[1] * 2, (cuuint64_t)strides_el[2] * 2,
+                        (cuuint64_t)strides_el[3] * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, TILE_W, TILE_H, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// shape coverage shared by fprop (K = Cin, N = Cout) and dgrad (K = Cout, N = Cin)
+bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn, const void* w, int taps) {
+  if (K % 32 || pick_n_tile(N) == 0) return false;
+  if (ldk % 8 || ldn % 8) return false;
+  if (((uintptr_t)pk & 15) || ((uintptr_t)pn & 15) || ((uintptr_t)w & 15)) return false;
+  if (taps > kMaxTaps) return false;
+  return true;
+}
+
+int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* who) {
+  const int a_bytes = 128 * kc * 2, b_bytes = P.n_tile * kc * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("%s: tile does not fit shared memory", who); return MVD_ERR_UNSUPPORTED; }
+  P.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * P.n_tile) cols <<= 1;
+  P.tmem_cols = cols;
+  P.idesc = make_idesc_bf16(128, P.n_tile, 0, 0);
+  static bool attr_done[2] = {false, false};
+  const int ki = (kc == 64) ? 0 : 1;
+  if (!attr_done[ki]) {
+    cudaError_t e = (kc == 64)
+                        ? cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024)
+                        : cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+      return MVD_ERR_CUDA;
+    }
+    attr_done[ki] = true;
+  }
+  const int total = P.num_m_tiles * P.num_n_tiles;
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  if (kc == 64) conv_tc_kernel<64><<<grid, kThreads, smem, st>>>(maps, P);
+  else conv_tc_kernel<32><<<grid, kThreads, smem, st>>>(maps, P);
+  MVD_LAUNCH_CHECK(who);
+  return MVD_OK;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// fprop: produced = y (conv output lattice), gathered = x.  Input coordinate o*s - p + t = s*(o + q) + r with
+// r = (t - p) mod s, q = floor((t - p)/s): tap -> (parity map r, shift q).
+// ---------------------------------------------------------------------------------------------------------------
+bool tc_fprop_supported(const mvd_conv3d_args* a) {
+  const int taps = a->kd * a->kh * a->kw;
+  if (!tc_shape_ok(a->Cin, a->Cout, a->ldx, a->ldy, a->x, a->y, a->w, taps)) return false;
+  if (a->sd * a->sh * a->sw > kMaxMaps) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+static inline void floordivmod(int v, int s, int& q, int& r) {
+  q = (v >= 0) ? v / s : -((-v + s - 1) / s);
+  r = v - q * s;
+}
+
+int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
+  const int kc = (a->Cin % 64 == 0) ? 64 : 32;
+  TcMaps maps;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  const bf16* x = (const bf16*)a->x;
+  const long long ld = a->ldx;
+  // parity sub-lattices of the input
+  for (int rd = 0; rd < a->sd; ++rd)
+    for (int rh = 0; rh < a->sh; ++rh)
+      for (int rw = 0; rw < a->sw; ++rw) {
+        const int mi = (rd * a->sh + rh) * a->sw + rw;
+        const int dims[4] = {cdiv(a->Wi - rw, a->sw), cdiv(a->Hi - rh, a->sh), cdiv(a->Di - rd, a->sd), a->B};
+        if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) {
+          // an empty lattice can never be hit by a valid tap; alias it to lattice 0 extents of 1 (all loads OOB)
+          const int d1[4] = {1, 1, 1, a->B};
+          const long long s1[4] = {ld, ld * a->Wi, ld * a->Wi * a->Hi, ld * a->Wi * a->Hi * a->Di};
+          if (!encode_act_map(&maps.a[mi], x, a->Cin, a->ldx, d1, s1, kc)) goto fail;
+          continue;
+        }
+        const long long strides[4] = {ld * a->sw, ld * a->Wi * a->sh, ld * a->Wi * a->Hi * a->sd,
+                                      ld * a->Wi * a->Hi * a->Di};
+        const bf16* base = x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ld;
+        if (!encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc)) goto fail;
+      }
+  {
+    const int taps = a->kd * a->kh * a->kw;
+    P.n_tile = pick_n_tile(a->Cout);
+    if (!encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cout, a->Cin, P.n_tile, kc)) goto fail;
+    int nt = 0;
+    for (int td = 0; td < a->kd; ++td)
+      for (int th = 0; th < a->kh; ++th)
+        for (int tw = 0; tw < a->kw; ++tw) {
+          int qd, rd, qh, rh, qw, rw;
+          floordivmod(td - a->pd, a->sd, qd, rd);
+          floordivmod(th - a->ph, a->sh, qh, rh);
+          floordivmod(tw - a->pw, a->sw, qw, rw);
+          TcTap& t = P.taps[nt++];
+          t.map = (rd * a->sh + rh) * a->sw + rw;
+          t.dz = qd; t.dy = qh; t.dx = qw;
+          t.wrow = ((td * a->kh + th) * a->kw + tw) * a->Cout;
+        }
+    P.ntaps = nt;
+    P.kchunks = a->Cin / kc;
+    P.B = a->B; P.Dt = a->Do; P.Ht = a->Ho; P.Wt = a->Wo;
+    P.tiles_w = cdiv(P.Wt, TILE_W); P.tiles_h = cdiv(P.Ht, TILE_H);
+    P.num_m_tiles = P.B * P.Dt * P.tiles_h * P.tiles_w;
+    P.num_n_tiles = a->Cout / P.n_tile;
+    P.out = (bf16*)a->y;
+    P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
+    P.bias = a->bias;
+    P.accumulate = 0;
+    return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
+  }
+fail:
+  set_error("conv3d_fprop(tcgen05): cuTensorMapEncodeTiled failed");
+  return MVD_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dgrad: produced = x (conv input lattice), gathered = y.  x[i] += y[(i + p - t)/s] W[t] when divisible: one launch
+// per parity class r = i mod s of the produced lattice; within it tap t contributes iff (r + p - t) mod s == 0, with
+// shift (r + p - t)/s on the (dense) y lattice.  Classes without taps (k < s) are zero-filled (+bias).
+// ---------------------------------------------------------------------------------------------------------------
+bool tc_dgrad_supported(const mvd_conv3d_args* a) {
+  const int taps = a->kd * a->kh * a->kw;
+  if (!tc_shape_ok(a->Cout, a->Cin, a->ldy, a->ldx, a->y, a->x, a->w, taps)) return false;
+  // every parity class must own at least one tap per axis, otherwise the class is a pure fill (not built here)
+  if (a->kd < a->sd || a->kh < a->sh || a->kw < a->sw) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
+  const int kc = (a->Cout % 64 == 0) ? 64 : 32;
+  TcMaps maps;
+  const bf16* y = (const bf16*)a->y;
+  const long long ldy = a->ldy;
+  const int dims[4] = {a->Wo, a->Ho, a->Do, a->B};
+  const long long strides[4] = {ldy, ldy * a->Wo, ldy * a->Wo * a->Ho, ldy * a->Wo * a->Ho * a->Do};
+  if (!encode_act_map(&maps.a[0], y, a->Cout, a->ldy, dims, strides, kc)) {
+    set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(A) failed");
+    return MVD_ERR_CUDA;
+  }
+  for (int i = 1; i < kMaxMaps; ++i) maps.a[i] = maps.a[0];
+  const int taps = a->kd * a->kh * a->kw;
+  const int n_tile = pick_n_tile(a->Cin);
+  if (!encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cin, a->Cout, n_tile, kc)) {
+    set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(W) failed");
+    return MVD_ERR_CUDA;
+  }
+  const long long ldx = a->ldx;
+  for (int rd = 0; rd < a->sd; ++rd)
+    for (int rh = 0; rh < a->sh; ++rh)
+      for (int rw = 0; rw < a->sw; ++rw) {
+        TcParams P;
+        memset(&P, 0, sizeof(P));
+        P.n_tile = n_tile;
+        P.Dt = cdiv(a->Di - rd, a->sd); P.Ht = cdiv(a->Hi - rh, a->sh); P.Wt = cdiv(a->Wi - rw, a->sw);
+        if (P.Dt <= 0 || P.Ht <= 0 || P.Wt <= 0) continue;
+        int nt = 0;
+        for (int td = 0; td < a->kd; ++td) {
+          if ((rd + a->pd - td) % a->sd) continue;
+          for (int th = 0; th < a->kh; ++th) {
+            if ((rh + a->ph - th) % a->sh) continue;
+            for (int tw = 0; tw < a->kw; ++tw) {
+              if ((rw + a->pw - tw) % a->sw) continue;
+              TcTap& t = P.taps[nt++];
+              t.map = 0;
+              t.dz = (rd + a->pd - td) / a->sd;   // exact (C++ % and / agree in sign on exact division)
+              t.dy = (rh + a->ph - th) / a->sh;
+              t.dx = (rw + a->pw - tw) / a->sw;
+              t.wrow = ((td * a->kh + th) * a->kw + tw) * a->Cin;
+            }
+          }
+        }
+        if (nt == 0) { set_error("conv3d_dgrad(tcgen05): parity class without taps"); return MVD_ERR_UNSUPPORTED; }
+        P.ntaps = nt;
+        P.kchunks = a->Cout / kc;
+        P.B = a->B;
+        P.tiles_w = cdiv(P.Wt, TILE_W); P.tiles_h = cdiv(P.Ht, TILE_H);
+        P.num_m_tiles = P.B * P.Dt * P.tiles_h * P.tiles_w;
+        P.num_n_tiles = a->Cin / n_tile;
+        P.out = (bf16*)a->x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ldx;
+        P.sw = ldx * a->sw; P.sh = ldx * a->Wi * a->sh; P.sd = ldx * a->Wi * a->Hi * a->sd;
+        P.sb = ldx * a->Wi * a->Hi * a->Di;
+        P.bias = a->bias;
+        P.accumulate = a->accumulate;
+        int rc = launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)");
+        if (rc) return rc;
+      }
+  return MVD_OK;
+}
+
 bool tc_wgrad_supported(const mvd_conv3d_args*) { return false; }
-int tc_fprop(const mvd_conv3d_args*, cudaStream_t) { return MVD_ERR_UNSUPPORTED; }
-int tc_dgrad(const mvd_conv3d_args*, cudaStream_t) { return MVD_ERR_UNSUPPORTED; }
 int tc_wgrad(const mvd_conv3d_args*, cudaStream_t) { return MVD_ERR_UNSUPPORTED; }
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args*) { return 0; }
+
+}  // namespace mvd
+
+extern "C" int mvd_tc_selftest(float*, int, mvd_stream_t) {
+  mvd::set_error("tc_selftest: not built in this revision");
+  return MVD_ERR_UNSUPPORTED;
 }
-extern "C" int mvd_tc_selftest(float*, int, mvd_stream_t) { return MVD_ERR_UNSUPPORTED; }

@@ -149,8 +149,9 @@ __global__ void __launch_bounds__(256) skel_update_kernel(const float* __restric
     float sk;
     if (first) sk = delta;
     else {
+      // no FMA contraction: PyTorch rounds skel*delta before the subtraction (soft_skeleton.py:36)
       float prev = skel_in[i];
-      sk = prev + fmaxf(delta - prev * delta, 0.f);
+      sk = __fadd_rn(prev, fmaxf(__fsub_rn(delta, __fmul_rn(prev, delta)), 0.f));
     }
     skel_out[i] = sk;
   }
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) skel_chain_bwd_kernel(const float* __rest
     for (int j = L - 1; j >= 1; --j) {
       float dl = delta[(long long)j * N + i];
       float sk = skel[(long long)(j - 1) * N + i];
-      bool m = (dl - sk * dl) > 0.f;
+      bool m = __fsub_rn(dl, __fmul_rn(sk, dl)) > 0.f;
       g_delta[(long long)j * N + i] = m ? G * (1.f - sk) : 0.f;
       G = m ? G * (1.f - dl) : G;
     }

@@ -12,7 +12,7 @@ BF = torch.bfloat16
 
 
 def rel_err(got, want):
-    got, want = got.double().flatten(), want.double().flatten()
+    got, want = got.detach().double().flatten(), want.detach().double().flatten()
     return float((got - want).norm() / want.norm().clamp_min(1e-30))
 
 
@@ -51,6 +51,14 @@ CONV_CASES = [
     (1, 1, 32, (8, 8, 8), 3, (1, 1, 1)),      # MVD stem: Cin = 1
     (1, 96, 40, (5, 5, 6), 3, (1, 1, 1)),     # odd extents, channels not multiples of 32
     (1, 16, 24, (4, 4, 4), 1, (1, 1, 1)),
+    # tcgen05 coverage: several K chunks, N tiles of 128 / 160 / 256, tails in every direction, tiny volumes
+    (2, 64, 64, (16, 16, 16), 3, (1, 1, 1)),
+    (1, 128, 128, (9, 17, 11), 3, (1, 1, 1)),
+    (1, 256, 320, (4, 4, 4), 3, (1, 1, 1)),
+    (1, 640, 320, (5, 5, 6), 3, (1, 1, 1)),
+    (1, 512, 256, (8, 8, 8), 3, (1, 1, 1)),
+    (1, 320, 320, (8, 8, 8), 3, (2, 2, 2)),
+    (1, 320, 320, (10, 10, 6), 3, (2, 2, 1)),
 ]
 
 
@@ -298,7 +306,7 @@ def test_morphology_golden_bit_exact(m, golden_skel, vol, fn):
     y = getattr(m, fn)(x)
     assert np.array_equal(y.detach().cpu().numpy(), g[f'{vol}.{fn}.out'])
     (y * torch.from_numpy(g[f'{vol}.{fn}.w']).to(dev())).sum().backward()
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.{fn}.grad'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.{fn}.grad'], rtol=1e-5, atol=1e-6)  # fp32 atomics: order-dependent last bits
 
 
 @pytest.mark.parametrize('vol', ['smooth', 'ties'])
@@ -309,7 +317,7 @@ def test_soft_skel_golden(m, golden_skel, vol, it):
     y = m.soft_skel(x, it)
     assert np.array_equal(y.detach().cpu().numpy(), g[f'{vol}.soft_skel{it}.out'])
     (y * torch.from_numpy(g[f'{vol}.soft_skel{it}.w']).to(dev())).sum().backward()
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.soft_skel{it}.grad'], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.soft_skel{it}.grad'], rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize('it', [3, 10])
