@@ -227,8 +227,10 @@ int pick_n_tile(int N) {
   return 0;
 }
 
-bool encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4] /*W,H,D,B extents*/,
-                    const long long strides_el[4] /*W,H,D,B strides in elements*/, int kc) {
+}  // namespace
+
+bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4] /*W,H,D,B extents*/,
+                       const long long strides_el[4] /*W,H,D,B strides in elements*/, int kc) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2], (cuuint64_t)dims[3]};
@@ -241,6 +243,8 @@ bool encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int d
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+namespace {
 
 bool encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -335,13 +339,13 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
           // an empty lattice can never be hit by a valid tap; alias it to lattice 0 extents of 1 (all loads OOB)
           const int d1[4] = {1, 1, 1, a->B};
           const long long s1[4] = {ld, ld * a->Wi, ld * a->Wi * a->Hi, ld * a->Wi * a->Hi * a->Di};
-          if (!encode_act_map(&maps.a[mi], x, a->Cin, a->ldx, d1, s1, kc)) goto fail;
+          if (!tc_encode_act_map(&maps.a[mi], x, a->Cin, a->ldx, d1, s1, kc)) goto fail;
           continue;
         }
         const long long strides[4] = {ld * a->sw, ld * a->Wi * a->sh, ld * a->Wi * a->Hi * a->sd,
                                       ld * a->Wi * a->Hi * a->Di};
         const bf16* base = x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ld;
-        if (!encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc)) goto fail;
+        if (!tc_encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc)) goto fail;
       }
   {
     const int taps = a->kd * a->kh * a->kw;
@@ -397,7 +401,7 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   const long long ldy = a->ldy;
   const int dims[4] = {a->Wo, a->Ho, a->Do, a->B};
   const long long strides[4] = {ldy, ldy * a->Wo, ldy * a->Wo * a->Ho, ldy * a->Wo * a->Ho * a->Do};
-  if (!encode_act_map(&maps.a[0], y, a->Cout, a->ldy, dims, strides, kc)) {
+  if (!tc_encode_act_map(&maps.a[0], y, a->Cout, a->ldy, dims, strides, kc)) {
     set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(A) failed");
     return MVD_ERR_CUDA;
   }
@@ -451,9 +455,6 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   return MVD_OK;
 }
 
-bool tc_wgrad_supported(const mvd_conv3d_args*) { return false; }
-int tc_wgrad(const mvd_conv3d_args*, cudaStream_t) { return MVD_ERR_UNSUPPORTED; }
-size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args*) { return 0; }
 
 }  // namespace mvd
 

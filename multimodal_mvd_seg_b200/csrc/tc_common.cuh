@@ -33,7 +33,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
-__device__ int g_tc_timeout_code;
+static __device__ int g_tc_timeout_code;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -135,5 +135,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
+// 5-D tensor map (C, W, H, D, B) over a pitched NDHWC bf16 lattice with box (box_c, 8, 16, 1, 1); swizzle 128B when
+// box_c == 64, 64B when box_c == 32.  dims / strides are the W,H,D,B extents and element strides of the lattice.
+bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4], const long long strides_el[4],
+                       int box_c);
 
 }  // namespace mvd
