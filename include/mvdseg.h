@@ -193,8 +193,11 @@ int mvd_channel_sum(const void* g, int ld, long long NV, int C, float* out, mvd_
 /* out[0] (+)= scale * in[0]: device-side double -> float scalar algebra (keeps the step free of host syncs) */
 int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream);
 int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int C, mvd_stream_t stream); /* dst += src */
-/* hardware probe used by tests/bench: runs the tcgen05 self-test (descriptor semantics); fills out[0..n) */
-int mvd_tc_selftest(float* out_dev, int n, mvd_stream_t stream);
+/* hardware probe (tests, DESIGN.md evidence): multiplies a TMA-loaded [256 rows][row_bytes] bf16 tile by an identity
+ * with a caller-built UMMA A descriptor (start offset, SBO, LBO, base offset, K- or MN-major) and returns
+ * D = float[2][128][16] (second slab: A start advanced by kadv_bytes), i.e. which smem rows/channels were fetched. */
+int mvd_tc_probe(const void* src, const void* ident, int row_bytes, int start_off, int sbo, int lbo, int base_off,
+                 int a_mn_major, int kadv_bytes, float* out, mvd_stream_t stream);
 
 #ifdef __cplusplus
 }

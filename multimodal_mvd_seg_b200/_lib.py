@@ -88,7 +88,7 @@ _SIGNATURES = {
     'mvd_channel_sum': (c_int, [P, I, LL, I, P, S]),
     'mvd_scalar_axpy': (c_int, [P, F, P, I, S]),
     'mvd_add_bf16': (c_int, [P, I, P, I, LL, I, S]),
-    'mvd_tc_selftest': (c_int, [P, I, S]),
+    'mvd_tc_probe': (c_int, [P, P, I, I, I, I, I, I, I, P, S]),
 }
 
 _UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count',

@@ -458,7 +458,3 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
 
 }  // namespace mvd
 
-extern "C" int mvd_tc_selftest(float*, int, mvd_stream_t) {
-  mvd::set_error("tc_selftest: not built in this revision");
-  return MVD_ERR_UNSUPPORTED;
-}

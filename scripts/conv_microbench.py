@@ -1,0 +1,46 @@
+"""GPU microbenchmark of one conv layer through the C ABI (CUDA-event timing, inputs larger than L2 or L2 flushed).
+usage: conv_microbench.py CIN COUT D H W [pass=fprop|dgrad|wgrad] [stride=1] [iters=10] [B=2] [k=3]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import multimodal_mvd_seg_b200 as m
+from multimodal_mvd_seg_b200 import ops
+
+a = sys.argv[1:]
+cin, cout, D, H, W = (int(v) for v in a[:5])
+which = a[5] if len(a) > 5 else 'fprop'
+s = int(a[6]) if len(a) > 6 else 1
+iters = int(a[7]) if len(a) > 7 else 10
+B = int(a[8]) if len(a) > 8 else 2
+k = int(a[9]) if len(a) > 9 else 3
+dev = torch.device('cuda:0')
+geom = ops.ConvGeom((k,) * 3, (s,) * 3, ((k - 1) // 2,) * 3)
+Do, Ho, Wo = geom.out_size((D, H, W))
+x = torch.randn((B, D, H, W, cin), device=dev).to(torch.bfloat16)
+y = torch.randn((B, Do, Ho, Wo, cout), device=dev).to(torch.bfloat16)
+w = torch.randn((cout, cin, k, k, k), device=dev) * 0.05
+bias = torch.zeros(cout, device=dev)
+wf, wd = ops.pack_weights(w)
+dw = torch.empty_like(w)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def run():
+    if which == 'fprop':
+        ops.conv_fprop(geom, x, y, wf, bias=bias)
+    elif which == 'dgrad':
+        ops.conv_dgrad(geom, x, y, wd)
+    else:
+        ops.conv_wgrad(geom, x, y, dw)
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+ts = []
+for _ in range(iters):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort()
+flops = 2.0 * B * Do * Ho * Wo * cout * cin * k ** 3
+med = ts[len(ts) // 2]
+print(f'{which} {cin}->{cout} {D}x{H}x{W} s{s} k{k} B{B}: median {med:.3f} ms  best {ts[0]:.3f} ms  {flops / med / 1e9:.1f} TFLOP/s (median)')
