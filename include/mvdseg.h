@@ -88,6 +88,11 @@ int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream); /* y = conv
 int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* x = conv^T(y, w)       (w = w_dgrad) */
 int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* dw = x (*) y, dbias = sum y          */
 
+/* stem (Cin = 1 or 2 input modalities): explicit im2col, X_col[v][tap*Cin + ci] (stride 1), zero-padded to Kpad columns
+ * (a multiple of 8); the stem's fprop / wgrad then run as single-tap tensor-core GEMMs over X_col. */
+int mvd_im2col_small(const void* x, int ldx, int B, int D, int H, int W, int Cin, int kd, int kh, int kw, int pd,
+                     int ph, int pw, void* out, int Kpad, mvd_stream_t stream);
+
 /* ---- InstanceNorm3d(affine, eps) + LeakyReLU -------------------------------------------------------------- */
 /* Replaces nn.InstanceNorm3d + nn.LeakyReLU(inplace) of every ConvDropoutNormReLU block
  * (get_network_from_plans.py:41-44).  stats = [B][C][2] doubles (sum, sumsq) over the V voxels of each (b,c). */

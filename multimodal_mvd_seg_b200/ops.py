@@ -286,11 +286,28 @@ class ConvNormActFn(torch.autograd.Function):
         Do, Ho, Wo = geom.out_size((Di, Hi, Wi))
         dev = x_cl.device
         need_dx = ctx.needs_input_grad[0]
-        wf, wd = pack_weights(weight, True, need_dx)
         y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
         stats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev)
         V = Do * Ho * Wo
-        conv_fprop(geom, x_cl, y, wf, bias=bias)
+        # stem (1-2 input modalities): explicit im2col + single-tap tensor-core GEMM (csrc/stem.cu)
+        stem = (Cin <= 4 and not need_dx and geom.s == (1, 1, 1) and Cout % 32 == 0 and _default_algo != 1)
+        ctx.stem = stem
+        if stem:
+            taps = geom.k[0] * geom.k[1] * geom.k[2]
+            kpad = 32 if taps * Cin <= 32 else 64
+            assert taps * Cin <= kpad
+            x_col = torch.empty((B, Di, Hi, Wi, kpad), dtype=BF16, device=dev)
+            lib.im2col_small(x_cl.data_ptr(), cl_pitch(x_cl), B, Di, Hi, Wi, Cin, *geom.k, *geom.p, x_col.data_ptr(),
+                             kpad, _stream())
+            # [Cout][Cin][taps] -> [1 tap][Cout][(tap, ci) zero-padded]: a 1.7k-element reshuffle, host-side plumbing
+            wcol = torch.zeros((1, Cout, kpad), dtype=BF16, device=dev)
+            wcol[0, :, :taps * Cin] = weight.detach().reshape(Cout, Cin, taps).permute(0, 2, 1).reshape(Cout, taps * Cin)
+            g1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
+            conv_fprop(g1, x_col, y, wcol, bias=bias)
+            x_cl, wd, geom = x_col, None, g1
+        else:
+            wf, wd = pack_weights(weight, True, need_dx)
+            conv_fprop(geom, x_cl, y, wf, bias=bias)
         lib.inorm_stats(y.data_ptr(), cl_pitch(y), B, V, Cout, stats.data_ptr(), _stream())
         z = out if out is not None else torch.empty_like(y)
         lib.inorm_lrelu_fwd(y.data_ptr(), cl_pitch(y), z.data_ptr(), cl_pitch(z), stats.data_ptr(), _ptr(gamma),
@@ -321,7 +338,15 @@ class ConvNormActFn(torch.autograd.Function):
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
         db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
         if dw is not None:
-            conv_wgrad(geom, x_cl, dy, dw, db)
+            if ctx.stem:
+                Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
+                kpad = x_cl.shape[-1]
+                dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
+                conv_wgrad(geom, x_cl, dy, dw_col, db)
+                dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
+                         .reshape(weight.shape))
+            else:
+                conv_wgrad(geom, x_cl, dy, dw, db)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
