@@ -204,6 +204,11 @@ int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int
 int mvd_tc_probe(const void* src, const void* ident, int row_bytes, int start_off, int sbo, int lbo, int base_off,
                  int a_mn_major, int kadv_bytes, float* out, mvd_stream_t stream);
 
+/* hardware probe: cycles for n_mma back-to-back tcgen05.mma (M=128, N=n, K=16) from resident shared memory, round-robin
+ * over n_acc accumulators; A start stepped by a_step bytes (mod a_steps_mod steps), 8-row-group pitch a_sbo. */
+int mvd_tc_mma_bench(int n, int n_mma, int n_acc, int a_sbo, int a_step, int a_steps_mod, int row_bytes, int mn_major,
+                     int b_step, int grid, int mode, long long* out_cycles, mvd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

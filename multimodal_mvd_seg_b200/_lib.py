@@ -89,6 +89,7 @@ _SIGNATURES = {
     'mvd_scalar_axpy': (c_int, [P, F, P, I, S]),
     'mvd_add_bf16': (c_int, [P, I, P, I, LL, I, S]),
     'mvd_tc_probe': (c_int, [P, P, I, I, I, I, I, I, I, P, S]),
+    'mvd_tc_mma_bench': (c_int, [I, I, I, I, I, I, I, I, I, I, I, P, S]),
     'mvd_im2col_small': (c_int, [P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, S]),
 }
 

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ================= TMA producer =================
       tma_prefetch_desc(&maps.b);
       int stage = 0;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ================= MMA issuer =================
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
@@ -244,9 +244,7 @@ bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const in
   return r == CUDA_SUCCESS;
 }
 
-namespace {
-
-bool encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc) {
+bool tc_encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -258,6 +256,8 @@ bool encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_ti
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+namespace {
 
 // shape coverage shared by fprop (K = Cin, N = Cout) and dgrad (K = Cout, N = Cin)
 bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn, const void* w, int taps) {
@@ -322,7 +322,18 @@ static inline void floordivmod(int v, int s, int& q, int& r) {
   r = v - q * s;
 }
 
+static bool is_k3s1p1(const mvd_conv3d_args* a) {
+  return a->kd == 3 && a->kh == 3 && a->kw == 3 && a->sd == 1 && a->sh == 1 && a->sw == 1 && a->pd == 1 &&
+         a->ph == 1 && a->pw == 1;
+}
+
 int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
+  if (is_k3s1p1(a) && tc_halo_enabled()) {
+    int wrow[27];
+    for (int i = 0; i < 27; ++i) wrow[i] = i * a->Cout;
+    return tc_halo_conv((const bf16*)a->x, a->ldx, a->Cin, (bf16*)a->y, a->ldy, a->Cout, (const bf16*)a->w, wrow,
+                        a->bias, 0, a->B, a->Do, a->Ho, a->Wo, st, "conv3d_fprop(tcgen05 halo)");
+  }
   const int kc = (a->Cin % 64 == 0) ? 64 : 32;
   TcMaps maps;
   TcParams P;
@@ -350,7 +361,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   {
     const int taps = a->kd * a->kh * a->kw;
     P.n_tile = pick_n_tile(a->Cout);
-    if (!encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cout, a->Cin, P.n_tile, kc)) goto fail;
+    if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cout, a->Cin, P.n_tile, kc)) goto fail;
     int nt = 0;
     for (int td = 0; td < a->kd; ++td)
       for (int th = 0; th < a->kh; ++th)
@@ -395,6 +406,12 @@ bool tc_dgrad_supported(const mvd_conv3d_args* a) {
 }
 
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
+  if (is_k3s1p1(a) && tc_halo_enabled()) {
+    int wrow[27];   // produced voxel i gathers y[i + 1 - t]: halo offset o = 2 - t per axis, i.e. tap 26 - idx
+    for (int i = 0; i < 27; ++i) wrow[i] = (26 - i) * a->Cin;
+    return tc_halo_conv((const bf16*)a->y, a->ldy, a->Cout, (bf16*)a->x, a->ldx, a->Cin, (const bf16*)a->w, wrow,
+                        a->bias, a->accumulate, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
+  }
   const int kc = (a->Cout % 64 == 0) ? 64 : 32;
   TcMaps maps;
   const bf16* y = (const bf16*)a->y;
@@ -408,7 +425,7 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   for (int i = 1; i < kMaxMaps; ++i) maps.a[i] = maps.a[0];
   const int taps = a->kd * a->kh * a->kw;
   const int n_tile = pick_n_tile(a->Cin);
-  if (!encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cin, a->Cout, n_tile, kc)) {
+  if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cin, a->Cout, n_tile, kc)) {
     set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(W) failed");
     return MVD_ERR_CUDA;
   }

@@ -1,0 +1,384 @@
+// conv_tc_halo.cu -- tcgen05 implicit GEMM for 3x3x3 / stride 1 / pad 1 convolutions (fprop, and dgrad via flipped
+// taps) with SHARED-MEMORY HALO REUSE.  These layers carry ~90 % of the network's FLOPs.
+//
+// The tap-by-tap kernel (conv_tc.cu) re-fetches every input voxel 27 times through TMA; ncu shows it bound by the
+// TMA request rate (~0.27 rows of <=128 B per clock per SM), not by the tensor pipe.  Here an input plane
+// [18 h][10 w][KC] (the 16 x 8 output brick plus a one-voxel halo) is loaded ONCE per channel chunk and feeds all nine
+// in-plane taps: the UMMA shared-memory descriptor is simply started (oy*10 + ox) rows further, with the stride
+// between 8-row groups (SBO) set to the plane's row pitch of 10 voxels.  This relies on the tensor core applying the
+// 128B/64B swizzle as a pure function of the shared-memory address (verified by scripts/umma_probe.py,
+// profiles/r1_umma_descriptor_probe.txt).  A CTA additionally produces MT output planes (consecutive d) per work
+// item from MT+2 input planes, so each plane and each weight tile serves up to MT x 9 (x3) MMAs:
+//   TMA rows per 128-voxel tile: 27*(128+N)  ->  ((MT+2)*180 + 27*N) / MT.
+// Roles (224 threads): warp 0 plane producer, warp 6 weight producer, warp 1 MMA issuer, warps 2..5 epilogue.
+// Accumulators: 2 (double buffer) x MT x N fp32 columns of TMEM.
+#include "conv_common.cuh"
+#include "tc_common.cuh"
+
+namespace mvd {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 224;
+constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2, PLANE_ROWS = HALO_W * HALO_H;
+constexpr int kMaxRing = 8, kMaxWStages = 8;
+
+struct alignas(64) HaloMaps {
+  CUtensorMap a;   // (C, W, H, D, B) box (KC, 10, 18, 1, 1)
+  CUtensorMap b;   // weights [27*N][K] box (KC, n_tile)
+};
+
+struct HaloParams {
+  int B, D, H, W;
+  int tiles_w, tiles_h, dgroups, num_n_tiles, total_items;
+  int MT, n_tile, kchunks, ring, wstages;
+  uint32_t idesc, tmem_cols;
+  bf16* out;
+  long long sb, sd, sh, sw;
+  const float* bias;
+  int accumulate;
+  long long* prof;   // optional [gridDim.x][8] cycle counters of the MMA issuer (debug / DESIGN.md evidence)
+  int wrow[27];
+};
+
+template <int KC, int MT>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps,
+                                                                const __grid_constant__ HaloParams P) {
+  constexpr int ROWB = KC * 2;
+  constexpr int PLANE_TX = PLANE_ROWS * ROWB;                       // bytes TMA delivers per plane
+  constexpr int PLANE_BYTES = (PLANE_TX + 1023) & ~1023;            // slot pitch (1 KB aligned)
+  constexpr uint64_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
+  constexpr uint32_t A_SBO = HALO_W * ROWB;                         // next 8-voxel row group = next h line of the plane
+  constexpr uint32_t B_SBO = 8 * ROWB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_pfull[kMaxRing], bar_pempty[kMaxRing], bar_wfull[kMaxWStages], bar_wempty[kMaxWStages],
+      bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_bytes = P.n_tile * ROWB;
+  uint8_t* smem_p = smem;
+  uint8_t* smem_w = smem + (size_t)P.ring * PLANE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NP = MT + 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.ring; ++s) { mbar_init(&bar_pfull[s], 1); mbar_init(&bar_pempty[s], 1); }
+    for (int s = 0; s < P.wstages; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  auto decode = [&](int item, int& n0, int& b, int& d0, int& h0, int& w0) {
+    const int nt = item % P.num_n_tiles;
+    int m = item / P.num_n_tiles;
+    n0 = nt * P.n_tile;
+    w0 = (m % P.tiles_w) * TILE_W; m /= P.tiles_w;
+    h0 = (m % P.tiles_h) * TILE_H; m /= P.tiles_h;
+    d0 = (m % P.dgroups) * MT;
+    b = m / P.dgroups;
+  };
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= plane producer =================
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        int n0, b, d0, h0, w0;
+        decode(item, n0, b, d0, h0, w0);
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          for (int p = 0; p < NP; ++p) {
+            mbar_wait(&bar_pempty[slot], phase ^ 1, 31);
+            mbar_arrive_expect_tx(&bar_pfull[slot], (uint32_t)PLANE_TX);
+            tma_load_5d(&maps.a, smem_p + (size_t)slot * PLANE_BYTES, &bar_pfull[slot], kc * KC, w0 - 1, h0 - 1,
+                        d0 + p - 1, b);
+            if (++slot == P.ring) { slot = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 6) {
+    if (elect_one_sync()) {
+      // ================= weight producer =================
+      int ws = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        const int n0 = (item % P.num_n_tiles) * P.n_tile;
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          for (int o = 0; o < 27; ++o) {
+            mbar_wait(&bar_wempty[ws], phase ^ 1, 32);
+            mbar_arrive_expect_tx(&bar_wfull[ws], (uint32_t)w_bytes);
+            tma_load_2d(&maps.b, smem_w + (size_t)ws * w_bytes, &bar_wfull[ws], kc * KC, P.wrow[o] + n0);
+            if (++ws == P.wstages) { ws = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer =================
+      // everything loop-invariant lives in registers: the single issuing thread has no ILP to hide constant-bank
+      // reloads or 64-bit address arithmetic between two tcgen05.mma
+      const int ring = P.ring, wstages = P.wstages, kchunks = P.kchunks, n_tile = P.n_tile;
+      const int total_items = P.total_items, gstride = gridDim.x;
+      const uint32_t idesc = P.idesc;
+      const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, A_SBO, LAYOUT) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, B_SBO, LAYOUT) >> 32);
+      const uint32_t p_base = (smem_u32(smem_p) >> 4) | (1u << 16);     // descriptor low word of ring slot 0
+      const uint32_t w_base = (smem_u32(smem_w) >> 4) | (1u << 16);
+      const uint32_t w_step = (uint32_t)w_bytes >> 4;
+      int acc = 0, ws = 0;
+      uint32_t accphase = 0, wphase = 0;
+      int base_slot = 0;          // ring slot of plane 0 of the current (item, chunk)
+      uint32_t base_phase = 0;    // its full-barrier parity; slots that wrap past the ring end use the flipped parity
+      long long c_tempty = 0, c_wfull = 0, c_pfull = 0;
+      const long long c_start = clock64();
+      for (int item = blockIdx.x; item < total_items; item += gstride) {
+        long long c0 = clock64();
+        mbar_wait(&bar_tempty[acc], accphase ^ 1, 33);
+        c_tempty += clock64() - c0;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * n_tile);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          uint32_t plo[NP];       // descriptor low words of this chunk's planes
+          uint32_t ppar = 0;      // bit p: parity of plane p's full barrier
+          int pslot[NP];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            int slot = base_slot + p;
+            uint32_t par = base_phase;
+            if (slot >= ring) { slot -= ring; par ^= 1; }
+            pslot[p] = slot;
+            ppar |= par << p;
+            plo[p] = p_base + (uint32_t)slot * (uint32_t)(PLANE_BYTES >> 4);
+          }
+#pragma unroll
+          for (int oz = 0; oz < 3; ++oz) {
+            for (int oyx = 0; oyx < 9; ++oyx) {
+              const int oy = oyx / 3, ox = oyx - oy * 3;
+              c0 = clock64();
+              mbar_wait(&bar_wfull[ws], wphase, 34);
+              c_wfull += clock64() - c0;
+              tcgen05_fence_after();
+              const uint32_t wlo = w_base + (uint32_t)ws * w_step;
+              const uint32_t tap_off = (uint32_t)(((oy * HALO_W + ox) * ROWB) >> 4);
+#pragma unroll
+              for (int t = 0; t < MT; ++t) {
+                const int p = t + oz;
+                // a plane is first touched at the first tap of the first oz phase that uses it
+                if (oyx == 0 && (oz == 0 || t == MT - 1)) {
+                  c0 = clock64();
+                  mbar_wait(&bar_pfull[pslot[p]], (ppar >> p) & 1u, 35);
+                  c_pfull += clock64() - c0;
+                  tcgen05_fence_after();
+                }
+                const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(plo[p] + tap_off);
+                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)wlo;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  umma_bf16(d_tmem + (uint32_t)(t * n_tile), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            (kc | oz | oyx | k) ? 1u : 0u);
+              }
+              umma_commit(&bar_wempty[ws]);
+              if (++ws == wstages) { ws = 0; wphase ^= 1; }
+            }
+            // planes whose last use was this oz phase: p with min(p, 2) == oz
+            if (oz < 2) {
+              umma_commit(&bar_pempty[pslot[oz]]);
+            } else {
+#pragma unroll
+              for (int p = 2; p < NP; ++p) umma_commit(&bar_pempty[pslot[p]]);
+            }
+          }
+          base_slot += NP;
+          if (base_slot >= ring) { base_slot -= ring; base_phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+      if (P.prof) {
+        long long* o = P.prof + (long long)blockIdx.x * 8;
+        o[0] = clock64() - c_start; o[1] = c_tempty; o[2] = c_wfull; o[3] = c_pfull;
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      int n0, b, d0, h0, w0;
+      decode(item, n0, b, d0, h0, w0);
+      mbar_wait(&bar_tfull[acc], accphase, 36);
+      tcgen05_fence_after();
+      const int r = q * 32 + lane;
+      const int h = h0 + (r >> 3), w = w0 + (r & 7);
+      const bool hw_ok = (h < P.H) && (w < P.W);
+      for (int t = 0; t < MT; ++t) {
+        const int d = d0 + t;
+        if (d >= P.D) break;   // uniform across the CTA
+        bf16* orow = P.out + (long long)b * P.sb + (long long)d * P.sd + (long long)h * P.sh + (long long)w * P.sw + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + t) * P.n_tile);
+        for (int c = 0; c < P.n_tile; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (hw_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] = __uint_as_float(v[g * 8 + j]);
+                if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + g * 8 + j));
+              }
+              bf16x8* dst = reinterpret_cast<bf16x8*>(orow + c + g * 8);
+              if (P.accumulate) {
+                float o[8];
+                unpack8(*dst, o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += o[j];
+              }
+              *dst = pack8(f);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+int pick_n_tile(int N) {
+  if (N % 32) return 0;
+  if (N <= 256) return N;
+  for (int t = 256; t >= 32; t -= 32)
+    if (N % t == 0) return t;
+  return 0;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+long long* g_halo_prof = nullptr;
+
+bool tc_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVD_NO_HALO");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
+                 const float* bias, int accumulate, int B, int D, int H, int W, cudaStream_t st, const char* who) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("%s: no cuTensorMapEncodeTiled", who); return MVD_ERR_CUDA; }
+  const int kc = (K % 64 == 0) ? 64 : 32;
+  HaloMaps maps;
+  HaloParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_tile = pick_n_tile(N);
+  if (P.n_tile == 0 || K % 32) { set_error("%s: unsupported channel counts", who); return MVD_ERR_UNSUPPORTED; }
+  {
+    const long long ld = lds;
+    cuuint64_t gdim[5] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * W * 2, (cuuint64_t)ld * W * H * 2,
+                          (cuuint64_t)ld * W * H * D * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kc, HALO_W, HALO_H, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)src, gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(planes) failed (%d)", who, (int)r); return MVD_ERR_CUDA; }
+  }
+  if (!tc_encode_w_map(&maps.b, w, (long long)27 * N, K, P.n_tile, kc)) {
+    set_error("%s: cuTensorMapEncodeTiled(weights) failed", who);
+    return MVD_ERR_CUDA;
+  }
+  // MT: as many output planes per item as TMEM (2 x MT x n_tile <= 512 columns) and shared memory allow, at most 4
+  int MT = 512 / (2 * P.n_tile);
+  if (MT > 4) MT = 4;
+  if (MT > D) MT = D;
+  if (MT == 3) MT = 2;
+  if (MT < 1) MT = 1;
+  const int rowb = kc * 2;
+  const int plane_bytes = (PLANE_ROWS * rowb + 1023) & ~1023;
+  const int w_bytes = P.n_tile * rowb;
+  const int budget = 198 * 1024;
+  int ring, wstages;
+  for (;;) {
+    ring = MT + 3;
+    if (ring > kMaxRing) ring = kMaxRing;
+    wstages = (budget - ring * plane_bytes) / w_bytes;
+    if (wstages >= 3 || MT == 1) break;
+    MT >>= 1;
+  }
+  if (wstages > kMaxWStages) wstages = kMaxWStages;
+  if (wstages < 2) {
+    ring = MT + 2;
+    wstages = (budget - ring * plane_bytes) / w_bytes;
+    if (wstages > kMaxWStages) wstages = kMaxWStages;
+    if (wstages < 2) { set_error("%s: tile does not fit shared memory", who); return MVD_ERR_UNSUPPORTED; }
+  }
+  P.MT = MT; P.ring = ring; P.wstages = wstages;
+  P.B = B; P.D = D; P.H = H; P.W = W;
+  P.tiles_w = cdiv(W, TILE_W); P.tiles_h = cdiv(H, TILE_H); P.dgroups = cdiv(D, MT);
+  P.num_n_tiles = N / P.n_tile;
+  P.total_items = B * P.dgroups * P.tiles_h * P.tiles_w * P.num_n_tiles;
+  P.kchunks = K / kc;
+  P.idesc = make_idesc_bf16(128, P.n_tile, 0, 0);
+  uint32_t cols = 32;
+  while ((int)cols < 2 * MT * P.n_tile) cols <<= 1;
+  P.tmem_cols = cols;
+  P.out = dst;
+  P.sw = ldd; P.sh = (long long)ldd * W; P.sd = P.sh * H; P.sb = P.sd * D;
+  P.bias = bias; P.accumulate = accumulate;
+  P.prof = g_halo_prof;
+  for (int i = 0; i < 27; ++i) P.wrow[i] = wrow[i];
+  const size_t smem = (size_t)ring * plane_bytes + (size_t)wstages * w_bytes + 1024;
+  int grid = num_sms();
+  if (grid > P.total_items) grid = P.total_items;
+  void (*kern)(const HaloMaps, const HaloParams) = nullptr;
+  int ki = 0;
+#define HALO_PICK(KCV, MTV, IDX)                         \
+  if (kc == KCV && MT == MTV) {                          \
+    kern = conv_halo_kernel<KCV, MTV>;                   \
+    ki = IDX;                                            \
+  }
+  HALO_PICK(64, 1, 0) HALO_PICK(64, 2, 1) HALO_PICK(64, 4, 2) HALO_PICK(32, 1, 3) HALO_PICK(32, 2, 4) HALO_PICK(32, 4, 5)
+#undef HALO_PICK
+  if (!kern) { set_error("%s: no halo kernel for kc=%d MT=%d", who, kc, MT); return MVD_ERR_UNSUPPORTED; }
+  static bool attr_done[6] = {false, false, false, false, false, false};
+  if (!attr_done[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+      return MVD_ERR_CUDA;
+    }
+    attr_done[ki] = true;
+  }
+  kern<<<grid, kThreads, smem, st>>>(maps, P);
+  MVD_LAUNCH_CHECK(who);
+  return MVD_OK;
+}
+
+}  // namespace mvd
+
+// debug hook: per-CTA cycle counters of the halo kernel's MMA issuer ([grid][8] int64, device memory) or NULL
+extern "C" void mvd_debug_set_halo_prof(long long* buf) { mvd::g_halo_prof = buf; }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   };
 
   if (warp == 0) {
-    if (lane == 0 && ng > 0) {
+    if (ng > 0 && elect_one_sync()) {
       // ================= TMA producer =================
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && ng > 0) {
+    if (ng > 0 && elect_one_sync()) {
       // ================= MMA issuer =================
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;

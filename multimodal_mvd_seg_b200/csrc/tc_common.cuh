@@ -45,6 +45,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
   }
 }
 
+// one lane of a fully converged warp (the pattern the compiler turns into straight-line uniform-datapath code:
+// UTCHMMA / UTMALDG issued from a divergent `if (lane == 0)` region are wrapped in a per-active-lane loop instead)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -139,5 +151,12 @@ PFN_encodeTiled get_encode_tiled();
 // box_c == 64, 64B when box_c == 32.  dims / strides are the W,H,D,B extents and element strides of the lattice.
 bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4], const long long strides_el[4],
                        int box_c);
+// 2-D map over packed weights [rows][K] with box (kc, n_tile)
+bool tc_encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc);
+// halo-plane kernel for 3x3x3 / stride 1 / pad 1 (conv_tc_halo.cu): dst[v][n] = sum_{o in {0,1,2}^3} sum_k
+// src[v + o - 1][k] * W[wrow[o] + n][k] (+ bias[n]); src/dst are pitched NDHWC lattices of the same extent B,D,H,W.
+bool tc_halo_enabled();
+int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
+                 const float* bias, int accumulate, int B, int D, int H, int W, cudaStream_t st, const char* who);
 
 }  // namespace mvd

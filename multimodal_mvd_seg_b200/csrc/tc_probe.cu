@@ -116,3 +116,109 @@ extern "C" int mvd_tc_probe(const void* src, const void* ident, int row_bytes, i
   return MVD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark: one CTA issues `n_mma` tcgen05.mma (M = 128, N = n, K = 16, bf16) back to back from
+// shared memory that is never refilled, round-robin over `n_acc` TMEM accumulators, optionally stepping the A start
+// address by `a_step` bytes and using `a_sbo` as the 8-row-group pitch.  out[0] = cycles from first issue to the
+// completion of the last MMA (tcgen05.commit -> mbarrier).
+// ---------------------------------------------------------------------------------------------------------------
+namespace mvd {
+namespace {
+struct MmaBenchParams {
+  int n, n_mma, n_acc, a_sbo, a_step, a_steps_mod, row_bytes, mn_major, b_step, mode;
+  long long* out;
+};
+
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(const __grid_constant__ MmaBenchParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (160 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar_done, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&s_tmem, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint64_t layout = (P.row_bytes == 128) ? kLayoutSw128 : kLayoutSw64;
+  const uint32_t sa = smem_u32(smem);
+  const uint32_t sb = smem_u32(smem) + 96 * 1024;
+  const uint32_t idesc = make_idesc_bf16(128, P.n, P.mn_major, 0);
+  const uint32_t lbo = P.mn_major ? 128 * P.row_bytes : 16;
+  if (P.mode == 0) {
+    // issue from a divergent single-lane region
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int i = 0; i < P.n_mma; ++i) {
+        const uint32_t ao = (uint32_t)((i & (P.a_steps_mod - 1)) * P.a_step);
+        const uint32_t bo = (uint32_t)((i & 3) * P.b_step);
+        const uint64_t adesc = make_smem_desc(sa + ao, lbo, (uint32_t)P.a_sbo, layout);
+        const uint64_t bdesc = make_smem_desc(sb + bo, 16, 8 * 128, kLayoutSw128);
+        umma_bf16(tmem + (uint32_t)((i & (P.n_acc - 1)) * P.n), adesc, bdesc, idesc, 1u);
+      }
+      umma_commit(&bar_done);
+      mbar_wait(&bar_done, 0, 41);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) P.out[0] = t1 - t0;
+    }
+  } else if (P.mode == 2 && warp == 0) {
+    // elect once, then the elected lane runs the whole issue loop (the CUTLASS / DeepGEMM pattern)
+    const long long t0 = clock64();
+    if (elect_one_sync()) {
+      const uint64_t adesc0 = make_smem_desc(sa, lbo, (uint32_t)P.a_sbo, layout);
+      const uint64_t bdesc0 = make_smem_desc(sb, 16, 8 * 128, kLayoutSw128);
+      const uint32_t astep = (uint32_t)P.a_step >> 4, bstep = (uint32_t)P.b_step >> 4;
+      const uint32_t amask = (uint32_t)P.a_steps_mod - 1, cmask = (uint32_t)P.n_acc - 1;
+#pragma unroll 4
+      for (int i = 0; i < P.n_mma; ++i) {
+        umma_bf16(tmem + (((uint32_t)i & cmask) * (uint32_t)P.n), adesc0 + (uint64_t)(((uint32_t)i & amask) * astep),
+                  bdesc0 + (uint64_t)(((uint32_t)i & 3u) * bstep), idesc, 1u);
+      }
+      umma_commit(&bar_done);
+    }
+    __syncwarp();
+    mbar_wait(&bar_done, 0, 41);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.out[0] = t1 - t0;
+  } else if (warp == 0) {
+    // the whole warp runs the loop converged; one elected lane issues
+    const long long t0 = clock64();
+    for (int i = 0; i < P.n_mma; ++i) {
+      const uint32_t ao = (uint32_t)((i & (P.a_steps_mod - 1)) * P.a_step);
+      const uint32_t bo = (uint32_t)((i & 3) * P.b_step);
+      const uint64_t adesc = make_smem_desc(sa + ao, lbo, (uint32_t)P.a_sbo, layout);
+      const uint64_t bdesc = make_smem_desc(sb + bo, 16, 8 * 128, kLayoutSw128);
+      if (elect_one_sync()) umma_bf16(tmem + (uint32_t)((i & (P.n_acc - 1)) * P.n), adesc, bdesc, idesc, 1u);
+    }
+    __syncwarp();
+    if (elect_one_sync()) umma_commit(&bar_done);
+    __syncwarp();
+    mbar_wait(&bar_done, 0, 41);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.out[0] = t1 - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+}  // namespace mvd
+
+extern "C" int mvd_tc_mma_bench(int n, int n_mma, int n_acc, int a_sbo, int a_step, int a_steps_mod, int row_bytes,
+                                int mn_major, int b_step, int grid, int mode, long long* out_cycles, mvd_stream_t stream) {
+  MVD_REQUIRE(out_cycles && n >= 16 && n <= 256 && n % 16 == 0 && n_mma > 0 && n_acc >= 1 && n_acc * n <= 512 &&
+                  a_steps_mod >= 1 && grid >= 1, "tc_mma_bench: bad arguments");
+  MmaBenchParams P{n, n_mma, n_acc, a_sbo, a_step, a_steps_mod, row_bytes, mn_major, b_step, mode, out_cycles};
+  static bool attr = false;
+  if (!attr) {
+    MVD_CUDA(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    attr = true;
+  }
+  mma_bench_kernel<<<grid, 128, 161 * 1024 + 1024, (cudaStream_t)stream>>>(P);
+  MVD_LAUNCH_CHECK("tc_mma_bench");
+  return MVD_OK;
+}

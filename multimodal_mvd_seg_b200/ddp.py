@@ -135,7 +135,7 @@ class GradArena:
                 self._launch(b)
         for h in self._handles:
             h.wait()
-        if self.comm_stream is not None:
+        if self.comm_stream is not None and self._handles:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self._handles = []
 

@@ -158,6 +158,8 @@ class nnUNetTrainer(object):
         self.grad_scaler = None  # bf16 path: the reference's no-scaler branch (nnUNetTrainer.py:921-924)
         self.loss = None
         self.was_initialized = False
+        self.use_cuda_graph = False
+        self.graph_warmup_steps = 2
         self._arenas: List[GradArena] = []
         self._set_batch_size_and_oversample()
 
@@ -267,9 +269,7 @@ class nnUNetTrainer(object):
         l = self.train_step_async(batch)
         return {'loss': l.detach().cpu().numpy()}
 
-    def train_step_async(self, batch: dict) -> torch.Tensor:
-        """the step without the device->host read of the loss (returned as a device scalar)."""
-        data, target = self._to_device(batch)
+    def _step_body(self, data, target) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)
         for a in self._arenas:
             a.begin_step()
@@ -281,7 +281,43 @@ class nnUNetTrainer(object):
             a.attach_grads()
             world = a.world_size
         self.optimizer.step(grad_scale=1.0 / world)
-        return l
+        return l.detach()
+
+    def train_step_async(self, batch: dict) -> torch.Tensor:
+        """the step without the device->host read of the loss (returned as a device scalar).
+
+        With ``self.use_cuda_graph`` the whole step (forward, losses, backward, gradient exchange, clip + SGD: a few
+        hundred launches) is captured once into a CUDA graph and replayed, which removes the launch gaps between the
+        many short kernels.  The first ``graph_warmup_steps`` steps run eagerly (lazy one-time initialisation must not
+        happen under capture); the graph is re-captured when the batch shapes or the learning rate (a kernel
+        argument, changed once per epoch by PolyLR) change."""
+        data, target = self._to_device(batch)
+        if not self.use_cuda_graph:
+            return self._step_body(data, target)
+        if not isinstance(target, list):
+            target = [target]
+        self._eager_steps_done = getattr(self, '_eager_steps_done', 0)
+        if self._eager_steps_done < self.graph_warmup_steps:
+            self._eager_steps_done += 1
+            return self._step_body(data, target)
+        key = (tuple(data.shape), tuple(tuple(t.shape) for t in target),
+               tuple(g['lr'] for g in self.optimizer.param_groups))
+        st = getattr(self, '_graph_state', None)
+        if st is None or st['key'] != key:
+            self._graph_state = None
+            sd = data.clone()
+            stg = [t.clone() for t in target]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._step_body(sd, stg)
+            st = self._graph_state = dict(key=key, graph=g, data=sd, target=stg, loss=loss)
+        else:
+            st['data'].copy_(data, non_blocking=True)
+            for a, b in zip(st['target'], target):
+                a.copy_(b, non_blocking=True)
+        st['graph'].replay()
+        return st['loss']
 
     def validation_step(self, batch: dict) -> dict:
         data, target = self._to_device(batch)

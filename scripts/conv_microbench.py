@@ -44,3 +44,14 @@ ts.sort()
 flops = 2.0 * B * Do * Ho * Wo * cout * cin * k ** 3
 med = ts[len(ts) // 2]
 print(f'{which} {cin}->{cout} {D}x{H}x{W} s{s} k{k} B{B}: median {med:.3f} ms  best {ts[0]:.3f} ms  {flops / med / 1e9:.1f} TFLOP/s (median)')
+if os.environ.get('HALO_PROF') == '1' and which in ('fprop', 'dgrad'):
+    import ctypes
+    cd = ctypes.CDLL(m.LIB_PATH)
+    buf = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+    cd.mvd_debug_set_halo_prof(ctypes.c_void_p(buf.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    cd.mvd_debug_set_halo_prof(ctypes.c_void_p(0))
+    b = buf.float().mean(0)
+    print(f'  MMA issuer cycles/CTA: total {b[0]:.0f}  wait tmem-empty {b[1]:.0f}  wait weights {b[2]:.0f}  wait planes {b[3]:.0f}  '
+          f'issue+other {b[0] - b[1] - b[2] - b[3]:.0f}')
