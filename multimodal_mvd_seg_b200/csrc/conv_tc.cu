@@ -142,21 +142,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == 1) {
     if (elect_one_sync()) {
       // ================= MMA issuer =================
+      const int n_tile = P.n_tile;
+      const uint32_t idesc = P.idesc;
+      const uint32_t hi = (uint32_t)(make_smem_desc(0, 16, SBO, LAYOUT) >> 32);
+      const uint32_t lo0 = (smem_u32(smem) >> 4) | (1u << 16);
+      const uint32_t st_step = (uint32_t)stage_bytes >> 4;
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&bar_tempty[acc], accphase ^ 1, 2);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.n_tile);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_tile);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&bar_full[stage], phase, 3);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_smem_desc(sa, 16, SBO, LAYOUT);
-          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, SBO, LAYOUT);
+          const uint32_t alo = lo0 + (uint32_t)stage * st_step;
+          const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)alo;
+          const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(alo + (uint32_t)(A_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)  // advance 32 bytes (16 bf16) along K inside the swizzle atom
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (it | k) ? 1u : 0u);
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
           umma_commit(&bar_empty[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }

@@ -126,25 +126,31 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     if (ng > 0 && elect_one_sync()) {
       // ================= MMA issuer =================
+      const int a_stages = P.a_stages, n_tile = P.n_tile;
+      const uint32_t idesc = P.idesc;
+      const uint32_t a_hi = (uint32_t)(make_smem_desc(0, A_BOX, A_SBO, A_LAYOUT) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, B_BOX, B_SBO, B_LAYOUT) >> 32);
+      const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) | ((uint32_t)(A_BOX >> 4) << 16);
+      const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) | ((uint32_t)(B_BOX >> 4) << 16);
+      const uint32_t b_step = (uint32_t)b_bytes >> 4;
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       for (int vt = vt_begin; vt < vt_end; ++vt) {
         mbar_wait(&bar_bfull[bs], bphase, 13);
         tcgen05_fence_after();
-        const uint32_t sb = smem_u32(smem_b + bs * b_bytes);
+        const uint64_t bdesc0 = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)bs * b_step);
+        const uint32_t first = (vt > vt_begin) ? 1u : 0u;
         for (int g = 0; g < ng; ++g) {
           mbar_wait(&bar_afull[as], aphase, 14);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem_a + as * A_STAGE);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * P.n_tile);
+          const uint64_t adesc0 = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)as * (uint32_t)(A_STAGE >> 4));
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g * n_tile);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {   // 16 voxels (two 8-row groups) per MMA
-            const uint64_t adesc = make_smem_desc(sa + k * 2 * A_SBO, A_BOX, A_SBO, A_LAYOUT);
-            const uint64_t bdesc = make_smem_desc(sb + k * 2 * B_SBO, B_BOX, B_SBO, B_LAYOUT);
-            umma_bf16(d_tmem, adesc, bdesc, P.idesc, (vt > vt_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 8; ++k)   // 16 voxels (two 8-row groups) per MMA
+            umma_bf16(d_tmem, adesc0 + (uint64_t)(k * ((2 * A_SBO) >> 4)), bdesc0 + (uint64_t)(k * ((2 * B_SBO) >> 4)),
+                      idesc, (k > 0) ? 1u : first);
           umma_commit(&bar_aempty[as]);
-          if (++as == P.a_stages) { as = 0; aphase ^= 1; }
+          if (++as == a_stages) { as = 0; aphase ^= 1; }
         }
         umma_commit(&bar_bempty[bs]);
         if (++bs == 2) { bs = 0; bphase ^= 1; }
