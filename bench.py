@@ -268,9 +268,18 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_s = float(t[0]), float(t[1])
-    if rank != 0:
+    def finish():
+        # leave without tearing NCCL down: destroy_process_group() can block behind the communicator references a
+        # captured CUDA graph holds; all ranks meet at a barrier first so nobody exits under a peer's collective
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     ms_per_step = ms_total / args.steps
@@ -317,8 +326,7 @@ def main():
             print(f'{kind:6s} {tag:44s} {d["ms"]:8.3f} ms/step '
                   f'{d["flops"] / (d["ms"] / 1e3) / 1e12:8.1f} TFLOP/s', file=sys.stderr)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == '__main__':
