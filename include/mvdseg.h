@@ -103,11 +103,12 @@ int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* 
 int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, const double* stats,
                               const float* gamma, const float* beta, int B, long long V, int C, float eps,
                               float slope, double* bstats, mvd_stream_t stream);
-/* dy = gamma*rstd*(g' - mean(g') - xhat*mean(g' xhat)); dgamma/dbeta (fp32 [C]) written when non-NULL */
+/* dy = gamma*rstd*(g' - mean(g') - xhat*mean(g' xhat)); dgamma/dbeta (fp32 [C]) written when non-NULL;
+ * dsum (fp32 [C], caller zeroes, may be NULL) += per-channel sum of dy = bias gradient of the conv in front of the norm */
 int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, void* dy, int lddy,
                               const double* stats, const double* bstats, const float* gamma, const float* beta,
                               int B, long long V, int C, float eps, float slope, float* dgamma, float* dbeta,
-                              mvd_stream_t stream);
+                              float* dsum, mvd_stream_t stream);
 
 /* ---- 1x1x1 segmentation heads (UNetDecoder.py:67-70) ------------------------------------------------------- */
 int mvd_head_fwd(const void* z, int ldz, const float* w /*[K][C] fp32*/, const float* bias /*[K]*/, void* logits,

@@ -61,7 +61,7 @@ _SIGNATURES = {
     'mvd_inorm_stats': (c_int, [P, I, I, LL, I, P, S]),
     'mvd_inorm_lrelu_fwd': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, S]),
     'mvd_inorm_lrelu_bwd_stats': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, P, S]),
-    'mvd_inorm_lrelu_bwd_apply': (c_int, [P, I, P, I, P, I, P, P, P, P, I, LL, I, F, F, P, P, S]),
+    'mvd_inorm_lrelu_bwd_apply': (c_int, [P, I, P, I, P, I, P, P, P, P, I, LL, I, F, F, P, P, P, S]),
     'mvd_head_fwd': (c_int, [P, I, P, P, P, I, LL, I, I, S]),
     'mvd_head_bwd': (c_int, [P, I, P, I, P, P, I, P, P, LL, I, I, S]),
     'mvd_dice_ce_fwd': (c_int, [P, I, P, I, LL, I, P, S]),

@@ -15,4 +15,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);
+// sliding-window halo variant for 3x3x3 / stride 1 (conv_tc_wgrad_halo.cu)
+bool tc_wgrad_halo_supported(const mvd_conv3d_args* a);
+int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st);
 }  // namespace mvd

@@ -234,6 +234,7 @@ bool tc_wgrad_supported(const mvd_conv3d_args* a) {
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args*) { return 0; }
 
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st) {
+  if (tc_wgrad_halo_supported(a)) return tc_wgrad_halo(a, st);
   const int SW = (a->Cin % 64 == 0) ? 64 : 32;
   const int BW = (a->Cout % 64 == 0) ? 64 : 32;
   const int taps = a->kd * a->kh * a->kw;

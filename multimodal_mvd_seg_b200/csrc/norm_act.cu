@@ -218,12 +218,14 @@ __global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_stats_kernel(
   }
 }
 
-// dy = gamma*rstd*(g' - S1/V - xhat*S2/V)
-__global__ void __launch_bounds__(256) inorm_lrelu_bwd_apply_kernel(
+// dy = gamma*rstd*(g' - S1/V - xhat*S2/V); optionally dsum[c] += sum_v dy[v][c] (the bias gradient of the conv in
+// front of the norm -- analytically zero, numerically the rounding noise the reference also produces).
+// Thread = (voxel row r, 8-channel group cg) with rows strided over the block's run, like the statistics kernels.
+__global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_apply_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, bf16* __restrict__ dy, int lddy,
     const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
-    float* __restrict__ dbeta) {
+    float* __restrict__ dbeta, float* __restrict__ dsum, long long rows_per_block) {
   extern __shared__ float sm[];
   const int b = blockIdx.y;
   float* sc = sm;
@@ -232,10 +234,12 @@ __global__ void __launch_bounds__(256) inorm_lrelu_bwd_apply_kernel(
   float* rstd = sm + 3 * C;
   float* m1 = sm + 4 * C;  // S1/V
   float* m2 = sm + 5 * C;  // S2/V
+  float* acc = sm + 6 * C; // per-channel sum of dy (block partial)
   load_scale_shift(stats, gamma, beta, b, C, V, eps, sc, sh, mean, rstd);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     m1[c] = (float)(bstats[((long long)b * C + c) * 2 + 0] / (double)V);
     m2[c] = (float)(bstats[((long long)b * C + c) * 2 + 1] / (double)V);
+    acc[c] = 0.f;
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma || dbeta)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -250,27 +254,49 @@ __global__ void __launch_bounds__(256) inorm_lrelu_bwd_apply_kernel(
   }
   __syncthreads();
   const int CG = C >> 3;
-  const long long nvec = V * CG;
+  const int rows = kStatThreads / CG;
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, r = tid / CG;
   const bf16* yb = y + (long long)b * V * ldy;
   const bf16* gb = dz + (long long)b * V * lddz;
   bf16* ob = dy + (long long)b * V * lddy;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i / CG;
-    int cg = (int)(i - v * CG);
-    bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-    bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
-    float fy[8], fg[8], o[8];
-    unpack8(py, fy);
-    unpack8(pg, fg);
+  long long v0 = (long long)blockIdx.x * rows_per_block;
+  long long v1 = v0 + rows_per_block;
+  if (v1 > V) v1 = V;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  if (r < rows) {
+    float csc[8], csh[8], cme[8], crs[8], cm1[8], cm2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = cg * 8 + k;
-      float pre = round_bf(fmaf(fy[k], sc[c], sh[c]));
-      float gp = pre > 0.f ? fg[k] : slope * fg[k];
-      float xh = (fy[k] - mean[c]) * rstd[c];
-      o[k] = sc[c] * (gp - m1[c] - xh * m2[c]);
+      csc[k] = sc[c]; csh[k] = sh[c]; cme[k] = mean[c]; crs[k] = rstd[c]; cm1[k] = m1[c]; cm2[k] = m2[c];
     }
-    *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pack8(o);
+    for (long long v = v0 + r; v < v1; v += rows) {
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      float fy[8], fg[8], o[8];
+      unpack8(py, fy);
+      unpack8(pg, fg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float pre = round_bf(fmaf(fy[k], csc[k], csh[k]));
+        float gp = pre > 0.f ? fg[k] : slope * fg[k];
+        float xh = (fy[k] - cme[k]) * crs[k];
+        o[k] = round_bf(csc[k] * (gp - cm1[k] - xh * cm2[k]));
+        s[k] += o[k];
+      }
+      *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pack8(o);
+    }
+  }
+  if (dsum) {
+    if (r < rows) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&acc[cg * 8 + k], s[k]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kStatThreads) atomicAdd(&dsum[c], acc[c]);
   }
 }
 
@@ -379,13 +405,21 @@ int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, 
 int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, void* dy, int lddy,
                               const double* stats, const double* bstats, const float* gamma, const float* beta,
                               int B, long long V, int C, float eps, float slope, float* dgamma, float* dbeta,
-                              mvd_stream_t stream) {
+                              float* dsum, mvd_stream_t stream) {
   MVD_REQUIRE(dz && y && dy && stats && bstats && B > 0 && V > 0, "inorm_lrelu_bwd_apply: bad arguments");
-  MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && vec_ok(dy, lddy, C), "inorm_lrelu_bwd_apply: alignment/C");
-  dim3 grid(grid_for(V * (C / 8), 256 * 4, num_sms() * 8), B);
-  inorm_lrelu_bwd_apply_kernel<<<grid, 256, 6 * C * sizeof(float), (cudaStream_t)stream>>>(
+  MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && vec_ok(dy, lddy, C) && C <= 2048,
+              "inorm_lrelu_bwd_apply: alignment/C");
+  const int rows = kStatThreads / (C / 8);
+  long long rpb = 2048;
+  long long nblk = (V + rpb - 1) / rpb;
+  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
+    rpb >>= 1;
+    nblk = (V + rpb - 1) / rpb;
+  }
+  dim3 grid((unsigned)nblk, B);
+  inorm_lrelu_bwd_apply_kernel<<<grid, kStatThreads, 7 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dz, lddz, (const bf16*)y, ldy, (bf16*)dy, lddy, stats, bstats, gamma, beta, B, V, C, eps, slope,
-      dgamma, dbeta);
+      dgamma, dbeta, dsum, rpb);
   MVD_LAUNCH_CHECK("inorm_lrelu_bwd_apply");
   return MVD_OK;
 }

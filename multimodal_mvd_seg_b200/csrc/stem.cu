@@ -8,37 +8,38 @@
 
 namespace mvd {
 
-__global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restrict__ x, int ldx, int B, int D, int H,
-                                                           int W, int Cin, int kd, int kh, int kw, int pd, int ph,
-                                                           int pw, bf16* __restrict__ out, int Kpad) {
-  const int groups = Kpad >> 3;
-  const long long V = (long long)B * D * H * W;
-  const long long total = V * groups;
-  const int Kreal = kd * kh * kw * Cin;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long v = i / groups;
-    const int g = (int)(i - v * groups);
-    long long t = v;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H); t /= H;
-    const int d = (int)(t % D);
-    const int b = (int)(t / D);
-    float f[8];
+// block = 256 threads = (256 / G) consecutive w positions of one (b, d, h) line x G = KPAD/8 column groups; thread
+// (w, g) writes one 16-byte group, so a voxel's KPAD*2-byte row is written by G adjacent threads (coalesced) and no
+// per-thread integer division is needed (tap decode is compile-time for the 3x3x3 stem).
+template <int CIN, int KPAD>
+__global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restrict__ x, int ldx, int D, int H, int W,
+                                                           bf16* __restrict__ out) {
+  constexpr int G = KPAD / 8;
+  constexpr int WPB = 256 / G;
+  constexpr int KREAL = 27 * CIN;
+  const int g = threadIdx.x % G;
+  const int w = blockIdx.x * WPB + threadIdx.x / G;
+  int line = blockIdx.y;                 // (b*D + d)*H + h
+  const int h = line % H; line /= H;
+  const int d = line % D;
+  const int b = line / D;
+  if (w >= W) return;
+  float f[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = g * 8 + e;
-      float val = 0.f;
-      if (j < Kreal) {
-        const int tap = j / Cin, ci = j - tap * Cin;
-        const int tw = tap % kw, th = (tap / kw) % kh, td = tap / (kw * kh);
-        const int z = d + td - pd, yy = h + th - ph, xx = w + tw - pw;
-        if (z >= 0 && z < D && yy >= 0 && yy < H && xx >= 0 && xx < W)
-          val = bf2f(x[((((long long)b * D + z) * H + yy) * W + xx) * ldx + ci]);
-      }
-      f[e] = val;
+  for (int e = 0; e < 8; ++e) {
+    const int j = g * 8 + e;
+    float val = 0.f;
+    if (j < KREAL) {
+      const int tap = j / CIN, ci = j % CIN;
+      const int tw = tap % 3, th = (tap / 3) % 3, td = tap / 9;
+      const int z = d + td - 1, yy = h + th - 1, xx = w + tw - 1;
+      if (z >= 0 && z < D && yy >= 0 && yy < H && xx >= 0 && xx < W)
+        val = bf2f(x[((((long long)b * D + z) * H + yy) * W + xx) * ldx + ci]);
     }
-    *reinterpret_cast<bf16x8*>(out + v * Kpad + g * 8) = pack8(f);
+    f[e] = val;
   }
+  const long long v = (((long long)b * D + d) * H + h) * W + w;
+  *reinterpret_cast<bf16x8*>(out + v * KPAD + g * 8) = pack8(f);
 }
 
 }  // namespace mvd
@@ -50,10 +51,14 @@ extern "C" int mvd_im2col_small(const void* x, int ldx, int B, int D, int H, int
   MVD_REQUIRE(x && out && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && ldx >= Cin, "im2col_small: bad arguments");
   MVD_REQUIRE(Kpad % 8 == 0 && Kpad >= kd * kh * kw * Cin && ((uintptr_t)out & 15) == 0,
               "im2col_small: Kpad must be a multiple of 8 covering taps*Cin, out 16-byte aligned");
-  const long long total = (long long)B * D * H * W * (Kpad / 8);
-  int grid = grid_for(total, 256, num_sms() * 16);
-  im2col_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, B, D, H, W, Cin, kd, kh, kw, pd, ph,
-                                                              pw, (bf16*)out, Kpad);
+  MVD_REQUIRE(kd == 3 && kh == 3 && kw == 3 && pd == 1 && ph == 1 && pw == 1 && (Cin == 1 || Cin == 2) &&
+                  Kpad == (Cin == 1 ? 32 : 64), "im2col_small: built for the 3x3x3 pad-1 stem with 1 or 2 input channels");
+  const int wpb = 256 / (Kpad / 8);
+  dim3 grid((W + wpb - 1) / wpb, (unsigned)((long long)B * D * H));
+  if (Cin == 1)
+    im2col_small_kernel<1, 32><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, D, H, W, (bf16*)out);
+  else
+    im2col_small_kernel<2, 64><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, D, H, W, (bf16*)out);
   MVD_LAUNCH_CHECK("im2col_small");
   return MVD_OK;
 }

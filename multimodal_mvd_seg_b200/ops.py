@@ -332,21 +332,23 @@ class ConvNormActFn(torch.autograd.Function):
         dy = torch.empty_like(y)
         dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
         dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
+        db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
+        if db is not None:
+            db.zero_()
         lib.inorm_lrelu_bwd_apply(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy),
                                   stats.data_ptr(), bstats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
-                                  _ptr(dgamma), _ptr(dbeta), st)
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
-        db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
         if dw is not None:
             if ctx.stem:
                 Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
                 kpad = x_cl.shape[-1]
                 dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
-                conv_wgrad(geom, x_cl, dy, dw_col, db)
+                conv_wgrad(geom, x_cl, dy, dw_col, None)
                 dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
                          .reshape(weight.shape))
             else:
-                conv_wgrad(geom, x_cl, dy, dw, db)
+                conv_wgrad(geom, x_cl, dy, dw, None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)

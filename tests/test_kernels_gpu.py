@@ -164,9 +164,11 @@ def test_instance_norm_lrelu_fwd_bwd(m, C, shape):
                               B, V, C, 1e-5, 0.01, bstats.data_ptr(), st)
     dy = torch.empty_like(y)
     dg, db = torch.empty_like(gamma), torch.empty_like(beta)
+    dsum = torch.zeros_like(gamma)
     lib.inorm_lrelu_bwd_apply(dz.data_ptr(), C, y.data_ptr(), C, dy.data_ptr(), C, stats.data_ptr(),
                               bstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, V, C, 1e-5, 0.01,
-                              dg.data_ptr(), db.data_ptr(), st)
+                              dg.data_ptr(), db.data_ptr(), dsum.data_ptr(), st)
+    np.testing.assert_allclose(dsum.cpu(), dy.float().sum((0, 1, 2, 3)).cpu(), rtol=1e-3, atol=2e-2)
     assert rel_err(dy.float().permute(0, 4, 1, 2, 3), yr.grad) < 1e-2
     assert rel_err(dg, gr.grad) < 5e-3
     assert rel_err(db, br.grad) < 5e-3
