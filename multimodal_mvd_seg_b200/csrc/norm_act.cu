@@ -66,7 +66,23 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows) {
-    for (long long v = v0 + r; v < v1; v += rows) {
+    long long v = v0 + r;
+    for (; v + 3LL * rows < v1; v += 4LL * rows) {   // four independent 16-byte loads in flight per thread
+      bf16x8 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const bf16x8*>(base + (v + (long long)u * rows) * ld + cg * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(p[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    for (; v < v1; v += rows) {
       bf16x8 p = *reinterpret_cast<const bf16x8*>(base + v * ld + cg * 8);
       float f[8];
       unpack8(p, f);
@@ -135,22 +151,34 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
   load_scale_shift(stats, gamma, beta, b, C, V, eps, sc, sh, nullptr, nullptr);
   __syncthreads();
   const int CG = C >> 3;
-  const long long nvec = V * CG;
+  const int rows = 256 / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
   const bf16* yb = y + (long long)b * V * ldy;
   bf16* zb = z + (long long)b * V * ldz;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i / CG;
-    int cg = (int)(i - v * CG);
-    bf16x8 p = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+  if (r >= rows) return;
+  float csc[8], csh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { csc[k] = sc[cg * 8 + k]; csh[k] = sh[cg * 8 + k]; }
+  auto body = [&](const bf16x8& p, long long v) {
     float f[8];
     unpack8(p, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float t = round_bf(fmaf(f[k], sc[cg * 8 + k], sh[cg * 8 + k]));
+      float t = round_bf(fmaf(f[k], csc[k], csh[k]));
       f[k] = t > 0.f ? t : slope * t;
     }
     *reinterpret_cast<bf16x8*>(zb + v * ldz + cg * 8) = pack8(f);
+  };
+  const long long step = (long long)gridDim.x * rows;
+  long long v = (long long)blockIdx.x * rows + r;
+  for (; v + 3 * step < V; v += 4 * step) {
+    bf16x8 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const bf16x8*>(yb + (v + u * step) * ldy + cg * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(p[u], v + u * step);
   }
+  for (; v < V; v += step) body(*reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8), v);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -182,21 +210,38 @@ __global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_stats_kernel(
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   if (r < rows) {
-    for (long long v = v0 + r; v < v1; v += rows) {
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+    float csc[8], csh[8], cme[8], crs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      csc[k] = sc[c]; csh[k] = sh[c]; cme[k] = mean[c]; crs[k] = rstd[c];
+    }
+    auto body = [&](const bf16x8& py, const bf16x8& pg) {
       float fy[8], fg[8];
       unpack8(py, fy);
       unpack8(pg, fg);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        float pre = round_bf(fmaf(fy[k], sc[c], sh[c]));
+        float pre = round_bf(fmaf(fy[k], csc[k], csh[k]));
         float gp = pre > 0.f ? fg[k] : slope * fg[k];
-        float xh = (fy[k] - mean[c]) * rstd[c];
+        float xh = (fy[k] - cme[k]) * crs[k];
         s1[k] += gp;
         s2[k] = fmaf(gp, xh, s2[k]);
       }
+    };
+    long long v = v0 + r;
+    for (; v + (long long)rows < v1; v += 2LL * rows) {   // four independent 16-byte loads in flight per thread
+      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + (v + rows) * ldy + cg * 8);
+      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + (v + rows) * lddz + cg * 8);
+      body(py0, pg0);
+      body(py1, pg1);
+    }
+    for (; v < v1; v += rows) {
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      body(py, pg);
     }
   }
   if (r < rows) {
@@ -273,9 +318,7 @@ __global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_apply_kernel(
       const int c = cg * 8 + k;
       csc[k] = sc[c]; csh[k] = sh[c]; cme[k] = mean[c]; crs[k] = rstd[c]; cm1[k] = m1[c]; cm2[k] = m2[c];
     }
-    for (long long v = v0 + r; v < v1; v += rows) {
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+    auto body = [&](const bf16x8& py, const bf16x8& pg, long long v) {
       float fy[8], fg[8], o[8];
       unpack8(py, fy);
       unpack8(pg, fg);
@@ -288,6 +331,20 @@ __global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_apply_kernel(
         s[k] += o[k];
       }
       *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pack8(o);
+    };
+    long long v = v0 + r;
+    for (; v + (long long)rows < v1; v += 2LL * rows) {
+      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + (v + rows) * ldy + cg * 8);
+      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + (v + rows) * lddz + cg * 8);
+      body(py0, pg0, v);
+      body(py1, pg1, v + rows);
+    }
+    for (; v < v1; v += rows) {
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+      body(py, pg, v);
     }
   }
   if (dsum) {
