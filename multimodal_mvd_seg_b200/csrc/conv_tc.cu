@@ -17,6 +17,7 @@
 #include <mutex>
 #include "conv_common.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace mvd {
 
@@ -39,6 +40,7 @@ using namespace tc;
 
 constexpr int kMaxTaps = 27;
 constexpr int kMaxMaps = 8;
+constexpr int kMaxClasses = 8;
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int kThreads = 192;
 
@@ -48,24 +50,37 @@ struct TcTap {
   int wrow;         // first row of this tap's [N][K] weight block in the 2-D weight map
 };
 
+// A launch covers up to 8 "classes": independent produced lattices that share the gathered tensor, the weights and
+// the output strides (the parity classes of a strided dgrad).  Plain convolutions have one class.
+struct TcClass {
+  int tap_begin, ntaps;
+  int Dt, Ht, Wt, tiles_w, tiles_h;
+  int tile_begin;                // first (m) tile index of this class
+  long long out_off;             // element offset of the class lattice origin inside `out`
+};
+
 struct alignas(64) TcMaps {
   CUtensorMap a[kMaxMaps];
   CUtensorMap b;
 };
 
 struct TcParams {
-  int B, Dt, Ht, Wt;             // lattice of produced voxels this launch covers
-  int tiles_w, tiles_h;
-  int num_m_tiles, num_n_tiles;
+  int B;
+  int nclasses, num_m_tiles, num_n_tiles;
   int n_tile;                    // UMMA N
-  int ntaps, kchunks;
+  int kchunks;
   int stages;
   uint32_t idesc;
   uint32_t tmem_cols;
-  bf16* out;                     // element (b,d,h,w,n) at out + b*sb + d*sd + h*sh + w*sw + n
+  bf16* out;                     // element (b,d,h,w,n) of a class at out + off + b*sb + d*sd + h*sh + w*sw + n
   long long sb, sd, sh, sw;
   const float* bias;             // per produced channel, may be null
   int accumulate;
+  // scatter mode (transposed conv, kernel == stride): the N axis is (parity, channel); column n goes to channel
+  // n % scatter_c of the voxel displaced by par_off[n / scatter_c]
+  int scatter_c;
+  long long par_off[8];
+  TcClass cls[kMaxClasses];
   TcTap taps[kMaxTaps];
 };
 
@@ -78,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) uint8_t s_stage[4][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
 
   // dynamic smem may only be 16-byte aligned by the runtime: align by hand (host adds 1 KB of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -85,7 +101,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int stage_bytes = A_BYTES + b_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = P.stages;
-  const int kiters = P.ntaps * P.kchunks;
   const int total_tiles = P.num_m_tiles * P.num_n_tiles;
 
   if (threadIdx.x == 0) {
@@ -105,16 +120,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  auto decode_tile = [&](int tile, int& n0, int& b, int& d, int& h0, int& w0) {
+  // tile -> (class, n0, b, d, h0, w0)
+  auto decode_tile = [&](int tile, int& c, int& n0, int& b, int& d, int& h0, int& w0) {
     const int nt = tile % P.num_n_tiles;
     int m = tile / P.num_n_tiles;
     n0 = nt * P.n_tile;
-    w0 = (m % P.tiles_w) * TILE_W;
-    m /= P.tiles_w;
-    h0 = (m % P.tiles_h) * TILE_H;
-    m /= P.tiles_h;
-    d = m % P.Dt;
-    b = m / P.Dt;
+    c = 0;
+    for (int i = 1; i < P.nclasses; ++i)
+      if (m >= P.cls[i].tile_begin) c = i;
+    m -= P.cls[c].tile_begin;
+    const int tw = P.cls[c].tiles_w, th = P.cls[c].tiles_h, Dt = P.cls[c].Dt;
+    w0 = (m % tw) * TILE_W;
+    m /= tw;
+    h0 = (m % th) * TILE_H;
+    m /= th;
+    d = m % Dt;
+    b = m / Dt;
   };
 
   if (warp == 0) {
@@ -124,9 +145,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n0, b, d, h0, w0;
-        decode_tile(tile, n0, b, d, h0, w0);
-        for (int t = 0; t < P.ntaps; ++t) {
+        int c, n0, b, d, h0, w0;
+        decode_tile(tile, c, n0, b, d, h0, w0);
+        const int t0 = P.cls[c].tap_begin, t1 = t0 + P.cls[c].ntaps;
+        for (int t = t0; t < t1; ++t) {
           const TcTap tap = P.taps[t];
           for (int kc = 0; kc < P.kchunks; ++kc) {
             mbar_wait(&bar_empty[stage], phase ^ 1, 1);
@@ -142,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == 1) {
     if (elect_one_sync()) {
       // ================= MMA issuer =================
-      const int n_tile = P.n_tile;
+      const int n_tile = P.n_tile, kchunks = P.kchunks, num_n_tiles = P.num_n_tiles, nclasses = P.nclasses;
       const uint32_t idesc = P.idesc;
       const uint32_t hi = (uint32_t)(make_smem_desc(0, 16, SBO, LAYOUT) >> 32);
       const uint32_t lo0 = (smem_u32(smem) >> 4) | (1u << 16);
@@ -150,6 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int c = 0;
+        const int m = tile / num_n_tiles;
+        for (int i = 1; i < nclasses; ++i)
+          if (m >= P.cls[i].tile_begin) c = i;
+        const int kiters = P.cls[c].ntaps * kchunks;
         mbar_wait(&bar_tempty[acc], accphase ^ 1, 2);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_tile);
@@ -176,38 +203,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int n0, b, d, h0, w0;
-      decode_tile(tile, n0, b, d, h0, w0);
+      int c, n0, b, d, h0, w0;
+      decode_tile(tile, c, n0, b, d, h0, w0);
       mbar_wait(&bar_tfull[acc], accphase, 4);
       tcgen05_fence_after();
-      const int r = q * 32 + lane;
-      const int h = h0 + (r >> 3), w = w0 + (r & 7);
-      const bool valid = (h < P.Ht) && (w < P.Wt);
-      bf16* orow = P.out + (long long)b * P.sb + (long long)d * P.sd + (long long)h * P.sh + (long long)w * P.sw + n0;
+      const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
+      bf16* tile_base = P.out + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd;
+      const long long sh = P.sh, sw = P.sw;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
-      for (int c = 0; c < P.n_tile; c += 32) {
+      for (int cc = 0; cc < P.n_tile; cc += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+        tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
         tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __uint_as_float(v[g * 8 + j]);
-              if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + g * 8 + j));
-            }
-            bf16x8* dst = reinterpret_cast<bf16x8*>(orow + c + g * 8);
-            if (P.accumulate) {
-              float o[8];
-              unpack8(*dst, o);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += o[j];
-            }
-            *dst = pack8(f);
-          }
+        int n = n0 + cc;          // first produced column of this 32-wide group
+        long long col_off;
+        if (P.scatter_c) {        // (parity, channel): 32-column groups never straddle a parity (scatter_c % 32 == 0)
+          const int par = n / P.scatter_c;
+          n -= par * P.scatter_c;
+          col_off = P.par_off[par] + n;
+        } else {
+          col_off = n;
         }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]);
+          if (P.bias) f[j] += round_bf(__ldg(P.bias + n + j));
+        }
+        store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
+          const int rr = q * 32 + R;
+          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+          return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
+        }, P.accumulate != 0);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -309,6 +336,19 @@ int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* wh
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// appends a class covering the lattice (Dt, Ht, Wt); returns false when the lattice is empty
+bool add_class(TcParams& P, int Dt, int Ht, int Wt, int tap_begin, int ntaps, long long out_off) {
+  if (Dt <= 0 || Ht <= 0 || Wt <= 0) return false;
+  TcClass& c = P.cls[P.nclasses++];
+  c.tap_begin = tap_begin; c.ntaps = ntaps;
+  c.Dt = Dt; c.Ht = Ht; c.Wt = Wt;
+  c.tiles_w = cdiv(Wt, TILE_W); c.tiles_h = cdiv(Ht, TILE_H);
+  c.tile_begin = P.num_m_tiles;
+  c.out_off = out_off;
+  P.num_m_tiles += P.B * Dt * c.tiles_h * c.tiles_w;
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -345,68 +385,61 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   memset(&P, 0, sizeof(P));
   const bf16* x = (const bf16*)a->x;
   const long long ld = a->ldx;
+  bool ok = true;
   // parity sub-lattices of the input
-  for (int rd = 0; rd < a->sd; ++rd)
-    for (int rh = 0; rh < a->sh; ++rh)
-      for (int rw = 0; rw < a->sw; ++rw) {
+  for (int rd = 0; rd < a->sd && ok; ++rd)
+    for (int rh = 0; rh < a->sh && ok; ++rh)
+      for (int rw = 0; rw < a->sw && ok; ++rw) {
         const int mi = (rd * a->sh + rh) * a->sw + rw;
-        const int dims[4] = {cdiv(a->Wi - rw, a->sw), cdiv(a->Hi - rh, a->sh), cdiv(a->Di - rd, a->sd), a->B};
-        if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) {
-          // an empty lattice can never be hit by a valid tap; alias it to lattice 0 extents of 1 (all loads OOB)
-          const int d1[4] = {1, 1, 1, a->B};
-          const long long s1[4] = {ld, ld * a->Wi, ld * a->Wi * a->Hi, ld * a->Wi * a->Hi * a->Di};
-          if (!tc_encode_act_map(&maps.a[mi], x, a->Cin, a->ldx, d1, s1, kc)) goto fail;
-          continue;
-        }
+        int dims[4] = {cdiv(a->Wi - rw, a->sw), cdiv(a->Hi - rh, a->sh), cdiv(a->Di - rd, a->sd), a->B};
+        const bf16* base = x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ld;
+        // an empty lattice can never be hit by a valid tap: alias it to a 1-voxel lattice (all loads out of bounds)
+        if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) { dims[0] = dims[1] = dims[2] = 1; base = x; }
         const long long strides[4] = {ld * a->sw, ld * a->Wi * a->sh, ld * a->Wi * a->Hi * a->sd,
                                       ld * a->Wi * a->Hi * a->Di};
-        const bf16* base = x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ld;
-        if (!tc_encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc)) goto fail;
+        ok = tc_encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc);
       }
-  {
-    const int taps = a->kd * a->kh * a->kw;
-    P.n_tile = pick_n_tile(a->Cout);
-    if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cout, a->Cin, P.n_tile, kc)) goto fail;
-    int nt = 0;
-    for (int td = 0; td < a->kd; ++td)
-      for (int th = 0; th < a->kh; ++th)
-        for (int tw = 0; tw < a->kw; ++tw) {
-          int qd, rd, qh, rh, qw, rw;
-          floordivmod(td - a->pd, a->sd, qd, rd);
-          floordivmod(th - a->ph, a->sh, qh, rh);
-          floordivmod(tw - a->pw, a->sw, qw, rw);
-          TcTap& t = P.taps[nt++];
-          t.map = (rd * a->sh + rh) * a->sw + rw;
-          t.dz = qd; t.dy = qh; t.dx = qw;
-          t.wrow = ((td * a->kh + th) * a->kw + tw) * a->Cout;
-        }
-    P.ntaps = nt;
-    P.kchunks = a->Cin / kc;
-    P.B = a->B; P.Dt = a->Do; P.Ht = a->Ho; P.Wt = a->Wo;
-    P.tiles_w = cdiv(P.Wt, TILE_W); P.tiles_h = cdiv(P.Ht, TILE_H);
-    P.num_m_tiles = P.B * P.Dt * P.tiles_h * P.tiles_w;
-    P.num_n_tiles = a->Cout / P.n_tile;
-    P.out = (bf16*)a->y;
-    P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
-    P.bias = a->bias;
-    P.accumulate = 0;
-    return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
-  }
-fail:
-  set_error("conv3d_fprop(tcgen05): cuTensorMapEncodeTiled failed");
-  return MVD_ERR_CUDA;
+  const int taps = a->kd * a->kh * a->kw;
+  P.n_tile = pick_n_tile(a->Cout);
+  ok = ok && tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cout, a->Cin, P.n_tile, kc);
+  if (!ok) { set_error("conv3d_fprop(tcgen05): cuTensorMapEncodeTiled failed"); return MVD_ERR_CUDA; }
+  int nt = 0;
+  for (int td = 0; td < a->kd; ++td)
+    for (int th = 0; th < a->kh; ++th)
+      for (int tw = 0; tw < a->kw; ++tw) {
+        int qd, rd, qh, rh, qw, rw;
+        floordivmod(td - a->pd, a->sd, qd, rd);
+        floordivmod(th - a->ph, a->sh, qh, rh);
+        floordivmod(tw - a->pw, a->sw, qw, rw);
+        TcTap& t = P.taps[nt++];
+        t.map = (rd * a->sh + rh) * a->sw + rw;
+        t.dz = qd; t.dy = qh; t.dx = qw;
+        t.wrow = ((td * a->kh + th) * a->kw + tw) * a->Cout;
+      }
+  P.kchunks = a->Cin / kc;
+  P.B = a->B;
+  add_class(P, a->Do, a->Ho, a->Wo, 0, nt, 0);
+  P.num_n_tiles = a->Cout / P.n_tile;
+  P.out = (bf16*)a->y;
+  P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
+  P.bias = a->bias;
+  P.accumulate = 0;
+  return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dgrad: produced = x (conv input lattice), gathered = y.  x[i] += y[(i + p - t)/s] W[t] when divisible: one launch
-// per parity class r = i mod s of the produced lattice; within it tap t contributes iff (r + p - t) mod s == 0, with
-// shift (r + p - t)/s on the (dense) y lattice.  Classes without taps (k < s) are zero-filled (+bias).
+// dgrad: produced = x (conv input lattice), gathered = y.  x[i] += y[(i + p - t)/s] W[t] when divisible: the produced
+// lattice splits into s^3 parity classes r = i mod s; within a class tap t contributes iff (r + p - t) mod s == 0, with
+// shift (r + p - t)/s on the (dense) y lattice.  All classes go into ONE launch.  kernel == stride (the transposed
+// convolutions of the decoder): every class has exactly one tap with shift 0, so the classes collapse into a single
+// GEMM with N = s^3 * Cin whose epilogue scatters the (parity, channel) columns.
 // ---------------------------------------------------------------------------------------------------------------
 bool tc_dgrad_supported(const mvd_conv3d_args* a) {
   const int taps = a->kd * a->kh * a->kw;
   if (!tc_shape_ok(a->Cout, a->Cin, a->ldy, a->ldx, a->y, a->x, a->w, taps)) return false;
   // every parity class must own at least one tap per axis, otherwise the class is a pure fill (not built here)
   if (a->kd < a->sd || a->kh < a->sh || a->kw < a->sw) return false;
+  if (a->sd * a->sh * a->sw > kMaxClasses) return false;
   return get_encode_tiled() != nullptr;
 }
 
@@ -419,6 +452,8 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   }
   const int kc = (a->Cout % 64 == 0) ? 64 : 32;
   TcMaps maps;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
   const bf16* y = (const bf16*)a->y;
   const long long ldy = a->ldy;
   const int dims[4] = {a->Wo, a->Ho, a->Do, a->B};
@@ -429,21 +464,47 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   }
   for (int i = 1; i < kMaxMaps; ++i) maps.a[i] = maps.a[0];
   const int taps = a->kd * a->kh * a->kw;
-  const int n_tile = pick_n_tile(a->Cin);
-  if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cin, a->Cout, n_tile, kc)) {
+  const long long ldx = a->ldx;
+  P.B = a->B;
+  P.kchunks = a->Cout / kc;
+  P.out = (bf16*)a->x;
+  P.sw = ldx * a->sw; P.sh = ldx * a->Wi * a->sh; P.sd = ldx * a->Wi * a->Hi * a->sd;
+  P.sb = ldx * a->Wi * a->Hi * a->Di;
+  P.bias = a->bias;
+  P.accumulate = a->accumulate;
+
+  const bool k_eq_s = (a->kd == a->sd && a->kh == a->sh && a->kw == a->sw && a->pd == 0 && a->ph == 0 && a->pw == 0 &&
+                       a->Di == a->Do * a->sd && a->Hi == a->Ho * a->sh && a->Wi == a->Wo * a->sw);
+  const int scatter_n = taps * a->Cin;
+  if (k_eq_s && taps <= 8 && a->Cin % 32 == 0 && pick_n_tile(scatter_n) != 0) {
+    // transposed-conv forward as one GEMM: tap == parity, weights [tap][Cin][Cout] are already the [taps*Cin][Cout] matrix
+    P.n_tile = pick_n_tile(scatter_n);
+    if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)scatter_n, a->Cout, P.n_tile, kc)) {
+      set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(W) failed");
+      return MVD_ERR_CUDA;
+    }
+    P.taps[0] = TcTap{0, 0, 0, 0, 0};
+    add_class(P, a->Do, a->Ho, a->Wo, 0, 1, 0);
+    P.num_n_tiles = scatter_n / P.n_tile;
+    P.scatter_c = a->Cin;
+    for (int td = 0; td < a->kd; ++td)
+      for (int th = 0; th < a->kh; ++th)
+        for (int tw = 0; tw < a->kw; ++tw)
+          P.par_off[(td * a->kh + th) * a->kw + tw] = ((long long)td * a->Hi * a->Wi + (long long)th * a->Wi + tw) * ldx;
+    return launch_tc(maps, P, kc, st, "conv_transpose3d_fprop(tcgen05)");
+  }
+
+  P.n_tile = pick_n_tile(a->Cin);
+  if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)taps * a->Cin, a->Cout, P.n_tile, kc)) {
     set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(W) failed");
     return MVD_ERR_CUDA;
   }
-  const long long ldx = a->ldx;
+  P.num_n_tiles = a->Cin / P.n_tile;
+  int nt = 0;
   for (int rd = 0; rd < a->sd; ++rd)
     for (int rh = 0; rh < a->sh; ++rh)
       for (int rw = 0; rw < a->sw; ++rw) {
-        TcParams P;
-        memset(&P, 0, sizeof(P));
-        P.n_tile = n_tile;
-        P.Dt = cdiv(a->Di - rd, a->sd); P.Ht = cdiv(a->Hi - rh, a->sh); P.Wt = cdiv(a->Wi - rw, a->sw);
-        if (P.Dt <= 0 || P.Ht <= 0 || P.Wt <= 0) continue;
-        int nt = 0;
+        const int tap_begin = nt;
         for (int td = 0; td < a->kd; ++td) {
           if ((rd + a->pd - td) % a->sd) continue;
           for (int th = 0; th < a->kh; ++th) {
@@ -459,24 +520,16 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
             }
           }
         }
-        if (nt == 0) { set_error("conv3d_dgrad(tcgen05): parity class without taps"); return MVD_ERR_UNSUPPORTED; }
-        P.ntaps = nt;
-        P.kchunks = a->Cout / kc;
-        P.B = a->B;
-        P.tiles_w = cdiv(P.Wt, TILE_W); P.tiles_h = cdiv(P.Ht, TILE_H);
-        P.num_m_tiles = P.B * P.Dt * P.tiles_h * P.tiles_w;
-        P.num_n_tiles = a->Cin / n_tile;
-        P.out = (bf16*)a->x + ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ldx;
-        P.sw = ldx * a->sw; P.sh = ldx * a->Wi * a->sh; P.sd = ldx * a->Wi * a->Hi * a->sd;
-        P.sb = ldx * a->Wi * a->Hi * a->Di;
-        P.bias = a->bias;
-        P.accumulate = a->accumulate;
-        int rc = launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)");
-        if (rc) return rc;
+        const int Dt = cdiv(a->Di - rd, a->sd), Ht = cdiv(a->Hi - rh, a->sh), Wt = cdiv(a->Wi - rw, a->sw);
+        if (nt == tap_begin) {
+          if (Dt > 0 && Ht > 0 && Wt > 0) { set_error("conv3d_dgrad(tcgen05): parity class without taps"); return MVD_ERR_UNSUPPORTED; }
+          continue;
+        }
+        add_class(P, Dt, Ht, Wt, tap_begin, nt - tap_begin,
+                  ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ldx);
       }
-  return MVD_OK;
+  if (P.nclasses == 0) return MVD_OK;
+  return launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)");
 }
 
-
 }  // namespace mvd
-

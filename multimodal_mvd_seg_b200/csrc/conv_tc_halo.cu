@@ -14,6 +14,7 @@
 // Accumulators: 2 (double buffer) x MT x N fp32 columns of TMEM.
 #include "conv_common.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace mvd {
 namespace {
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   __shared__ uint64_t bar_pfull[kMaxRing], bar_pempty[kMaxRing], bar_wfull[kMaxWStages], bar_wempty[kMaxWStages],
       bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) uint8_t s_stage[4][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_bytes = P.n_tile * ROWB;
   uint8_t* smem_p = smem;
@@ -216,37 +218,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       decode(item, n0, b, d0, h0, w0);
       mbar_wait(&bar_tfull[acc], accphase, 36);
       tcgen05_fence_after();
-      const int r = q * 32 + lane;
-      const int h = h0 + (r >> 3), w = w0 + (r & 7);
-      const bool hw_ok = (h < P.H) && (w < P.W);
+      const int H = P.H, W = P.W;
+      const long long sh = P.sh, sw = P.sw;
       for (int t = 0; t < MT; ++t) {
         const int d = d0 + t;
         if (d >= P.D) break;   // uniform across the CTA
-        bf16* orow = P.out + (long long)b * P.sb + (long long)d * P.sd + (long long)h * P.sh + (long long)w * P.sw + n0;
+        bf16* tile_base = P.out + (long long)b * P.sb + (long long)d * P.sd + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + t) * P.n_tile);
         for (int c = 0; c < P.n_tile; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
           tmem_ld_wait();
-          if (hw_ok) {
+          float f[32];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[j] = __uint_as_float(v[g * 8 + j]);
-                if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + g * 8 + j));
-              }
-              bf16x8* dst = reinterpret_cast<bf16x8*>(orow + c + g * 8);
-              if (P.accumulate) {
-                float o[8];
-                unpack8(*dst, o);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += o[j];
-              }
-              *dst = pack8(f);
-            }
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + j));
           }
+          store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
+            const int rr = q * 32 + R;
+            const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+            return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
+          }, P.accumulate != 0);
         }
       }
       tcgen05_fence_before();

@@ -1,0 +1,47 @@
+// tc_epilogue.cuh -- coalesced bf16 stores for the tcgen05 epilogues.
+// tcgen05.ld (32x32b) hands every lane one accumulator ROW (32 consecutive output channels of one voxel).  Storing
+// those 64 bytes straight from the owning lane makes each warp store instruction touch 32 different rows with 16 B
+// each (half-written sectors: ncu showed 7x write amplification between L1 and L2).  Here the warp transposes the
+// 32 x 64 B block through a private 2 KB shared-memory stage (XOR-swizzled, conflict-free in both directions) so that
+// every store instruction writes 8 complete rows = the 8 w-adjacent voxels of one h line (512 contiguous bytes when the
+// tensor is dense).
+#pragma once
+#include "common.cuh"
+
+namespace mvd {
+namespace tc {
+
+// f: the lane's 32 fp32 values (bias already added).  row_ptr(R) -> destination of channel 0 of this 32-channel group
+// for row R (0..31) of the warp's block, or nullptr when that voxel is outside the tensor.
+template <typename RowPtrFn>
+__device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, int lane, const float* f, RowPtrFn row_ptr,
+                                                     bool accumulate) {
+  const int sw_own = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<bf16x8*>(stage + lane * 64 + ((g ^ sw_own) << 4)) = pack8(f + g * 8);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + (lane >> 2);
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(stage + R * 64 + ((c ^ ((R >> 1) & 3)) << 4));
+    bf16* dst = row_ptr(R);
+    if (dst) {
+      bf16x8* d8 = reinterpret_cast<bf16x8*>(dst + c * 8);
+      if (accumulate) {
+        float a[8], o[8];
+        unpack8(v, a);
+        unpack8(*d8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += o[j];
+        v = pack8(a);
+      }
+      *d8 = v;
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace tc
+}  // namespace mvd
