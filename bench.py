@@ -68,7 +68,7 @@ def sample_clocks_start():
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
     try:
-        p = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '200',
+        p = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100',
                               '-i', os.environ.get('LOCAL_RANK', '0')], stdout=open(f.name, 'w'),
                              stderr=subprocess.DEVNULL)
     except Exception:
