@@ -32,9 +32,16 @@ int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = tc_fprop_supported(a);
   if (a->algo == 2 && !tc) { set_error("conv3d_fprop: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
-  rc = (a->algo != 1 && tc) ? tc_fprop(a, st) : generic_fprop(a, st);
+  const bool use_tc = (a->algo != 1 && tc);
+  // InstanceNorm statistics: fused into the tcgen05 epilogue where that epilogue has slack (narrow layers, which are
+  // also the ones with the most voxels); a separate streaming pass otherwise (measured: for N >= 128 the extra
+  // shuffle-reduction per 32-column group makes the epilogue the bottleneck and costs more than the pass it saves)
+  const bool fuse_stats = use_tc && a->stats && a->Cout <= 64;
+  mvd_conv3d_args b = *a;
+  if (!fuse_stats) b.stats = nullptr;
+  rc = use_tc ? tc_fprop(&b, st) : generic_fprop(&b, st);
   if (rc) return rc;
-  if (a->stats)
+  if (a->stats && !fuse_stats)
     return mvd_inorm_stats(a->y, a->ldy, a->B, (long long)a->Do * a->Ho * a->Wo, a->Cout, a->stats, stream);
   return MVD_OK;
 }

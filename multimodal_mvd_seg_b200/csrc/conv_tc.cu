@@ -76,6 +76,8 @@ struct TcParams {
   long long sb, sd, sh, sw;
   const float* bias;             // per produced channel, may be null
   int accumulate;
+  double* stats;                 // optional [B][Ntot][2] (sum, sumsq) of the bf16-rounded output
+  int Ntot;
   // scatter mode (transposed conv, kernel == stride): the N axis is (parity, channel); column n goes to channel
   // n % scatter_c of the voxel displaced by par_off[n / scatter_c]
   int scatter_c;
@@ -202,9 +204,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int q = warp & 3;  // the TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t accphase = 0;
+    StatsAcc sacc;
+    sacc.reset(-1, -1);
+    const int ngroups = P.n_tile / 32;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int c, n0, b, d, h0, w0;
       decode_tile(tile, c, n0, b, d, h0, w0);
+      if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
+        if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+        sacc.reset(b, n0);
+      }
       mbar_wait(&bar_tfull[acc], accphase, 4);
       tcgen05_fence_after();
       const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
@@ -230,6 +239,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           f[j] = __uint_as_float(v[j]);
           if (P.bias) f[j] += round_bf(__ldg(P.bias + n + j));
         }
+        if (P.stats) {
+          const int rr0 = q * 32 + lane;
+          const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
+          float fr[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
+          sacc.add(cc >> 5, fr, lane);
+        }
         store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
           const int rr = q * 32 + R;
           const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
@@ -242,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       acc ^= 1;
       if (acc == 0) accphase ^= 1;
     }
+    if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -377,7 +395,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
     int wrow[27];
     for (int i = 0; i < 27; ++i) wrow[i] = i * a->Cout;
     return tc_halo_conv((const bf16*)a->x, a->ldx, a->Cin, (bf16*)a->y, a->ldy, a->Cout, (const bf16*)a->w, wrow,
-                        a->bias, 0, a->B, a->Do, a->Ho, a->Wo, st, "conv3d_fprop(tcgen05 halo)");
+                        a->bias, 0, a->stats, a->B, a->Do, a->Ho, a->Wo, st, "conv3d_fprop(tcgen05 halo)");
   }
   const int kc = (a->Cin % 64 == 0) ? 64 : 32;
   TcMaps maps;
@@ -424,6 +442,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
   P.bias = a->bias;
   P.accumulate = 0;
+  P.stats = a->stats; P.Ntot = a->Cout;
   return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
 }
 
@@ -448,7 +467,7 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
     int wrow[27];   // produced voxel i gathers y[i + 1 - t]: halo offset o = 2 - t per axis, i.e. tap 26 - idx
     for (int i = 0; i < 27; ++i) wrow[i] = (26 - i) * a->Cin;
     return tc_halo_conv((const bf16*)a->y, a->ldy, a->Cout, (bf16*)a->x, a->ldx, a->Cin, (const bf16*)a->w, wrow,
-                        a->bias, a->accumulate, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
+                        a->bias, a->accumulate, nullptr, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
   }
   const int kc = (a->Cout % 64 == 0) ? 64 : 32;
   TcMaps maps;

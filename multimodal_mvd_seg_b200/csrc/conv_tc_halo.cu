@@ -39,6 +39,8 @@ struct HaloParams {
   long long sb, sd, sh, sw;
   const float* bias;
   int accumulate;
+  double* stats;     // optional [B][N][2] running (sum, sumsq) of the bf16-rounded output (InstanceNorm statistics)
+  int Ntot;
   long long* prof;   // optional [gridDim.x][8] cycle counters of the MMA issuer (debug / DESIGN.md evidence)
   int wrow[27];
 };
@@ -213,9 +215,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     const int q = warp & 3;
     int acc = 0;
     uint32_t accphase = 0;
+    StatsAcc sacc;
+    sacc.reset(-1, -1);
+    const int ngroups = P.n_tile / 32;
     for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
       int n0, b, d0, h0, w0;
       decode(item, n0, b, d0, h0, w0);
+      if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
+        if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+        sacc.reset(b, n0);
+      }
       mbar_wait(&bar_tfull[acc], accphase, 36);
       tcgen05_fence_after();
       const int H = P.H, W = P.W;
@@ -235,6 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             f[j] = __uint_as_float(v[j]);
             if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + j));
           }
+          if (P.stats) {
+            const int rr = q * 32 + lane;
+            const bool ok = (h0 + (rr >> 3) < H) && (w0 + (rr & 7) < W);
+            float fr[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
+            sacc.add(c >> 5, fr, lane);
+          }
           store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
             const int rr = q * 32 + R;
             const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       acc ^= 1;
       if (acc == 0) accphase ^= 1;
     }
+    if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -278,7 +296,8 @@ bool tc_halo_enabled() {
 }
 
 int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
-                 const float* bias, int accumulate, int B, int D, int H, int W, cudaStream_t st, const char* who) {
+                 const float* bias, int accumulate, double* stats, int B, int D, int H, int W, cudaStream_t st,
+                 const char* who) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("%s: no cuTensorMapEncodeTiled", who); return MVD_ERR_CUDA; }
   const int kc = (K % 64 == 0) ? 64 : 32;
@@ -342,6 +361,7 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   P.sw = ldd; P.sh = (long long)ldd * W; P.sd = P.sh * H; P.sb = P.sd * D;
   P.bias = bias; P.accumulate = accumulate;
   P.prof = g_halo_prof;
+  P.stats = stats; P.Ntot = N;
   for (int i = 0; i < 27; ++i) P.wrow[i] = wrow[i];
   const size_t smem = (size_t)ring * plane_bytes + (size_t)wstages * w_bytes + 1024;
   int grid = num_sms();

@@ -157,6 +157,7 @@ bool tc_encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n
 // src[v + o - 1][k] * W[wrow[o] + n][k] (+ bias[n]); src/dst are pitched NDHWC lattices of the same extent B,D,H,W.
 bool tc_halo_enabled();
 int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
-                 const float* bias, int accumulate, int B, int D, int H, int W, cudaStream_t st, const char* who);
+                 const float* bias, int accumulate, double* stats, int B, int D, int H, int W, cudaStream_t st,
+                 const char* who);
 
 }  // namespace mvd

@@ -43,5 +43,55 @@ __device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, int lane, c
   __syncwarp();
 }
 
+// ---- InstanceNorm statistics fused into the conv epilogue ---------------------------------------------------------
+// Every lane holds one accumulator row (32 channels).  Column sums over the warp's 32 rows are formed with a
+// recursive-halving exchange (16+8+4+2+1 = 31 shuffles per quantity instead of 5 x 32): afterwards lane l owns channel l.
+// Per-lane fp32 partials are carried across the CTA's tiles and flushed with one fp64 atomic per (channel, quantity)
+// when the (sample, channel-tile) changes and at kernel end.
+__device__ __forceinline__ float warp_column_sum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+struct StatsAcc {
+  float s[8], q[8];
+  int b, n0;
+  __device__ __forceinline__ void reset(int b_, int n0_) {
+    b = b_; n0 = n0_;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  }
+  // fr: this lane's 32 bf16-rounded outputs of column group g (zero for rows outside the tensor)
+  __device__ __forceinline__ void add(int g, const float* fr, int lane) {
+    float a[32], c[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { a[j] = fr[j]; c[j] = fr[j] * fr[j]; }
+    const float cs = warp_column_sum32(a, lane);
+    const float cq = warp_column_sum32(c, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i == g) { s[i] += cs; q[i] += cq; }
+  }
+  __device__ __forceinline__ void flush(double* stats, int C, int ngroups, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < ngroups) {
+        double* d = stats + ((long long)b * C + n0 + i * 32 + lane) * 2;
+        atomicAdd(d, (double)s[i]);
+        atomicAdd(d + 1, (double)q[i]);
+        s[i] = q[i] = 0.f;
+      }
+  }
+};
+
 }  // namespace tc
 }  // namespace mvd

@@ -303,12 +303,11 @@ class ConvNormActFn(torch.autograd.Function):
             wcol = torch.zeros((1, Cout, kpad), dtype=BF16, device=dev)
             wcol[0, :, :taps * Cin] = weight.detach().reshape(Cout, Cin, taps).permute(0, 2, 1).reshape(Cout, taps * Cin)
             g1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
-            conv_fprop(g1, x_col, y, wcol, bias=bias)
+            conv_fprop(g1, x_col, y, wcol, bias=bias, stats=stats)
             x_cl, wd, geom = x_col, None, g1
         else:
             wf, wd = pack_weights(weight, True, need_dx)
-            conv_fprop(geom, x_cl, y, wf, bias=bias)
-        lib.inorm_stats(y.data_ptr(), cl_pitch(y), B, V, Cout, stats.data_ptr(), _stream())
+            conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
         z = out if out is not None else torch.empty_like(y)
         lib.inorm_lrelu_fwd(y.data_ptr(), cl_pitch(y), z.data_ptr(), cl_pitch(z), stats.data_ptr(), _ptr(gamma),
                             _ptr(beta), B, V, Cout, eps, slope, _stream())

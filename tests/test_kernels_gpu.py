@@ -85,7 +85,12 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
         # fprop (pitched output: channel slice of a wider buffer)
         ybuf = torch.zeros((B, Do, Ho, Wo, Cout + 8), dtype=BF, device=dev())
         y = ybuf[..., 8:]
-        ops.conv_fprop(geom, x, y, wf, bias=b)
+        stats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev()) if Cout % 8 == 0 else None
+        ops.conv_fprop(geom, x, y, wf, bias=b, stats=stats)
+        if stats is not None:   # InstanceNorm sums of the bf16-rounded output (fused into the tcgen05 epilogue)
+            yd = y.double().reshape(B, -1, Cout)
+            np.testing.assert_allclose(stats[..., 0].cpu(), yd.sum(1).cpu(), rtol=1e-4, atol=1e-3)
+            np.testing.assert_allclose(stats[..., 1].cpu(), (yd * yd).sum(1).cpu(), rtol=1e-4, atol=1e-3)
         xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
         wr = w.to(BF).float().requires_grad_(True)
         yr = F.conv3d(xr, wr, b.to(BF).float(), stride=s, padding=(k - 1) // 2)
