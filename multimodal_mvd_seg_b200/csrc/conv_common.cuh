@@ -14,7 +14,9 @@ bool tc_wgrad_supported(const mvd_conv3d_args* a);
 int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
-size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);
+size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);   // fp32 scratch [taps][Cin][Cout]
+int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch);   // validates + zeroes the workspace
+int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st);                   // scratch -> dw[co][ci][tap] (+ dbias)
 // sliding-window halo variant for 3x3x3 / stride 1 (conv_tc_wgrad_halo.cu)
 bool tc_wgrad_halo_supported(const mvd_conv3d_args* a);
 int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st);

@@ -45,6 +45,78 @@ struct HaloParams {
   int wrow[27];
 };
 
+// work item -> (N tile, sample, first output plane, brick origin)
+__device__ __forceinline__ void halo_decode(const HaloParams& P, int MT, int item, int& n0, int& b, int& d0, int& h0,
+                                            int& w0) {
+  const int nt = item % P.num_n_tiles;
+  int m = item / P.num_n_tiles;
+  n0 = nt * P.n_tile;
+  w0 = (m % P.tiles_w) * TILE_W; m /= P.tiles_w;
+  h0 = (m % P.tiles_h) * TILE_H; m /= P.tiles_h;
+  d0 = (m % P.dgroups) * MT;
+  b = m / P.dgroups;
+}
+
+// epilogue warps (4 warps, q = TMEM lane quarter): accumulators [acc][t][n_tile] -> bias, InstanceNorm sums, bf16,
+// coalesced stores.  Shared by the tap-major and the depth-folded kernels.
+template <int MT>
+__device__ __forceinline__ void halo_epilogue(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
+                                              uint64_t* bar_tempty, uint8_t* stage, int q, int lane) {
+  int acc = 0;
+  uint32_t accphase = 0;
+  StatsAcc sacc;
+  sacc.reset(-1, -1);
+  const int ngroups = P.n_tile / 32;
+  for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+    int n0, b, d0, h0, w0;
+    halo_decode(P, MT, item, n0, b, d0, h0, w0);
+    if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
+      if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+      sacc.reset(b, n0);
+    }
+    mbar_wait(&bar_tfull[acc], accphase, 36);
+    tcgen05_fence_after();
+    const int H = P.H, W = P.W;
+    const long long sh = P.sh, sw = P.sw;
+    for (int t = 0; t < MT; ++t) {
+      const int d = d0 + t;
+      if (d >= P.D) break;   // uniform across the CTA
+      bf16* tile_base = P.out + (long long)b * P.sb + (long long)d * P.sd + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + t) * P.n_tile);
+      for (int c = 0; c < P.n_tile; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]);
+          if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + j));
+        }
+        if (P.stats) {
+          const int rr = q * 32 + lane;
+          const bool ok = (h0 + (rr >> 3) < H) && (w0 + (rr & 7) < W);
+          float fr[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
+          sacc.add(c >> 5, fr, lane);
+        }
+        store_rows_coalesced(stage, lane, f, [&](int R) -> bf16* {
+          const int rr = q * 32 + R;
+          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+          return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
+        }, P.accumulate != 0);
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+    acc ^= 1;
+    if (acc == 0) accphase ^= 1;
+  }
+  if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+}
+
 template <int KC, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps,
                                                                 const __grid_constant__ HaloParams P) {
@@ -79,13 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   const uint32_t tmem_base = s_tmem_base;
 
   auto decode = [&](int item, int& n0, int& b, int& d0, int& h0, int& w0) {
-    const int nt = item % P.num_n_tiles;
-    int m = item / P.num_n_tiles;
-    n0 = nt * P.n_tile;
-    w0 = (m % P.tiles_w) * TILE_W; m /= P.tiles_w;
-    h0 = (m % P.tiles_h) * TILE_H; m /= P.tiles_h;
-    d0 = (m % P.dgroups) * MT;
-    b = m / P.dgroups;
+    halo_decode(P, MT, item, n0, b, d0, h0, w0);
   };
 
   if (warp == 0) {
@@ -212,60 +278,162 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
   } else if (warp >= 2 && warp <= 5) {
     // ================= epilogue =================
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t accphase = 0;
-    StatsAcc sacc;
-    sacc.reset(-1, -1);
-    const int ngroups = P.n_tile / 32;
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      int n0, b, d0, h0, w0;
-      decode(item, n0, b, d0, h0, w0);
-      if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
-        if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
-        sacc.reset(b, n0);
-      }
-      mbar_wait(&bar_tfull[acc], accphase, 36);
-      tcgen05_fence_after();
-      const int H = P.H, W = P.W;
-      const long long sh = P.sh, sw = P.sw;
-      for (int t = 0; t < MT; ++t) {
-        const int d = d0 + t;
-        if (d >= P.D) break;   // uniform across the CTA
-        bf16* tile_base = P.out + (long long)b * P.sb + (long long)d * P.sd + n0;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + t) * P.n_tile);
-        for (int c = 0; c < P.n_tile; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + j));
+    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], warp & 3, lane);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Depth-folded variant for narrow layers (N = 32 / 64) whose 27 weight tiles fit in shared memory.
+//
+// One tcgen05.mma M128 x N x K16 costs max(N/2, 32 + N/4) cycles (profiles/r1_mma_issue_rate.txt): at N = 32 the 4 KB
+// A-operand read, not the tensor pipe, is the limit (40 cycles for 16 cycles of math).  Here the three depth taps are
+// folded into the N axis: input plane a of a work item contributes to the output planes t = a - oz (oz = 0..2), whose
+// accumulators sit side by side in TMEM ([t][N] columns), so ONE MMA with B = the weight rows [oz = 2 | 1 | 0] x N of
+// an in-plane tap (oy, ox) and N' = 3N columns does the work of three (56 instead of 120 cycles at N = 32).  The shift
+// along depth is carried by the TMEM column address -- no shift-add epilogue.  At the ends of the MT-plane run the MMA
+// narrows to 2N / N columns.
+// Loop order is plane-major (for plane a: all 9 in-plane taps x K steps), which needs all weight tiles resident (loaded
+// once per CTA) and lets the planes stream through a short ring across work items; MT is limited by TMEM only
+// (2 x MT x N <= 512 columns).  The first MMA that touches a new output plane is split off (accumulate = 0).
+// ------------------------------------------------------------------------------------------------------------------
+template <int KC, int MT>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __grid_constant__ HaloMaps maps,
+                                                                     const __grid_constant__ HaloParams P) {
+  constexpr int ROWB = KC * 2;
+  constexpr int PLANE_TX = PLANE_ROWS * ROWB;
+  constexpr int PLANE_BYTES = (PLANE_TX + 1023) & ~1023;
+  constexpr uint64_t LAYOUT = (KC == 64) ? kLayoutSw128 : kLayoutSw64;
+  constexpr uint32_t A_SBO = HALO_W * ROWB;
+  constexpr uint32_t B_SBO = 8 * ROWB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_pfull[kMaxRing], bar_pempty[kMaxRing], bar_wres, bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) uint8_t s_stage[4][2048];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = P.n_tile;
+  const int wtile_bytes = 3 * N * ROWB;                   // one (chunk, in-plane tap): rows [oz=2 | oz=1 | oz=0] x N
+  uint8_t* smem_w = smem;
+  uint8_t* smem_p = smem + (size_t)P.kchunks * 9 * wtile_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.ring; ++s) { mbar_init(&bar_pfull[s], 1); mbar_init(&bar_pempty[s], 1); }
+    mbar_init(&bar_wres, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= plane producer =================
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        int n0, b, d0, h0, w0;
+        halo_decode(P, MT, item, n0, b, d0, h0, w0);
+        const int mt = min(MT, P.D - d0);
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          for (int a = 0; a < mt + 2; ++a) {
+            mbar_wait(&bar_pempty[slot], phase ^ 1, 41);
+            mbar_arrive_expect_tx(&bar_pfull[slot], (uint32_t)PLANE_TX);
+            tma_load_5d(&maps.a, smem_p + (size_t)slot * PLANE_BYTES, &bar_pfull[slot], kc * KC, w0 - 1, h0 - 1,
+                        d0 + a - 1, b);
+            if (++slot == P.ring) { slot = 0; phase ^= 1; }
           }
-          if (P.stats) {
-            const int rr = q * 32 + lane;
-            const bool ok = (h0 + (rr >> 3) < H) && (w0 + (rr & 7) < W);
-            float fr[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
-            sacc.add(c >> 5, fr, lane);
-          }
-          store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
-            const int rr = q * 32 + R;
-            const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
-            return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
-          }, P.accumulate != 0);
-        }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) accphase ^= 1;
     }
-    if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+  } else if (warp == 6) {
+    if (elect_one_sync()) {
+      // ================= weights: all kchunks x 27 tiles, once =================
+      mbar_arrive_expect_tx(&bar_wres, (uint32_t)(P.kchunks * 9 * wtile_bytes));
+      for (int kc = 0; kc < P.kchunks; ++kc)
+        for (int oyx = 0; oyx < 9; ++oyx)
+          for (int j = 0; j < 3; ++j)   // row block j holds depth tap oz = 2 - j
+            tma_load_2d(&maps.b, smem_w + (size_t)(kc * 9 + oyx) * wtile_bytes + (size_t)j * N * ROWB, &bar_wres, kc * KC,
+                        P.wrow[(2 - j) * 9 + oyx]);
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer =================
+      const int ring = P.ring, kchunks = P.kchunks;
+      const int total_items = P.total_items, gstride = gridDim.x, D = P.D;
+      const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, A_SBO, LAYOUT) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, B_SBO, LAYOUT) >> 32);
+      const uint32_t p_base = (smem_u32(smem_p) >> 4) | (1u << 16);
+      const uint32_t w_base = (smem_u32(smem_w) >> 4) | (1u << 16);
+      const uint32_t wtile16 = (uint32_t)wtile_bytes >> 4;
+      const uint32_t nrow16 = (uint32_t)(N * ROWB) >> 4;
+      const uint32_t idesc1 = make_idesc_bf16(128, N, 0, 0), idesc2 = make_idesc_bf16(128, 2 * N, 0, 0),
+                     idesc3 = make_idesc_bf16(128, 3 * N, 0, 0);
+      int acc = 0, slot = 0;
+      uint32_t accphase = 0, pphase = 0;
+      long long c_tempty = 0, c_pfull = 0;
+      const long long c_start = clock64();
+      mbar_wait(&bar_wres, 0, 42);
+      tcgen05_fence_after();
+      for (int item = blockIdx.x; item < total_items; item += gstride) {
+        const int d0 = ((item / (P.tiles_w * P.tiles_h)) % P.dgroups) * MT;   // num_n_tiles == 1 in this kernel
+        const int mt = min(MT, D - d0);
+        long long c0 = clock64();
+        mbar_wait(&bar_tempty[acc], accphase ^ 1, 43);
+        c_tempty += clock64() - c0;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * N);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const uint32_t wk = w_base + (uint32_t)(kc * 9) * wtile16;
+          for (int a = 0; a < mt + 2; ++a) {
+            const int oz_hi = min(2, a), oz_lo = max(0, a - (mt - 1));
+            const int cnt = oz_hi - oz_lo + 1;                    // output planes t = a - oz_hi .. a - oz_lo
+            const uint32_t d_col = d_tmem + (uint32_t)((a - oz_hi) * N);
+            const uint32_t wrow0 = wk + (uint32_t)(2 - oz_hi) * nrow16;   // first weight row block used
+            const uint32_t idesc = (cnt == 3) ? idesc3 : ((cnt == 2) ? idesc2 : idesc1);
+            const bool fresh = (kc == 0) && (oz_lo == 0);         // plane t = a gets its first contribution here
+            c0 = clock64();
+            mbar_wait(&bar_pfull[slot], pphase, 44);
+            c_pfull += clock64() - c0;
+            tcgen05_fence_after();
+            const uint32_t plo = p_base + (uint32_t)slot * (uint32_t)(PLANE_BYTES >> 4);
+#pragma unroll
+            for (int oyx = 0; oyx < 9; ++oyx) {
+              const int oy = oyx / 3, ox = oyx - oy * 3;
+              const uint32_t tap_off = (uint32_t)(((oy * HALO_W + ox) * ROWB) >> 4);
+              const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(plo + tap_off);
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(wrow0 + (uint32_t)oyx * wtile16);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                if (oyx == 0 && k == 0 && fresh) {
+                  // the newest plane (last N columns / last row block) starts from zero; the older ones accumulate
+                  umma_bf16(d_col + (uint32_t)((cnt - 1) * N), adesc, bdesc + (uint64_t)((uint32_t)(cnt - 1) * nrow16),
+                            idesc1, 0u);
+                  if (cnt > 1) umma_bf16(d_col, adesc, bdesc, (cnt == 3) ? idesc2 : idesc1, 1u);
+                } else {
+                  umma_bf16(d_col, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                }
+              }
+            }
+            umma_commit(&bar_pempty[slot]);
+            if (++slot == ring) { slot = 0; pphase ^= 1; }
+          }
+        }
+        umma_commit(&bar_tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+      if (P.prof) {
+        long long* o = P.prof + (long long)blockIdx.x * 8;
+        o[0] = clock64() - c_start; o[1] = c_tempty; o[2] = 0; o[3] = c_pfull;
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], warp & 3, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -321,6 +489,67 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   if (!tc_encode_w_map(&maps.b, w, (long long)27 * N, K, P.n_tile, kc)) {
     set_error("%s: cuTensorMapEncodeTiled(weights) failed", who);
     return MVD_ERR_CUDA;
+  }
+  // narrow layers whose weights fit in shared memory: depth-folded kernel (see conv_halo_fold_kernel)
+  {
+    static int fold_enabled = -1;
+    if (fold_enabled < 0) {
+      const char* e = getenv("MVD_NO_HALO_FOLD");
+      fold_enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    const int rowb_f = kc * 2;
+    const int plane_bytes_f = (PLANE_ROWS * rowb_f + 1023) & ~1023;
+    const size_t w_res = (size_t)27 * N * K * 2;
+    const size_t budget_f = 216 * 1024;
+    if (fold_enabled && N == P.n_tile && (N == 32 || N == 64) && D >= 2 && w_res + 3 * (size_t)plane_bytes_f <= budget_f) {
+      int MTf = 512 / (2 * N);                 // 8 (N = 32) or 4 (N = 64)
+      while (MTf > D) MTf >>= 1;
+      int ringf = (int)((budget_f - w_res) / plane_bytes_f);
+      if (ringf > 6) ringf = 6;
+      P.MT = MTf; P.ring = ringf; P.wstages = 0;
+      P.B = B; P.D = D; P.H = H; P.W = W;
+      P.tiles_w = cdiv(W, TILE_W); P.tiles_h = cdiv(H, TILE_H); P.dgroups = cdiv(D, MTf);
+      P.num_n_tiles = 1;
+      P.total_items = B * P.dgroups * P.tiles_h * P.tiles_w;
+      P.kchunks = K / kc;
+      P.idesc = 0;
+      uint32_t colsf = 32;
+      while ((int)colsf < 2 * MTf * N) colsf <<= 1;
+      P.tmem_cols = colsf;
+      P.out = dst;
+      P.sw = ldd; P.sh = (long long)ldd * W; P.sd = P.sh * H; P.sb = P.sd * D;
+      P.bias = bias; P.accumulate = accumulate;
+      P.prof = g_halo_prof;
+      P.stats = stats; P.Ntot = N;
+      for (int i = 0; i < 27; ++i) P.wrow[i] = wrow[i];
+      const size_t smemf = w_res + (size_t)ringf * plane_bytes_f + 1024;
+      int gridf = num_sms();
+      if (gridf > P.total_items) gridf = P.total_items;
+      void (*kf)(const HaloMaps, const HaloParams) = nullptr;
+      int kif = 0;
+#define FOLD_PICK(KCV, MTV, IDX)                       \
+  if (kc == KCV && MTf == MTV) {                       \
+    kf = conv_halo_fold_kernel<KCV, MTV>;              \
+    kif = IDX;                                         \
+  }
+      FOLD_PICK(64, 2, 0) FOLD_PICK(64, 4, 1) FOLD_PICK(64, 8, 2) FOLD_PICK(32, 2, 3) FOLD_PICK(32, 4, 4) FOLD_PICK(32, 8, 5)
+#undef FOLD_PICK
+      if (kf) {
+        static bool fattr[6] = {false, false, false, false, false, false};
+        if (!fattr[kif]) {
+          cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+          if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            set_error("%s: cudaFuncSetAttribute(fold): %s", who, cudaGetErrorString(e));
+            return MVD_ERR_CUDA;
+          }
+          fattr[kif] = true;
+        }
+        kf<<<gridf, kThreads, smemf, st>>>(maps, P);
+        MVD_LAUNCH_CHECK(who);
+        return MVD_OK;
+      }
+    }
   }
   // MT: as many output planes per item as TMEM (2 x MT x n_tile <= 512 columns) and shared memory allow, at most 4
   int MT = 512 / (2 * P.n_tile);

@@ -8,7 +8,10 @@
 //   B = the y brick [128 v][n_tile co], MN-major as well, n_tile <= 128 (1..2 boxes of 64 or 1..4 boxes of 32 channels);
 //   K = 128 voxels per brick = 8 tcgen05.mma (K = 16) per slot group, start address advanced by 2 row groups per step.
 // All accumulators of a CTA (G slot groups x n_tile columns <= 512) stay in TMEM over the CTA's whole voxel range
-// (split-K across CTAs); a single epilogue adds them into dw with fp32 atomics (dw is zeroed by the entry point).
+// (split-K across CTAs); a single epilogue adds them with 16-byte vector reductions (red.global.add.v4.f32) into a
+// scratch laid out [tap][ci][co] (co = accumulator column, contiguous), which wgrad_finish_kernel then transposes into
+// the torch layout dw[co][ci][tap].  (Scalar atomics straight into dw are stride-27 scattered: one L2 sector each;
+// they took 60-90 % of the time of the low-resolution layers.)
 // Work decomposition: unit = (set of G slot groups, N tile); grid = units x ksplit.
 // Pipeline: warp 0 lane 0 TMA producer (B ring of 2 bricks + A ring of slot groups), warp 1 lane 0 MMA issuer,
 // warps 2..5 epilogue.
@@ -39,7 +42,7 @@ struct WgParams {
   int n_tile, num_n_tiles, ksplit;
   int a_stages;
   uint32_t idesc, tmem_cols;
-  float* dw;
+  float* dw;                                           // scratch [taps][Cin][Cout]
   WgTap tap[kMaxTaps];
 };
 
@@ -174,12 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid) {   // scratch [tap][ci][co]: this row's 32 columns are 128 contiguous bytes -> 8 vector reductions
+          float* dst = P.dw + ((long long)tp * P.Cin + ci) * P.Cout + n0 + c;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int co = n0 + c + e;
-            atomicAdd(&P.dw[((long long)co * P.Cin + ci) * P.taps + tp], __uint_as_float(v[e]));
-          }
+          for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
         }
       }
     }
@@ -187,6 +188,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// scratch [taps][Cin][Cout] -> dw [Cout][Cin][taps]; block = (ci, 64 output channels), transposed through smem
+__global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                                           int taps, int Cin, int Cout) {
+  __shared__ float tile[27][65];
+  const int ci = blockIdx.x, co0 = blockIdx.y * 64;
+  const int nco = min(64, Cout - co0);
+  for (int i = threadIdx.x; i < taps * 64; i += 128) {
+    const int t = i >> 6, c = i & 63;
+    if (c < nco) tile[t][c] = scratch[((long long)t * Cin + ci) * Cout + co0 + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nco * taps; i += 128) {
+    const int c = i / taps, t = i - c * taps;
+    dw[((long long)(co0 + c) * Cin + ci) * taps + t] = tile[t][c];
+  }
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -231,14 +249,38 @@ bool tc_wgrad_supported(const mvd_conv3d_args* a) {
   return get_encode_tiled() != nullptr;
 }
 
-size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args*) { return 0; }
+size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a) {
+  return sizeof(float) * (size_t)a->Cout * a->Cin * a->kd * a->kh * a->kw;
+}
+
+int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
+  const size_t need = tc_wgrad_workspace_bytes(a);
+  if (!a->workspace || a->workspace_bytes < need || ((uintptr_t)a->workspace & 15)) {
+    set_error("conv3d_wgrad(tcgen05): needs a 16-byte aligned workspace of %zu bytes (mvd_conv3d_workspace_bytes)", need);
+    return MVD_ERR_INVALID;
+  }
+  MVD_CUDA(cudaMemsetAsync(a->workspace, 0, need, st));
+  *scratch = (float*)a->workspace;
+  return MVD_OK;
+}
+
+int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st) {
+  const int taps = a->kd * a->kh * a->kw;
+  dim3 grid(a->Cin, (a->Cout + 63) / 64);
+  wgrad_finish_kernel<<<grid, 128, 0, st>>>((const float*)a->workspace, a->dw, taps, a->Cin, a->Cout);
+  MVD_LAUNCH_CHECK("conv3d_wgrad(finish)");
+  if (a->dbias)
+    return mvd_channel_sum(a->y, a->ldy, (long long)a->B * a->Do * a->Ho * a->Wo, a->Cout, a->dbias, (mvd_stream_t)st);
+  return MVD_OK;
+}
 
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (tc_wgrad_halo_supported(a)) return tc_wgrad_halo(a, st);
   const int SW = (a->Cin % 64 == 0) ? 64 : 32;
   const int BW = (a->Cout % 64 == 0) ? 64 : 32;
   const int taps = a->kd * a->kh * a->kw;
-  MVD_CUDA(cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->Cout * a->Cin * taps, st));
+  float* scratch = nullptr;
+  if (int rc0 = tc_wgrad_begin(a, st, &scratch)) return rc0;
   WgMaps maps;
   WgParams P;
   memset(&P, 0, sizeof(P));
@@ -297,7 +339,7 @@ int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (ksplit > P.num_v_tiles) ksplit = P.num_v_tiles;
   if (ksplit < 1) ksplit = 1;
   P.ksplit = ksplit;
-  P.dw = a->dw;
+  P.dw = scratch;
   const int b_bytes = P.n_tile * 128 * 2;
   const int a_stage = 32 * 1024;
   int a_stages = (196 * 1024 - 2 * b_bytes) / a_stage;
@@ -311,9 +353,7 @@ int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   else if (BW == 64) rc = launch_wg<32, 64>(maps, P, smem, grid, st);
   else rc = launch_wg<32, 32>(maps, P, smem, grid, st);
   if (rc) return rc;
-  if (a->dbias)
-    return mvd_channel_sum(a->y, a->ldy, (long long)a->B * a->Do * a->Ho * a->Wo, a->Cout, a->dbias, (mvd_stream_t)st);
-  return MVD_OK;
+  return tc_wgrad_finish(a, st);
 }
 
 }  // namespace mvd

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
 // ------------------------------------------------------------------------------------------------------------
 // backward statistics: g' = dz * (pre > 0 ? 1 : slope);  S1 = sum g',  S2 = sum g' * xhat   per (b,c)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_stats_kernel(
+__global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_stats_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, long long V, int C, float eps, float slope,
     double* __restrict__ bstats, long long rows_per_block) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_stats_kernel(
 // dy = gamma*rstd*(g' - S1/V - xhat*S2/V); optionally dsum[c] += sum_v dy[v][c] (the bias gradient of the conv in
 // front of the norm -- analytically zero, numerically the rounding noise the reference also produces).
 // Thread = (voxel row r, 8-channel group cg) with rows strided over the block's run, like the statistics kernels.
-__global__ void __launch_bounds__(kStatThreads) inorm_lrelu_bwd_apply_kernel(
+__global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_apply_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, bf16* __restrict__ dy, int lddy,
     const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
@@ -376,6 +376,26 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(bf16* __restrict__ dst, i
   }
 }
 
+// Grid for a streaming kernel over V voxel rows of B samples: exactly ONE resident wave (SM count x blocks that fit per
+// SM), every block with the same share of rows.  (ncu, round 1: 1024 blocks on 148 x 5 slots = 1.4 waves left half the
+// machine idle in the second wave -> 50 % of the HBM roofline.)  Returns blocks per sample; *rpb = rows per block, a
+// multiple of `gran`.
+template <typename K>
+static long long one_wave(K kernel, int threads, size_t smem, int B, long long V, long long gran, long long* rpb) {
+  int bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem) != cudaSuccess || bps < 1) {
+    (void)cudaGetLastError();
+    bps = 2;
+  }
+  long long nblk = ((long long)num_sms() * bps) / B;
+  if (nblk < 1) nblk = 1;
+  long long r = (V + nblk - 1) / nblk;
+  r = (r + gran - 1) / gran * gran;
+  if (r < gran) r = gran;
+  *rpb = r;
+  return (V + r - 1) / r;
+}
+
 static bool vec_ok(const void* p, int ld, int C) {
   return (C % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
@@ -414,15 +434,10 @@ int mvd_inorm_stats(const void* y, int ldy, int B, long long V, int C, double* s
   MVD_REQUIRE(vec_ok(y, ldy, C) && C <= 2048 && (kStatThreads / (C / 8)) >= 1,
               "inorm_stats: need C %% 8 == 0, ld %% 8 == 0, 16B-aligned pointer, C <= 2048 (C=%d ld=%d)", C, ldy);
   const int rows = kStatThreads / (C / 8);
-  long long rpb = 4096;  // bounded fp32 run per thread: 4096/rows terms
-  long long nblk = (V + rpb - 1) / rpb;
-  // aim for >= 4 blocks per SM when the volume allows it
-  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
-    rpb >>= 1;
-    nblk = (V + rpb - 1) / rpb;
-  }
-  dim3 grid((unsigned)nblk, B);
   size_t smem = (size_t)rows * C * 2 * sizeof(float);
+  long long rpb;
+  const long long nblk = one_wave(inorm_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 4, &rpb);
+  dim3 grid((unsigned)nblk, B);
   inorm_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, V, C, stats, rpb);
   MVD_LAUNCH_CHECK("inorm_stats");
   return MVD_OK;
@@ -432,7 +447,11 @@ int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* 
                         const float* beta, int B, long long V, int C, float eps, float slope, mvd_stream_t stream) {
   MVD_REQUIRE(y && z && stats && B > 0 && V > 0, "inorm_lrelu_fwd: bad arguments");
   MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(z, ldz, C), "inorm_lrelu_fwd: need C %% 8 == 0 and 16B-aligned pitched rows");
-  dim3 grid(grid_for(V * (C / 8), 256 * 4, num_sms() * 8), B);
+  // grid-stride kernel: one resident wave; small volumes get fewer blocks (>= 4 rows per thread slot)
+  long long rpb;
+  const int frows = 256 / ((C / 8) > 256 ? 256 : (C / 8));
+  const long long nblk = one_wave(inorm_lrelu_fwd_kernel, 256, 2 * C * sizeof(float), B, V, (long long)frows * 4, &rpb);
+  dim3 grid((unsigned)nblk, B);
   inorm_lrelu_fwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)y, ldy, (bf16*)z, ldz, stats, gamma, beta, V, C, eps, slope);
   MVD_LAUNCH_CHECK("inorm_lrelu_fwd");
@@ -445,14 +464,10 @@ int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, 
   MVD_REQUIRE(dz && y && stats && bstats && B > 0 && V > 0, "inorm_lrelu_bwd_stats: bad arguments");
   MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && C <= 2048, "inorm_lrelu_bwd_stats: alignment/C");
   const int rows = kStatThreads / (C / 8);
-  long long rpb = 4096;
-  long long nblk = (V + rpb - 1) / rpb;
-  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
-    rpb >>= 1;
-    nblk = (V + rpb - 1) / rpb;
-  }
-  dim3 grid((unsigned)nblk, B);
   size_t smem = (size_t)(4 * C + rows * C * 2) * sizeof(float);
+  long long rpb;
+  const long long nblk = one_wave(inorm_lrelu_bwd_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 2, &rpb);
+  dim3 grid((unsigned)nblk, B);
   inorm_lrelu_bwd_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(
       (const bf16*)dz, lddz, (const bf16*)y, ldy, stats, gamma, beta, V, C, eps, slope, bstats, rpb);
   MVD_LAUNCH_CHECK("inorm_lrelu_bwd_stats");
@@ -467,12 +482,9 @@ int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, 
   MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && vec_ok(dy, lddy, C) && C <= 2048,
               "inorm_lrelu_bwd_apply: alignment/C");
   const int rows = kStatThreads / (C / 8);
-  long long rpb = 2048;
-  long long nblk = (V + rpb - 1) / rpb;
-  while (nblk * B < (long long)num_sms() * 4 && rpb > rows * 8) {
-    rpb >>= 1;
-    nblk = (V + rpb - 1) / rpb;
-  }
+  long long rpb;
+  const long long nblk = one_wave(inorm_lrelu_bwd_apply_kernel, kStatThreads, 7 * C * sizeof(float), B, V,
+                                  (long long)rows * 2, &rpb);
   dim3 grid((unsigned)nblk, B);
   inorm_lrelu_bwd_apply_kernel<<<grid, kStatThreads, 7 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dz, lddz, (const bf16*)y, ldy, (bf16*)dy, lddy, stats, bstats, gamma, beta, B, V, C, eps, slope,

@@ -121,6 +121,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): one L2 transaction for four fp32 adds
+__device__ __forceinline__ void red_add_v4(float* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): start address >> 4 in [0,14), leading byte offset >> 4 in [16,30),
 // stride byte offset >> 4 in [32,46), version = 1 in [46,48), base offset in [49,52), layout type in [61,64)

@@ -59,6 +59,11 @@ CONV_CASES = [
     (1, 512, 256, (8, 8, 8), 3, (1, 1, 1)),
     (1, 320, 320, (8, 8, 8), 3, (2, 2, 2)),
     (1, 320, 320, (10, 10, 6), 3, (2, 2, 1)),
+    # depth-folded halo kernel (resident weights): K/N in {32, 64}, depth tails (D % MT != 0), D < MT
+    (1, 64, 32, (9, 17, 11), 3, (1, 1, 1)),
+    (1, 32, 64, (5, 6, 7), 3, (1, 1, 1)),
+    (2, 32, 32, (19, 8, 16), 3, (1, 1, 1)),
+    (1, 32, 32, (3, 20, 9), 3, (1, 1, 1)),
 ]
 
 
@@ -113,6 +118,26 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
         assert rel_err(db, dy.float().sum((0, 1, 2, 3))) < 1e-3
     finally:
         ops.set_conv_algo('auto')
+
+
+@pytest.mark.parametrize('cin,shape', [(1, (2, 5, 6, 7)), (2, (1, 9, 8, 10)), (2, (1, 3, 4, 70))])
+def test_stem_im2col_bit_exact(m, cin, shape):
+    """X_col[v][tap*Cin + ci] = x[v + tap - 1][ci] (zero outside the volume, zero padding columns): a pure gather."""
+    B, D, H, W = shape
+    x = rand_cl((B, D, H, W, cin), 21)
+    kpad = 32 if cin == 1 else 64
+    col = torch.full((B, D, H, W, kpad), 7.0, dtype=BF, device=dev())
+    m.lib.im2col_small(x.data_ptr(), cin, B, D, H, W, cin, 3, 3, 3, 1, 1, 1, col.data_ptr(), kpad,
+                       torch.cuda.current_stream().cuda_stream)
+    xp = F.pad(x.float(), (0, 0, 1, 1, 1, 1, 1, 1))
+    want = torch.zeros((B, D, H, W, kpad), device=dev())
+    t = 0
+    for td in range(3):
+        for th in range(3):
+            for tw in range(3):
+                want[..., t * cin:(t + 1) * cin] = xp[:, td:td + D, th:th + H, tw:tw + W, :]
+                t += 1
+    assert torch.equal(col.float(), want)
 
 
 @pytest.mark.parametrize('stride', [(2, 2, 2), (2, 2, 1)])
