@@ -24,6 +24,7 @@ using namespace tc;
 constexpr int kThreads = 224;
 constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2, PLANE_ROWS = HALO_W * HALO_H;
 constexpr int kMaxRing = 8, kMaxWStages = 8;
+constexpr int kMaxN = 1024;   // largest produced-channel count the tap-major kernel stages a bias vector for
 
 struct alignas(64) HaloMaps {
   CUtensorMap a;   // (C, W, H, D, B) box (KC, 10, 18, 1, 1)
@@ -59,25 +60,62 @@ __device__ __forceinline__ void halo_decode(const HaloParams& P, int MT, int ite
 
 // epilogue warps (4 warps, q = TMEM lane quarter): accumulators [acc][t][n_tile] -> bias, InstanceNorm sums, bf16,
 // coalesced stores.  Shared by the tap-major and the depth-folded kernels.
-template <int MT>
-__device__ __forceinline__ void halo_epilogue(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
-                                              uint64_t* bar_tempty, uint8_t* stage, int q, int lane) {
+//  * bias comes pre-rounded from shared memory (sbias[0..Ntot));
+//  * one packed conversion (F2FP, ALU pipe) per column pair serves both the store and the statistics;
+//  * InstanceNorm sums (fused for n_tile <= 64): every lane keeps fp32 partial sums of ITS accumulator row for all
+//    columns across the CTA's work items; the cross-lane reduction + fp64 atomics run once per (sample, CTA).
+template <int SC>   // number of 32-column chunks with fused statistics (0, 1, 2): sizes the register arrays
+struct HaloStats {
+  float s0[SC > 0 ? 32 : 1], q0[SC > 0 ? 32 : 1], s1[SC > 1 ? 32 : 1], q1[SC > 1 ? 32 : 1];
+  int b;
+  __device__ __forceinline__ void reset(int b_) {
+    b = b_;
+    if (SC > 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s0[i] = q0[i] = 0.f;
+    }
+    if (SC > 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s1[i] = q1[i] = 0.f;
+    }
+  }
+  __device__ __forceinline__ void flush(double* stats, int C, int lane) {
+    if (SC > 0) {
+      const float a = warp_column_sum32(s0, lane), c = warp_column_sum32(q0, lane);
+      double* d = stats + ((long long)b * C + lane) * 2;
+      atomicAdd(d, (double)a);
+      atomicAdd(d + 1, (double)c);
+      if (SC > 1) {
+        const float a1 = warp_column_sum32(s1, lane), c1 = warp_column_sum32(q1, lane);
+        atomicAdd(d + 64, (double)a1);
+        atomicAdd(d + 65, (double)c1);
+      }
+    }
+  }
+};
+
+template <int MT, int SC>
+__device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
+                                              uint64_t* bar_tempty, uint8_t* stage, const float* sbias, int q,
+                                              int lane) {
   int acc = 0;
   uint32_t accphase = 0;
-  StatsAcc sacc;
-  sacc.reset(-1, -1);
-  const int ngroups = P.n_tile / 32;
+  constexpr bool do_stats = SC > 0;           // host guarantees n_tile == Ntot == 32 * SC when statistics are fused
+  HaloStats<SC> hs;
+  hs.reset(-1);
   for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
     int n0, b, d0, h0, w0;
     halo_decode(P, MT, item, n0, b, d0, h0, w0);
-    if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
-      if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
-      sacc.reset(b, n0);
+    if (do_stats && b != hs.b) {
+      if (hs.b >= 0) hs.flush(P.stats, P.Ntot, lane);
+      hs.reset(b);
     }
     mbar_wait(&bar_tfull[acc], accphase, 36);
     tcgen05_fence_after();
     const int H = P.H, W = P.W;
     const long long sh = P.sh, sw = P.sw;
+    const int rr = q * 32 + lane;
+    const bool ok = (h0 + (rr >> 3) < H) && (w0 + (rr & 7) < W);
     for (int t = 0; t < MT; ++t) {
       const int d = d0 + t;
       if (d >= P.D) break;   // uniform across the CTA
@@ -87,23 +125,34 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& P, uint32_t tmem
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        float f[32];
+        uint32_t w2[16];
+        const float* bp = sbias + n0 + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]);
-          if (P.bias) f[j] += round_bf(__ldg(P.bias + n0 + c + j));
+        for (int j = 0; j < 32; j += 2) {
+          const float2 bb = *reinterpret_cast<const float2*>(bp + j);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y);
+          w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
         }
-        if (P.stats) {
-          const int rr = q * 32 + lane;
-          const bool ok = (h0 + (rr >> 3) < H) && (w0 + (rr & 7) < W);
-          float fr[32];
+        if (do_stats && ok) {
+          if (SC == 1 || c == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
-          sacc.add(c >> 5, fr, lane);
+            for (int j = 0; j < 32; j += 2) {
+              const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
+              hs.s0[j] += lo; hs.q0[j] = fmaf(lo, lo, hs.q0[j]);
+              hs.s0[j + 1] += hi; hs.q0[j + 1] = fmaf(hi, hi, hs.q0[j + 1]);
+            }
+          } else if (SC > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
+              hs.s1[j] += lo; hs.q1[j] = fmaf(lo, lo, hs.q1[j]);
+              hs.s1[j + 1] += hi; hs.q1[j + 1] = fmaf(hi, hi, hs.q1[j + 1]);
+            }
+          }
         }
-        store_rows_coalesced(stage, lane, f, [&](int R) -> bf16* {
-          const int rr = q * 32 + R;
-          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+        store_rows_coalesced_packed(stage, lane, w2, [&](int R) -> bf16* {
+          const int r2 = q * 32 + R;
+          const int h = h0 + (r2 >> 3), w = w0 + (r2 & 7);
           return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
         }, P.accumulate != 0);
       }
@@ -114,7 +163,21 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& P, uint32_t tmem
     acc ^= 1;
     if (acc == 0) accphase ^= 1;
   }
-  if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+  if (do_stats && hs.b >= 0) hs.flush(P.stats, P.Ntot, lane);
+}
+
+template <int MT>
+__device__ __forceinline__ void halo_epilogue(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
+                                              uint64_t* bar_tempty, uint8_t* stage, const float* sbias, int q,
+                                              int lane) {
+  if (!P.stats) halo_epilogue_sc<MT, 0>(P, tmem_base, bar_tfull, bar_tempty, stage, sbias, q, lane);
+  else if (P.n_tile <= 32) halo_epilogue_sc<MT, 1>(P, tmem_base, bar_tfull, bar_tempty, stage, sbias, q, lane);
+  else halo_epilogue_sc<MT, 2>(P, tmem_base, bar_tfull, bar_tempty, stage, sbias, q, lane);
+}
+
+// bias (rounded to bf16 as the reference's autocast conv does) -> shared memory, zero when absent; all threads, once
+__device__ __forceinline__ void halo_stage_bias(const HaloParams& P, float* sbias) {
+  for (int i = threadIdx.x; i < P.Ntot; i += blockDim.x) sbias[i] = P.bias ? round_bf(__ldg(P.bias + i)) : 0.f;
 }
 
 template <int KC, int MT>
@@ -131,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[4][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
+  __shared__ __align__(16) float s_bias[kMaxN];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_bytes = P.n_tile * ROWB;
   uint8_t* smem_p = smem;
@@ -144,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
     fence_barrier_init();
   }
+  halo_stage_bias(P, s_bias);
   if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
@@ -278,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
   } else if (warp >= 2 && warp <= 5) {
     // ================= epilogue =================
-    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], warp & 3, lane);
+    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], s_bias, warp & 3, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -312,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
   __shared__ uint64_t bar_pfull[kMaxRing], bar_pempty[kMaxRing], bar_wres, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[4][2048];
+  __shared__ __align__(16) float s_bias[64];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = P.n_tile;
   const int wtile_bytes = 3 * N * ROWB;                   // one (chunk, in-plane tap): rows [oz=2 | oz=1 | oz=0] x N
@@ -325,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
     for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
     fence_barrier_init();
   }
+  halo_stage_bias(P, s_bias);
   if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
@@ -433,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
       }
     }
   } else if (warp >= 2 && warp <= 5) {
-    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], warp & 3, lane);
+    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], s_bias, warp & 3, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -473,7 +540,8 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   HaloParams P;
   memset(&P, 0, sizeof(P));
   P.n_tile = pick_n_tile(N);
-  if (P.n_tile == 0 || K % 32) { set_error("%s: unsupported channel counts", who); return MVD_ERR_UNSUPPORTED; }
+  if (P.n_tile == 0 || K % 32 || N > kMaxN) { set_error("%s: unsupported channel counts", who); return MVD_ERR_UNSUPPORTED; }
+  if (stats && N != 32 && N != 64) { set_error("%s: fused InstanceNorm sums need N = 32 or 64", who); return MVD_ERR_UNSUPPORTED; }
   {
     const long long ld = lds;
     cuuint64_t gdim[5] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};

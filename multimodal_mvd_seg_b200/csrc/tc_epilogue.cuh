@@ -43,6 +43,38 @@ __device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, int lane, c
   __syncwarp();
 }
 
+// same, for values already converted: w[i] = bf16x2 of columns (2i, 2i+1)
+template <typename RowPtrFn>
+__device__ __forceinline__ void store_rows_coalesced_packed(uint8_t* stage, int lane, const uint32_t* w, RowPtrFn row_ptr,
+                                                            bool accumulate) {
+  const int sw_own = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ sw_own) << 4)) =
+        make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + (lane >> 2);
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(stage + R * 64 + ((c ^ ((R >> 1) & 3)) << 4));
+    bf16* dst = row_ptr(R);
+    if (dst) {
+      bf16x8* d8 = reinterpret_cast<bf16x8*>(dst + c * 8);
+      if (accumulate) {
+        float a[8], o[8];
+        unpack8(v, a);
+        unpack8(*d8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += o[j];
+        v = pack8(a);
+      }
+      *d8 = v;
+    }
+  }
+  __syncwarp();
+}
+
 // ---- InstanceNorm statistics fused into the conv epilogue ---------------------------------------------------------
 // Every lane holds one accumulator row (32 channels).  Column sums over the warp's 32 rows are formed with a
 // recursive-halving exchange (16+8+4+2+1 = 31 shuffles per quantity instead of 5 x 32): afterwards lane l owns channel l.
