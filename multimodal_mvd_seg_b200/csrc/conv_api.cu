@@ -36,7 +36,7 @@ int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream) {
   // InstanceNorm statistics: fused into the tcgen05 epilogue where that epilogue has slack (narrow layers, which are
   // also the ones with the most voxels); a separate streaming pass otherwise (measured: for N >= 128 the extra
   // shuffle-reduction per 32-column group makes the epilogue the bottleneck and costs more than the pass it saves)
-  const bool fuse_stats = use_tc && a->stats && a->Cout <= 64;
+  const bool fuse_stats = use_tc && a->stats && (a->Cout == 32 || a->Cout == 64);
   mvd_conv3d_args b = *a;
   if (!fuse_stats) b.stats = nullptr;
   rc = use_tc ? tc_fprop(&b, st) : generic_fprop(&b, st);

@@ -15,6 +15,7 @@
 //   warps 2..5    : epilogue        -- tcgen05.ld 32 columns at a time, + bias, bf16, 16-byte global stores
 // smem full/empty mbarriers between producer and issuer, tmem full/empty mbarriers between issuer and epilogue.
 #include <mutex>
+#include <type_traits>
 #include "conv_common.cuh"
 #include "tc_common.cuh"
 #include "tc_epilogue.cuh"
@@ -43,6 +44,7 @@ constexpr int kMaxMaps = 8;
 constexpr int kMaxClasses = 8;
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int kThreads = 192;
+constexpr int kMaxBias = 1024;   // produced channels a bias vector is staged for
 
 struct TcTap {
   int map;          // which A tensor map
@@ -78,6 +80,7 @@ struct TcParams {
   int accumulate;
   double* stats;                 // optional [B][Ntot][2] (sum, sumsq) of the bf16-rounded output
   int Ntot;
+  int nbias;                     // channels the bias vector covers (scatter_c in scatter mode, else the produced channels)
   // scatter mode (transposed conv, kernel == stride): the N axis is (parity, channel); column n goes to channel
   // n % scatter_c of the voxel displaced by par_off[n / scatter_c]
   int scatter_c;
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[4][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
+  __shared__ __align__(16) float s_bias[kMaxBias];     // bias rounded to bf16 (zero when absent), indexed by channel
 
   // dynamic smem may only be 16-byte aligned by the runtime: align by hand (host adds 1 KB of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < P.nbias; i += blockDim.x) s_bias[i] = P.bias ? round_bf(__ldg(P.bias + i)) : 0.f;
   if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
@@ -201,65 +206,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else {
     // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;  // the TMEM lane quarter this warp may access
-    int acc = 0;
-    uint32_t accphase = 0;
-    StatsAcc sacc;
-    sacc.reset(-1, -1);
-    const int ngroups = P.n_tile / 32;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int c, n0, b, d, h0, w0;
-      decode_tile(tile, c, n0, b, d, h0, w0);
-      if (P.stats && (b != sacc.b || n0 != sacc.n0)) {
-        if (sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
-        sacc.reset(b, n0);
+    // bias from shared memory, one packed conversion per column pair, per-lane InstanceNorm partials (tc_epilogue.cuh);
+    // SC = number of 32-column chunks with fused statistics (host: n_tile == Ntot == 32 * SC, no scatter)
+    auto run_epilogue = [&](auto sc_tag) {
+      constexpr int SC = decltype(sc_tag)::value;
+      const int q = warp & 3;  // the TMEM lane quarter this warp may access
+      int acc = 0;
+      uint32_t accphase = 0;
+      LaneStats<SC> st;
+      st.reset(-1);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int c, n0, b, d, h0, w0;
+        decode_tile(tile, c, n0, b, d, h0, w0);
+        if (SC > 0 && b != st.b) {
+          if (st.b >= 0) st.flush(P.stats, P.Ntot, lane);
+          st.reset(b);
+        }
+        mbar_wait(&bar_tfull[acc], accphase, 4);
+        tcgen05_fence_after();
+        const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
+        bf16* tile_base = P.out + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd;
+        const long long sh = P.sh, sw = P.sw;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
+        const int rr0 = q * 32 + lane;
+        const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
+        for (int cc = 0; cc < P.n_tile; cc += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
+          tmem_ld_wait();
+          int n = n0 + cc;          // first produced column of this 32-wide group
+          long long col_off;
+          if (P.scatter_c) {        // (parity, channel): 32-column groups never straddle a parity (scatter_c % 32 == 0)
+            const int par = n / P.scatter_c;
+            n -= par * P.scatter_c;
+            col_off = P.par_off[par] + n;
+          } else {
+            col_off = n;
+          }
+          uint32_t w2[16];
+          epilogue_chunk<SC>(v, s_bias + n, st, cc, ok, w2);
+          store_rows_coalesced_packed(s_stage[q], lane, w2, [&](int R) -> bf16* {
+            const int rr = q * 32 + R;
+            const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+            return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
+          }, P.accumulate != 0);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
       }
-      mbar_wait(&bar_tfull[acc], accphase, 4);
-      tcgen05_fence_after();
-      const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
-      bf16* tile_base = P.out + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd;
-      const long long sh = P.sh, sw = P.sw;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
-      for (int cc = 0; cc < P.n_tile; cc += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
-        tmem_ld_wait();
-        int n = n0 + cc;          // first produced column of this 32-wide group
-        long long col_off;
-        if (P.scatter_c) {        // (parity, channel): 32-column groups never straddle a parity (scatter_c % 32 == 0)
-          const int par = n / P.scatter_c;
-          n -= par * P.scatter_c;
-          col_off = P.par_off[par] + n;
-        } else {
-          col_off = n;
-        }
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]);
-          if (P.bias) f[j] += round_bf(__ldg(P.bias + n + j));
-        }
-        if (P.stats) {
-          const int rr0 = q * 32 + lane;
-          const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
-          float fr[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) fr[j] = ok ? round_bf(f[j]) : 0.f;
-          sacc.add(cc >> 5, fr, lane);
-        }
-        store_rows_coalesced(s_stage[q], lane, f, [&](int R) -> bf16* {
-          const int rr = q * 32 + R;
-          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
-          return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
-        }, P.accumulate != 0);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) accphase ^= 1;
-    }
-    if (P.stats && sacc.b >= 0) sacc.flush(P.stats, P.Ntot, ngroups, lane);
+      if (SC > 0 && st.b >= 0) st.flush(P.stats, P.Ntot, lane);
+    };
+    if (!P.stats) run_epilogue(std::integral_constant<int, 0>{});
+    else if (P.n_tile <= 32) run_epilogue(std::integral_constant<int, 1>{});
+    else run_epilogue(std::integral_constant<int, 2>{});
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -319,6 +321,7 @@ bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn,
 }
 
 int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* who) {
+  if (P.nbias > kMaxBias) { set_error("%s: more than %d produced channels", who, kMaxBias); return MVD_ERR_UNSUPPORTED; }
   const int a_bytes = 128 * kc * 2, b_bytes = P.n_tile * kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
   int stages = (200 * 1024) / stage_bytes;
@@ -443,6 +446,11 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   P.bias = a->bias;
   P.accumulate = 0;
   P.stats = a->stats; P.Ntot = a->Cout;
+  P.nbias = a->Cout;
+  if (P.stats && (P.n_tile != a->Cout || (a->Cout != 32 && a->Cout != 64))) {
+    set_error("conv3d_fprop(tcgen05): fused InstanceNorm sums need Cout = 32 or 64");
+    return MVD_ERR_UNSUPPORTED;
+  }
   return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
 }
 
@@ -491,6 +499,7 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   P.sb = ldx * a->Wi * a->Hi * a->Di;
   P.bias = a->bias;
   P.accumulate = a->accumulate;
+  P.nbias = a->Cin;
 
   const bool k_eq_s = (a->kd == a->sd && a->kh == a->sh && a->kw == a->sw && a->pd == 0 && a->ph == 0 && a->pw == 0 &&
                        a->Di == a->Do * a->sd && a->Hi == a->Ho * a->sh && a->Wi == a->Wo * a->sw);

@@ -64,36 +64,6 @@ __device__ __forceinline__ void halo_decode(const HaloParams& P, int MT, int ite
 //  * one packed conversion (F2FP, ALU pipe) per column pair serves both the store and the statistics;
 //  * InstanceNorm sums (fused for n_tile <= 64): every lane keeps fp32 partial sums of ITS accumulator row for all
 //    columns across the CTA's work items; the cross-lane reduction + fp64 atomics run once per (sample, CTA).
-template <int SC>   // number of 32-column chunks with fused statistics (0, 1, 2): sizes the register arrays
-struct HaloStats {
-  float s0[SC > 0 ? 32 : 1], q0[SC > 0 ? 32 : 1], s1[SC > 1 ? 32 : 1], q1[SC > 1 ? 32 : 1];
-  int b;
-  __device__ __forceinline__ void reset(int b_) {
-    b = b_;
-    if (SC > 0) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) s0[i] = q0[i] = 0.f;
-    }
-    if (SC > 1) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) s1[i] = q1[i] = 0.f;
-    }
-  }
-  __device__ __forceinline__ void flush(double* stats, int C, int lane) {
-    if (SC > 0) {
-      const float a = warp_column_sum32(s0, lane), c = warp_column_sum32(q0, lane);
-      double* d = stats + ((long long)b * C + lane) * 2;
-      atomicAdd(d, (double)a);
-      atomicAdd(d + 1, (double)c);
-      if (SC > 1) {
-        const float a1 = warp_column_sum32(s1, lane), c1 = warp_column_sum32(q1, lane);
-        atomicAdd(d + 64, (double)a1);
-        atomicAdd(d + 65, (double)c1);
-      }
-    }
-  }
-};
-
 template <int MT, int SC>
 __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
                                               uint64_t* bar_tempty, uint8_t* stage, const float* sbias, int q,
@@ -101,7 +71,7 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
   int acc = 0;
   uint32_t accphase = 0;
   constexpr bool do_stats = SC > 0;           // host guarantees n_tile == Ntot == 32 * SC when statistics are fused
-  HaloStats<SC> hs;
+  LaneStats<SC> hs;
   hs.reset(-1);
   for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
     int n0, b, d0, h0, w0;
@@ -126,30 +96,7 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
         uint32_t w2[16];
-        const float* bp = sbias + n0 + c;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float2 bb = *reinterpret_cast<const float2*>(bp + j);
-          __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y);
-          w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
-        }
-        if (do_stats && ok) {
-          if (SC == 1 || c == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
-              hs.s0[j] += lo; hs.q0[j] = fmaf(lo, lo, hs.q0[j]);
-              hs.s0[j + 1] += hi; hs.q0[j + 1] = fmaf(hi, hi, hs.q0[j + 1]);
-            }
-          } else if (SC > 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
-              hs.s1[j] += lo; hs.q1[j] = fmaf(lo, lo, hs.q1[j]);
-              hs.s1[j + 1] += hi; hs.q1[j + 1] = fmaf(hi, hi, hs.q1[j + 1]);
-            }
-          }
-        }
+        epilogue_chunk<SC>(v, sbias + n0 + c, hs, c, ok, w2);
         store_rows_coalesced_packed(stage, lane, w2, [&](int R) -> bf16* {
           const int r2 = q * 32 + R;
           const int h = h0 + (r2 >> 3), w = w0 + (r2 & 7);

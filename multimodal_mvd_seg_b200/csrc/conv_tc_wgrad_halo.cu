@@ -243,10 +243,13 @@ bool tc_wgrad_halo_supported(const mvd_conv3d_args* a) {
     const char* e = getenv("MVD_NO_WGRAD_HALO");
     enabled = (e && e[0] == '1') ? 0 : 1;
   }
-  // measured (microbench, round 1): the sliding-window kernel wins for Cout == 32 and for small volumes; for Cout >= 64
-  // on >= 32^3 x 2 voxels the tap-by-tap kernel with N = 64/128 MMAs is on par or slightly ahead
+  static int all_sizes = -1;   // MVD_WGRAD_HALO_NARROW=1 restores the round-1 rule (Cout == 32 or small volumes only)
+  if (all_sizes < 0) {
+    const char* e = getenv("MVD_WGRAD_HALO_NARROW");
+    all_sizes = (e && e[0] == '1') ? 0 : 1;
+  }
   const long long vox = (long long)a->B * a->Do * a->Ho * a->Wo;
-  if (a->Cout >= 64 && vox >= 65536) return false;
+  if (!all_sizes && a->Cout >= 64 && vox >= 65536) return false;
   return enabled == 1 && get_encode_tiled() != nullptr;
 }
 

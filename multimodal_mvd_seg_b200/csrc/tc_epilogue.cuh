@@ -125,5 +125,70 @@ struct StatsAcc {
   }
 };
 
+// ---- per-lane statistics (no shuffles in the tile loop) ----------------------------------------------------------
+// Every lane keeps fp32 partial sums of ITS accumulator row for all columns across the CTA's work items; the cross-lane
+// reduction + fp64 atomics run once per (sample, CTA).  Valid while n_tile == C == 32 * SC and the N-tile origin is 0.
+template <int SC>   // number of 32-column chunks with fused statistics (0, 1, 2): sizes the register arrays
+struct LaneStats {
+  float s0[SC > 0 ? 32 : 1], q0[SC > 0 ? 32 : 1], s1[SC > 1 ? 32 : 1], q1[SC > 1 ? 32 : 1];
+  int b;
+  __device__ __forceinline__ void reset(int b_) {
+    b = b_;
+    if (SC > 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s0[i] = q0[i] = 0.f;
+    }
+    if (SC > 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s1[i] = q1[i] = 0.f;
+    }
+  }
+  __device__ __forceinline__ void flush(double* stats, int C, int lane) {
+    if (SC > 0) {
+      const float a = warp_column_sum32(s0, lane), c = warp_column_sum32(q0, lane);
+      double* d = stats + ((long long)b * C + lane) * 2;
+      atomicAdd(d, (double)a);
+      atomicAdd(d + 1, (double)c);
+      if (SC > 1) {
+        const float a1 = warp_column_sum32(s1, lane), c1 = warp_column_sum32(q1, lane);
+        atomicAdd(d + 64, (double)a1);
+        atomicAdd(d + 65, (double)c1);
+      }
+    }
+  }
+};
+
+
+// One 32-column accumulator chunk of a lane's row: + bias (pre-rounded, from shared memory), ONE packed fp32->bf16
+// conversion per column pair (F2FP on the ALU pipe) that serves both the store (w2[16] = bf16x2 words) and the
+// InstanceNorm sums of the rounded values (per-lane fp32 partials, see LaneStats).
+template <int SC>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t* v, const float* bias32, LaneStats<SC>& st, int c,
+                                               bool ok, uint32_t* w2) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float2 bb = *reinterpret_cast<const float2*>(bias32 + j);
+    __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y);
+    w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+  }
+  if (SC > 0 && ok) {
+    if (SC == 1 || c == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
+        st.s0[j] += lo; st.q0[j] = fmaf(lo, lo, st.q0[j]);
+        st.s0[j + 1] += hi; st.q0[j + 1] = fmaf(hi, hi, st.q0[j + 1]);
+      }
+    } else if (SC > 1) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float lo = __uint_as_float(w2[j >> 1] << 16), hi = __uint_as_float(w2[j >> 1] & 0xffff0000u);
+        st.s1[j] += lo; st.q1[j] = fmaf(lo, lo, st.q1[j]);
+        st.s1[j + 1] += hi; st.q1[j + 1] = fmaf(hi, hi, st.q1[j + 1]);
+      }
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace mvd
