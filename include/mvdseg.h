@@ -81,8 +81,16 @@ typedef struct {
  *   w_fprop [tap][Cout][Cin]  (B operand of fprop:  N = Cout rows, K = Cin contiguous)
  *   w_dgrad [tap][Cin][Cout]  (B operand of dgrad:  N = Cin rows,  K = Cout contiguous)
  * either output may be NULL. tap = (kd*KH + kh)*KW + kw. */
-int mvd_pack_conv_weights(const float* w, int Cout, int Cin, int taps, void* w_fprop, void* w_dgrad,
-                          mvd_stream_t stream);
+typedef struct mvd_pack_desc {
+  const float* w;         /* fp32 [Cout][Cin][taps]                                                         */
+  void* w_fprop;          /* bf16 [tap][Cout][Cin] or NULL                                                  */
+  void* w_dgrad;          /* bf16 [tap][Cin][Cout] or NULL                                                  */
+  int Cout, Cin, taps;    /* taps <= 27                                                                     */
+  int block_begin;        /* first thread block of this layer: running sum of mvd_pack_blocks() over the table */
+} mvd_pack_desc;
+/* packs a whole table of layers (device memory, n entries, ascending block_begin) in one launch of total_blocks blocks */
+int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int total_blocks, mvd_stream_t stream);
+int mvd_pack_blocks(int Cout, int Cin);   /* thread blocks one layer occupies in the table */
 size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass /*0 fprop,1 dgrad,2 wgrad*/);
 int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream); /* y = conv(x, w) + bias  (w = w_fprop) */
 int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* x = conv^T(y, w)       (w = w_dgrad) */

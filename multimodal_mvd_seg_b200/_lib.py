@@ -53,7 +53,8 @@ _SIGNATURES = {
     'mvd_shutdown': (c_int, []),
     'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, P, I, I, LL, I, S]),
     'mvd_ndhwc_bf16_to_ncdhw_f32': (c_int, [P, I, P, I, I, LL, S]),
-    'mvd_pack_conv_weights': (c_int, [P, I, I, I, P, P, S]),
+    'mvd_pack_conv_weights_multi': (c_int, [P, I, I, S]),
+    'mvd_pack_blocks': (c_int, [I, I]),
     'mvd_conv3d_workspace_bytes': (c_size_t, [POINTER(ConvArgs), I]),
     'mvd_conv3d_fprop': (c_int, [POINTER(ConvArgs), S]),
     'mvd_conv3d_dgrad': (c_int, [POINTER(ConvArgs), S]),
@@ -94,7 +95,7 @@ _SIGNATURES = {
 }
 
 _UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count',
-              'mvd_conv3d_workspace_bytes'}
+              'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks'}
 
 
 def _load():

@@ -113,9 +113,194 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const bf16* __rest
   if (dbias && tid < K) atomicAdd(&dbias[tid], sacc[K * C + tid]);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast paths for C = 8*CG with CG a power of two <= 32 (C = 32 .. 256: every head but the 320-channel 8^3 one).
+// Thread = (voxel row r, 8-channel group cg): one coalesced 16-byte load of z per row, the thread's K x 8 weights live
+// in registers (no shared-memory reads in the loop), 4 rows in flight per thread, logits / gradient rows moved with
+// one 8-byte access when K == 4.  Grids are one resident wave.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void load_row_k(const bf16* p, bool vec, float* g) {
+  if (K == 4 && vec) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    g[0] = __uint_as_float(u.x << 16); g[1] = __uint_as_float(u.x & 0xffff0000u);
+    g[2] = __uint_as_float(u.y << 16); g[3] = __uint_as_float(u.y & 0xffff0000u);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) g[k] = bf2f(p[k]);
+  }
+}
+
+template <int K, int CG>
+__global__ void __launch_bounds__(256) head_fwd_cg_kernel(const bf16* __restrict__ z, int ldz,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          bf16* __restrict__ out, int ldl, long long NV, int vec) {
+  constexpr int C = CG * 8, ROWS = 256 / CG, U = 4;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  float wr[K][8], bz[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    bz[k] = bias ? round_bf(bias[k]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[k][j] = round_bf(w[k * C + cg * 8 + j]);
+  }
+  const long long stride = (long long)gridDim.x * ROWS;
+  for (long long base = (long long)blockIdx.x * ROWS; base < NV; base += U * stride) {
+    bf16x8 p[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = base + u * stride + r;
+      ok[u] = v < NV;
+      if (ok[u]) p[u] = *reinterpret_cast<const bf16x8*>(z + v * ldz + cg * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8], acc[K];
+      if (ok[u]) unpack8(p[u], f);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(f[j], wr[k][j], a);
+#pragma unroll
+        for (int off = CG / 2; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        acc[k] = a + bz[k];
+      }
+      if (ok[u] && cg == 0) {
+        bf16* op = out + (base + u * stride + r) * ldl;
+        if (K == 4 && vec) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
+          *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b));
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) op[k] = f2bf(acc[k]);
+        }
+      }
+    }
+  }
+}
+
+// dz[v][c] = sum_k dl[v][k] * w[k][c]  and  dw[k][c] += sum_v dl[v][k] * z[v][c], dbias[k] += sum_v dl[v][k]
+// in ONE pass over the rows (dz may be null).
+template <int K, int CG>
+__global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict__ dl, int ldl,
+                                                          const bf16* __restrict__ z, int ldz,
+                                                          const float* __restrict__ w, bf16* __restrict__ dz, int lddz,
+                                                          float* __restrict__ dw, float* __restrict__ dbias,
+                                                          long long NV, int vec) {
+  constexpr int C = CG * 8, ROWS = 256 / CG, U = 4;
+  __shared__ float sacc[K * C + K];
+  for (int i = threadIdx.x; i < K * C + K; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  float wr[K][8], acc[K][8], accb[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wr[k][j] = round_bf(w[k * C + cg * 8 + j]); acc[k][j] = 0.f; }
+  }
+  const long long stride = (long long)gridDim.x * ROWS;
+  for (long long base = (long long)blockIdx.x * ROWS + r; base < NV; base += U * stride) {
+    bf16x8 p[U];
+    float g[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = base + u * stride;
+      if (v < NV) {
+        if (dw) p[u] = *reinterpret_cast<const bf16x8*>(z + v * ldz + cg * 8);
+        load_row_k<K>(dl + v * ldl, vec != 0, g[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) g[u][k] = 0.f;
+        p[u] = bf16x8{};
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = base + u * stride;
+      if (v >= NV) continue;
+      if (dz) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) a = fmaf(g[u][k], wr[k][j], a);
+          o[j] = a;
+        }
+        *reinterpret_cast<bf16x8*>(dz + v * lddz + cg * 8) = pack8(o);
+      }
+      if (dw) {
+        float f[8];
+        unpack8(p[u], f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          accb[k] += g[u][k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g[u][k], f[j], acc[k][j]);
+        }
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[k * C + cg * 8 + j], acc[k][j]);
+      if (cg == 0) atomicAdd(&sacc[K * C + k], accb[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * C; i += 256) atomicAdd(&dw[i], sacc[i]);
+    if (dbias && threadIdx.x < K) atomicAdd(&dbias[threadIdx.x], sacc[K * C + threadIdx.x]);
+  }
+}
+
+template <typename Kern>
+static int head_wave_grid(Kern kern, long long NV, int rows) {
+  int bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, 0) != cudaSuccess || bps < 1) {
+    (void)cudaGetLastError();
+    bps = 2;
+  }
+  long long g = (long long)num_sms() * bps;
+  const long long need = (NV + rows - 1) / rows;
+  if (g > need) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+template <int K, int CG>
+static int head_fwd_cg_launch(const bf16* z, int ldz, const float* w, const float* b, bf16* out, int ldl, long long NV,
+                              cudaStream_t st) {
+  const int vec = (K == 4 && ldl % 4 == 0 && ((uintptr_t)out & 7) == 0) ? 1 : 0;
+  const int grid = head_wave_grid(head_fwd_cg_kernel<K, CG>, NV, 256 / CG);
+  head_fwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(z, ldz, w, b, out, ldl, NV, vec);
+  MVD_LAUNCH_CHECK("head_fwd");
+  return MVD_OK;
+}
+
+template <int K, int CG>
+static int head_bwd_cg_launch(const bf16* dl, int ldl, const bf16* z, int ldz, const float* w, bf16* dz, int lddz,
+                              float* dw, float* db, long long NV, cudaStream_t st) {
+  const int vec = (K == 4 && ldl % 4 == 0 && ((uintptr_t)dl & 7) == 0) ? 1 : 0;
+  const int grid = head_wave_grid(head_bwd_cg_kernel<K, CG>, NV, 256 / CG);
+  head_bwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, vec);
+  MVD_LAUNCH_CHECK("head_bwd");
+  return MVD_OK;
+}
+
 template <int K>
 static int head_fwd_launch(const bf16* z, int ldz, const float* w, const float* b, bf16* out, int ldl, long long NV,
                            int C, cudaStream_t st) {
+  if (C == 32) return head_fwd_cg_launch<K, 4>(z, ldz, w, b, out, ldl, NV, st);
+  if (C == 64) return head_fwd_cg_launch<K, 8>(z, ldz, w, b, out, ldl, NV, st);
+  if (C == 128) return head_fwd_cg_launch<K, 16>(z, ldz, w, b, out, ldl, NV, st);
+  if (C == 256) return head_fwd_cg_launch<K, 32>(z, ldz, w, b, out, ldl, NV, st);
   int grid = grid_for(NV, 256, num_sms() * 8);
   head_fwd_kernel<K><<<grid, 256, (K * C + K) * sizeof(float), st>>>(z, ldz, w, b, out, ldl, NV, C);
   MVD_LAUNCH_CHECK("head_fwd");
@@ -125,6 +310,10 @@ static int head_fwd_launch(const bf16* z, int ldz, const float* w, const float* 
 template <int K>
 static int head_bwd_launch(const bf16* dl, int ldl, const bf16* z, int ldz, const float* w, bf16* dz, int lddz,
                            float* dw, float* db, long long NV, int C, cudaStream_t st) {
+  if (C == 32) return head_bwd_cg_launch<K, 4>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
+  if (C == 64) return head_bwd_cg_launch<K, 8>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
+  if (C == 128) return head_bwd_cg_launch<K, 16>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
+  if (C == 256) return head_bwd_cg_launch<K, 32>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
   if (dz) {
     int grid = grid_for(NV * (C / 8), 256 * 2, num_sms() * 8);
     head_bwd_data_kernel<K><<<grid, 256, K * C * sizeof(float), st>>>(dl, ldl, w, dz, lddz, NV, C);

@@ -216,15 +216,20 @@ __global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_stats_kernel(
       const int c = cg * 8 + k;
       csc[k] = sc[c]; csh[k] = sh[c]; cme[k] = mean[c]; crs[k] = rstd[c];
     }
+    // sign(round_bf(t)) == sign(t) (bf16 keeps the fp32 exponent range), so the LeakyReLU mask needs no rounding;
+    // xhat = y*rstd - mean*rstd is one FMA
+    float cxm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cxm[k] = -cme[k] * crs[k];
     auto body = [&](const bf16x8& py, const bf16x8& pg) {
       float fy[8], fg[8];
       unpack8(py, fy);
       unpack8(pg, fg);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float pre = round_bf(fmaf(fy[k], csc[k], csh[k]));
-        float gp = pre > 0.f ? fg[k] : slope * fg[k];
-        float xh = (fy[k] - cme[k]) * crs[k];
+        const float t = fmaf(fy[k], csc[k], csh[k]);
+        const float gp = fg[k] * (t > 0.f ? 1.f : slope);
+        const float xh = fmaf(fy[k], crs[k], cxm[k]);
         s1[k] += gp;
         s2[k] = fmaf(gp, xh, s2[k]);
       }
@@ -312,11 +317,16 @@ __global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_apply_kernel(
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.f;
   if (r < rows) {
-    float csc[8], csh[8], cme[8], crs[8], cm1[8], cm2[8];
+    // dy = sc*(g' - m1 - xhat*m2) with xhat = (y - mean)*rstd  ==  fma(y, p1, fma(g', sc, p2)),
+    //   p1 = -sc*rstd*m2,  p2 = sc*(mean*rstd*m2 - m1): two FMAs per element (fp32 reassociation only)
+    float csc[8], csh[8], p1[8], p2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = cg * 8 + k;
-      csc[k] = sc[c]; csh[k] = sh[c]; cme[k] = mean[c]; crs[k] = rstd[c]; cm1[k] = m1[c]; cm2[k] = m2[c];
+      csc[k] = sc[c]; csh[k] = sh[c];
+      const float rm2 = rstd[c] * m2[c];
+      p1[k] = -csc[k] * rm2;
+      p2[k] = csc[k] * (mean[c] * rm2 - m1[c]);
     }
     auto body = [&](const bf16x8& py, const bf16x8& pg, long long v) {
       float fy[8], fg[8], o[8];
@@ -324,13 +334,17 @@ __global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_apply_kernel(
       unpack8(pg, fg);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float pre = round_bf(fmaf(fy[k], csc[k], csh[k]));
-        float gp = pre > 0.f ? fg[k] : slope * fg[k];
-        float xh = (fy[k] - cme[k]) * crs[k];
-        o[k] = round_bf(csc[k] * (gp - cm1[k] - xh * cm2[k]));
-        s[k] += o[k];
+        const float t = fmaf(fy[k], csc[k], csh[k]);
+        const float gp = fg[k] * (t > 0.f ? 1.f : slope);
+        o[k] = fmaf(fy[k], p1[k], fmaf(gp, csc[k], p2[k]));
       }
-      *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pack8(o);
+      const bf16x8 pk = pack8(o);
+      *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pk;
+      if (dsum) {          // bias gradient = sum of the ROUNDED dy (what the reference's conv backward sums)
+        unpack8(pk, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += o[k];
+      }
     };
     long long v = v0 + r;
     for (; v + (long long)rows < v1; v += 2LL * rows) {

@@ -71,20 +71,41 @@ __global__ void __launch_bounds__(256) sgd_nesterov_clip_kernel(const uint64_t* 
   }
 }
 
-// fp32 torch layout [Cout][Cin][taps] -> bf16 [tap][Cout][Cin] and/or [tap][Cin][Cout]
-__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int Cin,
-                                                                int taps, bf16* __restrict__ wf,
-                                                                bf16* __restrict__ wd) {
-  const long long total = (long long)Cout * Cin * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // i indexes the fprop layout [tap][co][ci] so that its writes are coalesced
-    int ci = (int)(i % Cin);
-    long long r = i / Cin;
-    int co = (int)(r % Cout);
-    int tap = (int)(r / Cout);
-    bf16 v = f2bf(w[((long long)co * Cin + ci) * taps + tap]);
-    if (wf) wf[i] = v;
-    if (wd) wd[((long long)tap * Cin + ci) * Cout + co] = v;
+// fp32 torch layout [Cout][Cin][taps] -> bf16 [tap][Cout][Cin] and/or [tap][Cin][Cout], for a whole TABLE of layers in
+// one launch (mvd_pack_desc, device memory).  Block = a 16 (co) x 16 (ci) tile of one layer: every co row of the tile is
+// 16*taps contiguous floats (coalesced, all loads of a thread independent); both packed layouts are then written in
+// 32-byte runs (16 consecutive ci, resp. 16 consecutive co).
+constexpr int kPackTile = 16, kPackMaxTaps = 27;
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const mvd_pack_desc* __restrict__ descs, int n) {
+  __shared__ float tile[kPackTile][kPackTile * kPackMaxTaps + 1];
+  // which layer does this block belong to (n <= a few dozen: linear scan)
+  int li = 0;
+  while (li + 1 < n && (int)blockIdx.x >= descs[li + 1].block_begin) ++li;
+  const mvd_pack_desc d = descs[li];
+  const int Cout = d.Cout, Cin = d.Cin, taps = d.taps;
+  const int tiles_ci = (Cin + kPackTile - 1) / kPackTile;
+  const int tb = (int)blockIdx.x - d.block_begin;
+  const int ci0 = (tb % tiles_ci) * kPackTile, co0 = (tb / tiles_ci) * kPackTile;
+  const int nci = min(kPackTile, Cin - ci0), nco = min(kPackTile, Cout - co0);
+  const int rowlen = nci * taps;
+  const float* w = d.w;
+  for (int i = threadIdx.x; i < nco * rowlen; i += 256) {
+    const int r = i / rowlen, c = i - r * rowlen;
+    tile[r][c] = w[((long long)(co0 + r) * Cin + ci0) * taps + c];
+  }
+  __syncthreads();
+  const int a = threadIdx.x >> 4, b = threadIdx.x & 15;
+  bf16* wf = (bf16*)d.w_fprop;
+  bf16* wd = (bf16*)d.w_dgrad;
+  if (wf && a < nco && b < nci) {          // a = co, b = ci (fastest)
+#pragma unroll 9
+    for (int t = 0; t < taps; ++t)
+      wf[((long long)t * Cout + co0 + a) * Cin + ci0 + b] = f2bf(tile[a][b * taps + t]);
+  }
+  if (wd && a < nci && b < nco) {          // a = ci, b = co (fastest)
+#pragma unroll 9
+    for (int t = 0; t < taps; ++t)
+      wd[((long long)t * Cin + ci0 + a) * Cout + co0 + b] = f2bf(tile[b][a * taps + t]);
   }
 }
 
@@ -117,13 +138,15 @@ int mvd_sgd_nesterov_clip(const uint64_t* ptrs, const long long* numel, const in
   return MVD_OK;
 }
 
-int mvd_pack_conv_weights(const float* w, int Cout, int Cin, int taps, void* w_fprop, void* w_dgrad,
-                          mvd_stream_t stream) {
-  MVD_REQUIRE(w && Cout > 0 && Cin > 0 && taps > 0 && (w_fprop || w_dgrad), "pack_conv_weights: bad arguments");
-  int grid = grid_for((long long)Cout * Cin * taps, 256, num_sms() * 8);
-  pack_conv_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, taps, (bf16*)w_fprop, (bf16*)w_dgrad);
+int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int total_blocks, mvd_stream_t stream) {
+  MVD_REQUIRE(descs_device && n > 0 && total_blocks > 0, "pack_conv_weights_multi: bad arguments");
+  pack_conv_weights_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_device, n);
   MVD_LAUNCH_CHECK("pack_conv_weights");
   return MVD_OK;
+}
+
+int mvd_pack_blocks(int Cout, int Cin) {
+  return ((Cout + kPackTile - 1) / kPackTile) * ((Cin + kPackTile - 1) / kPackTile);
 }
 
 int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream) {

@@ -258,8 +258,34 @@ class PlainConvUNet(nn.Module):
                                         n_conv_per_stage, conv_bias, return_skips=True)
         self.decoder = UNetDecoder(self.encoder, num_classes, n_conv_per_stage_decoder, deep_supervision)
 
+    def _weight_packer(self):
+        """one launch refreshes the bf16 GEMM layouts of every conv / transposed-conv weight (ops.WeightPacker);
+        rebuilt when a weight's storage moved (``.to(device)``)."""
+        ws = [m.conv.weight for m in self.modules() if isinstance(m, ConvDropoutNormReLU) and m.conv.weight.shape[1] > 4]
+        ws += [t.weight for t in self.decoder.transpconvs]
+        seen, uniq = set(), []
+        for w in ws:   # decoder.encoder aliases the encoder modules
+            if id(w) not in seen:
+                seen.add(id(w))
+                uniq.append(w)
+        sig = tuple(w.data_ptr() for w in uniq)
+        if getattr(self, '_packer_sig', None) != sig:
+            self._packer = ops.WeightPacker([(w, True, True) for w in uniq])
+            self._packer_sig = sig
+        return self._packer
+
     def forward(self, x: torch.Tensor):
         x_cl = _to_cl(x)
+        if x_cl.is_cuda and ops._default_algo != 1:
+            pk = self._weight_packer()
+            pk.run()
+            ops.set_active_packer(pk)
+        try:
+            return self._forward_impl(x_cl)
+        finally:
+            ops.set_active_packer(None)
+
+    def _forward_impl(self, x_cl: torch.Tensor):
         B, D, H, W, _ = x_cl.shape
         shapes, cur = [], [D, H, W]
         for s, st in enumerate(self.encoder.strides):

@@ -5,6 +5,7 @@ the hand-written sm_100a library.  Activations travel as bf16 tensors of logical
 possibly a channel slice of a wider buffer (voxel pitch ld > C), see include/mvdseg.h.
 """
 import ctypes
+import numpy as np
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -153,18 +154,82 @@ def _conv_args(geom: ConvGeom, x_cl: torch.Tensor, y_cl: torch.Tensor, w_packed=
     return a
 
 
+class WeightPacker:
+    """bf16 GEMM layouts of a whole set of conv weights, refreshed by ONE kernel launch (mvd_pack_conv_weights_multi).
+
+    entries: iterable of (weight fp32 [Cout][Cin][kd][kh][kw] (or [CinT][CoutT][k..] for a transposed conv: same
+    indexing), want_fprop, want_dgrad).  The packed buffers and the device-side descriptor table are persistent
+    (CUDA-graph friendly); ``run()`` re-reads the current weight values."""
+
+    _DESC = np.dtype([('w', '<u8'), ('wf', '<u8'), ('wd', '<u8'), ('Cout', '<i4'), ('Cin', '<i4'), ('taps', '<i4'),
+                      ('block_begin', '<i4')])
+
+    def __init__(self, entries):
+        entries = list(entries)
+        assert entries
+        self.packed = {}
+        rows = np.zeros(len(entries), dtype=self._DESC)
+        blocks = 0
+        self._keep = []
+        for i, (w, want_f, want_d) in enumerate(entries):
+            require_cuda(w, 'WeightPacker')
+            wd_ = w.detach()
+            if wd_.dtype != torch.float32 or not wd_.is_contiguous():
+                raise MvdError('WeightPacker: weights must be contiguous fp32')
+            Cout, Cin = wd_.shape[0], wd_.shape[1]
+            taps = int(np.prod(wd_.shape[2:]))
+            if taps > 27:
+                raise MvdError('WeightPacker: at most 27 taps')
+            wf = torch.empty((taps, Cout, Cin), dtype=BF16, device=w.device) if want_f else None
+            wdg = torch.empty((taps, Cin, Cout), dtype=BF16, device=w.device) if want_d else None
+            rows[i] = (wd_.data_ptr(), _ptr(wf) or 0, _ptr(wdg) or 0, Cout, Cin, taps, blocks)
+            blocks += lib.pack_blocks(Cout, Cin)
+            self.packed[id(w)] = (wf, wdg)
+            self._keep.append(w)
+        self.n, self.blocks = len(entries), blocks
+        self.table = torch.from_numpy(rows.view(np.uint8).copy()).to(entries[0][0].device)
+
+    def run(self):
+        lib.pack_conv_weights_multi(self.table.data_ptr(), self.n, self.blocks, _stream())
+
+    def get(self, w):
+        return self.packed[id(w)]
+
+
+_single_packers = {}
+_active_packer: Optional[WeightPacker] = None   # set by PlainConvUNet.forward for the duration of one forward pass
+
+
+def set_active_packer(pk: Optional[WeightPacker]):
+    global _active_packer
+    _active_packer = pk
+
+
+def _packed_for(weight, want_fprop=True, want_dgrad=True):
+    """the bf16 layouts of `weight`: from the network-wide packer when a forward pass armed one (already refreshed by
+    its single launch), else packed here."""
+    if _active_packer is not None:
+        hit = _active_packer.packed.get(id(weight))
+        if hit is not None:
+            return hit
+    return pack_weights(weight, want_fprop, want_dgrad)
+
+
 def pack_weights(w: torch.Tensor, want_fprop=True, want_dgrad=True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """fp32 [Cout][Cin][kd][kh][kw] -> bf16 [tap][Cout][Cin] and [tap][Cin][Cout]."""
+    """fp32 [Cout][Cin][kd][kh][kw] -> bf16 [tap][Cout][Cin] and [tap][Cin][Cout] for ONE layer.  The packed buffers are
+    cached per (storage address, shape): repeated calls refresh and return the same tensors."""
     require_cuda(w, 'pack_weights')
     w = w.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    Cout, Cin = w.shape[0], w.shape[1]
-    taps = w.shape[2] * w.shape[3] * w.shape[4]
-    wf = torch.empty((taps, Cout, Cin), dtype=BF16, device=w.device) if want_fprop else None
-    wd = torch.empty((taps, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
-    lib.pack_conv_weights(w.data_ptr(), Cout, Cin, taps, _ptr(wf), _ptr(wd), _stream())
-    return wf, wd
+    key = (w.data_ptr(), tuple(w.shape), bool(want_fprop), bool(want_dgrad), w.device)
+    pk = _single_packers.get(key)
+    if pk is None:
+        if len(_single_packers) > 512:
+            _single_packers.clear()
+        pk = _single_packers[key] = (WeightPacker([(w, want_fprop, want_dgrad)]), w)
+    pk[0].run()
+    return next(iter(pk[0].packed.values()))
 
 
 class ConvTimer:
@@ -243,14 +308,56 @@ def set_grad_allocator(fn):
     """fn(param) -> fp32 tensor view (same shape) the weight gradient is written into (DDP bucket arena), or None."""
     global _grad_alloc
     _grad_alloc = fn
+    _arena_ids.clear()
+
+
+_arena_ids = set()
+
+# ---- per-step pool of zero-initialised scratch (InstanceNorm sums, loss accumulators): ONE memset per step instead of
+# ---- ~80 tiny fill kernels.  Armed by begin_step() (the trainer calls it at the top of every step); without it, or
+# ---- when the pool runs out, zeros() falls back to torch.zeros.
+_ZERO_POOL_BYTES = 2 << 20
+_zero_pool = {}   # device -> [uint8 tensor, offset]
+
+
+def begin_step(device):
+    ent = _zero_pool.get(device)
+    if ent is None:
+        ent = _zero_pool[device] = [torch.empty((_ZERO_POOL_BYTES,), dtype=torch.uint8, device=device), 0]
+    ent[0].zero_()
+    ent[1] = 0
+
+
+def zeros(shape, dtype, device):
+    ent = _zero_pool.get(device)
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    if ent is None or ent[1] + n > _ZERO_POOL_BYTES:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    off = ent[1]
+    ent[1] = (off + n + 255) // 256 * 256
+    return ent[0][off:off + n].view(dtype).view(shape)
 
 
 def _grad_like(p: torch.Tensor) -> torch.Tensor:
     if _grad_alloc is not None:
         g = _grad_alloc(p)
         if g is not None:
+            _arena_ids.add(id(g))   # the arena's views are persistent objects
             return g
     return torch.empty(p.shape, dtype=torch.float32, device=p.device)
+
+
+def _ret(g: Optional[torch.Tensor], p: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """what a Function's backward hands to autograd for a parameter gradient.  When the kernel wrote it into the
+    gradient arena, the arena view is attached as ``p.grad`` right here and autograd gets nothing: handing the view
+    over would make AccumulateGrad clone it (108 device-to-device copies per step).  Consequence: with an arena a
+    second backward without zero_grad overwrites instead of accumulating (the trainer never does that,
+    nnUNetTrainer.py:901)."""
+    if g is None or id(g) not in _arena_ids:
+        return g
+    if p is not None and p.grad is not g:
+        p.grad = g
+    return None
 
 
 _backward_hooks = []
@@ -287,7 +394,7 @@ class ConvNormActFn(torch.autograd.Function):
         dev = x_cl.device
         need_dx = ctx.needs_input_grad[0]
         y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
-        stats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev)
+        stats = zeros((B, Cout, 2), torch.float64, dev)
         V = Do * Ho * Wo
         # stem (1-2 input modalities): explicit im2col + single-tap tensor-core GEMM (csrc/stem.cu)
         stem = (Cin <= 4 and not need_dx and geom.s == (1, 1, 1) and Cout % 32 == 0 and _default_algo != 1)
@@ -306,7 +413,7 @@ class ConvNormActFn(torch.autograd.Function):
             conv_fprop(g1, x_col, y, wcol, bias=bias, stats=stats)
             x_cl, wd, geom = x_col, None, g1
         else:
-            wf, wd = pack_weights(weight, True, need_dx)
+            wf, wd = _packed_for(weight, True, need_dx)
             conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
         z = out if out is not None else torch.empty_like(y)
         lib.inorm_lrelu_fwd(y.data_ptr(), cl_pitch(y), z.data_ptr(), cl_pitch(z), stats.data_ptr(), _ptr(gamma),
@@ -325,7 +432,7 @@ class ConvNormActFn(torch.autograd.Function):
         V = Do * Ho * Wo
         dev = y.device
         st = _stream()
-        bstats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=dev)
+        bstats = zeros((B, Cout, 2), torch.float64, dev)
         lib.inorm_lrelu_bwd_stats(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), stats.data_ptr(),
                                   _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, bstats.data_ptr(), st)
         dy = torch.empty_like(y)
@@ -354,7 +461,7 @@ class ConvNormActFn(torch.autograd.Function):
             conv_dgrad(geom, dx, dy, wd)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
-        return dx, dw, db, dgamma, dbeta, None, None, None, None, None
+        return dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -371,7 +478,7 @@ class ConvTransposeFn(torch.autograd.Function):
         s = tuple(stride)
         geom = ConvGeom(s, s, (0, 0, 0))  # adjoint conv: hi-res (CoutT) -> lo-res (CinT)
         dev = x_cl.device
-        wf, wd = pack_weights(weight, True, True)
+        wf, wd = _packed_for(weight, True, True)
         up = out if out is not None else torch.empty((B, d * s[0], h * s[1], w * s[2], CoutT), dtype=BF16, device=dev)
         conv_dgrad(geom, up, x_cl, wd, bias=bias)
         ctx.geom = geom
@@ -399,7 +506,7 @@ class ConvTransposeFn(torch.autograd.Function):
             conv_fprop(geom, dup, dx, wf)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
-        return dx, dw, db, None, None, None
+        return dx, _ret(dw, weight), _ret(db, bias), None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -462,7 +569,7 @@ class HeadFn(torch.autograd.Function):
                      C if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, _stream())
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
-        return dz, dw, db, None
+        return dz, _ret(dw, weight), _ret(db, bias), None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -499,7 +606,7 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
             B, D, H, W, C = lg.shape
             V = D * H * W
             tg = _target_f32(targets[i])
-            acc = torch.zeros((B * C * 3 + 1,), dtype=torch.float64, device=dev)
+            acc = zeros((B * C * 3 + 1,), torch.float64, dev)
             lib.dice_ce_fwd(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, V, C, acc.data_ptr(), st)
             gscale = 1.0
             if cfg['batch_dice'] and cfg['ddp'] and torch.distributed.is_available() and torch.distributed.is_initialized():

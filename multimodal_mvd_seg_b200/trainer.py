@@ -271,6 +271,7 @@ class nnUNetTrainer(object):
 
     def _step_body(self, data, target) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)
+        ops.begin_step(data.device)
         for a in self._arenas:
             a.begin_step()
         l, _ = self._forward_loss(data, target)

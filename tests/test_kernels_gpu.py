@@ -204,7 +204,7 @@ def test_instance_norm_lrelu_fwd_bwd(m, C, shape):
     assert rel_err(db, br.grad) < 5e-3
 
 
-@pytest.mark.parametrize('C,K', [(32, 4), (320, 4), (64, 3)])
+@pytest.mark.parametrize('C,K', [(32, 4), (320, 4), (64, 3), (128, 4), (256, 4), (64, 4)])
 def test_head(m, C, K):
     ops = m.ops
     z = rand_cl((2, 5, 6, 7, C), 31)
