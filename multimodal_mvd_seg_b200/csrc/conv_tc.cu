@@ -222,11 +222,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (st.b >= 0) st.flush(P.stats, P.Ntot, lane);
           st.reset(b);
         }
-        mbar_wait(&bar_tfull[acc], accphase, 4);
-        tcgen05_fence_after();
         const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
         bf16* tile_base = P.out + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd;
         const long long sh = P.sh, sw = P.sw;
+        // destination of channel 0 of the 32-column group starting at produced column n0 + cc, for row R of this warp
+        auto col_offset = [&](int cc) -> long long {
+          int n = n0 + cc;
+          if (P.scatter_c) {        // (parity, channel): 32-column groups never straddle a parity (scatter_c % 32 == 0)
+            const int par = n / P.scatter_c;
+            return P.par_off[par] + (n - par * P.scatter_c);
+          }
+          return n;
+        };
+        auto row_ptr_at = [&](int R, long long col_off) -> bf16* {
+          const int rr = q * 32 + R;
+          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+          return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
+        };
+        const bool accum = P.accumulate != 0;
+        bf16x8 old[4];
+        bool has[4] = {false, false, false, false};
+        if (accum) {   // old values of the first chunk fly while the MMAs of this tile finish
+          const long long co0 = col_offset(0);
+          prefetch_rows(lane, [&](int R) { return row_ptr_at(R, co0); }, old, has);
+        }
+        mbar_wait(&bar_tfull[acc], accphase, 4);
+        tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
         const int rr0 = q * 32 + lane;
         const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
@@ -234,22 +255,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
           tmem_ld_wait();
-          int n = n0 + cc;          // first produced column of this 32-wide group
-          long long col_off;
-          if (P.scatter_c) {        // (parity, channel): 32-column groups never straddle a parity (scatter_c % 32 == 0)
-            const int par = n / P.scatter_c;
-            n -= par * P.scatter_c;
-            col_off = P.par_off[par] + n;
-          } else {
-            col_off = n;
-          }
+          const long long col_off = col_offset(cc);
+          int n = n0 + cc;          // bias index: channel within the parity in scatter mode
+          if (P.scatter_c) n -= (n / P.scatter_c) * P.scatter_c;
           uint32_t w2[16];
           epilogue_chunk<SC>(v, s_bias + n, st, cc, ok, w2);
-          store_rows_coalesced_packed(s_stage[q], lane, w2, [&](int R) -> bf16* {
-            const int rr = q * 32 + R;
-            const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
-            return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
-          }, P.accumulate != 0);
+          if (accum) {
+            bf16x8 cur[4];
+            bool chas[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { cur[i] = old[i]; chas[i] = has[i]; }
+            if (cc + 32 < P.n_tile) {   // next chunk's old values
+              const long long con = col_offset(cc + 32);
+              prefetch_rows(lane, [&](int R) { return row_ptr_at(R, con); }, old, has);
+            }
+            store_rows_accumulate_packed(s_stage[q], lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, cur, chas);
+          } else {
+            store_rows_coalesced_packed(s_stage[q], lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, false);
+          }
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -75,6 +75,47 @@ __device__ __forceinline__ void store_rows_coalesced_packed(uint8_t* stage, int 
   __syncwarp();
 }
 
+// Accumulating variant with the OLD destination values prefetched by the caller (old[i] belongs to row 8*i + lane/4,
+// 16-byte column group lane&3 -- the same mapping the stores use; has[i] says whether that row exists).  Lets the
+// global loads fly while the warp still waits for its accumulator / converts, instead of a load-add-store chain with
+// the full memory latency exposed four times per chunk.
+template <typename RowPtrFn>
+__device__ __forceinline__ void prefetch_rows(int lane, RowPtrFn row_ptr, bf16x8* old, bool* has) {
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bf16* src = row_ptr(8 * i + (lane >> 2));
+    has[i] = src != nullptr;
+    if (has[i]) old[i] = *reinterpret_cast<const bf16x8*>(src + c * 8);
+  }
+}
+
+template <typename RowPtrFn>
+__device__ __forceinline__ void store_rows_accumulate_packed(uint8_t* stage, int lane, const uint32_t* w, RowPtrFn row_ptr,
+                                                             const bf16x8* old, const bool* has) {
+  const int sw_own = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ sw_own) << 4)) =
+        make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int R = 8 * i + (lane >> 2);
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(stage + R * 64 + ((c ^ ((R >> 1) & 3)) << 4));
+    if (has[i]) {
+      float a[8], o[8];
+      unpack8(v, a);
+      unpack8(old[i], o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += o[j];
+      *reinterpret_cast<bf16x8*>(row_ptr(R) + c * 8) = pack8(a);
+    }
+  }
+  __syncwarp();
+}
+
 // ---- InstanceNorm statistics fused into the conv epilogue ---------------------------------------------------------
 // Every lane holds one accumulator row (32 channels).  Column sums over the warp's 32 rows are formed with a
 // recursive-halving exchange (16+8+4+2+1 = 31 shuffles per quantity instead of 5 x 32): afterwards lane l owns channel l.

@@ -276,6 +276,7 @@ class PlainConvUNet(nn.Module):
 
     def forward(self, x: torch.Tensor):
         x_cl = _to_cl(x)
+        ops.reset_skip_registry()
         if x_cl.is_cuda and ops._default_algo != 1:
             pk = self._weight_packer()
             pk.run()

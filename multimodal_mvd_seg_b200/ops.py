@@ -54,6 +54,14 @@ def cl_pitch(t: torch.Tensor) -> int:
     return ld
 
 
+def cl_pitch_ok(t: torch.Tensor) -> bool:
+    """is t a pitched NDHWC tensor the kernels can address in place (16-byte aligned rows)?"""
+    try:
+        return t.dim() == 5 and cl_pitch(t) % 8 == 0 and t.data_ptr() % 16 == 0
+    except MvdError:
+        return False
+
+
 def as_cl(t: torch.Tensor) -> torch.Tensor:
     """returns t if it is a valid pitched NDHWC bf16 tensor, else a dense copy."""
     if t.dtype != BF16:
@@ -379,6 +387,22 @@ def _notify(params):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Skip-connection gradient: an encoder stage output feeds the next encoder stage AND the decoder's concat buffer, so
+# autograd would add the two gradients with a separate elementwise kernel (read 2, write 1 full-resolution tensors).
+# Instead the decoder-side gradient (a channel slice of the concat buffer's gradient, produced first) is parked here
+# and the next encoder stage's dgrad ACCUMULATES into it in its epilogue; ConcatViewFn then reports no gradient of its
+# own for the skip.  Only armed when the forward pass saw exactly one dgrad consumer of that tensor.
+# ---------------------------------------------------------------------------------------------------------------
+_dx_consumers = {}     # data_ptr of a conv input that needs a gradient -> number of conv consumers (this forward)
+_pending_skip = {}     # data_ptr -> decoder-side gradient view, between ConcatViewFn.backward and the consumer's dgrad
+
+
+def reset_skip_registry():
+    _dx_consumers.clear()
+    _pending_skip.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Conv3d -> InstanceNorm3d(affine) -> LeakyReLU   (one ConvDropoutNormReLU block)
 # ---------------------------------------------------------------------------------------------------------------
 class ConvNormActFn(torch.autograd.Function):
@@ -393,6 +417,9 @@ class ConvNormActFn(torch.autograd.Function):
         Do, Ho, Wo = geom.out_size((Di, Hi, Wi))
         dev = x_cl.device
         need_dx = ctx.needs_input_grad[0]
+        if need_dx:
+            _dx_consumers[x_cl.data_ptr()] = _dx_consumers.get(x_cl.data_ptr(), 0) + 1
+        ctx.x_ptr = x_cl.data_ptr()
         y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
         stats = zeros((B, Cout, 2), torch.float64, dev)
         V = Do * Ho * Wo
@@ -457,8 +484,13 @@ class ConvNormActFn(torch.autograd.Function):
                 conv_wgrad(geom, x_cl, dy, dw, None)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
-            conv_dgrad(geom, dx, dy, wd)
+            pend = _pending_skip.pop(ctx.x_ptr, None)
+            if pend is not None and tuple(pend.shape) == tuple(x_cl.shape):
+                dx = pend     # the decoder's share of this skip tensor's gradient: add ours in the dgrad epilogue
+                conv_dgrad(geom, dx, dy, wd, accumulate=True)
+            else:
+                dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
+                conv_dgrad(geom, dx, dy, wd)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None
@@ -520,10 +552,16 @@ class ConcatViewFn(torch.autograd.Function):
         assert up.data_ptr() == buf.data_ptr() and skip.data_ptr() == buf.data_ptr() + c1 * buf.element_size()
         assert buf.shape[-1] == c1 + skip.shape[-1]
         ctx.c1 = c1
+        ctx.skip_ptr = skip.data_ptr()
+        # exactly one conv takes a gradient w.r.t. the skip tensor (the next encoder stage): it will fold our share in
+        ctx.defer = ctx.needs_input_grad[1] and _dx_consumers.get(ctx.skip_ptr, 0) == 1
         return buf.view(buf.shape)  # a fresh tensor object aliasing the buffer
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.defer and g.dtype == BF16 and cl_pitch_ok(g[..., ctx.c1:]):
+            _pending_skip[ctx.skip_ptr] = g[..., ctx.c1:]
+            return g[..., :ctx.c1], None, None
         return g[..., :ctx.c1], g[..., ctx.c1:], None
 
 

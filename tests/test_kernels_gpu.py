@@ -120,7 +120,7 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
         ops.set_conv_algo('auto')
 
 
-@pytest.mark.parametrize('cin,shape', [(1, (2, 5, 6, 7)), (2, (1, 9, 8, 10)), (2, (1, 3, 4, 70))])
+@pytest.mark.parametrize('cin,shape', [(1, (2, 5, 6, 7)), (2, (1, 9, 8, 10)), (2, (1, 3, 4, 70)), (2, (2, 4, 5, 16)), (1, (1, 3, 4, 24))])
 def test_stem_im2col_bit_exact(m, cin, shape):
     """X_col[v][tap*Cin + ci] = x[v + tap - 1][ci] (zero outside the volume, zero padding columns): a pure gather."""
     B, D, H, W = shape
