@@ -304,6 +304,13 @@ def main():
                 'per_pass': {k: {'tflops': d['flops'] / (d['ms'] / 1e3) / 1e12, 'ms_per_step': d['ms'],
                                  'launches_per_step': d['launches']} for k, d in conv.items()},
                 'algorithmic_conv_gflop_per_step': conv_flops_per_step(patch, PER_GPU_BATCH, 1 if dual else 2, dual) / 1e9}
+    try:   # DRAM bytes of the step's largest kernel from the committed ncu --set full capture (per launch)
+        tr_ = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
+        roofline['traffic'] = tr_['dram_bytes_per_launch']
+        roofline['traffic_kernel'] = tr_['kernel']
+        roofline['traffic_algorithmic_bytes'] = tr_['algorithmic_bytes_per_launch']
+    except Exception:
+        pass
     line = {'metric': metric, 'value': value, 'unit': 'patches/s', 'n_gpus': n_gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
