@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
 // ------------------------------------------------------------------------------------------------------------
 // backward statistics: g' = dz * (pre > 0 ? 1 : slope);  S1 = sum g',  S2 = sum g' * xhat   per (b,c)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_stats_kernel(
+__global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, long long V, int C, float eps, float slope,
     double* __restrict__ bstats, long long rows_per_block) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_stats_kernel(
 // dy = gamma*rstd*(g' - S1/V - xhat*S2/V); optionally dsum[c] += sum_v dy[v][c] (the bias gradient of the conv in
 // front of the norm -- analytically zero, numerically the rounding noise the reference also produces).
 // Thread = (voxel row r, 8-channel group cg) with rows strided over the block's run, like the statistics kernels.
-__global__ void __launch_bounds__(kStatThreads, 4) inorm_lrelu_bwd_apply_kernel(
+__global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, bf16* __restrict__ dy, int lddy,
     const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
