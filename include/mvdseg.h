@@ -165,6 +165,12 @@ int mvd_skel_update(const float* Ej, const float* Ej1, const float* skel_in, flo
                     int first, int B, int D, int H, int W, mvd_stream_t stream);
 /* pointwise backward of the skeleton recursion for all levels: E/delta/skel are [L][N] stacks (L = iter+1),
  * g_skel [N] in, g_delta [L][N] out */
+/* Fused forward pass over n_levels (1..4) consecutive soft_skel levels j0 .. j0+n-1, all iterations in shared memory:
+ *   E_in = E_j0, skel_in = skeleton after level j0-1 (NULL when j0 == 0);
+ *   E_next[l] (E_{j0+l+1}), delta[l], skel[l]: per-level outputs, each may be NULL except skel[n_levels-1].
+ * Bit-identical to mvd_soft_erode + mvd_skel_update level by level.  (soft_skeleton.py:29-37) */
+int mvd_soft_skel_fused(const float* E_in, const float* skel_in, int n_levels, float* const* E_next,
+                        float* const* delta, float* const* skel, int B, int D, int H, int W, mvd_stream_t stream);
 int mvd_skel_chain_bwd(const float* delta, const float* skel, const float* g_skel, float* g_delta, int L,
                        long long N, mvd_stream_t stream);
 /* gE_j += g_delta_j * [delta_j > 0];  gE_j1 (via dilate backward) -= same   (one level) */

@@ -6,6 +6,7 @@
 //   * relu'(0) = 0
 // Round-1 form: one streaming stencil kernel per level (neighbour taps served by L1/L2; 4 B/voxel of HBM per read
 // or written volume).  The backward scatters with fp32 atomics.
+#include <string.h>
 #include "common.cuh"
 
 namespace mvd {
@@ -192,6 +193,153 @@ __global__ void __launch_bounds__(256) skel_level_bwd_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused forward: up to kSkelMaxLevels levels of soft_skel (soft_skeleton.py:29-37) per launch, all iterations ON CHIP.
+//
+// A CTA owns a 32 x 16 x TZ tile of the volume.  It stages E_j0 for the tile plus a halo of R = n + 1 voxels in shared
+// memory (cells outside the volume hold +inf: min-pooling ignores them; the 3x3x3 max-pool skips them explicitly),
+// then per level l:   B = erode(A)  (7-point cross minimum, every interior cell of the box)
+//                     opened = max27(B); delta = relu(A - opened); skel update          (tile cells only)
+//                     swap(A, B)
+// The halo shrinks by one valid layer per level, so after n levels the tile itself is still exact.  The running
+// skeleton of the tile stays in shared memory.  HBM traffic of a pass: E_j0 (+ skel_in) read once, skel_out (+ the
+// per-level E / delta / skel stacks the backward needs, when asked for) written once -- instead of 7 volume passes per
+// level in the level-by-level form (mvd_soft_erode + mvd_skel_update).  Arithmetic is identical (min / max / the same
+// rounded adds and multiplies), so results are bit-identical to the unfused kernels and to the reference.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSkelMaxLevels = 4, kSkelTX = 32, kSkelTY = 16, kSkelThreads = 512;
+
+struct SkelPass {
+  const float* E_in;                  // E_j0
+  const float* skel_in;               // skeleton after level j0 - 1, NULL when j0 == 0
+  float* E_next[kSkelMaxLevels];      // E_{j0 + l + 1} or NULL
+  float* delta[kSkelMaxLevels];       // delta_{j0 + l} or NULL
+  float* skel[kSkelMaxLevels];        // skeleton after level j0 + l or NULL (the last one is required)
+  int n, TZ;
+  Vol s;
+  int tiles_x, tiles_y, tiles_z;
+};
+
+__global__ void __launch_bounds__(kSkelThreads) skel_fused_kernel(const __grid_constant__ SkelPass P) {
+  extern __shared__ float sk_smem[];
+  const int R = P.n + 1;
+  const int SX = kSkelTX + 2 * R, SY = kSkelTY + 2 * R, SZ = P.TZ + 2 * R;
+  const int SXY = SX * SY, SN = SXY * SZ;
+  float* A = sk_smem;
+  float* Bf = sk_smem + SN;
+  float* SK = sk_smem + 2 * SN;           // running skeleton of the tile [TZ][TY][TX]
+  const float INF = __int_as_float(0x7f800000);
+  int t = blockIdx.x;
+  const int tx = t % P.tiles_x; t /= P.tiles_x;
+  const int ty = t % P.tiles_y; t /= P.tiles_y;
+  const int tz = t % P.tiles_z;
+  const int b = t / P.tiles_z;
+  const int x0 = tx * kSkelTX, y0 = ty * kSkelTY, z0 = tz * P.TZ;
+  const int W = P.s.W, H = P.s.H, D = P.s.D;
+  const long long vol = (long long)D * H * W;
+  const float* src = P.E_in + (long long)b * vol;
+  // box cells inside the volume: [lx, hx) x [ly, hy) x [lz, hz) in box coordinates
+  const int lx = max(0, R - x0), hx = min(SX, W - x0 + R);
+  const int ly = max(0, R - y0), hy = min(SY, H - y0 + R);
+  const int lz = max(0, R - z0), hz = min(SZ, D - z0 + R);
+  const bool touches = (lx > 0) || (ly > 0) || (lz > 0) || (hx < SX) || (hy < SY) || (hz < SZ);
+  // stage the box row by row (one warp per x row: no per-element index arithmetic)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int row = warp; row < SY * SZ; row += nwarps) {
+      const int sy = row % SY, sz = row / SY;
+      const bool row_in = sy >= ly && sy < hy && sz >= lz && sz < hz;
+      const float* grow = src + ((long long)(z0 - R + sz) * H + (y0 - R + sy)) * W + (x0 - R);
+      float* arow = A + row * SX;
+      for (int sx = lane; sx < SX; sx += 32) arow[sx] = (row_in && sx >= lx && sx < hx) ? grow[sx] : INF;
+    }
+  }
+  const int TN = kSkelTX * kSkelTY * P.TZ;
+  if (P.skel_in) {
+    const float* sk_src = P.skel_in + (long long)b * vol;
+    for (int i = threadIdx.x; i < TN; i += kSkelThreads) {
+      const int ix = i % kSkelTX, r = i / kSkelTX;
+      const int iy = r % kSkelTY, iz = r / kSkelTY;
+      const int x = x0 + ix, y = y0 + iy, z = z0 + iz;
+      SK[i] = (x < W && y < H && z < D) ? sk_src[((long long)z * H + y) * W + x] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int l = 0; l < P.n; ++l) {
+    // ---- B = erode(A) on the cells that can still be exact at this level: box shrunk by l + 1 layers.
+    // Each thread walks columns along z with a 3-deep register window (5 shared loads per cell instead of 7).
+    {
+      const int lo = l + 1;
+      const int wx = SX - 2 * lo, wy = SY - 2 * lo, z_lo = lo, z_hi = SZ - lo;   // [z_lo, z_hi)
+      for (int p = threadIdx.x; p < wx * wy; p += kSkelThreads) {
+        const int sx = lo + p % wx, sy = lo + p / wx;
+        const bool col_in = sx >= lx && sx < hx && sy >= ly && sy < hy;
+        int c = z_lo * SXY + sy * SX + sx;
+        float a_prev = A[c - SXY], a_cur = A[c];
+        for (int sz = z_lo; sz < z_hi; ++sz, c += SXY) {
+          const float a_next = A[c + SXY];
+          float m = fminf(fminf(a_cur, fminf(a_prev, a_next)),
+                          fminf(fminf(A[c - 1], A[c + 1]), fminf(A[c - SX], A[c + SX])));
+          if (touches && !(col_in && sz >= lz && sz < hz)) m = INF;
+          Bf[c] = m;
+          a_prev = a_cur;
+          a_cur = a_next;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- tile cells: opened = max27(B) as a sliding maximum along z of in-plane 3x3 maxima (9 loads per cell),
+    // delta, skeleton
+    const bool first = (P.skel_in == nullptr) && (l == 0);
+    float* gE = P.E_next[l] ? P.E_next[l] + (long long)b * vol : nullptr;
+    float* gD = P.delta[l] ? P.delta[l] + (long long)b * vol : nullptr;
+    float* gS = P.skel[l] ? P.skel[l] + (long long)b * vol : nullptr;
+    for (int p = threadIdx.x; p < kSkelTX * kSkelTY; p += kSkelThreads) {
+      const int ix = p % kSkelTX, iy = p / kSkelTX;
+      const int x = x0 + ix, y = y0 + iy;
+      if (x >= W || y >= H) continue;
+      int c = (R - 1) * SXY + (iy + R) * SX + (ix + R);      // plane z = -1 of the tile
+      auto plane_max = [&](int cc) -> float {
+        float m = -INF;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            float v = Bf[cc + dy * SX + dx];
+            if (touches && v == INF) v = -INF;
+            m = fmaxf(m, v);
+          }
+        return m;
+      };
+      float m_prev = plane_max(c), m_cur = plane_max(c + SXY);
+      c += SXY;                                              // plane z = 0
+      const int nz = min(P.TZ, D - z0);
+      for (int iz = 0; iz < nz; ++iz, c += SXY) {
+        const float m_next = plane_max(c + SXY);
+        const float opened = fmaxf(m_cur, fmaxf(m_prev, m_next));
+        m_prev = m_cur;
+        m_cur = m_next;
+        const float delta = fmaxf(A[c] - opened, 0.f);
+        const int i = (iz * kSkelTY + iy) * kSkelTX + ix;
+        float sk;
+        if (first) sk = delta;
+        else {
+          // no FMA contraction: PyTorch rounds skel*delta before the subtraction (soft_skeleton.py:36)
+          const float prev = SK[i];
+          sk = __fadd_rn(prev, fmaxf(__fsub_rn(delta, __fmul_rn(prev, delta)), 0.f));
+        }
+        SK[i] = sk;
+        const long long g = ((long long)(z0 + iz) * H + y) * W + x;
+        if (gE) gE[g] = Bf[c];
+        if (gD) gD[g] = delta;
+        if (gS) gS[g] = sk;
+      }
+    }
+    __syncthreads();
+    float* tmp = A; A = Bf; Bf = tmp;
+  }
+}
+
 static int vol_grid(long long N) { return grid_for(N, 256 * 2, num_sms() * 16); }
 
 }  // namespace mvd
@@ -248,6 +396,46 @@ int mvd_skel_update(const float* Ej, const float* Ej1, const float* skel_in, flo
   skel_update_kernel<<<vol_grid((long long)B * D * H * W), 256, 0, (cudaStream_t)stream>>>(Ej, Ej1, skel_in, delta_out,
                                                                                              skel_out, first, s);
   MVD_LAUNCH_CHECK("skel_update");
+  return MVD_OK;
+}
+
+int mvd_soft_skel_fused(const float* E_in, const float* skel_in, int n_levels, float* const* E_next,
+                        float* const* delta, float* const* skel, int B, int D, int H, int W, mvd_stream_t stream) {
+  MVD_REQUIRE(E_in && E_next && delta && skel && n_levels >= 1 && n_levels <= kSkelMaxLevels,
+              "soft_skel_fused: 1..%d levels per pass", kSkelMaxLevels);
+  VOL_CHECK("soft_skel_fused");
+  MVD_REQUIRE(skel[n_levels - 1] != nullptr, "soft_skel_fused: the last level's skeleton output is required");
+  SkelPass P;
+  memset(&P, 0, sizeof(P));
+  P.E_in = E_in; P.skel_in = skel_in; P.n = n_levels;
+  for (int l = 0; l < n_levels; ++l) { P.E_next[l] = E_next[l]; P.delta[l] = delta[l]; P.skel[l] = skel[l]; }
+  P.s = Vol{B, D, H, W};
+  const int R = n_levels + 1;
+  // deepest tile whose two halo'd boxes + skeleton tile fit in ~200 KB of shared memory
+  int TZ = 16;
+  size_t smem = 0;
+  for (; TZ >= 2; TZ -= 2) {
+    const size_t sn = (size_t)(kSkelTX + 2 * R) * (kSkelTY + 2 * R) * (TZ + 2 * R);
+    smem = (2 * sn + (size_t)kSkelTX * kSkelTY * TZ) * sizeof(float);
+    if (smem <= 200 * 1024) break;
+  }
+  MVD_REQUIRE(TZ >= 2, "soft_skel_fused: tile does not fit shared memory");
+  if (TZ > D) TZ = D;
+  {
+    const size_t sn = (size_t)(kSkelTX + 2 * R) * (kSkelTY + 2 * R) * (TZ + 2 * R);
+    smem = (2 * sn + (size_t)kSkelTX * kSkelTY * TZ) * sizeof(float);
+  }
+  P.TZ = TZ;
+  P.tiles_x = (W + kSkelTX - 1) / kSkelTX; P.tiles_y = (H + kSkelTY - 1) / kSkelTY; P.tiles_z = (D + TZ - 1) / TZ;
+  const long long tiles = (long long)B * P.tiles_x * P.tiles_y * P.tiles_z;
+  MVD_REQUIRE(tiles < (1LL << 31), "soft_skel_fused: too many tiles");
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    MVD_CUDA(cudaFuncSetAttribute(skel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    attr_smem = 204 * 1024;
+  }
+  skel_fused_kernel<<<(unsigned)tiles, kSkelThreads, smem, (cudaStream_t)stream>>>(P);
+  MVD_LAUNCH_CHECK("soft_skel_fused");
   return MVD_OK;
 }
 

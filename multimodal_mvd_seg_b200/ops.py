@@ -794,22 +794,50 @@ class SoftDilateFn(torch.autograd.Function):
         return gin
 
 
+_SKEL_LEVELS_PER_PASS = 4   # levels kept on chip per launch (csrc/softskel.cu: kSkelMaxLevels)
+
+
 def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
-    """runs soft_skel's levels; returns (skel, E stack [L+1], delta stack [L], skel stack [L]) (stacks None if !keep)."""
+    """runs soft_skel's iters + 1 levels with the fused on-chip kernel (<= 4 levels per launch); returns
+    (skel, E stack [L+1], delta stack [L], skel stack [L]) -- the stacks (what the backward needs) only if ``keep``."""
     dims = _vol_dims(img)
     N = img.numel()
     L = iters + 1
     st = _stream()
     dev = img.device
-    E = torch.empty((L + 1, N), dtype=torch.float32, device=dev)
-    E[0].copy_(img.reshape(-1))
-    delta = torch.empty((L, N), dtype=torch.float32, device=dev) if keep else None
-    skel = torch.empty((L, N), dtype=torch.float32, device=dev)
-    for j in range(L):
-        lib.soft_erode(E[j].data_ptr(), E[j + 1].data_ptr(), *dims, st)
-        lib.skel_update(E[j].data_ptr(), E[j + 1].data_ptr(), skel[j - 1].data_ptr() if j > 0 else None,
-                        delta[j].data_ptr() if keep else None, skel[j].data_ptr(), 1 if j == 0 else 0, *dims, st)
-    return skel[L - 1].view(img.shape), (E if keep else None), delta, (skel if keep else None)
+    flat = img.reshape(-1)
+    if keep:
+        E = torch.empty((L + 1, N), dtype=torch.float32, device=dev)
+        E[0].copy_(flat)
+        delta = torch.empty((L, N), dtype=torch.float32, device=dev)
+        skel = torch.empty((L, N), dtype=torch.float32, device=dev)
+    else:
+        E = delta = skel = None
+        tmpE = [torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(2 if L > _SKEL_LEVELS_PER_PASS else 0)]
+        tmpS = [torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(2 if L > _SKEL_LEVELS_PER_PASS else 1)]
+    PtrArr = ctypes.c_void_p * _SKEL_LEVELS_PER_PASS
+    e_in, s_in, last = (E[0] if keep else flat), None, None
+    for pi, j0 in enumerate(range(0, L, _SKEL_LEVELS_PER_PASS)):
+        n = min(_SKEL_LEVELS_PER_PASS, L - j0)
+        more = j0 + n < L
+        en, dl, sk = PtrArr(), PtrArr(), PtrArr()
+        e_out = None
+        for l in range(n):
+            if keep:
+                en[l], dl[l], sk[l] = E[j0 + l + 1].data_ptr(), delta[j0 + l].data_ptr(), skel[j0 + l].data_ptr()
+            elif l == n - 1:
+                last = tmpS[pi % len(tmpS)]
+                sk[l] = last.data_ptr()
+                if more:
+                    e_out = tmpE[pi % 2]
+                    en[l] = e_out.data_ptr()
+        lib.soft_skel_fused(e_in.data_ptr(), _ptr(s_in), n, en, dl, sk, *dims, st)
+        if keep:
+            e_in, s_in = E[j0 + n], skel[j0 + n - 1]
+        else:
+            e_in, s_in = e_out, last
+    out = skel[L - 1] if keep else last
+    return out.view(img.shape), E, delta, skel
 
 
 def _skel_backward(g_skel: torch.Tensor, E, delta, skel, dims):

@@ -78,3 +78,11 @@ dlt = [torch.empty_like(aa[0]) for _ in range(NSETS)]
 ns = aa[0].numel()
 report('soft_erode (2x160x160x96 fp32)', timeit(lambda i: lib.soft_erode(aa[i].data_ptr(), bb[i].data_ptr(), Bs, Ds, Hs, Ws, st)), ns * 8)
 report('skel_update (dilate+delta+skel)', timeit(lambda i: lib.skel_update(aa[i].data_ptr(), bb[i].data_ptr(), sk[i].data_ptr(), dlt[i].data_ptr(), sk[i].data_ptr(), 0, Bs, Ds, Hs, Ws, st)), ns * 20)
+import ctypes
+from multimodal_mvd_seg_b200 import ops
+for it in (3, 10):
+    L = it + 1
+    ms = timeit(lambda i: ops._skel_forward(aa[i].unsqueeze(1), it, False), iters=8)
+    report(f'soft_skel fused fwd, iter_={it} (no stacks)', ms, ns * 8)
+    ms = timeit(lambda i: ops._skel_forward(aa[i].unsqueeze(1), it, True), iters=8)
+    report(f'soft_skel fused fwd, iter_={it} (+E/delta/skel stacks)', ms, ns * 4 * (2 + 3 * L))

@@ -352,6 +352,28 @@ def test_soft_skel_golden(m, golden_skel, vol, it):
     np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{vol}.soft_skel{it}.grad'], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize('shape,it', [((2, 37, 21, 45), 3), ((1, 9, 40, 70), 10), ((1, 3, 5, 4), 6)])
+def test_soft_skel_fused_equals_level_by_level(m, shape, it):
+    """the on-chip multi-level kernel (<= 4 levels per launch, tiles with halos, volume borders) against the
+    level-by-level kernels (mvd_soft_erode + mvd_skel_update): bit-identical skeleton, E, delta and skeleton stacks."""
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(shape, generator=g).to(dev())
+    x[x < 0.3] = 0.0            # plateaus -> ties
+    B, D, H, W = shape
+    N, L, st = x.numel(), it + 1, torch.cuda.current_stream().cuda_stream
+    x5 = x.unsqueeze(1)
+    sk, E, delta, skel = m.ops._skel_forward(x5, it, True)
+    sk2, _, _, _ = m.ops._skel_forward(x5, it, False)
+    Er = torch.empty((L + 1, N), device=dev()); Er[0] = x.reshape(-1)
+    dr = torch.empty((L, N), device=dev()); sr = torch.empty((L, N), device=dev())
+    for j in range(L):
+        m.lib.soft_erode(Er[j].data_ptr(), Er[j + 1].data_ptr(), B, D, H, W, st)
+        m.lib.skel_update(Er[j].data_ptr(), Er[j + 1].data_ptr(), sr[j - 1].data_ptr() if j else None,
+                          dr[j].data_ptr(), sr[j].data_ptr(), 1 if j == 0 else 0, B, D, H, W, st)
+    assert torch.equal(E, Er) and torch.equal(delta, dr) and torch.equal(skel, sr)
+    assert torch.equal(sk.reshape(-1), sr[L - 1]) and torch.equal(sk2.reshape(-1), sr[L - 1])
+
+
 @pytest.mark.parametrize('it', [3, 10])
 def test_soft_cldice_matches_oracle(m, it):
     import oracle
