@@ -488,6 +488,40 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   memset(&P, 0, sizeof(P));
   P.n_tile = pick_n_tile(N);
   if (P.n_tile == 0 || K % 32 || N > kMaxN) { set_error("%s: unsupported channel counts", who); return MVD_ERR_UNSUPPORTED; }
+  // Low-resolution layers have too few (brick, N-tile) work items for 148 SMs with the widest N tile: pick the tile
+  // width that minimises  waves x planes-per-item x cycles-per-MMA  (MMA M128 x n x K16 = max(n/2, 32 + n/4) cycles),
+  // keeping the widest tile unless a narrower one is predicted >= 20 % faster.  Fused statistics need n_tile == N.
+  int mt_cap = 4;
+  if (!stats && N > 64) {   // N <= 64 belongs to the depth-folded kernel below
+    // per channel chunk: MMA cycles vs TMA box rows (3.7 cycles each) of one work item; whole launch = waves x that
+    auto predicted = [&](int nt, int mt) -> double {
+      const long long items = (long long)B * cdiv(D, mt) * cdiv(H, TILE_H) * cdiv(W, TILE_W) * (N / nt);
+      const long long waves = (items + num_sms() - 1) / num_sms();
+      const int mma = (nt / 2 > 32 + nt / 4) ? nt / 2 : 32 + nt / 4;
+      const double t_mma = 27.0 * mt * (kc / 16) * mma;
+      const double t_tma = 3.7 * (mt + 2) * PLANE_ROWS + 1.8 * 27.0 * nt;   // dense weight rows stream faster
+      // + a fixed ~8k cycles per wave: pipeline fill, first-plane latency, epilogue drain of a short item
+      return (double)waves * ((t_mma > t_tma ? t_mma : t_tma) * (K / kc) + 8000.0);
+    };
+    auto mt_max = [&](int nt) {
+      int mt = 512 / (2 * nt);
+      if (mt > 4) mt = 4;
+      if (mt > D) mt = D;
+      if (mt == 3) mt = 2;
+      return mt < 1 ? 1 : mt;
+    };
+    double best = predicted(P.n_tile, mt_max(P.n_tile));
+    mt_cap = mt_max(P.n_tile);
+    const int nt0 = P.n_tile;
+    for (int nt = nt0; nt >= 32; nt -= 32) {
+      if (N % nt) continue;
+      for (int mt = mt_max(nt); mt >= 1; mt >>= 1) {
+        if (nt == nt0 && mt == mt_max(nt0)) continue;
+        const double c = predicted(nt, mt);
+        if (c < 0.8 * best) { best = c; P.n_tile = nt; mt_cap = mt; }
+      }
+    }
+  }
   if (stats && N != 32 && N != 64) { set_error("%s: fused InstanceNorm sums need N = 32 or 64", who); return MVD_ERR_UNSUPPORTED; }
   {
     const long long ld = lds;
@@ -569,6 +603,7 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   // MT: as many output planes per item as TMEM (2 x MT x n_tile <= 512 columns) and shared memory allow, at most 4
   int MT = 512 / (2 * P.n_tile);
   if (MT > 4) MT = 4;
+  if (MT > mt_cap) MT = mt_cap;
   if (MT > D) MT = D;
   if (MT == 3) MT = 2;
   if (MT < 1) MT = 1;
