@@ -494,6 +494,7 @@ bool tc_dgrad_supported(const mvd_conv3d_args* a) {
 }
 
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
+  if (tc_subpixel_dgrad_supported(a)) return tc_subpixel_dgrad(a, st);
   if (is_k3s1p1(a) && tc_halo_enabled()) {
     int wrow[27];   // produced voxel i gathers y[i + 1 - t]: halo offset o = 2 - t per axis, i.e. tap 26 - idx
     for (int i = 0; i < 27; ++i) wrow[i] = (26 - i) * a->Cin;

@@ -64,6 +64,9 @@ CONV_CASES = [
     (1, 32, 64, (5, 6, 7), 3, (1, 1, 1)),
     (2, 32, 32, (19, 8, 16), 3, (1, 1, 1)),
     (1, 32, 32, (3, 20, 9), 3, (1, 1, 1)),
+    # sub-pixel strided dgrad (Cin = 32, Cout = 64, s = 2): odd extents, several bricks, depth runs with tails
+    (2, 32, 64, (9, 14, 18), 3, (2, 2, 2)),
+    (1, 32, 64, (22, 34, 16), 3, (2, 2, 2)),
 ]
 
 
