@@ -43,7 +43,7 @@ constexpr int kMaxTaps = 27;
 constexpr int kMaxMaps = 8;
 constexpr int kMaxClasses = 8;
 constexpr int TILE_W = 8, TILE_H = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kMaxBias = 1024;   // produced channels a bias vector is staged for
 
 struct TcTap {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) uint8_t s_stage[4][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
+  __shared__ __align__(16) uint8_t s_stage[8][2048];   // per epilogue warp: 32 rows x 64 B transpose buffer
   __shared__ __align__(16) float s_bias[kMaxBias];     // bias rounded to bf16 (zero when absent), indexed by channel
 
   // dynamic smem may only be 16-byte aligned by the runtime: align by hand (host adds 1 KB of slack)
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bar_tfull[a], 1);
-      mbar_init(&bar_tempty[a], 4);
+      mbar_init(&bar_tempty[a], 8);
     }
     fence_barrier_init();
   }
@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     auto run_epilogue = [&](auto sc_tag) {
       constexpr int SC = decltype(sc_tag)::value;
       const int q = warp & 3;  // the TMEM lane quarter this warp may access
+      const int half = (warp - 2) >> 2;   // the two warps of a quarter take alternating 32-column chunks
+      uint8_t* stage = s_stage[warp - 2];
       int acc = 0;
       uint32_t accphase = 0;
       LaneStats<SC> st;
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const bool accum = P.accumulate != 0;
         bf16x8 old[4];
         bool has[4] = {false, false, false, false};
-        if (accum) {   // old values of the first chunk fly while the MMAs of this tile finish
-          const long long co0 = col_offset(0);
+        if (accum && 32 * half < P.n_tile) {   // old values of the first chunk fly while the MMAs of this tile finish
+          const long long co0 = col_offset(32 * half);
           prefetch_rows(lane, [&](int R) { return row_ptr_at(R, co0); }, old, has);
         }
         mbar_wait(&bar_tfull[acc], accphase, 4);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
         const int rr0 = q * 32 + lane;
         const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
-        for (int cc = 0; cc < P.n_tile; cc += 32) {
+        for (int cc = 32 * half; cc < P.n_tile; cc += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
           tmem_ld_wait();
@@ -265,13 +267,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             bool chas[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { cur[i] = old[i]; chas[i] = has[i]; }
-            if (cc + 32 < P.n_tile) {   // next chunk's old values
-              const long long con = col_offset(cc + 32);
+            if (cc + 64 < P.n_tile) {   // next chunk's old values
+              const long long con = col_offset(cc + 64);
               prefetch_rows(lane, [&](int R) { return row_ptr_at(R, con); }, old, has);
             }
-            store_rows_accumulate_packed(s_stage[q], lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, cur, chas);
+            store_rows_accumulate_packed(stage, lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, cur, chas);
           } else {
-            store_rows_coalesced_packed(s_stage[q], lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, false);
+            store_rows_coalesced_packed(stage, lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, false);
           }
         }
         tcgen05_fence_before();
@@ -347,7 +349,7 @@ int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* wh
   if (P.nbias > kMaxBias) { set_error("%s: more than %d produced channels", who, kMaxBias); return MVD_ERR_UNSUPPORTED; }
   const int a_bytes = 128 * kc * 2, b_bytes = P.n_tile * kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (192 * 1024) / stage_bytes;   // + 21 KB of static shared memory (epilogue stages, bias)
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("%s: tile does not fit shared memory", who); return MVD_ERR_UNSUPPORTED; }
   P.stages = stages;
