@@ -77,6 +77,17 @@ typedef struct {
   int accumulate;             /* dgrad: add into the output instead of overwriting it                       */
 } mvd_conv3d_args;
 
+/* The stem (first conv: Cin = 1 or 2 modalities -> 32 features, 3x3x3, stride 1, pad 1) as a tensor-core GEMM whose
+ * im2col tile is built in shared memory (csrc/stem_tc.cu); replaces nn.Conv3d(Cin, 32, 3, padding=1) of
+ * get_network_from_plans.py:75-77 for the first block.
+ *   x     : DENSE bf16 NDHWC input [B][D][H][W][Cin]
+ *   wcol  : bf16 [32][KPAD], KPAD = 32*Cin, column k = tap*Cin + ci (tap = (kd*3 + kh)*3 + kw), zero padded
+ *   fprop : y (pitch ldy) = conv + bias (bf16), optional InstanceNorm sums stats [B][32][2] accumulated
+ *   wgrad : dw_col fp32 [32][KPAD] = sum_v dy[v][co] * col[v][k] (overwritten) */
+int mvd_stem_conv_fprop(const void* x, int B, int D, int H, int W, int Cin, const void* wcol, const float* bias,
+                        void* y, int ldy, double* stats, mvd_stream_t stream);
+int mvd_stem_conv_wgrad(const void* x, int B, int D, int H, int W, int Cin, const void* dy, int lddy, float* dw_col,
+                        mvd_stream_t stream);
 /* pack fp32 torch-layout weights [Cout][Cin][kd][kh][kw] into the two bf16 GEMM layouts:
  *   w_fprop [tap][Cout][Cin]  (B operand of fprop:  N = Cout rows, K = Cin contiguous)
  *   w_dgrad [tap][Cin][Cout]  (B operand of dgrad:  N = Cin rows,  K = Cout contiguous)

@@ -127,6 +127,15 @@ class ConvGeom:
         return tuple((i + 2 * p - k) // s + 1 for i, k, s, p in zip(in_size, self.k, self.s, self.p))
 
 
+_stem_mode = 'fused'   # 'im2col' selects the explicit X_col form (csrc/stem.cu); test / A-B hook
+
+
+def set_stem_mode(mode: str):
+    global _stem_mode
+    assert mode in ('fused', 'im2col')
+    _stem_mode = mode
+
+
 _ALGO = {'auto': 0, 'generic': 1, 'tc': 2}
 _default_algo = 0
 
@@ -423,22 +432,30 @@ class ConvNormActFn(torch.autograd.Function):
         y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
         stats = zeros((B, Cout, 2), torch.float64, dev)
         V = Do * Ho * Wo
-        # stem (1-2 input modalities): explicit im2col + single-tap tensor-core GEMM (csrc/stem.cu)
+        # stem (1-2 input modalities): tensor-core GEMM over an im2col tile built in shared memory (csrc/stem_tc.cu);
+        # other thin stems: explicit im2col + single-tap tensor-core GEMM (csrc/stem.cu)
         stem = (Cin <= 4 and not need_dx and geom.s == (1, 1, 1) and Cout % 32 == 0 and _default_algo != 1)
-        ctx.stem = stem
+        fused_stem = (stem and Cin in (1, 2) and Cout == 32 and geom.k == (3, 3, 3) and geom.p == (1, 1, 1)
+                      and cl_pitch(x_cl) == Cin and x_cl.data_ptr() % 4 == 0 and _stem_mode != 'im2col')
+        ctx.stem, ctx.fused_stem = stem, fused_stem
         if stem:
             taps = geom.k[0] * geom.k[1] * geom.k[2]
-            kpad = 32 if taps * Cin <= 32 else 64
+            kpad = 32 * Cin if fused_stem else (32 if taps * Cin <= 32 else 64)
             assert taps * Cin <= kpad
-            x_col = torch.empty((B, Di, Hi, Wi, kpad), dtype=BF16, device=dev)
-            lib.im2col_small(x_cl.data_ptr(), cl_pitch(x_cl), B, Di, Hi, Wi, Cin, *geom.k, *geom.p, x_col.data_ptr(),
-                             kpad, _stream())
             # [Cout][Cin][taps] -> [1 tap][Cout][(tap, ci) zero-padded]: a 1.7k-element reshuffle, host-side plumbing
             wcol = torch.zeros((1, Cout, kpad), dtype=BF16, device=dev)
             wcol[0, :, :taps * Cin] = weight.detach().reshape(Cout, Cin, taps).permute(0, 2, 1).reshape(Cout, taps * Cin)
-            g1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
-            conv_fprop(g1, x_col, y, wcol, bias=bias, stats=stats)
-            x_cl, wd, geom = x_col, None, g1
+            if fused_stem:
+                lib.stem_conv_fprop(x_cl.data_ptr(), B, Di, Hi, Wi, Cin, wcol.data_ptr(), _ptr(bias), y.data_ptr(),
+                                    cl_pitch(y), stats.data_ptr(), _stream())
+                wd = None
+            else:
+                x_col = torch.empty((B, Di, Hi, Wi, kpad), dtype=BF16, device=dev)
+                lib.im2col_small(x_cl.data_ptr(), cl_pitch(x_cl), B, Di, Hi, Wi, Cin, *geom.k, *geom.p,
+                                 x_col.data_ptr(), kpad, _stream())
+                g1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
+                conv_fprop(g1, x_col, y, wcol, bias=bias, stats=stats)
+                x_cl, wd, geom = x_col, None, g1
         else:
             wf, wd = _packed_for(weight, True, need_dx)
             conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
@@ -475,9 +492,14 @@ class ConvNormActFn(torch.autograd.Function):
         if dw is not None:
             if ctx.stem:
                 Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
-                kpad = x_cl.shape[-1]
+                kpad = 32 * Cin_w if ctx.fused_stem else x_cl.shape[-1]
                 dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
-                conv_wgrad(geom, x_cl, dy, dw_col, None)
+                if ctx.fused_stem:
+                    Bx, Dx, Hx, Wx, _ = x_cl.shape
+                    lib.stem_conv_wgrad(x_cl.data_ptr(), Bx, Dx, Hx, Wx, Cin_w, dy.data_ptr(), cl_pitch(dy),
+                                        dw_col.data_ptr(), st)
+                else:
+                    conv_wgrad(geom, x_cl, dy, dw_col, None)
                 dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
                          .reshape(weight.shape))
             else:

@@ -143,6 +143,39 @@ def test_stem_im2col_bit_exact(m, cin, shape):
     assert torch.equal(col.float(), want)
 
 
+@pytest.mark.parametrize('mode', ['fused', 'im2col'])
+@pytest.mark.parametrize('cin,shape', [(2, (2, 9, 20, 13)), (1, (1, 6, 17, 24)), (2, (1, 3, 16, 8))])
+def test_stem_block_matches_torch(m, mode, cin, shape):
+    """first block (Conv3d(cin, 32, 3, padding=1) + InstanceNorm + LeakyReLU): tensor-core GEMM over the in-smem im2col
+    tile (and the explicit X_col form) against torch, forward and all parameter gradients."""
+    ops = m.ops
+    ops.set_stem_mode(mode)
+    try:
+        B, D, H, W = shape
+        x = rand_cl((B, D, H, W, cin), 41)
+        w = (torch.randn(32, cin, 3, 3, 3) / np.sqrt(27 * cin)).to(dev()).requires_grad_(True)
+        b = (torch.randn(32) * 0.1).to(dev()).requires_grad_(True)
+        gam = (1 + 0.1 * torch.randn(32)).to(dev()).requires_grad_(True)
+        bet = (0.1 * torch.randn(32)).to(dev()).requires_grad_(True)
+        geom = ops.ConvGeom((3, 3, 3), (1, 1, 1), (1, 1, 1))
+        z = ops.ConvNormActFn.apply(x, w, b, gam, bet, geom, 1e-5, 0.01, None, None)
+        xr = x.float().permute(0, 4, 1, 2, 3)
+        wr = w.detach().to(BF).float().requires_grad_(True)
+        br = b.detach().to(BF).float().requires_grad_(True)
+        gr = gam.detach().clone().requires_grad_(True)
+        ber = bet.detach().clone().requires_grad_(True)
+        yr = F.conv3d(xr, wr, br, padding=1).to(BF).float()
+        zr = F.leaky_relu(F.instance_norm(yr, weight=gr, bias=ber, eps=1e-5), 0.01)
+        assert rel_err(z.float().permute(0, 4, 1, 2, 3), zr) < 1e-2
+        g = rand_cl(tuple(z.shape), 42)
+        z.backward(g)
+        zr.backward(g.float().permute(0, 4, 1, 2, 3))
+        assert rel_err(w.grad, wr.grad) < 2e-2
+        assert rel_err(gam.grad, gr.grad) < 2e-2 and rel_err(bet.grad, ber.grad) < 2e-2
+    finally:
+        ops.set_stem_mode('fused')
+
+
 @pytest.mark.parametrize('stride', [(2, 2, 2), (2, 2, 1)])
 @pytest.mark.parametrize('cin,cout', [(64, 32), (320, 320), (48, 24)])
 def test_conv_transpose(m, stride, cin, cout):
