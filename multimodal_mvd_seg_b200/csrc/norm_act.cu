@@ -4,6 +4,7 @@
 //
 // Reference ops replaced: nn.InstanceNorm3d(eps=1e-5, affine=True) + nn.LeakyReLU(inplace=True)
 // (nnunetv2/utilities/get_network_from_plans.py:41-44) and their autograd.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mvd {
@@ -49,9 +50,15 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, int ld, floa
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kStatThreads = 256;
 
+// Sweep direction.  Every streaming kernel walks the volume in BANDS (all blocks side by side, band after band).
+// Experiment (round 1): sweeping a tensor the previous kernel has just written BACK TO FRONT (rev = 1), so that the part
+// still resident in the 126 MB L2 is met first, was measured in the cfg-2 step and changed nothing (bwd_apply 0.973 vs
+// 0.976 ms, bwd_stats 0.818 vs 0.826 ms, fwd 0.663 vs 0.648 ms per step) -- it stays available behind MVD_SWEEP_REV=1.
+__device__ __forceinline__ long long sweep_row(long long v, long long V, int rev) { return rev ? (V - 1 - v) : v; }
+
 __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* __restrict__ y, int ld, long long V,
                                                                    int C, double* __restrict__ stats,
-                                                                   long long rows_per_block) {
+                                                                   int rev) {
   extern __shared__ float sm[];  // [rows][CG*8][2]
   const int b = blockIdx.y;
   const int CG = C >> 3;
@@ -59,18 +66,17 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
   const int tid = threadIdx.x;
   const int cg = tid % CG, r = tid / CG;
   const bf16* base = y + (long long)b * V * ld;
-  long long v0 = (long long)blockIdx.x * rows_per_block;
-  long long v1 = v0 + rows_per_block;
-  if (v1 > V) v1 = V;
+  const long long step = (long long)gridDim.x * rows;   // band sweep: iteration i covers rows [i*step, (i+1)*step)
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows) {
-    long long v = v0 + r;
-    for (; v + 3LL * rows < v1; v += 4LL * rows) {   // four independent 16-byte loads in flight per thread
+    long long v = (long long)blockIdx.x * rows + r;
+    for (; v + 3 * step < V; v += 4 * step) {   // four independent 16-byte loads in flight per thread
       bf16x8 p[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const bf16x8*>(base + (v + (long long)u * rows) * ld + cg * 8);
+      for (int u = 0; u < 4; ++u)
+        p[u] = *reinterpret_cast<const bf16x8*>(base + sweep_row(v + u * step, V, rev) * ld + cg * 8);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -82,8 +88,8 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
         }
       }
     }
-    for (; v < v1; v += rows) {
-      bf16x8 p = *reinterpret_cast<const bf16x8*>(base + v * ld + cg * 8);
+    for (; v < V; v += step) {
+      bf16x8 p = *reinterpret_cast<const bf16x8*>(base + sweep_row(v, V, rev) * ld + cg * 8);
       float f[8];
       unpack8(p, f);
 #pragma unroll
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
                                                               const double* __restrict__ stats,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, long long V, int C,
-                                                              float eps, float slope) {
+                                                              float eps, float slope, int rev) {
   extern __shared__ float sm[];
   float* sc = sm;
   float* sh = sm + C;
@@ -174,11 +180,15 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
   for (; v + 3 * step < V; v += 4 * step) {
     bf16x8 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const bf16x8*>(yb + (v + u * step) * ldy + cg * 8);
+    for (int u = 0; u < 4; ++u)
+      p[u] = *reinterpret_cast<const bf16x8*>(yb + sweep_row(v + u * step, V, rev) * ldy + cg * 8);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(p[u], v + u * step);
+    for (int u = 0; u < 4; ++u) body(p[u], sweep_row(v + u * step, V, rev));
   }
-  for (; v < V; v += step) body(*reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8), v);
+  for (; v < V; v += step) {
+    const long long w = sweep_row(v, V, rev);
+    body(*reinterpret_cast<const bf16x8*>(yb + w * ldy + cg * 8), w);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
 __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, long long V, int C, float eps, float slope,
-    double* __restrict__ bstats, long long rows_per_block) {
+    double* __restrict__ bstats, int rev) {
   extern __shared__ float sm[];
   const int b = blockIdx.y;
   const int CG = C >> 3;
@@ -203,9 +213,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
   const int cg = tid % CG, r = tid / CG;
   const bf16* yb = y + (long long)b * V * ldy;
   const bf16* gb = dz + (long long)b * V * lddz;
-  long long v0 = (long long)blockIdx.x * rows_per_block;
-  long long v1 = v0 + rows_per_block;
-  if (v1 > V) v1 = V;
+  const long long step = (long long)gridDim.x * rows;
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -234,18 +242,20 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
         s2[k] = fmaf(gp, xh, s2[k]);
       }
     };
-    long long v = v0 + r;
-    for (; v + (long long)rows < v1; v += 2LL * rows) {   // four independent 16-byte loads in flight per thread
-      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
-      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + (v + rows) * ldy + cg * 8);
-      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + (v + rows) * lddz + cg * 8);
+    long long v = (long long)blockIdx.x * rows + r;
+    for (; v + step < V; v += 2 * step) {   // four independent 16-byte loads in flight per thread
+      const long long w0 = sweep_row(v, V, rev), w1 = sweep_row(v + step, V, rev);
+      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
+      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
+      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + w1 * ldy + cg * 8);
+      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + w1 * lddz + cg * 8);
       body(py0, pg0);
       body(py1, pg1);
     }
-    for (; v < v1; v += rows) {
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
+    for (; v < V; v += step) {
+      const long long w0 = sweep_row(v, V, rev);
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
       body(py, pg);
     }
   }
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, bf16* __restrict__ dy, int lddy,
     const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, float* __restrict__ dsum, long long rows_per_block) {
+    float* __restrict__ dbeta, float* __restrict__ dsum, int rev) {
   extern __shared__ float sm[];
   const int b = blockIdx.y;
   float* sc = sm;
@@ -310,9 +320,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
   const bf16* yb = y + (long long)b * V * ldy;
   const bf16* gb = dz + (long long)b * V * lddz;
   bf16* ob = dy + (long long)b * V * lddy;
-  long long v0 = (long long)blockIdx.x * rows_per_block;
-  long long v1 = v0 + rows_per_block;
-  if (v1 > V) v1 = V;
+  const long long step = (long long)gridDim.x * rows;
   float s[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.f;
@@ -346,19 +354,21 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
         for (int k = 0; k < 8; ++k) s[k] += o[k];
       }
     };
-    long long v = v0 + r;
-    for (; v + (long long)rows < v1; v += 2LL * rows) {
-      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
-      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + (v + rows) * ldy + cg * 8);
-      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + (v + rows) * lddz + cg * 8);
-      body(py0, pg0, v);
-      body(py1, pg1, v + rows);
+    long long v = (long long)blockIdx.x * rows + r;
+    for (; v + step < V; v += 2 * step) {
+      const long long w0 = sweep_row(v, V, rev), w1 = sweep_row(v + step, V, rev);
+      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
+      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
+      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + w1 * ldy + cg * 8);
+      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + w1 * lddz + cg * 8);
+      body(py0, pg0, w0);
+      body(py1, pg1, w1);
     }
-    for (; v < v1; v += rows) {
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + v * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + v * lddz + cg * 8);
-      body(py, pg, v);
+    for (; v < V; v += step) {
+      const long long w0 = sweep_row(v, V, rev);
+      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
+      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
+      body(py, pg, w0);
     }
   }
   if (dsum) {
@@ -410,6 +420,16 @@ static long long one_wave(K kernel, int threads, size_t smem, int B, long long V
   return (V + r - 1) / r;
 }
 
+// MVD_SWEEP_REV=1 turns the back-to-front sweeps on (experiment switch; default: every kernel sweeps front to back)
+static int sweep_rev(int want) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MVD_SWEEP_REV");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on ? want : 0;
+}
+
 static bool vec_ok(const void* p, int ld, int C) {
   return (C % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
@@ -452,7 +472,7 @@ int mvd_inorm_stats(const void* y, int ldy, int B, long long V, int C, double* s
   long long rpb;
   const long long nblk = one_wave(inorm_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 4, &rpb);
   dim3 grid((unsigned)nblk, B);
-  inorm_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, V, C, stats, rpb);
+  inorm_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>((const bf16*)y, ldy, V, C, stats, sweep_rev(1));
   MVD_LAUNCH_CHECK("inorm_stats");
   return MVD_OK;
 }
@@ -467,7 +487,7 @@ int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* 
   const long long nblk = one_wave(inorm_lrelu_fwd_kernel, 256, 2 * C * sizeof(float), B, V, (long long)frows * 4, &rpb);
   dim3 grid((unsigned)nblk, B);
   inorm_lrelu_fwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)y, ldy, (bf16*)z, ldz, stats, gamma, beta, V, C, eps, slope);
+      (const bf16*)y, ldy, (bf16*)z, ldz, stats, gamma, beta, V, C, eps, slope, sweep_rev(1));
   MVD_LAUNCH_CHECK("inorm_lrelu_fwd");
   return MVD_OK;
 }
@@ -483,7 +503,7 @@ int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, 
   const long long nblk = one_wave(inorm_lrelu_bwd_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 2, &rpb);
   dim3 grid((unsigned)nblk, B);
   inorm_lrelu_bwd_stats_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(
-      (const bf16*)dz, lddz, (const bf16*)y, ldy, stats, gamma, beta, V, C, eps, slope, bstats, rpb);
+      (const bf16*)dz, lddz, (const bf16*)y, ldy, stats, gamma, beta, V, C, eps, slope, bstats, sweep_rev(1));
   MVD_LAUNCH_CHECK("inorm_lrelu_bwd_stats");
   return MVD_OK;
 }
@@ -502,7 +522,7 @@ int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, 
   dim3 grid((unsigned)nblk, B);
   inorm_lrelu_bwd_apply_kernel<<<grid, kStatThreads, 7 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dz, lddz, (const bf16*)y, ldy, (bf16*)dy, lddy, stats, bstats, gamma, beta, B, V, C, eps, slope,
-      dgamma, dbeta, dsum, rpb);
+      dgamma, dbeta, dsum, sweep_rev(0));
   MVD_LAUNCH_CHECK("inorm_lrelu_bwd_apply");
   return MVD_OK;
 }

@@ -298,6 +298,18 @@ def _timed(kind, a: ConvArgs, fn):
     _conv_timer.records.append((kind, flops, e0, e1, tag))
 
 
+def _timed_call(kind, flops, tag, fn):
+    """same bracket for conv launches that do not go through mvd_conv3d_* (the fused stem)."""
+    if _conv_timer is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    _conv_timer.records.append((kind, flops, e0, e1, tag))
+
+
 def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None):
     a = _conv_args(geom, x_cl, y_cl, w_packed=wf, bias=bias, stats=stats)
     _timed('fprop', a, lib.conv3d_fprop)
@@ -446,8 +458,9 @@ class ConvNormActFn(torch.autograd.Function):
             wcol = torch.zeros((1, Cout, kpad), dtype=BF16, device=dev)
             wcol[0, :, :taps * Cin] = weight.detach().reshape(Cout, Cin, taps).permute(0, 2, 1).reshape(Cout, taps * Cin)
             if fused_stem:
-                lib.stem_conv_fprop(x_cl.data_ptr(), B, Di, Hi, Wi, Cin, wcol.data_ptr(), _ptr(bias), y.data_ptr(),
-                                    cl_pitch(y), stats.data_ptr(), _stream())
+                _timed_call('fprop', 2.0 * B * V * Cout * Cin * taps, f'stem {Cin}->{Cout} k333 out{Do}x{Ho}x{Wo}',
+                            lambda: lib.stem_conv_fprop(x_cl.data_ptr(), B, Di, Hi, Wi, Cin, wcol.data_ptr(), _ptr(bias),
+                                                        y.data_ptr(), cl_pitch(y), stats.data_ptr(), _stream()))
                 wd = None
             else:
                 x_col = torch.empty((B, Di, Hi, Wi, kpad), dtype=BF16, device=dev)
@@ -496,8 +509,10 @@ class ConvNormActFn(torch.autograd.Function):
                 dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
                 if ctx.fused_stem:
                     Bx, Dx, Hx, Wx, _ = x_cl.shape
-                    lib.stem_conv_wgrad(x_cl.data_ptr(), Bx, Dx, Hx, Wx, Cin_w, dy.data_ptr(), cl_pitch(dy),
-                                        dw_col.data_ptr(), st)
+                    _timed_call('wgrad', 2.0 * Bx * Dx * Hx * Wx * Cout * Cin_w * taps,
+                                f'stem {Cin_w}->{Cout} k333 out{Dx}x{Hx}x{Wx}',
+                                lambda: lib.stem_conv_wgrad(x_cl.data_ptr(), Bx, Dx, Hx, Wx, Cin_w, dy.data_ptr(),
+                                                            cl_pitch(dy), dw_col.data_ptr(), st))
                 else:
                     conv_wgrad(geom, x_cl, dy, dw_col, None)
                 dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
