@@ -77,6 +77,12 @@ typedef struct {
   int accumulate;             /* dgrad: add into the output instead of overwriting it                       */
 } mvd_conv3d_args;
 
+/* Sliding-window inference accumulators (inference/predict_from_raw_data.py:703-712):
+ *   acc[k][z0+z][y0+y][x0+x] += pred[z][y][x][k] * scale * g[z][y][x];  npred[...] += g  (g = 1 when gaussian == NULL;
+ *   npred may be NULL).  pred: bf16 NDHWC tile [d][h][w][K] with voxel pitch ldp; acc fp32 [K][D][H][W]; npred fp32. */
+int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float scale, float* acc, float* npred, int K,
+                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, mvd_stream_t stream);
+int mvd_sw_finalize(float* acc, const float* npred, int K, long long vol, mvd_stream_t stream);   /* acc /= npred */
 /* The stem (first conv: Cin = 1 or 2 modalities -> 32 features, 3x3x3, stride 1, pad 1) as a tensor-core GEMM whose
  * im2col tile is built in shared memory (csrc/stem_tc.cu); replaces nn.Conv3d(Cin, 32, 3, padding=1) of
  * get_network_from_plans.py:75-77 for the first block.

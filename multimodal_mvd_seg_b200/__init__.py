@@ -14,3 +14,4 @@ from .ddp import GradArena, split_batch_for_rank
 from .trainer import nnUNetTrainer, MVDTrainer, make_plans, PlansManager, ConfigurationManager, LabelManager
 
 __version__ = '0.1.0'
+from .inference import SlidingWindowPredictor, compute_gaussian, compute_steps_for_sliding_window

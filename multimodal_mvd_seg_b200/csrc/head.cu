@@ -332,6 +332,42 @@ static int head_bwd_launch(const bf16* dl, int ldl, const bf16* z, int ldz, cons
   return MVD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Sliding-window inference (inference/predict_from_raw_data.py:703-712): one tile's logits, weighted by the Gaussian
+// importance map, are added into the full-volume accumulators
+//     acc[k][z0+z][y0+y][x0+x] += pred[z][y][x][k] * g[z][y][x];   npred[z0+z][y0+y][x0+x] += g[z][y][x]
+// (g = 1 when no map is given).  pred is the network's bf16 NDHWC output; acc / npred are fp32 (the reference keeps
+// them in fp16: fp32 accumulation is the more accurate superset).  One thread per tile voxel, x fastest.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) sw_accumulate_kernel(const bf16* __restrict__ pred, int ldp,
+                                                            const float* __restrict__ g, float scale,
+                                                            float* __restrict__ acc, float* __restrict__ npred, int d,
+                                                            int h, int w, int D, int H, int W, int z0, int y0, int x0) {
+  const long long n = (long long)d * h * w;
+  const long long vol = (long long)D * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const long long r = i / w;
+    const int y = (int)(r % h), z = (int)(r / h);
+    const float gw = g ? g[i] : 1.f;
+    const long long o = ((long long)(z0 + z) * H + (y0 + y)) * W + (x0 + x);
+    float v[K];
+    load_row_k<K>(pred + i * ldp, K == 4 && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 7) == 0), v);
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[(long long)k * vol + o] += v[k] * scale * gw;
+    if (npred) npred[o] += gw;
+  }
+}
+
+__global__ void __launch_bounds__(256) sw_finalize_kernel(float* __restrict__ acc, const float* __restrict__ npred,
+                                                          int K, long long vol) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += (long long)gridDim.x * blockDim.x) {
+    const float inv = 1.f / npred[i];
+    for (int k = 0; k < K; ++k) acc[(long long)k * vol + i] *= inv;
+  }
+}
+
 }  // namespace mvd
 
 using namespace mvd;
@@ -375,6 +411,33 @@ int mvd_head_bwd(const void* dlogits, int ldl, const void* z, int ldz, const flo
   HEAD_DISPATCH(K, CALL)
 #undef CALL
   return MVD_ERR_UNSUPPORTED;
+}
+
+int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float scale, float* acc, float* npred, int K,
+                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, mvd_stream_t stream) {
+  MVD_REQUIRE(pred && acc && K >= 1 && K <= kMaxHeadK && ldp >= K, "sw_accumulate: bad arguments");
+  MVD_REQUIRE(d > 0 && h > 0 && w > 0 && z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + d <= D && y0 + h <= H && x0 + w <= W,
+              "sw_accumulate: tile outside the volume");
+  const int grid = grid_for((long long)d * h * w, 256, num_sms() * 8);
+#define SW_CASE(KK)                                                                                              \
+  case KK:                                                                                                       \
+    sw_accumulate_kernel<KK><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, ldp, gaussian, scale, acc, \
+                                                                     npred, d, h, w, D, H, W, z0, y0, x0);         \
+    break;
+  switch (K) {
+    SW_CASE(1) SW_CASE(2) SW_CASE(3) SW_CASE(4) SW_CASE(5) SW_CASE(6) SW_CASE(7) SW_CASE(8)
+    default: break;
+  }
+#undef SW_CASE
+  MVD_LAUNCH_CHECK("sw_accumulate");
+  return MVD_OK;
+}
+
+int mvd_sw_finalize(float* acc, const float* npred, int K, long long vol, mvd_stream_t stream) {
+  MVD_REQUIRE(acc && npred && K >= 1 && vol > 0, "sw_finalize: bad arguments");
+  sw_finalize_kernel<<<grid_for(vol, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(acc, npred, K, vol);
+  MVD_LAUNCH_CHECK("sw_finalize");
+  return MVD_OK;
 }
 
 }  // extern "C"

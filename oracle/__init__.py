@@ -35,3 +35,4 @@ from .step import mvd_step_loss, single_net_step_loss, sgd_nesterov_clip_step, P
 from .synthetic import make_batch, structured_labels
 
 __all__ = [n for n in dir() if not n.startswith('_')]
+from . import inference

@@ -11,6 +11,8 @@ Files executed (nnUNet/nnunetv2/...):
   utilities/network_initialization.py   InitWeights_He
   utilities/tensor_utilities.py         sum_tensor
   experiment_planning/experiment_planners/network_topology.py   get_pool_and_conv_props
+  inference/sliding_window_prediction.py:10-58   compute_gaussian, compute_steps_for_sliding_window (function texts
+                                                 exec'd: the module imports acvl_utils, absent)  -> inference.npz
 """
 import importlib.util
 import os
@@ -32,7 +34,38 @@ def load(rel, name):
     return mod
 
 
+def golden_inference():
+    """exec the two pure functions of inference/sliding_window_prediction.py and record their outputs."""
+    import re
+    from functools import lru_cache
+    from typing import Union, Tuple, List
+    from scipy.ndimage import gaussian_filter
+    src = open(os.path.join(REF, 'inference/sliding_window_prediction.py')).read()
+    a = src.index('@lru_cache(maxsize=2)')
+    b = src.index("if __name__ == '__main__':")
+    ns = dict(np=np, torch=torch, lru_cache=lru_cache, Union=Union, Tuple=Tuple, List=List, gaussian_filter=gaussian_filter)
+    exec(src[a:b], ns)
+    out = {}
+    for i, tile in enumerate([(8, 8, 8), (12, 10, 6), (32, 20, 16), (5, 7, 9)]):
+        g = ns['compute_gaussian'](tile, sigma_scale=1. / 8, value_scaling_factor=1000, dtype=torch.float32,
+                                   device=torch.device('cpu'))
+        out[f'gauss{i}.tile'] = np.array(tile)
+        out[f'gauss{i}.out'] = g.numpy()
+    cases = [((40, 48, 37), (32, 32, 32), 0.5), ((110, 64, 70), (64, 64, 64), 0.5), ((32, 32, 32), (32, 32, 32), 0.5),
+             ((100, 90, 33), (32, 48, 32), 0.25), ((65, 130, 64), (64, 64, 64), 1.0)]
+    for i, (img, tile, step) in enumerate(cases):
+        st = ns['compute_steps_for_sliding_window'](img, tile, step)
+        out[f'steps{i}.img'] = np.array(img)
+        out[f'steps{i}.tile'] = np.array(tile)
+        out[f'steps{i}.step'] = np.array(step)
+        for ax in range(3):
+            out[f'steps{i}.ax{ax}'] = np.array(st[ax])
+    np.savez_compressed(os.path.join(OUT, 'inference.npz'), **out)
+    print('wrote inference.npz', len(out), 'arrays')
+
+
 def main():
+    golden_inference()
     torch.manual_seed(20261018)
     sk = load('training/loss/soft_skeleton.py', 'ref_soft_skeleton')
     g = torch.Generator().manual_seed(7)
