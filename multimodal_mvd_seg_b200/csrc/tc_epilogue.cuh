@@ -11,39 +11,8 @@
 namespace mvd {
 namespace tc {
 
-// f: the lane's 32 fp32 values (bias already added).  row_ptr(R) -> destination of channel 0 of this 32-channel group
-// for row R (0..31) of the warp's block, or nullptr when that voxel is outside the tensor.
-template <typename RowPtrFn>
-__device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, int lane, const float* f, RowPtrFn row_ptr,
-                                                     bool accumulate) {
-  const int sw_own = (lane >> 1) & 3;
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<bf16x8*>(stage + lane * 64 + ((g ^ sw_own) << 4)) = pack8(f + g * 8);
-  __syncwarp();
-  const int c = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int R = 8 * i + (lane >> 2);
-    bf16x8 v = *reinterpret_cast<const bf16x8*>(stage + R * 64 + ((c ^ ((R >> 1) & 3)) << 4));
-    bf16* dst = row_ptr(R);
-    if (dst) {
-      bf16x8* d8 = reinterpret_cast<bf16x8*>(dst + c * 8);
-      if (accumulate) {
-        float a[8], o[8];
-        unpack8(v, a);
-        unpack8(*d8, o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += o[j];
-        v = pack8(a);
-      }
-      *d8 = v;
-    }
-  }
-  __syncwarp();
-}
-
-// same, for values already converted: w[i] = bf16x2 of columns (2i, 2i+1)
+// row_ptr(R) -> destination of channel 0 of this 32-channel group for row R (0..31) of the warp's block, or nullptr when
+// that voxel is outside the tensor.  w[i] = bf16x2 of columns (2i, 2i+1) of the lane's own row (bias already added).
 template <typename RowPtrFn>
 __device__ __forceinline__ void store_rows_coalesced_packed(uint8_t* stage, int lane, const uint32_t* w, RowPtrFn row_ptr,
                                                             bool accumulate) {
@@ -119,8 +88,7 @@ __device__ __forceinline__ void store_rows_accumulate_packed(uint8_t* stage, int
 // ---- InstanceNorm statistics fused into the conv epilogue ---------------------------------------------------------
 // Every lane holds one accumulator row (32 channels).  Column sums over the warp's 32 rows are formed with a
 // recursive-halving exchange (16+8+4+2+1 = 31 shuffles per quantity instead of 5 x 32): afterwards lane l owns channel l.
-// Per-lane fp32 partials are carried across the CTA's tiles and flushed with one fp64 atomic per (channel, quantity)
-// when the (sample, channel-tile) changes and at kernel end.
+// (used once per flush by LaneStats and per tile by the stem kernel, whose register budget is too small for LaneStats)
 __device__ __forceinline__ float warp_column_sum32(float* v, int lane) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -134,37 +102,6 @@ __device__ __forceinline__ float warp_column_sum32(float* v, int lane) {
   }
   return v[0];
 }
-
-struct StatsAcc {
-  float s[8], q[8];
-  int b, n0;
-  __device__ __forceinline__ void reset(int b_, int n0_) {
-    b = b_; n0 = n0_;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  }
-  // fr: this lane's 32 bf16-rounded outputs of column group g (zero for rows outside the tensor)
-  __device__ __forceinline__ void add(int g, const float* fr, int lane) {
-    float a[32], c[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { a[j] = fr[j]; c[j] = fr[j] * fr[j]; }
-    const float cs = warp_column_sum32(a, lane);
-    const float cq = warp_column_sum32(c, lane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i == g) { s[i] += cs; q[i] += cq; }
-  }
-  __device__ __forceinline__ void flush(double* stats, int C, int ngroups, int lane) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < ngroups) {
-        double* d = stats + ((long long)b * C + n0 + i * 32 + lane) * 2;
-        atomicAdd(d, (double)s[i]);
-        atomicAdd(d + 1, (double)q[i]);
-        s[i] = q[i] = 0.f;
-      }
-  }
-};
 
 // ---- per-lane statistics (no shuffles in the tile loop) ----------------------------------------------------------
 // Every lane keeps fp32 partial sums of ITS accumulator row for all columns across the CTA's work items; the cross-lane
