@@ -148,6 +148,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--per-layer', action='store_true', help='print a per-layer conv timing table to stderr')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--split-graph', type=int, default=1, help='1: forward and backward as two CUDA graphs so that the H2D copy of the targets overlaps the forward pass (affects e2e only)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     patch, dual, topo_iter = WORKLOADS[args.workload]
@@ -235,6 +236,7 @@ def main():
 
     # ---- warm-up of the timed configuration (CUDA-graph capture happens here)
     tr.use_cuda_graph = not args.no_graph
+    tr.split_graph = bool(args.split_graph)
     tr.graph_warmup_steps = 0
     for _ in range(args.warmup):
         tr.train_step_async(resident)

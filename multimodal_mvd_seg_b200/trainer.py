@@ -159,6 +159,8 @@ class nnUNetTrainer(object):
         self.loss = None
         self.was_initialized = False
         self.use_cuda_graph = False
+        self.split_graph = False   # capture forward and (loss + backward + optimiser) as two graphs: the H2D copy of
+                                   # the targets then overlaps the forward pass (see train_step_async)
         self.graph_warmup_steps = 2
         self._arenas: List[GradArena] = []
         self._set_batch_size_and_oversample()
@@ -252,9 +254,15 @@ class nnUNetTrainer(object):
         self.lr_scheduler.step(self.current_epoch)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _forward_loss(self, data, target):
-        output = self.network(data)
+    def _forward(self, data):
+        """network forward only (everything the step can do before it has the targets)."""
+        return self.network(data)
+
+    def _loss(self, output, target):
         return self.loss(output, target), output
+
+    def _forward_loss(self, data, target):
+        return self._loss(self._forward(data), target)
 
     def _to_device(self, batch):
         data = batch['data'].to(self.device, non_blocking=True)
@@ -269,12 +277,18 @@ class nnUNetTrainer(object):
         l = self.train_step_async(batch)
         return {'loss': l.detach().cpu().numpy()}
 
-    def _step_body(self, data, target) -> torch.Tensor:
+    def _step_forward(self, data):
         self.optimizer.zero_grad(set_to_none=True)
         ops.begin_step(data.device)
         for a in self._arenas:
             a.begin_step()
-        l, _ = self._forward_loss(data, target)
+        return self._forward(data)
+
+    def _step_body(self, data, target) -> torch.Tensor:
+        return self._step_backward(self._step_forward(data), target)
+
+    def _step_backward(self, output, target) -> torch.Tensor:
+        l, _ = self._loss(output, target)
         l.backward()
         world = 1
         for a in self._arenas:
@@ -301,11 +315,7 @@ class nnUNetTrainer(object):
             key = (tuple(data.shape), tuple(tuple(t.shape) for t in target),
                    tuple(g['lr'] for g in self.optimizer.param_groups))
             if st['key'] == key and data.dtype == st['data'].dtype and all(a.dtype == b.dtype for a, b in zip(st['target'], target)):
-                st['data'].copy_(data, non_blocking=True)
-                for a, b in zip(st['target'], target):
-                    a.copy_(b, non_blocking=True)
-                st['graph'].replay()
-                return st['loss']
+                return self._replay(st, data, target)
         data, target = self._to_device(batch)
         if not self.use_cuda_graph:
             return self._step_body(data, target)
@@ -322,15 +332,51 @@ class nnUNetTrainer(object):
             sd = data.clone()
             stg = [t.clone() for t in target]
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss = self._step_body(sd, stg)
-            st = self._graph_state = dict(key=key, graph=g, data=sd, target=stg, loss=loss)
-        else:
+            if self.split_graph:
+                # two graphs sharing one memory pool: the forward pass only needs `data`, so the host->device copy of
+                # the targets (36 % of the batch bytes) can run on a copy stream underneath it
+                pool = torch.cuda.graph_pool_handle()
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, pool=pool):
+                    outs = self._step_forward(sd)
+                with torch.cuda.graph(g2, pool=pool):
+                    loss = self._step_backward(outs, stg)
+                st = self._graph_state = dict(key=key, graph=g1, graph2=g2, data=sd, target=stg, loss=loss, outs=outs,
+                                              copy_stream=torch.cuda.Stream(device=sd.device),
+                                              ev_targets=torch.cuda.Event(), ev_done=torch.cuda.Event())
+                st['ev_done'].record()
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self._step_body(sd, stg)
+                st = self._graph_state = dict(key=key, graph=g, graph2=None, data=sd, target=stg, loss=loss)
+            st['graph'].replay()
+            if st['graph2'] is not None:
+                st['graph2'].replay()
+                st['ev_done'].record()
+            return st['loss']
+        return self._replay(st, data, target)
+
+    def _replay(self, st, data, target) -> torch.Tensor:
+        """copy a batch (host or device tensors) into the graph's static inputs and replay."""
+        if st['graph2'] is None:
             st['data'].copy_(data, non_blocking=True)
             for a, b in zip(st['target'], target):
                 a.copy_(b, non_blocking=True)
-        st['graph'].replay()
+            st['graph'].replay()
+            return st['loss']
+        main = torch.cuda.current_stream()
+        side = st['copy_stream']
+        st['data'].copy_(data, non_blocking=True)
+        side.wait_event(st['ev_done'])              # the previous step has finished reading the static targets
+        with torch.cuda.stream(side):
+            for a, b in zip(st['target'], target):
+                a.copy_(b, non_blocking=True)
+            st['ev_targets'].record(side)
+        st['graph'].replay()                         # forward: needs `data` only
+        main.wait_event(st['ev_targets'])
+        st['graph2'].replay()                        # losses, backward, exchange, optimiser
+        st['ev_done'].record(main)
         return st['loss']
 
     def validation_step(self, batch: dict) -> dict:
@@ -413,9 +459,11 @@ class MVDTrainer(nnUNetTrainer):
     def _networks(self):
         return [self.network, self.network2]
 
-    def _forward_loss(self, data, target):
-        out1 = self.network(data[:, 0:1])
-        out2 = self.network2(data[:, 1:2])
+    def _forward(self, data):
+        return self.network(data[:, 0:1]), self.network2(data[:, 1:2])
+
+    def _loss(self, output, target):
+        out1, out2 = output
         l = self.loss(out1, target) + self.loss(out2, target)
         c = self.vessel_class
         if self.kl_vessel_only:

@@ -350,3 +350,30 @@ def test_checkpoint_roundtrip(tmp_path):
     tr2.load_checkpoint(ck)
     for a, b in zip(tr.network.parameters(), tr2.network.parameters()):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dual', [False, True])
+def test_cuda_graph_steps_match_eager(dual):
+    """the captured step (one graph, and forward / backward as two graphs with the target copy on a side stream) walks
+    the same loss trajectory as eager launches, from host batches through train_step()."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    dev = torch.device('cuda:0')
+    patch = (32, 32, 32)
+    plans, dj = m.make_plans(patch, batch_size=2, n_modalities=2, n_classes=4)
+    topo = oracle.topology_for_patch(patch)
+    batches = [oracle.make_batch(2, 2, patch, topo['strides'], kind='structured', seed=100 + i) for i in range(5)]
+    traj = {}
+    for mode in ('eager', 'graph', 'split'):
+        torch.manual_seed(0)
+        tr = (m.MVDTrainer(plans, '3d_fullres', 0, dj, device=dev, topo_iter=3) if dual
+              else m.nnUNetTrainer(plans, '3d_fullres', 0, dj, device=dev))
+        tr.initialize()
+        tr.on_train_epoch_start()
+        tr.use_cuda_graph = mode != 'eager'
+        tr.split_graph = mode == 'split'
+        tr.graph_warmup_steps = 1
+        traj[mode] = [float(tr.train_step(b)['loss']) for b in batches]
+    for mode in ('graph', 'split'):
+        np.testing.assert_allclose(traj[mode], traj['eager'], rtol=2e-2, atol=2e-3)
