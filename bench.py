@@ -150,6 +150,15 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph')
     ap.add_argument('--split-graph', type=int, default=1, help='1: forward and backward as two CUDA graphs so that the H2D copy of the targets overlaps the forward pass (affects e2e only)')
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 on their own (NCCL prints its version
+    # banner there) are pointed at stderr for the whole run; emit() writes the result to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + '\n').encode())
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     patch, dual, topo_iter = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -174,7 +183,7 @@ def main():
                                  'sample': 'each step = 1 patch, 64^3 crop (1/8 of a 128^3 patch), same 6-stage '
                                            'network, fp32 CPU (oracle port of the reference step)'},
                 'e2e': {'value': val, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -334,7 +343,7 @@ def main():
         for (kind, tag), d in rows:
             print(f'{kind:6s} {tag:44s} {d["ms"]:8.3f} ms/step '
                   f'{d["flops"] / (d["ms"] / 1e3) / 1e12:8.1f} TFLOP/s', file=sys.stderr)
-    print(json.dumps(line))
+    emit(line)
     finish()
 
 
