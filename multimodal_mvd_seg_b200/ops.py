@@ -424,6 +424,59 @@ def reset_skip_registry():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Backward overlap: the weight gradient and the data gradient of a conv both only READ dy, so the wgrad kernel is
+# forked onto a side stream and joined again before the function returns (fork/join events: also valid inside CUDA
+# graph capture, and every buffer involved outlives the join).  The low-resolution layers, whose kernels occupy a
+# fraction of the SMs and are latency-bound, then run two at a time; at full resolution the second kernel fills the
+# first one's tail.  Off while bench.py's per-kernel conv timer is armed (overlapped kernels cannot be timed one by one).
+# ---------------------------------------------------------------------------------------------------------------
+import os as _os
+_bwd_overlap = _os.environ.get('MVD_NO_BWD_OVERLAP', '0') != '1'
+_side_streams = {}
+
+
+def set_backward_overlap(on: bool):
+    global _bwd_overlap
+    _bwd_overlap = bool(on)
+
+
+class _ForkedWgrad:
+    """with _ForkedWgrad(dev, enabled): <launch wgrad> ; later .join() on the main stream."""
+
+    def __init__(self, dev, enabled: bool):
+        self.enabled = enabled and _bwd_overlap and _conv_timer is None
+        self.dev = dev
+        self.ev_join = None
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        self.main = torch.cuda.current_stream(self.dev)
+        side = _side_streams.get(self.dev)
+        if side is None:
+            side = _side_streams[self.dev] = torch.cuda.Stream(device=self.dev)
+        self.side = side
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        side.wait_event(ev)
+        return self
+
+    def __exit__(self, *exc):
+        if not self.enabled:
+            return False
+        self.ev_join = torch.cuda.Event()
+        self.ev_join.record(self.side)
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled and self.ev_join is not None:
+            self.main.wait_event(self.ev_join)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Conv3d -> InstanceNorm3d(affine) -> LeakyReLU   (one ConvDropoutNormReLU block)
 # ---------------------------------------------------------------------------------------------------------------
 class ConvNormActFn(torch.autograd.Function):
@@ -502,6 +555,7 @@ class ConvNormActFn(torch.autograd.Function):
                                   stats.data_ptr(), bstats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
                                   _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
+        fork = None
         if dw is not None:
             if ctx.stem:
                 Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
@@ -518,7 +572,9 @@ class ConvNormActFn(torch.autograd.Function):
                 dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
                          .reshape(weight.shape))
             else:
-                conv_wgrad(geom, x_cl, dy, dw, None)
+                fork = _ForkedWgrad(dev, ctx.needs_input_grad[0])
+                with fork:
+                    conv_wgrad(geom, x_cl, dy, dw, None)
         dx = None
         if ctx.needs_input_grad[0]:
             pend = _pending_skip.pop(ctx.x_ptr, None)
@@ -528,6 +584,8 @@ class ConvNormActFn(torch.autograd.Function):
             else:
                 dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
                 conv_dgrad(geom, dx, dy, wd)
+        if fork is not None:
+            fork.join()
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None
@@ -563,8 +621,11 @@ class ConvTransposeFn(torch.autograd.Function):
         dev = dup.device
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
         db = None
+        fork = None
         if dw is not None:
-            conv_wgrad(geom, dup, x_cl, dw, None)
+            fork = _ForkedWgrad(dev, ctx.needs_input_grad[0])
+            with fork:
+                conv_wgrad(geom, dup, x_cl, dw, None)
         if bias is not None and ctx.needs_input_grad[2]:
             db = _grad_like(bias)
             B, D, H, W, C = dup.shape
@@ -573,6 +634,8 @@ class ConvTransposeFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
             conv_fprop(geom, dup, dx, wf)
+        if fork is not None:
+            fork.join()
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dx, _ret(dw, weight), _ret(db, bias), None, None, None
