@@ -113,10 +113,18 @@ class GradArena:
         self._launched[b] = True
         chunk = self.flat[bk['start']:bk['end']]
         if self.comm_stream is not None:
+            from . import ops   # deferred weight gradients run on ops' side stream: the exchange must follow them too
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
+            side = ops.side_stream(chunk.device)
+            ev_side = None
+            if side is not None:
+                ev_side = torch.cuda.Event()
+                ev_side.record(side)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if ev_side is not None:
+                    self.comm_stream.wait_event(ev_side)
                 self._handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             self._handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -424,15 +424,22 @@ def reset_skip_registry():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Backward overlap: the weight gradient and the data gradient of a conv both only READ dy, so the wgrad kernel is
-# forked onto a side stream and joined again before the function returns (fork/join events: also valid inside CUDA
-# graph capture, and every buffer involved outlives the join).  The low-resolution layers, whose kernels occupy a
-# fraction of the SMs and are latency-bound, then run two at a time; at full resolution the second kernel fills the
-# first one's tail.  Off while bench.py's per-kernel conv timer is armed (overlapped kernels cannot be timed one by one).
+# Backward overlap.  The weight gradient of a conv is needed by nobody until the optimiser (or the bucket all-reduce),
+# so it is DEFERRED onto a side stream: the main stream runs the dependency chain
+#     IN-backward(L) -> dgrad(L) -> IN-backward(L-1) -> dgrad(L-1) -> ...
+# while the side stream runs wgrad(L), wgrad(L-1), ... one after the other, each forked after its layer's dgrad.  The
+# tensor-pipe-bound wgrad kernels (one 190-thread CTA per SM, ~10 K registers) leave room on every SM for the HBM-bound
+# InstanceNorm blocks of the NEXT layer, so the two run side by side; dgrad and wgrad (both one big CTA per SM) simply
+# time-share.  Buffers a deferred wgrad reads stay referenced in _pending until the main stream has waited for it; the
+# whole queue is joined by an autograd end-of-backward callback (so .grad is complete when backward() returns, also
+# inside CUDA graph capture).  Off while bench.py's per-kernel conv timer is armed.
 # ---------------------------------------------------------------------------------------------------------------
 import os as _os
 _bwd_overlap = _os.environ.get('MVD_NO_BWD_OVERLAP', '0') != '1'
 _side_streams = {}
+_pending = []            # (completion event on the side stream, main stream, tensors kept alive)
+_callback_queued = False
+_MAX_PENDING = 2         # deferred wgrads allowed in flight before the main stream waits for the oldest
 
 
 def set_backward_overlap(on: bool):
@@ -440,40 +447,55 @@ def set_backward_overlap(on: bool):
     _bwd_overlap = bool(on)
 
 
-class _ForkedWgrad:
-    """with _ForkedWgrad(dev, enabled): <launch wgrad> ; later .join() on the main stream."""
+def side_stream(dev, create: bool = False):
+    """the stream deferred weight gradients run on (None if none was ever forked on this device)."""
+    key = torch.device(dev)
+    if key.index is None:
+        key = torch.device('cuda', torch.cuda.current_device())
+    st = _side_streams.get(key)
+    if st is None and create:
+        st = _side_streams[key] = torch.cuda.Stream(device=key)
+    return st
 
-    def __init__(self, dev, enabled: bool):
-        self.enabled = enabled and _bwd_overlap and _conv_timer is None
-        self.dev = dev
-        self.ev_join = None
 
-    def __enter__(self):
-        if not self.enabled:
-            return self
-        self.main = torch.cuda.current_stream(self.dev)
-        side = _side_streams.get(self.dev)
-        if side is None:
-            side = _side_streams[self.dev] = torch.cuda.Stream(device=self.dev)
-        self.side = side
-        ev = torch.cuda.Event()
-        ev.record(self.main)
-        self.ctx = torch.cuda.stream(side)
-        self.ctx.__enter__()
-        side.wait_event(ev)
-        return self
+def _flush_pending(keep: int = 0):
+    while len(_pending) > keep:
+        ev, main, _refs = _pending.pop(0)
+        main.wait_event(ev)
 
-    def __exit__(self, *exc):
-        if not self.enabled:
-            return False
-        self.ev_join = torch.cuda.Event()
-        self.ev_join.record(self.side)
-        self.ctx.__exit__(*exc)
+
+def join_pending():
+    """make the compute stream wait for every deferred weight gradient (end of backward)."""
+    global _callback_queued
+    _callback_queued = False
+    _flush_pending(0)
+
+
+def _defer_wgrad(dev, launch, keepalive):
+    """run `launch()` (the wgrad launches) on the side stream after everything enqueued so far on the current stream;
+    returns False (nothing launched) when overlap is off."""
+    global _callback_queued
+    if not (_bwd_overlap and _conv_timer is None):
         return False
-
-    def join(self):
-        if self.enabled and self.ev_join is not None:
-            self.main.wait_event(self.ev_join)
+    main = torch.cuda.current_stream(dev)
+    side = side_stream(dev, create=True)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        launch()
+        done = torch.cuda.Event()
+        done.record(side)
+    _pending.append((done, main, keepalive))
+    if not _callback_queued:
+        _callback_queued = True
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_pending)
+        except RuntimeError:      # not inside a backward pass (a Function's backward called by hand): join right away
+            join_pending()
+            return True
+    _flush_pending(_MAX_PENDING)
+    return True
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -555,7 +577,7 @@ class ConvNormActFn(torch.autograd.Function):
                                   stats.data_ptr(), bstats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
                                   _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
-        fork = None
+        plain_wgrad = False
         if dw is not None:
             if ctx.stem:
                 Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
@@ -572,9 +594,7 @@ class ConvNormActFn(torch.autograd.Function):
                 dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
                          .reshape(weight.shape))
             else:
-                fork = _ForkedWgrad(dev, ctx.needs_input_grad[0])
-                with fork:
-                    conv_wgrad(geom, x_cl, dy, dw, None)
+                plain_wgrad = True
         dx = None
         if ctx.needs_input_grad[0]:
             pend = _pending_skip.pop(ctx.x_ptr, None)
@@ -584,8 +604,9 @@ class ConvNormActFn(torch.autograd.Function):
             else:
                 dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
                 conv_dgrad(geom, dx, dy, wd)
-        if fork is not None:
-            fork.join()
+        if plain_wgrad:   # after the dgrad: deferred onto the side stream (see "Backward overlap"), else right here
+            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, x_cl, dy, dw, None), (x_cl, dy, dw)):
+                conv_wgrad(geom, x_cl, dy, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None
@@ -621,11 +642,6 @@ class ConvTransposeFn(torch.autograd.Function):
         dev = dup.device
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
         db = None
-        fork = None
-        if dw is not None:
-            fork = _ForkedWgrad(dev, ctx.needs_input_grad[0])
-            with fork:
-                conv_wgrad(geom, dup, x_cl, dw, None)
         if bias is not None and ctx.needs_input_grad[2]:
             db = _grad_like(bias)
             B, D, H, W, C = dup.shape
@@ -634,8 +650,9 @@ class ConvTransposeFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
             conv_fprop(geom, dup, dx, wf)
-        if fork is not None:
-            fork.join()
+        if dw is not None:
+            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, dup, x_cl, dw, None), (dup, x_cl, dw)):
+                conv_wgrad(geom, dup, x_cl, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dx, _ret(dw, weight), _ret(db, bias), None, None, None
