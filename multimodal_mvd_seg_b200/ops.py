@@ -439,7 +439,7 @@ _bwd_overlap = _os.environ.get('MVD_NO_BWD_OVERLAP', '0') != '1'
 _side_streams = {}
 _pending = []            # (completion event on the side stream, main stream, tensors kept alive)
 _callback_queued = False
-_MAX_PENDING = 2         # deferred wgrads allowed in flight before the main stream waits for the oldest
+_MAX_PENDING = int(_os.environ.get('MVD_MAX_PENDING_WGRAD', '2'))   # deferred wgrads in flight before the main stream waits for the oldest
 
 
 def set_backward_overlap(on: bool):
