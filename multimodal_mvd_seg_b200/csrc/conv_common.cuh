@@ -20,6 +20,9 @@ int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st);                 
 // sub-pixel data gradient of the stride-2 3x3x3 conv with 32 input channels (conv_tc_subpixel.cu)
 bool tc_subpixel_dgrad_supported(const mvd_conv3d_args* a);
 int tc_subpixel_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
+// halo-plane forward of the stride-2 3x3x3 conv with 32 input channels (conv_tc_halo.cu)
+bool tc_halo_s2_fprop_supported(const mvd_conv3d_args* a);
+int tc_halo_s2_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 // sliding-window halo variant for 3x3x3 / stride 1 (conv_tc_wgrad_halo.cu)
 bool tc_wgrad_halo_supported(const mvd_conv3d_args* a);
 int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st);

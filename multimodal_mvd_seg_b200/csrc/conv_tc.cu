@@ -425,6 +425,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
     return tc_halo_conv((const bf16*)a->x, a->ldx, a->Cin, (bf16*)a->y, a->ldy, a->Cout, (const bf16*)a->w, wrow,
                         a->bias, 0, a->stats, a->B, a->Do, a->Ho, a->Wo, st, "conv3d_fprop(tcgen05 halo)");
   }
+  if (tc_halo_s2_fprop_supported(a)) return tc_halo_s2_fprop(a, st);
   const int kc = (a->Cin % 64 == 0) ? 64 : 32;
   TcMaps maps;
   TcParams P;

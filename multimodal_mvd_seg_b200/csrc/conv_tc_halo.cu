@@ -454,6 +454,175 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Stride-2 forward (3x3x3, pad 1, Cin = 32, Cout = 32 / 64: the first down-sampling conv, 128^3 -> 64^3).
+//
+// The parity-class form in conv_tc.cu fetches one 128-voxel box per tap (27 boxes of 64-byte rows per tile) and is bound
+// by the TMA row rate (0.28 ms, 210 TFLOP/s for 32 -> 64 at 2 x 128^3).  Here every input plane is fetched ONCE, split
+// by the parity of (h, w) into four dense sub-planes (one strided tensor map each), so that an in-plane tap is again
+// just a descriptor start inside a sub-plane:
+//     input h = 2 oy + ty - 1:  ty = 1 -> even rows, line oy;  ty = 0 / 2 -> odd rows (first line = 2 oy0 - 1), line oy / oy + 1
+//     (same along w); a sub-plane is [16 | 17 lines][8 | 9 voxels][32 ch], 8-row-group pitch = its line pitch.
+// Depth: input plane a of a work item (d_in = 2 od0 - 1 + a, a = 0 .. 2 mt) is odd-numbered (a = 2t + 1) -> centre tap of
+// output plane t, or even-numbered (a = 2t) -> tap 0 of output plane t AND tap 2 of output plane t - 1: those two are
+// folded into one MMA of N' = 2N whose B operand is the weight rows [tz = 2 | tz = 0] and whose accumulator columns are
+// the adjacent TMEM blocks of planes t - 1 and t (as in conv_halo_fold_kernel).  All 27 weight tiles stay resident.
+// Per 128-voxel output tile: 18 MMAs of N' = 128 + 18 of N = 64 (2,016 cycles) against 1,122 TMA rows (~4,150 cycles).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int S2_KC = 32, S2_ROWB = S2_KC * 2, S2_MT = 4, S2_RING = 3;
+constexpr int S2_NH0 = TILE_H, S2_NH1 = TILE_H + 1, S2_NW0 = TILE_W, S2_NW1 = TILE_W + 1;
+constexpr int s2_align1k(int v) { return (v + 1023) & ~1023; }
+constexpr int S2_SZ00 = S2_NH0 * S2_NW0 * S2_ROWB, S2_SZ01 = S2_NH0 * S2_NW1 * S2_ROWB,
+              S2_SZ10 = S2_NH1 * S2_NW0 * S2_ROWB, S2_SZ11 = S2_NH1 * S2_NW1 * S2_ROWB;
+constexpr int S2_OFF00 = 0, S2_OFF01 = s2_align1k(S2_OFF00 + S2_SZ00), S2_OFF10 = s2_align1k(S2_OFF01 + S2_SZ01),
+              S2_OFF11 = s2_align1k(S2_OFF10 + S2_SZ10), S2_SLOT_BYTES = s2_align1k(S2_OFF11 + S2_SZ11);
+constexpr int S2_PLANE_TX = S2_SZ00 + S2_SZ01 + S2_SZ10 + S2_SZ11;
+
+struct alignas(64) S2Maps {
+  CUtensorMap a[4];   // [h parity * 2 + w parity]: (C, W/2, H/2, D, B) with doubled W / H strides
+  CUtensorMap b;      // weights [27 * N][32] box (32, N)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_s2_kernel(const __grid_constant__ S2Maps maps,
+                                                                   const __grid_constant__ HaloParams P) {
+  constexpr int MT = S2_MT;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_pfull[S2_RING], bar_pempty[S2_RING], bar_wres, bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) uint8_t s_stage[4][2048];
+  __shared__ __align__(16) float s_bias[64];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = P.n_tile;
+  const int ntile_bytes = N * S2_ROWB;                      // one tap: N rows x 64 B
+  uint8_t* smem_we = smem;                                  // 9 x [tz = 2 | tz = 0]
+  uint8_t* smem_wo = smem + (size_t)18 * ntile_bytes;       // 9 x [tz = 1]
+  uint8_t* smem_p = smem + (size_t)27 * ntile_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S2_RING; ++s) { mbar_init(&bar_pfull[s], 1); mbar_init(&bar_pempty[s], 1); }
+    mbar_init(&bar_wres, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+    fence_barrier_init();
+  }
+  halo_stage_bias(P, s_bias);
+  if (warp == 1) tmem_alloc(&s_tmem_base, P.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ================= plane producer: four parity sub-planes per input plane, one barrier =================
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        int n0, b, d0, h0, w0;
+        halo_decode(P, MT, item, n0, b, d0, h0, w0);
+        const int mt = min(MT, P.D - d0);
+        for (int a = 0; a <= 2 * mt; ++a) {
+          mbar_wait(&bar_pempty[slot], phase ^ 1, 71);
+          mbar_arrive_expect_tx(&bar_pfull[slot], (uint32_t)S2_PLANE_TX);
+          uint8_t* dst = smem_p + (size_t)slot * S2_SLOT_BYTES;
+          const int din = 2 * d0 - 1 + a;
+          tma_load_5d(&maps.a[0], dst + S2_OFF00, &bar_pfull[slot], 0, w0, h0, din, b);
+          tma_load_5d(&maps.a[1], dst + S2_OFF01, &bar_pfull[slot], 0, w0 - 1, h0, din, b);
+          tma_load_5d(&maps.a[2], dst + S2_OFF10, &bar_pfull[slot], 0, w0, h0 - 1, din, b);
+          tma_load_5d(&maps.a[3], dst + S2_OFF11, &bar_pfull[slot], 0, w0 - 1, h0 - 1, din, b);
+          if (++slot == S2_RING) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (elect_one_sync()) {
+      // ================= weights: 27 tiles, once =================
+      mbar_arrive_expect_tx(&bar_wres, (uint32_t)(27 * ntile_bytes));
+      for (int oyx = 0; oyx < 9; ++oyx) {
+        tma_load_2d(&maps.b, smem_we + (size_t)(2 * oyx) * ntile_bytes, &bar_wres, 0, P.wrow[18 + oyx]);
+        tma_load_2d(&maps.b, smem_we + (size_t)(2 * oyx + 1) * ntile_bytes, &bar_wres, 0, P.wrow[oyx]);
+        tma_load_2d(&maps.b, smem_wo + (size_t)oyx * ntile_bytes, &bar_wres, 0, P.wrow[9 + oyx]);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ================= MMA issuer =================
+      const int total_items = P.total_items, gstride = gridDim.x, D = P.D;
+      const uint32_t a_hi0 = (uint32_t)(make_smem_desc(0, 16, S2_NW0 * S2_ROWB, kLayoutSw64) >> 32);
+      const uint32_t a_hi1 = (uint32_t)(make_smem_desc(0, 16, S2_NW1 * S2_ROWB, kLayoutSw64) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * S2_ROWB, kLayoutSw64) >> 32);
+      const uint32_t p_base = (smem_u32(smem_p) >> 4) | (1u << 16);
+      const uint32_t we_base = (smem_u32(smem_we) >> 4) | (1u << 16);
+      const uint32_t wo_base = (smem_u32(smem_wo) >> 4) | (1u << 16);
+      const uint32_t ntile16 = (uint32_t)ntile_bytes >> 4;
+      const uint32_t idesc1 = make_idesc_bf16(128, N, 0, 0), idesc2 = make_idesc_bf16(128, 2 * N, 0, 0);
+      int acc = 0, slot = 0;
+      uint32_t accphase = 0, pphase = 0;
+      mbar_wait(&bar_wres, 0, 72);
+      tcgen05_fence_after();
+      for (int item = blockIdx.x; item < total_items; item += gstride) {
+        const int d0 = ((item / (P.tiles_w * P.tiles_h)) % P.dgroups) * MT;   // num_n_tiles == 1
+        const int mt = min(MT, D - d0);
+        mbar_wait(&bar_tempty[acc], accphase ^ 1, 73);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * N);
+        for (int a = 0; a <= 2 * mt; ++a) {
+          // which output planes this input plane feeds, and with which weight rows
+          uint32_t d_col, wlo, wstep, idesc;
+          bool fresh_hi = false, both = false;
+          if (a & 1) {                                   // centre tap of plane t = (a - 1) / 2
+            d_col = d_tmem + (uint32_t)((a >> 1) * N);
+            wlo = wo_base; wstep = ntile16; idesc = idesc1;
+          } else {
+            const int t_hi = a >> 1, t_lo = t_hi - 1;    // tap 0 of t_hi, tap 2 of t_lo
+            wstep = 2 * ntile16;
+            if (t_lo >= 0 && t_hi < mt) { d_col = d_tmem + (uint32_t)(t_lo * N); wlo = we_base; idesc = idesc2; both = true; fresh_hi = true; }
+            else if (t_lo < 0) { d_col = d_tmem; wlo = we_base + ntile16; idesc = idesc1; fresh_hi = true; }
+            else { d_col = d_tmem + (uint32_t)(t_lo * N); wlo = we_base; idesc = idesc1; }
+          }
+          mbar_wait(&bar_pfull[slot], pphase, 74);
+          tcgen05_fence_after();
+          const uint32_t plo = p_base + (uint32_t)slot * (uint32_t)(S2_SLOT_BYTES >> 4);
+#pragma unroll
+          for (int oyx = 0; oyx < 9; ++oyx) {
+            const int ty = oyx / 3, tx = oyx - ty * 3;
+            const int hp = (ty != 1), wp = (tx != 1), dy = (ty == 2), dx = (tx == 2);
+            const int sub_off = hp ? (wp ? S2_OFF11 : S2_OFF10) : (wp ? S2_OFF01 : S2_OFF00);
+            const int nw = wp ? S2_NW1 : S2_NW0;
+            const uint32_t alo = plo + (uint32_t)((sub_off + (dy * nw + dx) * S2_ROWB) >> 4);
+            const uint64_t adesc = ((uint64_t)(wp ? a_hi1 : a_hi0) << 32) | (uint64_t)alo;
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(wlo + (uint32_t)oyx * wstep);
+#pragma unroll
+            for (int k = 0; k < S2_KC / 16; ++k) {
+              if (oyx == 0 && k == 0 && fresh_hi) {
+                // output plane t_hi receives its first contribution here: start it from zero
+                if (both) {
+                  umma_bf16(d_col + (uint32_t)N, adesc, bdesc + (uint64_t)ntile16, idesc1, 0u);
+                  umma_bf16(d_col, adesc, bdesc, idesc1, 1u);
+                } else {
+                  umma_bf16(d_col, adesc, bdesc, idesc1, 0u);
+                }
+              } else {
+                umma_bf16(d_col, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              }
+            }
+          }
+          umma_commit(&bar_pempty[slot]);
+          if (++slot == S2_RING) { slot = 0; pphase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], s_bias, warp & 3, lane);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
 int pick_n_tile(int N) {
   if (N % 32) return 0;
   if (N <= 256) return N;
@@ -666,6 +835,83 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
     attr_done[ki] = true;
   }
   kern<<<grid, kThreads, smem, st>>>(maps, P);
+  MVD_LAUNCH_CHECK(who);
+  return MVD_OK;
+}
+
+// ---- stride-2 forward (conv_halo_s2_kernel) ----------------------------------------------------------------------
+bool tc_halo_s2_fprop_supported(const mvd_conv3d_args* a) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MVD_NO_S2HALO");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!enabled || !tc_halo_enabled()) return false;
+  if (!(a->kd == 3 && a->kh == 3 && a->kw == 3 && a->sd == 2 && a->sh == 2 && a->sw == 2 && a->pd == 1 && a->ph == 1 &&
+        a->pw == 1))
+    return false;
+  if (a->Cin != S2_KC || (a->Cout != 32 && a->Cout != 64)) return false;
+  if (a->Di < 2 || a->Hi < 2 || a->Wi < 2) return false;   // every parity lattice must be non-empty
+  if (a->ldx % 8 || a->ldy % 8 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15) || ((uintptr_t)a->w & 15)) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+int tc_halo_s2_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
+  const char* who = "conv3d_fprop(tcgen05 stride-2 halo)";
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_error("%s: no cuTensorMapEncodeTiled", who); return MVD_ERR_CUDA; }
+  S2Maps maps;
+  HaloParams P;
+  memset(&P, 0, sizeof(P));
+  const int N = a->Cout;
+  const long long ld = a->ldx;
+  for (int hp = 0; hp < 2; ++hp)
+    for (int wp = 0; wp < 2; ++wp) {
+      // even lattice: h = 2i; odd lattice: h = 2i + 1 (the kernel asks for line oy0 - 1 = input row 2 oy0 - 1)
+      const bf16* base = (const bf16*)a->x + ((long long)hp * a->Wi + wp) * ld;
+      cuuint64_t gdim[5] = {(cuuint64_t)S2_KC, (cuuint64_t)((a->Wi + 1 - wp) / 2), (cuuint64_t)((a->Hi + 1 - hp) / 2),
+                            (cuuint64_t)a->Di, (cuuint64_t)a->B};
+      cuuint64_t gstr[4] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * a->Wi * 4, (cuuint64_t)ld * a->Wi * a->Hi * 2,
+                            (cuuint64_t)ld * a->Wi * a->Hi * a->Di * 2};
+      cuuint32_t box[5] = {(cuuint32_t)S2_KC, (cuuint32_t)(wp ? S2_NW1 : S2_NW0), (cuuint32_t)(hp ? S2_NH1 : S2_NH0), 1, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&maps.a[hp * 2 + wp], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, gdim, gstr, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(planes) failed (%d)", who, (int)r); return MVD_ERR_CUDA; }
+    }
+  if (!tc_encode_w_map(&maps.b, (const bf16*)a->w, (long long)27 * N, S2_KC, N, S2_KC)) {
+    set_error("%s: cuTensorMapEncodeTiled(weights) failed", who);
+    return MVD_ERR_CUDA;
+  }
+  P.MT = S2_MT; P.ring = S2_RING; P.wstages = 0;
+  P.n_tile = N; P.num_n_tiles = 1; P.kchunks = 1;
+  P.B = a->B; P.D = a->Do; P.H = a->Ho; P.W = a->Wo;
+  P.tiles_w = cdiv(a->Wo, TILE_W); P.tiles_h = cdiv(a->Ho, TILE_H); P.dgroups = cdiv(a->Do, S2_MT);
+  P.total_items = a->B * P.dgroups * P.tiles_h * P.tiles_w;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * S2_MT * N) cols <<= 1;
+  P.tmem_cols = cols;
+  P.out = (bf16*)a->y;
+  P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
+  P.bias = a->bias; P.accumulate = 0;
+  P.stats = a->stats; P.Ntot = N;
+  for (int i = 0; i < 27; ++i) P.wrow[i] = i * N;
+  const size_t smem = (size_t)27 * N * S2_ROWB + (size_t)S2_RING * S2_SLOT_BYTES + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         27 * 64 * S2_ROWB + S2_RING * S2_SLOT_BYTES + 1024);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+      return MVD_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  int grid = num_sms();
+  if (grid > P.total_items) grid = P.total_items;
+  conv_halo_s2_kernel<<<grid, kThreads, smem, st>>>(maps, P);
   MVD_LAUNCH_CHECK(who);
   return MVD_OK;
 }

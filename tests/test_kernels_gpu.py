@@ -123,6 +123,33 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
         ops.set_conv_algo('auto')
 
 
+@pytest.mark.parametrize('cout', [64, 32])
+@pytest.mark.parametrize('shape', [(2, 7, 9, 11), (1, 18, 34, 20), (1, 2, 2, 2), (1, 9, 40, 16)])
+def test_conv_s2_halo_fprop_pitched(m, shape, cout):
+    """Stride-2 halo-plane forward (conv_halo_s2_kernel): the input is the second channel half of a wider buffer (the
+    encoder skip lives inside the decoder's concat buffer), odd extents in every direction, depth tails, bit-for-bit
+    equal to the tap-by-tap tcgen05 kernel up to accumulation order."""
+    ops = m.ops
+    B, D, H, W = shape
+    xbuf = rand_cl((B, D, H, W, 64), 11)
+    x = xbuf[..., 32:]
+    w = (torch.randn(cout, 32, 3, 3, 3) * (1.0 / np.sqrt(32 * 27))).to(dev())
+    b = torch.randn(cout).to(dev()) * 0.1
+    geom = ops.ConvGeom((3,) * 3, (2,) * 3, (1,) * 3)
+    Do, Ho, Wo = geom.out_size((D, H, W))
+    wf, _ = ops.pack_weights(w)
+    ybuf = torch.zeros((B, Do, Ho, Wo, cout + 8), dtype=BF, device=dev())
+    y = ybuf[..., 8:]
+    stats = torch.zeros((B, cout, 2), dtype=torch.float64, device=dev())
+    ops.conv_fprop(geom, x, y, wf, bias=b, stats=stats)
+    yr = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.to(BF).float(), b.to(BF).float(), stride=2, padding=1)
+    assert rel_err(y.float().permute(0, 4, 1, 2, 3), yr) < 1e-2
+    assert float(ybuf[..., :8].abs().max()) == 0.0
+    yd = y.double().reshape(B, -1, cout)
+    np.testing.assert_allclose(stats[..., 0].cpu(), yd.sum(1).cpu(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[..., 1].cpu(), (yd * yd).sum(1).cpu(), rtol=1e-4, atol=1e-3)
+
+
 @pytest.mark.parametrize('cin,shape', [(1, (2, 5, 6, 7)), (2, (1, 9, 8, 10)), (2, (1, 3, 4, 70)), (2, (2, 4, 5, 16)), (1, (1, 3, 4, 24))])
 def test_stem_im2col_bit_exact(m, cin, shape):
     """X_col[v][tap*Cin + ci] = x[v + tap - 1][ci] (zero outside the volume, zero padding columns): a pure gather."""
