@@ -23,7 +23,7 @@ using namespace tc;
 
 constexpr int kThreads = 224;
 constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2, PLANE_ROWS = HALO_W * HALO_H;
-constexpr int kMaxRing = 8, kMaxWStages = 8;
+constexpr int kMaxRing = 8, kMaxWStages = 16;
 constexpr int kMaxN = 1024;   // largest produced-channel count the tap-major kernel stages a bias vector for
 
 struct alignas(64) HaloMaps {
@@ -636,6 +636,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 long long* g_halo_prof = nullptr;
+int g_plan_nt = 0, g_plan_mt = 0, g_plan_wst = 0;   // debug overrides of the tap-major kernel's plan (0 = automatic)
 
 bool tc_halo_enabled() {
   static int v = -1;
@@ -690,6 +691,10 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
         if (c < 0.8 * best) { best = c; P.n_tile = nt; mt_cap = mt; }
       }
     }
+  }
+  if (!stats && N > 64 && g_plan_nt > 0 && N % g_plan_nt == 0 && g_plan_nt % 32 == 0 && g_plan_nt <= 256) {
+    P.n_tile = g_plan_nt;
+    mt_cap = g_plan_mt > 0 ? g_plan_mt : 4;
   }
   if (stats && N != 32 && N != 64) { set_error("%s: fused InstanceNorm sums need N = 32 or 64", who); return MVD_ERR_UNSUPPORTED; }
   {
@@ -789,6 +794,7 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
     MT >>= 1;
   }
   if (wstages > kMaxWStages) wstages = kMaxWStages;
+  if (g_plan_wst > 0 && wstages > g_plan_wst) wstages = g_plan_wst;
   if (wstages < 2) {
     ring = MT + 2;
     wstages = (budget - ring * plane_bytes) / w_bytes;
@@ -920,3 +926,7 @@ int tc_halo_s2_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
 
 // debug hook: per-CTA cycle counters of the halo kernel's MMA issuer ([grid][8] int64, device memory) or NULL
 extern "C" void mvd_debug_set_halo_prof(long long* buf) { mvd::g_halo_prof = buf; }
+// debug hook: force the tap-major halo kernel's N-tile width / planes per item / weight-ring depth (0 = automatic)
+extern "C" void mvd_debug_set_halo_plan(int n_tile, int mt, int wstages) {
+  mvd::g_plan_nt = n_tile; mvd::g_plan_mt = mt; mvd::g_plan_wst = wstages;
+}

@@ -48,6 +48,14 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, int ld, floa
 // per step.  Per-thread fp32 partials over a bounded run (<= 4096 rows), block tree in shared memory, then one double
 // atomicAdd per (channel, block) -- contention is B*C addresses x gridDim.x adds, negligible.
 // ------------------------------------------------------------------------------------------------------------
+// 16-byte loads spelled as one ld.global.nc.v4: a plain `*reinterpret_cast<const bf16x8*>(p)` of the 4 x bf16x2 struct
+// gets scalarised into four 32-bit LDG.CONSTANT that the scheduler then serialises with the math (seen in SASS)
+__device__ __forceinline__ bf16x8 ld16(const bf16* p) {
+  // volatile: the compiler otherwise sinks each load next to its use, behind the previous vector's store
+  uint4 u;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p) : "memory");
+  return *reinterpret_cast<const bf16x8*>(&u);
+}
 constexpr int kStatThreads = 256;
 
 // Sweep direction.  Every streaming kernel walks the volume in BANDS (all blocks side by side, band after band).
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
       bf16x8 p[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        p[u] = *reinterpret_cast<const bf16x8*>(base + sweep_row(v + u * step, V, rev) * ld + cg * 8);
+        p[u] = ld16(base + sweep_row(v + u * step, V, rev) * ld + cg * 8);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
       }
     }
     for (; v < V; v += step) {
-      bf16x8 p = *reinterpret_cast<const bf16x8*>(base + sweep_row(v, V, rev) * ld + cg * 8);
+      bf16x8 p = ld16(base + sweep_row(v, V, rev) * ld + cg * 8);
       float f[8];
       unpack8(p, f);
 #pragma unroll
@@ -122,6 +130,26 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Launch shape of the read+write kernels (scripts/probes/stream_probe.cu on B200, 2 x 128^3 x 32 bf16): 4 resident blocks
+// of 256 threads per SM with 4 x 16 B loads in flight per thread and streaming (evict-first) stores reach 6.08 TB/s
+// (93 % of the copy rate); 6 blocks/SM with default stores -- the previous shape -- 4.74 TB/s.
+__device__ __forceinline__ void st_stream(bf16* p, const bf16x8& v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(&v);
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+// The two-input backward kernels stage their loads through shared memory with cp.async: every thread owns a private
+// ring of kStage 16-byte slots per input, so the bytes in flight cost no registers (the direct-load form needs 80+
+// registers for 2 x 2 loads in flight, which caps it at 3 blocks/SM and ~49 KB in flight per SM -- 81 % of the copy
+// rate in the probe; the staged form reaches 100 %).  A thread only ever reads back its own slots: no block barrier.
+constexpr int kStage = 4;
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr size_t kRingBytes = (size_t)2 * kStage * kStatThreads * 16;   // two inputs
+
 // forward apply:  t = bf16(gamma*(y-mean)*rstd + beta);  z = t > 0 ? t : bf16(slope*t)
 // (two roundings, as the reference's bf16 InstanceNorm followed by an in-place bf16 LeakyReLU produces)
 // ------------------------------------------------------------------------------------------------------------
@@ -165,7 +193,14 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
   float csc[8], csh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { csc[k] = sc[cg * 8 + k]; csh[k] = sh[cg * 8 + k]; }
-  auto body = [&](const bf16x8& p, long long v) {
+  // plain pointer walk (one 64-bit add per vector): with the row index recomputed per load the scheduler sank every load
+  // next to its use, i.e. ONE 16-byte load in flight per thread (SASS) -- the kernel sat at 75 % of the copy rate
+  const long long step = (long long)gridDim.x * rows;
+  long long v = (long long)blockIdx.x * rows + r;
+  const bf16* yp = yb + v * ldy + cg * 8;
+  bf16* zp = zb + v * ldz + cg * 8;
+  const long long ys = step * ldy, zs = step * ldz;
+  auto body = [&](const bf16x8& p, bf16* dst) {
     float f[8];
     unpack8(p, f);
 #pragma unroll
@@ -173,22 +208,16 @@ __global__ void __launch_bounds__(256) inorm_lrelu_fwd_kernel(const bf16* __rest
       float t = round_bf(fmaf(f[k], csc[k], csh[k]));
       f[k] = t > 0.f ? t : slope * t;
     }
-    *reinterpret_cast<bf16x8*>(zb + v * ldz + cg * 8) = pack8(f);
+    st_stream(dst, pack8(f));
   };
-  const long long step = (long long)gridDim.x * rows;
-  long long v = (long long)blockIdx.x * rows + r;
-  for (; v + 3 * step < V; v += 4 * step) {
+  for (; v + 3 * step < V; v += 4 * step, yp += 4 * ys, zp += 4 * zs) {
     bf16x8 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      p[u] = *reinterpret_cast<const bf16x8*>(yb + sweep_row(v + u * step, V, rev) * ldy + cg * 8);
+    for (int u = 0; u < 4; ++u) p[u] = ld16(yp + u * ys);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(p[u], sweep_row(v + u * step, V, rev));
+    for (int u = 0; u < 4; ++u) body(p[u], zp + u * zs);
   }
-  for (; v < V; v += step) {
-    const long long w = sweep_row(v, V, rev);
-    body(*reinterpret_cast<const bf16x8*>(yb + w * ldy + cg * 8), w);
-  }
+  for (; v < V; v += step, yp += ys, zp += zs) body(ld16(yp), zp);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -198,7 +227,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
     const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y, int ldy, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, long long V, int C, float eps, float slope,
     double* __restrict__ bstats, int rev) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y;
   const int CG = C >> 3;
   const int rows = kStatThreads / CG;
@@ -242,23 +271,31 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_stats_kernel(
         s2[k] = fmaf(gp, xh, s2[k]);
       }
     };
-    long long v = (long long)blockIdx.x * rows + r;
-    for (; v + step < V; v += 2 * step) {   // four independent 16-byte loads in flight per thread
-      const long long w0 = sweep_row(v, V, rev), w1 = sweep_row(v + step, V, rev);
-      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
-      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
-      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + w1 * ldy + cg * 8);
-      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + w1 * lddz + cg * 8);
-      body(py0, pg0);
-      body(py1, pg1);
-    }
-    for (; v < V; v += step) {
-      const long long w0 = sweep_row(v, V, rev);
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
+    // staged sweep: iteration i covers row v0 + i*step; kStage - 1 iterations are in flight ahead of the consumer
+    const long long v0 = (long long)blockIdx.x * rows + r;
+    const long long iters = v0 < V ? (V - v0 + step - 1) / step : 0;
+    const bf16x8* ring = reinterpret_cast<const bf16x8*>(red) + tid;      // slot s of input j: ring[(j * kStage + s) * 256]
+    const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(ring);
+    auto issue = [&](long long i) {
+      if (i < iters) {
+        const long long w = sweep_row(v0 + i * step, V, rev);
+        const uint32_t slot = ring_u + (uint32_t)(i & (kStage - 1)) * (kStatThreads * 16);
+        cp_async16(slot, yb + w * ldy + cg * 8);
+        cp_async16(slot + kStage * kStatThreads * 16, gb + w * lddz + cg * 8);
+      }
+      cp_async_commit();
+    };
+    for (int i = 0; i < kStage - 1; ++i) issue(i);
+    for (long long i = 0; i < iters; ++i) {
+      issue(i + kStage - 1);
+      cp_async_wait<kStage - 1>();
+      const int sl = (int)(i & (kStage - 1));
+      const bf16x8 py = ring[sl * kStatThreads], pg = ring[(kStage + sl) * kStatThreads];
       body(py, pg);
     }
+    cp_async_wait<0>();
   }
+  __syncthreads();   // the reduction buffer below aliases the staging ring
   if (r < rows) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -286,7 +323,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
     const double* __restrict__ stats, const double* __restrict__ bstats, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, long long V, int C, float eps, float slope, float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ dsum, int rev) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y;
   float* sc = sm;
   float* sh = sm + C;
@@ -347,29 +384,35 @@ __global__ void __launch_bounds__(kStatThreads, 3) inorm_lrelu_bwd_apply_kernel(
         o[k] = fmaf(fy[k], p1[k], fmaf(gp, csc[k], p2[k]));
       }
       const bf16x8 pk = pack8(o);
-      *reinterpret_cast<bf16x8*>(ob + v * lddy + cg * 8) = pk;
+      st_stream(ob + v * lddy + cg * 8, pk);
       if (dsum) {          // bias gradient = sum of the ROUNDED dy (what the reference's conv backward sums)
         unpack8(pk, o);
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] += o[k];
       }
     };
-    long long v = (long long)blockIdx.x * rows + r;
-    for (; v + step < V; v += 2 * step) {
-      const long long w0 = sweep_row(v, V, rev), w1 = sweep_row(v + step, V, rev);
-      bf16x8 py0 = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
-      bf16x8 pg0 = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
-      bf16x8 py1 = *reinterpret_cast<const bf16x8*>(yb + w1 * ldy + cg * 8);
-      bf16x8 pg1 = *reinterpret_cast<const bf16x8*>(gb + w1 * lddz + cg * 8);
-      body(py0, pg0, w0);
-      body(py1, pg1, w1);
+    const long long v0 = (long long)blockIdx.x * rows + r;
+    const long long iters = v0 < V ? (V - v0 + step - 1) / step : 0;
+    const bf16x8* ring = reinterpret_cast<const bf16x8*>(sm + 7 * C) + tid;
+    const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(ring);
+    auto issue = [&](long long i) {
+      if (i < iters) {
+        const long long w = sweep_row(v0 + i * step, V, rev);
+        const uint32_t slot = ring_u + (uint32_t)(i & (kStage - 1)) * (kStatThreads * 16);
+        cp_async16(slot, yb + w * ldy + cg * 8);
+        cp_async16(slot + kStage * kStatThreads * 16, gb + w * lddz + cg * 8);
+      }
+      cp_async_commit();
+    };
+    for (int i = 0; i < kStage - 1; ++i) issue(i);
+    for (long long i = 0; i < iters; ++i) {
+      issue(i + kStage - 1);
+      cp_async_wait<kStage - 1>();
+      const int sl = (int)(i & (kStage - 1));
+      const bf16x8 py = ring[sl * kStatThreads], pg = ring[(kStage + sl) * kStatThreads];
+      body(py, pg, sweep_row(v0 + i * step, V, rev));
     }
-    for (; v < V; v += step) {
-      const long long w0 = sweep_row(v, V, rev);
-      bf16x8 py = *reinterpret_cast<const bf16x8*>(yb + w0 * ldy + cg * 8);
-      bf16x8 pg = *reinterpret_cast<const bf16x8*>(gb + w0 * lddz + cg * 8);
-      body(py, pg, w0);
-    }
+    cp_async_wait<0>();
   }
   if (dsum) {
     if (r < rows) {
@@ -405,12 +448,14 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(bf16* __restrict__ dst, i
 // machine idle in the second wave -> 50 % of the HBM roofline.)  Returns blocks per sample; *rpb = rows per block, a
 // multiple of `gran`.
 template <typename K>
-static long long one_wave(K kernel, int threads, size_t smem, int B, long long V, long long gran, long long* rpb) {
+static long long one_wave(K kernel, int threads, size_t smem, int B, long long V, long long gran, long long* rpb,
+                          int max_bps = 0) {
   int bps = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem) != cudaSuccess || bps < 1) {
     (void)cudaGetLastError();
     bps = 2;
   }
+  if (max_bps > 0 && bps > max_bps) bps = max_bps;
   long long nblk = ((long long)num_sms() * bps) / B;
   if (nblk < 1) nblk = 1;
   long long r = (V + nblk - 1) / nblk;
@@ -428,6 +473,16 @@ static int sweep_rev(int want) {
     on = (e && e[0] == '1') ? 1 : 0;
   }
   return on ? want : 0;
+}
+
+// dynamic shared memory above 48 KB needs an opt-in, once per kernel
+template <typename K>
+static cudaError_t allow_big_smem(K kernel, int idx) {
+  static bool done[4] = {false, false, false, false};
+  if (done[idx]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+  if (e == cudaSuccess) done[idx] = true;
+  return e;
 }
 
 static bool vec_ok(const void* p, int ld, int C) {
@@ -484,7 +539,7 @@ int mvd_inorm_lrelu_fwd(const void* y, int ldy, void* z, int ldz, const double* 
   // grid-stride kernel: one resident wave; small volumes get fewer blocks (>= 4 rows per thread slot)
   long long rpb;
   const int frows = 256 / ((C / 8) > 256 ? 256 : (C / 8));
-  const long long nblk = one_wave(inorm_lrelu_fwd_kernel, 256, 2 * C * sizeof(float), B, V, (long long)frows * 4, &rpb);
+  const long long nblk = one_wave(inorm_lrelu_fwd_kernel, 256, 2 * C * sizeof(float), B, V, (long long)frows * 4, &rpb, 4);
   dim3 grid((unsigned)nblk, B);
   inorm_lrelu_fwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)y, ldy, (bf16*)z, ldz, stats, gamma, beta, V, C, eps, slope, sweep_rev(1));
@@ -498,7 +553,9 @@ int mvd_inorm_lrelu_bwd_stats(const void* dz, int lddz, const void* y, int ldy, 
   MVD_REQUIRE(dz && y && stats && bstats && B > 0 && V > 0, "inorm_lrelu_bwd_stats: bad arguments");
   MVD_REQUIRE(vec_ok(y, ldy, C) && vec_ok(dz, lddz, C) && C <= 2048, "inorm_lrelu_bwd_stats: alignment/C");
   const int rows = kStatThreads / (C / 8);
-  size_t smem = (size_t)(4 * C + rows * C * 2) * sizeof(float);
+  size_t red_bytes = (size_t)rows * C * 2 * sizeof(float);
+  size_t smem = (size_t)4 * C * sizeof(float) + (red_bytes > kRingBytes ? red_bytes : kRingBytes);
+  MVD_CUDA(allow_big_smem(inorm_lrelu_bwd_stats_kernel, 0));
   long long rpb;
   const long long nblk = one_wave(inorm_lrelu_bwd_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 2, &rpb);
   dim3 grid((unsigned)nblk, B);
@@ -517,10 +574,11 @@ int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, 
               "inorm_lrelu_bwd_apply: alignment/C");
   const int rows = kStatThreads / (C / 8);
   long long rpb;
-  const long long nblk = one_wave(inorm_lrelu_bwd_apply_kernel, kStatThreads, 7 * C * sizeof(float), B, V,
-                                  (long long)rows * 2, &rpb);
+  const size_t smem = (size_t)7 * C * sizeof(float) + kRingBytes;
+  MVD_CUDA(allow_big_smem(inorm_lrelu_bwd_apply_kernel, 1));
+  const long long nblk = one_wave(inorm_lrelu_bwd_apply_kernel, kStatThreads, smem, B, V, (long long)rows * 2, &rpb);
   dim3 grid((unsigned)nblk, B);
-  inorm_lrelu_bwd_apply_kernel<<<grid, kStatThreads, 7 * C * sizeof(float), (cudaStream_t)stream>>>(
+  inorm_lrelu_bwd_apply_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(
       (const bf16*)dz, lddz, (const bf16*)y, ldy, (bf16*)dy, lddy, stats, bstats, gamma, beta, B, V, C, eps, slope,
       dgamma, dbeta, dsum, sweep_rev(0));
   MVD_LAUNCH_CHECK("inorm_lrelu_bwd_apply");
