@@ -74,6 +74,17 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 
+// 16-byte global accesses go through the built-in uint4: a load/store of the bf16x8 STRUCT is split by the compiler into
+// four 32-bit LDG/STG (seen in SASS: every tcgen05 epilogue store was 4 requests of 16 partially written sectors; ncu
+// l1tex throughput 78 % in the transposed-conv scatter) whenever the value is also touched element-wise.
+__device__ __forceinline__ bf16x8 ldg16(const void* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  return *reinterpret_cast<const bf16x8*>(&u);
+}
+__device__ __forceinline__ void stg16(void* p, const bf16x8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

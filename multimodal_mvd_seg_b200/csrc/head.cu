@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
     const bf16* zp = z + v * ldz;
     for (int c0 = 0; c0 < C; c0 += 8) {
-      bf16x8 p = *reinterpret_cast<const bf16x8*>(zp + c0);
+      bf16x8 p = ldg16(zp + c0);
       float f[8];
       unpack8(p, f);
 #pragma unroll
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const bf16* __restri
       for (int k = 0; k < K; ++k) a = fmaf(g[k], sw[k * C + cg * 8 + j], a);
       o[j] = a;
     }
-    *reinterpret_cast<bf16x8*>(dz + v * lddz + cg * 8) = pack8(o);
+    stg16(dz + v * lddz + cg * 8, pack8(o));
   }
 }
 
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const bf16* __rest
   }
   if (r < rows) {
     for (long long v = v0 + r; v < v1; v += rows) {
-      bf16x8 p = *reinterpret_cast<const bf16x8*>(z + v * ldz + cg * 8);
+      bf16x8 p = ldg16(z + v * ldz + cg * 8);
       float f[8];
       unpack8(p, f);
 #pragma unroll
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) head_fwd_cg_kernel(const bf16* __restrict
     for (int u = 0; u < U; ++u) {
       const long long v = base + u * stride + r;
       ok[u] = v < NV;
-      if (ok[u]) p[u] = *reinterpret_cast<const bf16x8*>(z + v * ldz + cg * 8);
+      if (ok[u]) p[u] = ldg16(z + v * ldz + cg * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict
     for (int u = 0; u < U; ++u) {
       const long long v = base + u * stride;
       if (v < NV) {
-        if (dw) p[u] = *reinterpret_cast<const bf16x8*>(z + v * ldz + cg * 8);
+        if (dw) p[u] = ldg16(z + v * ldz + cg * 8);
         load_row_k<K>(dl + v * ldl, vec != 0, g[u]);
       } else {
 #pragma unroll
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict
           for (int k = 0; k < K; ++k) a = fmaf(g[u][k], wr[k][j], a);
           o[j] = a;
         }
-        *reinterpret_cast<bf16x8*>(dz + v * lddz + cg * 8) = pack8(o);
+        stg16(dz + v * lddz + cg * 8, pack8(o));
       }
       if (dw) {
         float f[8];

@@ -432,14 +432,14 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(bf16* __restrict__ dst, i
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     long long v = i / CG;
     int cg = (int)(i - v * CG);
-    bf16x8 a = *reinterpret_cast<const bf16x8*>(dst + v * ldd + cg * 8);
-    bf16x8 s = *reinterpret_cast<const bf16x8*>(src + v * lds + cg * 8);
+    bf16x8 a = ldg16(dst + v * ldd + cg * 8);
+    bf16x8 s = ldg16(src + v * lds + cg * 8);
     float fa[8], fs[8];
     unpack8(a, fa);
     unpack8(s, fs);
 #pragma unroll
     for (int k = 0; k < 8; ++k) fa[k] += fs[k];
-    *reinterpret_cast<bf16x8*>(dst + v * ldd + cg * 8) = pack8(fa);
+    stg16(dst + v * ldd + cg * 8, pack8(fa));
   }
 }
 

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restric
       }
       oe[e] = val;
     }
-    *reinterpret_cast<bf16x8*>(out + (v0 + w) * KPAD + g * 8) = o;
+    stg16(out + (v0 + w) * KPAD + g * 8, o);
   }
 }
 

@@ -29,16 +29,16 @@ __device__ __forceinline__ void store_rows_coalesced_packed(uint8_t* stage, int 
     bf16x8 v = *reinterpret_cast<const bf16x8*>(stage + R * 64 + ((c ^ ((R >> 1) & 3)) << 4));
     bf16* dst = row_ptr(R);
     if (dst) {
-      bf16x8* d8 = reinterpret_cast<bf16x8*>(dst + c * 8);
+      bf16* d8 = dst + c * 8;
       if (accumulate) {
         float a[8], o[8];
         unpack8(v, a);
-        unpack8(*d8, o);
+        unpack8(ldg16(d8), o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += o[j];
         v = pack8(a);
       }
-      *d8 = v;
+      stg16(d8, v);
     }
   }
   __syncwarp();
@@ -55,7 +55,7 @@ __device__ __forceinline__ void prefetch_rows(int lane, RowPtrFn row_ptr, bf16x8
   for (int i = 0; i < 4; ++i) {
     const bf16* src = row_ptr(8 * i + (lane >> 2));
     has[i] = src != nullptr;
-    if (has[i]) old[i] = *reinterpret_cast<const bf16x8*>(src + c * 8);
+    if (has[i]) old[i] = ldg16(src + c * 8);
   }
 }
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ void store_rows_accumulate_packed(uint8_t* stage, int
       unpack8(old[i], o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += o[j];
-      *reinterpret_cast<bf16x8*>(row_ptr(R) + c * 8) = pack8(a);
+      stg16(row_ptr(R) + c * 8, pack8(a));
     }
   }
   __syncwarp();
