@@ -81,9 +81,24 @@ __device__ __forceinline__ bf16x8 ldg16(const void* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   return *reinterpret_cast<const bf16x8*>(&u);
 }
+// Same load as volatile asm: ptxas otherwise sinks each of a batch of independent loads next to its use (one or two
+// loads in flight per thread instead of the batch -- seen in SASS of the streaming kernels)
+__device__ __forceinline__ bf16x8 ldg16_pinned(const void* p) {
+  uint4 u;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p) : "memory");
+  return *reinterpret_cast<const bf16x8*>(&u);
+}
 __device__ __forceinline__ void stg16(void* p, const bf16x8& v) {
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
 }
+
+// cp.async (LDGSTS) building blocks of the streaming kernels' private per-thread staging rings
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

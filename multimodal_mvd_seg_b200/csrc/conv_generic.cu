@@ -312,6 +312,53 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16* __restrict
   for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&out[i], sacc[i]);
 }
 
+// vector form (C % 8 == 0, 16-byte aligned pitched rows): thread = (voxel row r, 8-channel group cg), one resident wave,
+// band sweep staged through a private cp.async ring of eight 16-byte slots per thread (a read-only stream needs ~100 KB
+// in flight per SM to reach the HBM copy rate, scripts/probes/stream_probe.cu; plain load batches get serialised by ptxas); per-thread fp32 partials, one shared-memory reduction
+// and one atomicAdd per (channel, block).  The scalar kernel above moved 2 bytes per load (0.2 ms per step at cfg-2).
+__global__ void __launch_bounds__(256) channel_sum_vec_kernel(const bf16* __restrict__ g, int ld, long long NV, int C,
+                                                              float* __restrict__ out) {
+  extern __shared__ __align__(16) float sacc[];   // [C] sums, then the cp.async staging ring (8 x 256 x 16 B)
+  for (int i = threadIdx.x; i < C; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int CG = C >> 3, rows = 256 / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  if (r < rows) {
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    const long long step = (long long)gridDim.x * rows;
+    long long v = (long long)blockIdx.x * rows + r;
+    const bf16* p = g + v * ld + cg * 8;
+    const long long ps = step * ld;
+    auto add = [&](const bf16x8& q) {
+      float f[8];
+      unpack8(q, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    };
+    const long long iters = v < NV ? (NV - v + step - 1) / step : 0;
+    const bf16x8* ring = reinterpret_cast<const bf16x8*>(sacc + C) + threadIdx.x;   // private slots: [stage][256]
+    const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(ring);
+    constexpr int D = 8;
+    auto issue = [&](long long i) {
+      if (i < iters) cp_async16(ring_u + (uint32_t)(i & (D - 1)) * 4096, p + i * ps);
+      cp_async_commit();
+    };
+    for (int i = 0; i < D - 1; ++i) issue(i);
+    for (long long i = 0; i < iters; ++i) {
+      issue(i + D - 1);
+      cp_async_wait<D - 1>();
+      add(ring[(int)(i & (D - 1)) * 256]);
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sacc[cg * 8 + i], s[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&out[i], sacc[i]);
+}
+
 int generic_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   IgemmParams P;
   P.src = (const bf16*)a->x; P.lds = a->ldx; P.Kc = a->Cin; P.Ds = a->Di; P.Hs = a->Hi; P.Ws = a->Wi;
@@ -399,6 +446,15 @@ extern "C" int mvd_channel_sum(const void* g, int ld, long long NV, int C, float
     nblk = (NV + rpb - 1) / rpb;
   }
   MVD_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, (cudaStream_t)stream));
+  if (C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ((uintptr_t)g & 15) == 0) {
+    const int rows = 256 / (C / 8);
+    long long nb = (long long)num_sms() * 4;
+    const long long need = (NV + rows - 1) / rows;
+    if (nb > need) nb = need;
+    channel_sum_vec_kernel<<<(unsigned)nb, 256, C * sizeof(float) + 8 * 4096, (cudaStream_t)stream>>>((const bf16*)g, ld, NV, C, out);
+    MVD_LAUNCH_CHECK("channel_sum");
+    return MVD_OK;
+  }
   channel_sum_kernel<<<(unsigned)nblk, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)g, ld, NV, C, out, rpb);
   MVD_LAUNCH_CHECK("channel_sum");
   return MVD_OK;

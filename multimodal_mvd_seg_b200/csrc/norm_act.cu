@@ -48,15 +48,9 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, int ld, floa
 // per step.  Per-thread fp32 partials over a bounded run (<= 4096 rows), block tree in shared memory, then one double
 // atomicAdd per (channel, block) -- contention is B*C addresses x gridDim.x adds, negligible.
 // ------------------------------------------------------------------------------------------------------------
-// 16-byte loads spelled as one ld.global.nc.v4: a plain `*reinterpret_cast<const bf16x8*>(p)` of the 4 x bf16x2 struct
-// gets scalarised into four 32-bit LDG.CONSTANT that the scheduler then serialises with the math (seen in SASS)
-__device__ __forceinline__ bf16x8 ld16(const bf16* p) {
-  // volatile: the compiler otherwise sinks each load next to its use, behind the previous vector's store
-  uint4 u;
-  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p) : "memory");
-  return *reinterpret_cast<const bf16x8*>(&u);
-}
+__device__ __forceinline__ bf16x8 ld16(const bf16* p) { return ldg16_pinned(p); }
 constexpr int kStatThreads = 256;
+constexpr int kStage1 = 8;   // ring depth of the one-input streaming reductions (32 KB per block)
 
 // Sweep direction.  Every streaming kernel walks the volume in BANDS (all blocks side by side, band after band).
 // Experiment (round 1): sweeping a tensor the previous kernel has just written BACK TO FRONT (rev = 1), so that the part
@@ -67,7 +61,7 @@ __device__ __forceinline__ long long sweep_row(long long v, long long V, int rev
 __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* __restrict__ y, int ld, long long V,
                                                                    int C, double* __restrict__ stats,
                                                                    int rev) {
-  extern __shared__ float sm[];  // [rows][CG*8][2]
+  extern __shared__ __align__(16) float sm[];  // staging ring, then [rows][CG*8][2]
   const int b = blockIdx.y;
   const int CG = C >> 3;
   const int rows = kStatThreads / CG;  // voxel rows handled in parallel
@@ -79,34 +73,34 @@ __global__ void __launch_bounds__(kStatThreads) inorm_stats_kernel(const bf16* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows) {
-    long long v = (long long)blockIdx.x * rows + r;
-    for (; v + 3 * step < V; v += 4 * step) {   // four independent 16-byte loads in flight per thread
-      bf16x8 p[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        p[u] = ld16(base + sweep_row(v + u * step, V, rev) * ld + cg * 8);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float f[8];
-        unpack8(p[u], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] += f[i];
-          q[i] = fmaf(f[i], f[i], q[i]);
-        }
-      }
-    }
-    for (; v < V; v += step) {
-      bf16x8 p = ld16(base + sweep_row(v, V, rev) * ld + cg * 8);
+    // cp.async-staged band sweep (private ring of kStage1 slots per thread: bytes in flight cost no registers, and the
+    // assembler cannot sink an async copy next to its use as it does with batches of plain loads)
+    const long long v0 = (long long)blockIdx.x * rows + r;
+    const long long iters = v0 < V ? (V - v0 + step - 1) / step : 0;
+    const bf16x8* ring = reinterpret_cast<const bf16x8*>(sm) + tid;
+    const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(ring);
+    auto issue = [&](long long i) {
+      if (i < iters)
+        cp_async16(ring_u + (uint32_t)(i & (kStage1 - 1)) * (kStatThreads * 16),
+                   base + sweep_row(v0 + i * step, V, rev) * ld + cg * 8);
+      cp_async_commit();
+    };
+    for (int i = 0; i < kStage1 - 1; ++i) issue(i);
+    for (long long i = 0; i < iters; ++i) {
+      issue(i + kStage1 - 1);
+      cp_async_wait<kStage1 - 1>();
+      const bf16x8 p = ring[(int)(i & (kStage1 - 1)) * kStatThreads];
       float f[8];
       unpack8(p, f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] = fmaf(f[i], f[i], q[i]);
+      for (int k = 0; k < 8; ++k) {
+        s[k] += f[k];
+        q[k] = fmaf(f[k], f[k], q[k]);
       }
     }
+    cp_async_wait<0>();
   }
+  __syncthreads();   // the reduction buffers below alias the staging ring
   // reduce across the `rows` threads that share a channel group
   float* ss = sm;                       // [rows][C]
   float* qq = sm + rows * C;            // [rows][C]
@@ -143,11 +137,6 @@ __device__ __forceinline__ void st_stream(bf16* p, const bf16x8& v) {
 // registers for 2 x 2 loads in flight, which caps it at 3 blocks/SM and ~49 KB in flight per SM -- 81 % of the copy
 // rate in the probe; the staged form reaches 100 %).  A thread only ever reads back its own slots: no block barrier.
 constexpr int kStage = 4;
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr size_t kRingBytes = (size_t)2 * kStage * kStatThreads * 16;   // two inputs
 
 // forward apply:  t = bf16(gamma*(y-mean)*rstd + beta);  z = t > 0 ? t : bf16(slope*t)
@@ -524,6 +513,7 @@ int mvd_inorm_stats(const void* y, int ldy, int B, long long V, int C, double* s
               "inorm_stats: need C %% 8 == 0, ld %% 8 == 0, 16B-aligned pointer, C <= 2048 (C=%d ld=%d)", C, ldy);
   const int rows = kStatThreads / (C / 8);
   size_t smem = (size_t)rows * C * 2 * sizeof(float);
+  if (smem < (size_t)kStage1 * kStatThreads * 16) smem = (size_t)kStage1 * kStatThreads * 16;
   long long rpb;
   const long long nblk = one_wave(inorm_stats_kernel, kStatThreads, smem, B, V, (long long)rows * 4, &rpb);
   dim3 grid((unsigned)nblk, B);
