@@ -474,6 +474,275 @@ __global__ void cldice_finalize_kernel(const double* __restrict__ s, float smoot
   out4[3] = (float)(dLs / (s[3] + sm));                              // dL/dS3
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Quad-staged forms for the production shape (C = 4 classes, dense logits rows of 8 bytes, V % 4 == 0).
+// The per-voxel kernels above keep 2 x 12 bytes in flight per thread (~37 KB per SM): they are latency-bound at 25-40 %
+// of the HBM copy rate, not instruction-bound.  Here a thread takes FOUR consecutive voxels per step -- two 16-byte
+// vectors of logits and one of targets -- through a private cp.async ring of kLossStage steps (no registers for the
+// bytes in flight, and the assembler cannot sink the copies next to their uses): ~150 KB in flight per SM.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kLossStage = 4;
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ void unpack_logits_pair(uint32_t lo, uint32_t hi, float* z) {
+  z[0] = __uint_as_float(lo << 16); z[1] = __uint_as_float(lo & 0xffff0000u);
+  z[2] = __uint_as_float(hi << 16); z[3] = __uint_as_float(hi & 0xffff0000u);
+}
+
+// generic software pipeline over `iters` steps: issue_step(i, stage) queues the cp.async copies of step i into ring
+// stage `stage`, body(i, stage) consumes them kLossStage - 1 steps later
+template <typename Issue, typename Body>
+__device__ __forceinline__ void staged_sweep(long long iters, Issue issue_step, Body body) {
+  auto issue = [&](long long i) {
+    if (i < iters) issue_step(i, (int)(i & (kLossStage - 1)));
+    cp_async_commit();
+  };
+  for (int i = 0; i < kLossStage - 1; ++i) issue(i);
+  for (long long i = 0; i < iters; ++i) {
+    issue(i + kLossStage - 1);
+    cp_async_wait<kLossStage - 1>();
+    body(i, (int)(i & (kLossStage - 1)));
+  }
+  cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(kLossThreads) dice_ce_fwd_quad_kernel(const bf16* __restrict__ logits,
+                                                                        const float* __restrict__ target, long long V,
+                                                                        double* __restrict__ acc, int B) {
+  constexpr int C = 4, NS = 3;
+  extern __shared__ __align__(16) uint4 ring4[];
+  const int b = blockIdx.y;
+  const uint4* lq = reinterpret_cast<const uint4*>(logits + (long long)b * V * C);   // 2 vectors per quad
+  const uint4* tq = reinterpret_cast<const uint4*>(target + (long long)b * V);       // 1 vector per quad
+  const long long Q = V >> 2, step = (long long)gridDim.x * kLossThreads;
+  const long long q0 = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  const long long iters = q0 < Q ? (Q - q0 + step - 1) / step : 0;
+  const uint4* mine = ring4 + threadIdx.x;
+  const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
+  float vals[3 * C + 1];
+#pragma unroll
+  for (int i = 0; i < 3 * C + 1; ++i) vals[i] = 0.f;
+  staged_sweep(
+      iters,
+      [&](long long i, int st) {
+        const long long q = q0 + i * step;
+        const uint32_t d = mine_u + (uint32_t)(st * NS) * (kLossThreads * 16);
+        cp_async16(d, lq + 2 * q);
+        cp_async16(d + kLossThreads * 16, lq + 2 * q + 1);
+        cp_async16(d + 2 * kLossThreads * 16, tq + q);
+      },
+      [&](long long, int st) {
+        const uint4 l0 = mine[(st * NS) * kLossThreads], l1 = mine[(st * NS + 1) * kLossThreads];
+        const uint4 tv = mine[(st * NS + 2) * kLossThreads];
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float tf[4] = {__uint_as_float(tv.x), __uint_as_float(tv.y), __uint_as_float(tv.z), __uint_as_float(tv.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float z[C];
+          unpack_logits_pair(lw[2 * j], lw[2 * j + 1], z);
+          const int t = (int)tf[j];
+          float zt = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) zt = (c == t) ? z[c] : zt;
+          const float lse = softmax_inplace<C>(z);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float y = (c == t) ? 1.f : 0.f;
+            vals[3 * c + 0] += z[c] * y;
+            vals[3 * c + 1] += z[c];
+            vals[3 * c + 2] += y;
+          }
+          vals[3 * C] += (t >= 0 && t < C) ? (lse - zt) : 0.f;
+        }
+      });
+  __shared__ float red[8][3 * C + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 3 * C + 1; ++i) {
+    float sum = warp_sum(vals[i]);
+    if (lane == 0) red[warp][i] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C + 1) {
+    double a = 0.0;
+    for (int w = 0; w < kLossThreads / 32; ++w) a += (double)red[w][threadIdx.x];
+    if (threadIdx.x < 3 * C) atomicAdd(&acc[(long long)b * C * 3 + threadIdx.x], a);
+    else atomicAdd(&acc[(long long)B * C * 3], a);
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads) dice_ce_bwd_quad_kernel(const bf16* __restrict__ logits,
+                                                                        const float* __restrict__ target, long long V,
+                                                                        const float* __restrict__ coef, float ce_scale,
+                                                                        float weight, const float* __restrict__ gout,
+                                                                        bf16* __restrict__ dlogits) {
+  constexpr int C = 4, NS = 3;
+  extern __shared__ __align__(16) uint4 ring4[];
+  const int b = blockIdx.y;
+  const uint4* lq = reinterpret_cast<const uint4*>(logits + (long long)b * V * C);
+  const uint4* tq = reinterpret_cast<const uint4*>(target + (long long)b * V);
+  uint4* dq = reinterpret_cast<uint4*>(dlogits + (long long)b * V * C);
+  float A[C], E[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    A[c] = coef[((long long)b * C + c) * 2 + 0];
+    E[c] = coef[((long long)b * C + c) * 2 + 1];
+  }
+  const float g = (gout ? gout[0] : 1.f) * weight;
+  const long long Q = V >> 2, step = (long long)gridDim.x * kLossThreads;
+  const long long q0 = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  const long long iters = q0 < Q ? (Q - q0 + step - 1) / step : 0;
+  const uint4* mine = ring4 + threadIdx.x;
+  const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
+  staged_sweep(
+      iters,
+      [&](long long i, int st) {
+        const long long q = q0 + i * step;
+        const uint32_t d = mine_u + (uint32_t)(st * NS) * (kLossThreads * 16);
+        cp_async16(d, lq + 2 * q);
+        cp_async16(d + kLossThreads * 16, lq + 2 * q + 1);
+        cp_async16(d + 2 * kLossThreads * 16, tq + q);
+      },
+      [&](long long i, int st) {
+        const uint4 l0 = mine[(st * NS) * kLossThreads], l1 = mine[(st * NS + 1) * kLossThreads];
+        const uint4 tv = mine[(st * NS + 2) * kLossThreads];
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float tf[4] = {__uint_as_float(tv.x), __uint_as_float(tv.y), __uint_as_float(tv.z), __uint_as_float(tv.w)};
+        uint32_t ow[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float p[C];
+          unpack_logits_pair(lw[2 * j], lw[2 * j + 1], p);
+          const int t = (int)tf[j];
+          softmax_inplace<C>(p);
+          float qv[C], dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            qv[c] = ((c == t) ? A[c] : 0.f) - E[c];
+            dot = fmaf(p[c], qv[c], dot);
+          }
+          float o[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float dce = (p[c] - ((c == t) ? 1.f : 0.f)) * ce_scale;
+            o[c] = g * (dce + p[c] * (qv[c] - dot));
+          }
+          __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), bb = __floats2bfloat162_rn(o[2], o[3]);
+          ow[2 * j] = *reinterpret_cast<uint32_t*>(&a);
+          ow[2 * j + 1] = *reinterpret_cast<uint32_t*>(&bb);
+        }
+        const long long q = q0 + i * step;
+        dq[2 * q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        dq[2 * q + 1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      });
+}
+
+// KL, C = 4 dense: a thread takes four consecutive voxels per step (2 + 2 vectors of logits), same staging as above.
+template <bool BWD>
+__global__ void __launch_bounds__(kLossThreads) kl_quad_kernel(const bf16* __restrict__ ys, const bf16* __restrict__ yt,
+                                                               long long NV, float invT, double* __restrict__ loss_sum,
+                                                               float scale, const float* __restrict__ gout,
+                                                               bf16* __restrict__ dys, bf16* __restrict__ dyt) {
+  constexpr int C = 4, NS = 4;
+  extern __shared__ __align__(16) uint4 ring4[];
+  const uint4* sq = reinterpret_cast<const uint4*>(ys);
+  const uint4* tq = reinterpret_cast<const uint4*>(yt);
+  const long long Q = NV >> 2, step = (long long)gridDim.x * kLossThreads;
+  const long long q0 = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  const long long iters = q0 < Q ? (Q - q0 + step - 1) / step : 0;
+  const uint4* mine = ring4 + threadIdx.x;
+  const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
+  const float g = BWD ? (gout ? gout[0] : 1.f) * scale * invT : 0.f;
+  float acc = 0.f;
+  staged_sweep(
+      iters,
+      [&](long long i, int st) {
+        const long long q = q0 + i * step;
+        const uint32_t d = mine_u + (uint32_t)(st * NS) * (kLossThreads * 16);
+        cp_async16(d, sq + 2 * q);
+        cp_async16(d + kLossThreads * 16, sq + 2 * q + 1);
+        cp_async16(d + 2 * kLossThreads * 16, tq + 2 * q);
+        cp_async16(d + 3 * kLossThreads * 16, tq + 2 * q + 1);
+      },
+      [&](long long i, int st) {
+        const uint4 s0 = mine[(st * NS) * kLossThreads], s1 = mine[(st * NS + 1) * kLossThreads];
+        const uint4 t0 = mine[(st * NS + 2) * kLossThreads], t1 = mine[(st * NS + 3) * kLossThreads];
+        const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        uint32_t os[8], ot[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float us[C], ut[C], ps[C], pt[C];
+          unpack_logits_pair(sw[2 * j], sw[2 * j + 1], us);
+          unpack_logits_pair(tw[2 * j], tw[2 * j + 1], ut);
+#pragma unroll
+          for (int c = 0; c < C; ++c) { us[c] *= invT; ut[c] *= invT; ps[c] = us[c]; pt[c] = ut[c]; }
+          const float lse_s = softmax_inplace<C>(ps);
+          const float lse_t = softmax_inplace<C>(pt);
+          float d[C], dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            d[c] = (ut[c] - lse_t) - (us[c] - lse_s);
+            if (BWD) dot = fmaf(pt[c], d[c], dot);
+            else acc += pt[c] > 0.f ? pt[c] * d[c] : 0.f;
+          }
+          if (BWD) {
+            float o[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[c] = g * (ps[c] - pt[c]);
+            __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+            os[2 * j] = *reinterpret_cast<uint32_t*>(&a); os[2 * j + 1] = *reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[c] = g * pt[c] * (d[c] - dot);
+            a = __floats2bfloat162_rn(o[0], o[1]); b = __floats2bfloat162_rn(o[2], o[3]);
+            ot[2 * j] = *reinterpret_cast<uint32_t*>(&a); ot[2 * j + 1] = *reinterpret_cast<uint32_t*>(&b);
+          }
+        }
+        if (BWD) {
+          const long long q = q0 + i * step;
+          if (dys) {
+            uint4* o4 = reinterpret_cast<uint4*>(dys) + 2 * q;
+            o4[0] = make_uint4(os[0], os[1], os[2], os[3]);
+            o4[1] = make_uint4(os[4], os[5], os[6], os[7]);
+          }
+          if (dyt) {
+            uint4* o4 = reinterpret_cast<uint4*>(dyt) + 2 * q;
+            o4[0] = make_uint4(ot[0], ot[1], ot[2], ot[3]);
+            o4[1] = make_uint4(ot[4], ot[5], ot[6], ot[7]);
+          }
+        }
+      });
+  if (!BWD) {
+    float vals[1] = {acc};
+    block_accumulate<1>(vals, loss_sum);
+  }
+}
+
+// one resident wave of quad-kernel blocks per sample; quad_ok() is false when the shape is not the dense C = 4 one
+static bool quad_ok(const void* logits, int ld, const float* target, long long V, int C) {
+  return C == 4 && ld == 4 && (V & 3) == 0 && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)target & 15) == 0;
+}
+template <typename K>
+static int quad_grid(K kernel, size_t smem, int B, long long V, int idx) {
+  static bool done[8] = {false, false, false, false, false, false, false, false};
+  if (!done[idx]) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    done[idx] = true;
+  }
+  int bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, kLossThreads, smem) != cudaSuccess || bps < 1) {
+    (void)cudaGetLastError();
+    bps = 2;
+  }
+  long long nb = ((long long)num_sms() * bps) / (B > 0 ? B : 1);
+  const long long need = ((V >> 2) + kLossThreads - 1) / kLossThreads;
+  if (nb > need) nb = need;
+  return nb < 1 ? 1 : (int)nb;
+}
+
 }  // namespace mvd
 
 using namespace mvd;
@@ -496,6 +765,16 @@ extern "C" {
 int mvd_dice_ce_fwd(const void* logits, int ld, const float* target, int B, long long V, int C, double* acc,
                     mvd_stream_t stream) {
   MVD_REQUIRE(logits && target && acc && B > 0 && V > 0 && ld >= C, "dice_ce_fwd: bad arguments");
+  if (quad_ok(logits, ld, target, V, C)) {
+    const size_t smem = (size_t)kLossStage * 3 * kLossThreads * 16;
+    const int nb = quad_grid(dice_ce_fwd_quad_kernel, smem, B, V, 0);
+    if (nb > 0) {
+      dice_ce_fwd_quad_kernel<<<dim3((unsigned)nb, B), kLossThreads, smem, (cudaStream_t)stream>>>(
+          (const bf16*)logits, target, V, acc, B);
+      MVD_LAUNCH_CHECK("dice_ce_fwd");
+      return MVD_OK;
+    }
+  }
   dim3 grid(grid_for(V, 256 * 4, (num_sms() * 8) / (B > 0 ? B : 1) > 0 ? (num_sms() * 8) / B : 1), B);
 #define CALL(CC) dice_ce_fwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, target, V, acc, B)
   C_DISPATCH(C, CALL)
@@ -516,6 +795,16 @@ int mvd_dice_ce_finalize(const double* acc, int B, long long V, int C, float smo
 int mvd_dice_ce_bwd(const void* logits, int ld, const float* target, int B, long long V, int C, const float* coef,
                     float w_ce, float weight, const float* gout, void* dlogits, int ldd, mvd_stream_t stream) {
   MVD_REQUIRE(logits && target && coef && dlogits && B > 0 && V > 0 && ld >= C && ldd >= C, "dice_ce_bwd: bad arguments");
+  if (quad_ok(logits, ld, target, V, C) && ldd == 4 && ((uintptr_t)dlogits & 15) == 0) {
+    const size_t smem = (size_t)kLossStage * 3 * kLossThreads * 16;
+    const int nb = quad_grid(dice_ce_bwd_quad_kernel, smem, B, V, 1);
+    if (nb > 0) {
+      dice_ce_bwd_quad_kernel<<<dim3((unsigned)nb, B), kLossThreads, smem, (cudaStream_t)stream>>>(
+          (const bf16*)logits, target, V, coef, w_ce / ((float)B * (float)V), weight, gout, (bf16*)dlogits);
+      MVD_LAUNCH_CHECK("dice_ce_bwd");
+      return MVD_OK;
+    }
+  }
   dim3 grid(grid_for(V, 256 * 4, (num_sms() * 8) / B > 0 ? (num_sms() * 8) / B : 1), B);
   const float ce_scale = w_ce / ((float)B * (float)V);
 #define CALL(CC)                                                                                                   \
@@ -542,6 +831,16 @@ int mvd_argmax_tp_fp_fn(const void* logits, int ld, const float* target, int B, 
 int mvd_kl_fwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, double* loss_sum,
                mvd_stream_t stream) {
   MVD_REQUIRE(ys && yt && loss_sum && NV > 0 && lds >= C && ldt >= C && T > 0.f, "kl_fwd: bad arguments");
+  if (C == 4 && lds == 4 && ldt == 4 && (NV & 3) == 0 && (((uintptr_t)ys | (uintptr_t)yt) & 15) == 0) {
+    const size_t smem = (size_t)kLossStage * 4 * kLossThreads * 16;
+    const int nb = quad_grid(kl_quad_kernel<false>, smem, 1, NV, 2);
+    if (nb > 0) {
+      kl_quad_kernel<false><<<nb, kLossThreads, smem, (cudaStream_t)stream>>>((const bf16*)ys, (const bf16*)yt, NV, 1.f / T,
+                                                                             loss_sum, 0.f, nullptr, nullptr, nullptr);
+      MVD_LAUNCH_CHECK("kl_fwd");
+      return MVD_OK;
+    }
+  }
   int grid = grid_for(NV, 256 * 2, num_sms() * 8);
 #define CALL(CC) kl_fwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)ys, lds, (const bf16*)yt, ldt, NV, 1.f / T, loss_sum)
   C_DISPATCH(C, CALL)
@@ -553,6 +852,17 @@ int mvd_kl_fwd(const void* ys, int lds, const void* yt, int ldt, long long NV, i
 int mvd_kl_bwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, float scale,
                const float* gout, void* dys, int ldds, void* dyt, int lddt, mvd_stream_t stream) {
   MVD_REQUIRE(ys && yt && NV > 0 && lds >= C && ldt >= C && T > 0.f && (dys || dyt), "kl_bwd: bad arguments");
+  if (C == 4 && lds == 4 && ldt == 4 && (NV & 3) == 0 && (((uintptr_t)ys | (uintptr_t)yt) & 15) == 0 &&
+      (!dys || (ldds == 4 && ((uintptr_t)dys & 15) == 0)) && (!dyt || (lddt == 4 && ((uintptr_t)dyt & 15) == 0))) {
+    const size_t smem = (size_t)kLossStage * 4 * kLossThreads * 16;
+    const int nb = quad_grid(kl_quad_kernel<true>, smem, 1, NV, 3);
+    if (nb > 0) {
+      kl_quad_kernel<true><<<nb, kLossThreads, smem, (cudaStream_t)stream>>>((const bf16*)ys, (const bf16*)yt, NV, 1.f / T,
+                                                                            nullptr, scale, gout, (bf16*)dys, (bf16*)dyt);
+      MVD_LAUNCH_CHECK("kl_bwd");
+      return MVD_OK;
+    }
+  }
   int grid = grid_for(NV, 256 * 2, num_sms() * 8);
 #define CALL(CC)                                                                                                 \
   kl_bwd_kernel<CC><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)ys, lds, (const bf16*)yt, ldt, NV, 1.f / T, \

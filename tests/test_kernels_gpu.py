@@ -304,9 +304,10 @@ def _logits_targets(B, C, shape, seed, scales=1):
 
 @pytest.mark.parametrize('batch_dice', [False, True])
 @pytest.mark.parametrize('C', [4, 3])
-def test_dc_and_ce_matches_oracle(m, batch_dice, C):
+@pytest.mark.parametrize('shape', [(9, 10, 11), (8, 10, 12), (40, 36, 44)])   # V % 4 != 0 (per-voxel kernels) / == 0 (quad-staged)
+def test_dc_and_ce_matches_oracle(m, batch_dice, C, shape):
     import oracle
-    (lg,), (tg,) = _logits_targets(2, C, (9, 10, 11), 41)
+    (lg,), (tg,) = _logits_targets(2, C, shape, 41)
     mine = m.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {},
                             weight_ce=1, weight_dice=1, ignore_label=None, dice_class=m.MemoryEfficientSoftDiceLoss)
     ref = oracle.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {},
@@ -361,10 +362,11 @@ def test_argmax_tp_fp_fn(m):
 
 
 @pytest.mark.parametrize('C,T', [(4, 1.0), (4, 2.0), (1, 1.0)])
-def test_distill_kl_matches_oracle(m, C, T):
+@pytest.mark.parametrize('shape', [(8, 9, 10), (7, 9, 5), (36, 40, 44)])   # NV % 4 == 0 (quad-staged) / != 0 (per-voxel)
+def test_distill_kl_matches_oracle(m, C, T, shape):
     import oracle
-    (a,), _ = _logits_targets(2, 4, (8, 9, 10), 51)
-    (b,), _ = _logits_targets(2, 4, (8, 9, 10), 52)
+    (a,), _ = _logits_targets(2, 4, shape, 51)
+    (b,), _ = _logits_targets(2, 4, shape, 52)
     av, bv = m.ops.ncdhw_view(a), m.ops.ncdhw_view(b)
     ar, br = a.float().permute(0, 4, 1, 2, 3), b.float().permute(0, 4, 1, 2, 3)
     if C == 1:   # the vessel-channel call site (MVDTrainer.py:897-899): a strided one-channel view
