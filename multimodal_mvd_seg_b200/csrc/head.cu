@@ -261,6 +261,172 @@ __global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// cp.async-staged forms of the two kernels above for K = 4 classes with 8-byte logit rows (the production heads).
+// The direct-load forms need 94 / 128 registers for 4 rows in flight (2 blocks/SM, ~49 KB in flight per SM: half the HBM
+// copy rate in the step profile); here the rows wait in a private ring of kHeadStage slots per thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kHeadStage = 8;
+
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+
+template <int CG>
+__global__ void __launch_bounds__(256, 3) head_fwd_cg4_staged_kernel(const bf16* __restrict__ z, int ldz,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias,
+                                                                     bf16* __restrict__ out, int ldl, long long NV) {
+  constexpr int K = 4, C = CG * 8, ROWS = 256 / CG;
+  extern __shared__ __align__(16) uint4 hring[];
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  float wr[K][8], bz[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    bz[k] = bias ? round_bf(bias[k]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[k][j] = round_bf(w[k * C + cg * 8 + j]);
+  }
+  const long long step = (long long)gridDim.x * ROWS;
+  const long long v0 = (long long)blockIdx.x * ROWS + r;
+  // all lanes of a warp must run the same number of steps (the class sums are reduced with warp shuffles)
+  const long long vw = (long long)blockIdx.x * ROWS + (threadIdx.x & ~31) / CG;
+  const long long iters = vw < NV ? (NV - vw + step - 1) / step : 0;
+  const uint4* mine = hring + threadIdx.x;
+  const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
+  auto issue = [&](long long i) {
+    const long long v = v0 + i * step;
+    if (i < iters && v < NV) cp_async16(mine_u + (uint32_t)(i & (kHeadStage - 1)) * 4096, z + v * ldz + cg * 8);
+    cp_async_commit();
+  };
+  for (int i = 0; i < kHeadStage - 1; ++i) issue(i);
+  for (long long i = 0; i < iters; ++i) {
+    issue(i + kHeadStage - 1);
+    cp_async_wait<kHeadStage - 1>();
+    const long long v = v0 + i * step;
+    const bool ok = v < NV;
+    float f[8];
+    if (ok) {
+      const uint4 u = mine[(int)(i & (kHeadStage - 1)) * 256];
+      unpack8(*reinterpret_cast<const bf16x8*>(&u), f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(f[j], wr[k][j], a);
+#pragma unroll
+      for (int off = CG / 2; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      acc[k] = a + bz[k];
+    }
+    if (ok && cg == 0) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
+      *reinterpret_cast<uint2*>(out + v * ldl) = make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b));
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int CG>
+__global__ void __launch_bounds__(256, 2) head_bwd_cg4_staged_kernel(const bf16* __restrict__ dl, int ldl,
+                                                                     const bf16* __restrict__ z, int ldz,
+                                                                     const float* __restrict__ w, bf16* __restrict__ dz,
+                                                                     int lddz, float* __restrict__ dw,
+                                                                     float* __restrict__ dbias, long long NV) {
+  constexpr int K = 4, C = CG * 8, ROWS = 256 / CG;
+  extern __shared__ __align__(16) uint4 hring[];     // [stage][256] z vectors, then [stage][256] 8-byte logit-gradient rows
+  __shared__ float sacc[K * C + K];
+  for (int i = threadIdx.x; i < K * C + K; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  float wr[K][8], acc[K][8], accb[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wr[k][j] = round_bf(w[k * C + cg * 8 + j]); acc[k][j] = 0.f; }
+  }
+  const long long step = (long long)gridDim.x * ROWS;
+  const long long v0 = (long long)blockIdx.x * ROWS + r;
+  const long long iters = v0 < NV ? (NV - v0 + step - 1) / step : 0;
+  const uint4* mine = hring + threadIdx.x;
+  const uint2* mine_g = reinterpret_cast<const uint2*>(hring + kHeadStage * 256) + threadIdx.x;
+  const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
+  const uint32_t mine_gu = (uint32_t)__cvta_generic_to_shared(mine_g);
+  const bool need_z = dw != nullptr;
+  auto issue = [&](long long i) {
+    if (i < iters) {
+      const long long v = v0 + i * step;
+      const int st = (int)(i & (kHeadStage - 1));
+      if (need_z) cp_async16(mine_u + (uint32_t)st * 4096, z + v * ldz + cg * 8);
+      cp_async8(mine_gu + (uint32_t)st * 2048, dl + v * ldl);
+    }
+    cp_async_commit();
+  };
+  for (int i = 0; i < kHeadStage - 1; ++i) issue(i);
+  for (long long i = 0; i < iters; ++i) {
+    issue(i + kHeadStage - 1);
+    cp_async_wait<kHeadStage - 1>();
+    const int st = (int)(i & (kHeadStage - 1));
+    const long long v = v0 + i * step;
+    const uint2 gu = mine_g[st * 256];
+    float g[K];
+    g[0] = __uint_as_float(gu.x << 16); g[1] = __uint_as_float(gu.x & 0xffff0000u);
+    g[2] = __uint_as_float(gu.y << 16); g[3] = __uint_as_float(gu.y & 0xffff0000u);
+    if (dz) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a = fmaf(g[k], wr[k][j], a);
+        o[j] = a;
+      }
+      stg16(dz + v * lddz + cg * 8, pack8(o));
+    }
+    if (need_z) {
+      const uint4 u = mine[st * 256];
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&u), f);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        accb[k] += g[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g[k], f[j], acc[k][j]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (dw) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[k * C + cg * 8 + j], acc[k][j]);
+      if (cg == 0) atomicAdd(&sacc[K * C + k], accb[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * C; i += 256) atomicAdd(&dw[i], sacc[i]);
+    if (dbias && threadIdx.x < K) atomicAdd(&dbias[threadIdx.x], sacc[K * C + threadIdx.x]);
+  }
+}
+
+template <typename Kern>
+static int head_staged_grid(Kern kern, size_t smem, long long NV, int rows) {
+  int bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, smem) != cudaSuccess || bps < 1) {
+    (void)cudaGetLastError();
+    bps = 2;
+  }
+  long long g = (long long)num_sms() * bps;
+  const long long need = (NV + rows - 1) / rows;
+  if (g > need) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
 template <typename Kern>
 static int head_wave_grid(Kern kern, long long NV, int rows) {
   int bps = 0;
@@ -278,6 +444,15 @@ template <int K, int CG>
 static int head_fwd_cg_launch(const bf16* z, int ldz, const float* w, const float* b, bf16* out, int ldl, long long NV,
                               cudaStream_t st) {
   const int vec = (K == 4 && ldl % 4 == 0 && ((uintptr_t)out & 7) == 0) ? 1 : 0;
+  if constexpr (K == 4) {
+    if (vec && ldz % 8 == 0 && ((uintptr_t)z & 15) == 0) {
+      const size_t smem = (size_t)kHeadStage * 4096;
+      const int grid = head_staged_grid(head_fwd_cg4_staged_kernel<CG>, smem, NV, 256 / CG);
+      head_fwd_cg4_staged_kernel<CG><<<grid, 256, smem, st>>>(z, ldz, w, b, out, ldl, NV);
+      MVD_LAUNCH_CHECK("head_fwd");
+      return MVD_OK;
+    }
+  }
   const int grid = head_wave_grid(head_fwd_cg_kernel<K, CG>, NV, 256 / CG);
   head_fwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(z, ldz, w, b, out, ldl, NV, vec);
   MVD_LAUNCH_CHECK("head_fwd");
@@ -288,6 +463,20 @@ template <int K, int CG>
 static int head_bwd_cg_launch(const bf16* dl, int ldl, const bf16* z, int ldz, const float* w, bf16* dz, int lddz,
                               float* dw, float* db, long long NV, cudaStream_t st) {
   const int vec = (K == 4 && ldl % 4 == 0 && ((uintptr_t)dl & 7) == 0) ? 1 : 0;
+  if constexpr (K == 4) {
+    if (vec && ldz % 8 == 0 && ((uintptr_t)z & 15) == 0 && (!dz || (lddz % 8 == 0 && ((uintptr_t)dz & 15) == 0))) {
+      const size_t smem = (size_t)kHeadStage * (4096 + 2048);
+      static bool attr_done = false;   // dynamic + static shared memory exceeds the 48 KB default
+      if (!attr_done) {
+        MVD_CUDA(cudaFuncSetAttribute(head_bwd_cg4_staged_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+      }
+      const int grid = head_staged_grid(head_bwd_cg4_staged_kernel<CG>, smem, NV, 256 / CG);
+      head_bwd_cg4_staged_kernel<CG><<<grid, 256, smem, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV);
+      MVD_LAUNCH_CHECK("head_bwd");
+      return MVD_OK;
+    }
+  }
   const int grid = head_wave_grid(head_bwd_cg_kernel<K, CG>, NV, 256 / CG);
   head_bwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, vec);
   MVD_LAUNCH_CHECK("head_bwd");
