@@ -83,6 +83,13 @@ typedef struct {
 int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float scale, float* acc, float* npred, int K,
                       int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, mvd_stream_t stream);
 int mvd_sw_finalize(float* acc, const float* npred, int K, long long vol, mvd_stream_t stream);   /* acc /= npred */
+/* Deep-supervision targets on the GPU.  Replaces DownsampleSegForDSTransform2.__call__
+ * (training/data_augmentation/custom_transforms/deep_supervision_donwsampling.py:27-55; batchgenerators'
+ * resize_segmentation with order 0): nearest-neighbour with pixel-centre alignment, src = floor((o + 0.5) * I / O) per
+ * axis.  seg: fp32 [BC][Di][Hi][Wi] (BC = batch x seg channels); dst[s]: fp32 [BC][Do_s][Ho_s][Wo_s] with
+ * out_dhw = {Do_0, Ho_0, Wo_0, Do_1, ...} (HOST arrays, n_scales <= 8); all scales in one launch. */
+int mvd_downsample_seg_nearest(const float* seg, int BC, int Di, int Hi, int Wi, int n_scales, float* const* dst,
+                               const int* out_dhw, mvd_stream_t stream);
 /* The stem (first conv: Cin = 1 or 2 modalities -> 32 features, 3x3x3, stride 1, pad 1) as a tensor-core GEMM whose
  * im2col tile is built in shared memory (csrc/stem_tc.cu); replaces nn.Conv3d(Cin, 32, 3, padding=1) of
  * get_network_from_plans.py:75-77 for the first block.

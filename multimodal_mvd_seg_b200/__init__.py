@@ -15,3 +15,4 @@ from .trainer import nnUNetTrainer, MVDTrainer, make_plans, PlansManager, Config
 
 __version__ = '0.1.0'
 from .inference import SlidingWindowPredictor, compute_gaussian, compute_steps_for_sliding_window
+from .ds_targets import DownsampleSegForDSTransform2, downsample_seg_for_ds

@@ -55,6 +55,7 @@ _SIGNATURES = {
     'mvd_ndhwc_bf16_to_ncdhw_f32': (c_int, [P, I, P, I, I, LL, S]),
     'mvd_sw_accumulate': (c_int, [P, I, P, F, P, P, I, I, I, I, I, I, I, I, I, I, S]),
     'mvd_sw_finalize': (c_int, [P, P, I, LL, S]),
+    'mvd_downsample_seg_nearest': (c_int, [P, I, I, I, I, I, P, P, S]),
     'mvd_stem_conv_fprop': (c_int, [P, I, I, I, I, I, P, P, P, I, P, S]),
     'mvd_stem_conv_wgrad': (c_int, [P, I, I, I, I, I, P, I, P, S]),
     'mvd_pack_conv_weights_multi': (c_int, [P, I, I, S]),

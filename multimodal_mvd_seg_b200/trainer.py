@@ -23,6 +23,7 @@ from torch import nn
 
 from . import ops
 from .ddp import GradArena, split_batch_for_rank
+from .ds_targets import downsample_seg_for_ds
 from .losses import (DC_and_CE_loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss, distill_kl, soft_cldice,
                      softmax_channel)
 from .network import get_network_from_plans
@@ -271,6 +272,10 @@ class nnUNetTrainer(object):
             target = [i.to(self.device, non_blocking=True) for i in target]
         else:
             target = target.to(self.device, non_blocking=True)
+            if self.enable_deep_supervision:
+                # a batch that carries only the full-resolution segmentation: the coarser deep-supervision targets are
+                # produced on the GPU (the reference's CPU workers run DownsampleSegForDSTransform2, MVDTrainer.py:757-760)
+                target = downsample_seg_for_ds(target, self._get_deep_supervision_scales())
         return data, target
 
     def train_step(self, batch: dict) -> dict:

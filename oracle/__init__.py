@@ -36,3 +36,4 @@ from .synthetic import make_batch, structured_labels
 
 __all__ = [n for n in dir() if not n.startswith('_')]
 from . import inference
+from . import ds_targets

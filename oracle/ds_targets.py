@@ -1,0 +1,62 @@
+"""ORACLE (test infrastructure only; never imported by the product path): CPU restatement of the deep-supervision
+target transform.
+
+Follows ``DownsampleSegForDSTransform2.__call__`` (nnunetv2/training/data_augmentation/custom_transforms/
+deep_supervision_donwsampling.py:27-55) line by line.  The resampling itself lives in a third-party dependency that is
+NOT in the tree and not installable here: ``batchgenerators>=0.25`` (setup.py:20) ``augmentations.utils.
+resize_segmentation(segmentation, new_shape, order)``, which for order 0 returns ``skimage.transform.resize(
+segmentation.astype(float), new_shape, order=0, mode="edge", clip=True, anti_aliasing=False).astype(dtype)``;
+scikit-image >= 0.19 implements that call as ``scipy.ndimage.zoom(image, new/old, order=0, mode='nearest',
+grid_mode=True)``.  scipy IS installed, so ``resize_segmentation`` below calls exactly that, and
+``nearest_index`` states the closed form the CUDA kernel uses (src = floor((o + 0.5) * I / O)); the CPU tests pin one
+against the other.  PARITY UNPINNED by the reference's own tests (it has none for this transform)."""
+import numpy as np
+from scipy import ndimage
+
+
+def nearest_index(out_size: int, in_size: int) -> np.ndarray:
+    o = np.arange(out_size, dtype=np.int64)
+    return np.minimum(((2 * o + 1) * in_size) // (2 * out_size), in_size - 1)
+
+
+def resize_segmentation(segmentation: np.ndarray, new_shape, order: int = 0) -> np.ndarray:
+    assert order == 0, 'only the nearest-neighbour branch is restated'
+    assert len(segmentation.shape) == len(new_shape)
+    zoom = [n / o for n, o in zip(new_shape, segmentation.shape)]
+    out = ndimage.zoom(segmentation.astype(float), zoom, order=0, mode='nearest', grid_mode=True)
+    assert out.shape == tuple(new_shape)
+    return out.astype(segmentation.dtype)
+
+
+def resize_segmentation_closed_form(segmentation: np.ndarray, new_shape) -> np.ndarray:
+    idx = [nearest_index(n, o) for n, o in zip(new_shape, segmentation.shape)]
+    return segmentation[np.ix_(*idx)]
+
+
+class DownsampleSegForDSTransform2:
+    def __init__(self, ds_scales, order: int = 0, input_key: str = 'seg', output_key: str = 'seg', axes=None):
+        self.axes, self.output_key, self.input_key, self.order, self.ds_scales = axes, output_key, input_key, order, ds_scales
+
+    def __call__(self, **data_dict):
+        seg = data_dict[self.input_key]
+        axes = list(range(2, len(seg.shape))) if self.axes is None else self.axes          # :28-31
+        output = []
+        for s in self.ds_scales:                                                               # :34
+            if not isinstance(s, (tuple, list)):
+                s = [s] * len(axes)
+            else:
+                assert len(s) == len(axes)
+            if all(i == 1 for i in s):                                                         # :43-44
+                output.append(seg)
+            else:
+                new_shape = np.array(seg.shape).astype(float)                                  # :46-49
+                for i, a in enumerate(axes):
+                    new_shape[a] *= s[i]
+                new_shape = np.round(new_shape).astype(int)
+                out_seg = np.zeros(new_shape, dtype=seg.dtype)                                 # :50
+                for b in range(seg.shape[0]):
+                    for c in range(seg.shape[1]):
+                        out_seg[b, c] = resize_segmentation(seg[b, c], new_shape[2:], self.order)   # :51-52
+                output.append(out_seg)
+        data_dict[self.output_key] = output
+        return data_dict

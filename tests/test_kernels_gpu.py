@@ -486,3 +486,53 @@ def test_sgd_nesterov_clip_matches_torch(m):
         for a, b in zip(p_ref, p_mine):
             assert rel_err(b.detach(), a.detach()) < 1e-6
         ref.param_groups[0]['lr'] = mine.param_groups[0]['lr'] = 5e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# deep-supervision targets on the GPU (mvd_downsample_seg_nearest): bit-exact against the oracle transform
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape,scales', [
+    ((2, 1, 16, 16, 12), [[1, 1, 1], [0.5, 0.5, 0.5], [0.25, 0.25, 0.25], [0.125, 0.125, 0.25]]),
+    ((1, 2, 20, 18, 9), [[0.5, 0.5, 0.5], [1, 1, 1], [0.25, 0.25, 1]]),
+    ((2, 1, 40, 40, 24), [[1, 1, 1], [0.5, 0.5, 0.5], [0.25, 0.25, 0.25], [0.125, 0.125, 0.125], [0.0625, 0.0625, 0.125]]),
+])
+def test_ds_targets_match_oracle(m, shape, scales):
+    from oracle import ds_targets
+    rng = np.random.default_rng(9)
+    seg = rng.integers(-1, 4, size=shape).astype(np.float32)
+    want = ds_targets.DownsampleSegForDSTransform2(scales, 0, input_key='target', output_key='target')(target=seg)['target']
+    x = torch.from_numpy(seg).to(dev())
+    got = m.DownsampleSegForDSTransform2(scales, 0, input_key='target', output_key='target')(target=x)['target']
+    assert len(got) == len(want)
+    for g, w, s in zip(got, want, scales):
+        if all(v == 1 for v in s):
+            assert g is x
+        assert tuple(g.shape) == w.shape and np.array_equal(g.cpu().numpy(), w)
+    with pytest.raises(RuntimeError):
+        m.downsample_seg_for_ds(torch.from_numpy(seg), scales)      # no CPU path
+    with pytest.raises(NotImplementedError):
+        m.DownsampleSegForDSTransform2(scales, order=1)
+
+
+def test_train_step_builds_ds_targets_on_gpu(m):
+    """a batch carrying only the full-resolution target gives the same loss as the list the oracle transform builds."""
+    from oracle import ds_targets
+    patch = (32, 32, 32)
+    plans, dj = m.make_plans(patch, batch_size=2, n_modalities=2, n_classes=4)
+    losses = []
+    for mode in ('list', 'full'):
+        torch.manual_seed(0)
+        tr = m.nnUNetTrainer(plans, '3d_fullres', 0, dj, device=dev())
+        tr.initialize()
+        tr.on_train_epoch_start()
+        g = torch.Generator().manual_seed(5)
+        data = torch.rand((2, 2) + patch, generator=g)
+        full = torch.round(torch.rand((2, 1) + patch, generator=g) * 3)
+        scales = tr._get_deep_supervision_scales()
+        if mode == 'list':
+            tl = ds_targets.DownsampleSegForDSTransform2(scales, 0, input_key='t', output_key='t')(t=full.numpy())['t']
+            target = [torch.from_numpy(np.ascontiguousarray(t)) for t in tl]
+        else:
+            target = full
+        losses.append(float(tr.train_step({'data': data, 'target': target})['loss']))
+    assert losses[0] == losses[1]

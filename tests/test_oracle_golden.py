@@ -115,3 +115,31 @@ def test_ds_weights_and_step_helpers():
         _, bufs = oracle.sgd_nesterov_clip_step(p_mine, grads, bufs, 1e-2)
         for a, b in zip(p_ref, p_mine):
             np.testing.assert_allclose(a.detach().numpy(), b.numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# deep-supervision target transform (oracle/ds_targets.py): the restated third-party resampling (scipy.ndimage.zoom,
+# what skimage.transform.resize(order=0) calls) against the closed form the CUDA kernel implements
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape,new', [((16, 16, 12), (8, 8, 6)), ((20, 20, 12), (10, 10, 12)), ((9, 7, 5), (4, 4, 2)),
+                                       ((12, 10, 6), (3, 2, 2)), ((5, 6, 7), (5, 3, 7))])
+def test_ds_resize_segmentation_closed_form(shape, new):
+    from oracle import ds_targets
+    rng = np.random.default_rng(7)
+    seg = rng.integers(-1, 4, size=shape).astype(np.int16)
+    a = ds_targets.resize_segmentation(seg, new, 0)
+    b = ds_targets.resize_segmentation_closed_form(seg, new)
+    assert a.dtype == seg.dtype and np.array_equal(a, b)
+    if all(o == 2 * n for o, n in zip(shape, new)):     # factor-2 pyramid: the odd voxel of every pair
+        assert np.array_equal(a, seg[1::2, 1::2, 1::2])
+
+
+def test_ds_transform_oracle_contract():
+    from oracle import ds_targets
+    rng = np.random.default_rng(8)
+    seg = rng.integers(0, 4, size=(2, 1, 16, 16, 12)).astype(np.float32)
+    scales = [[1, 1, 1], [0.5, 0.5, 0.5], [0.25, 0.25, 0.5]]
+    out = ds_targets.DownsampleSegForDSTransform2(scales, 0, input_key='target', output_key='target')(target=seg)['target']
+    assert out[0] is seg                                           # all-ones scale: the input object itself (:43-44)
+    assert out[1].shape == (2, 1, 8, 8, 6) and out[2].shape == (2, 1, 4, 4, 6)
+    assert np.array_equal(out[1], seg[:, :, 1::2, 1::2, 1::2])
