@@ -303,7 +303,75 @@ class nnUNetTrainer(object):
         self.optimizer.step(grad_scale=1.0 / world)
         return l.detach()
 
+    # ---- one-batch-ahead upload ---------------------------------------------------------------------------------
+    def prefetching(self, batches):
+        """iterate host batches with the NEXT batch's host->device copy already in flight.
+
+        ``for batch in trainer.prefetching(loader): trainer.train_step(batch)`` is the training loop of
+        ``run_training`` (MVDTrainer.py:1323-1331: ``self.train_step(next(self.dataloader_train))``) with the upload of
+        batch i+1 issued on a copy stream before batch i is stepped, so the PCIe transfer (50 MB per cfg-2 batch,
+        ~0.6 ms) runs underneath the previous step's kernels instead of in front of its own forward pass.  The yielded
+        objects are the host batches themselves; ``train_step`` recognises them and takes the staged device copies."""
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        self._stage_upload(nxt)
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                self._stage_upload(nxt)
+            yield cur
+
+    def _stage_upload(self, batch: dict) -> None:
+        st = self.__dict__.setdefault('_upload_state', dict(stream=torch.cuda.Stream(device=self.device), slots=[None, None],
+                                                             turn=0, staged={}))
+        k = st['turn']
+        st['turn'] ^= 1
+        target = batch['target'] if isinstance(batch['target'], list) else [batch['target']]
+        slot = st['slots'][k]
+        shapes = (tuple(batch['data'].shape), tuple(tuple(t.shape) for t in target))
+        if slot is None or slot['shapes'] != shapes:
+            slot = st['slots'][k] = dict(shapes=shapes,
+                                         data=torch.empty(batch['data'].shape, dtype=batch['data'].dtype, device=self.device),
+                                         target=[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in target],
+                                         ready=torch.cuda.Event(), consumed=None)
+        side = st['stream']
+        if slot['consumed'] is not None:
+            side.wait_event(slot['consumed'])     # the step that used this slot has copied it into the graph inputs
+        with torch.cuda.stream(side):
+            slot['data'].copy_(batch['data'], non_blocking=True)
+            for a, b in zip(slot['target'], target):
+                a.copy_(b, non_blocking=True)
+            slot['ready'].record(side)
+        for key in [i for i, v in st['staged'].items() if v is slot]:
+            del st['staged'][key]
+        st['staged'][id(batch)] = slot
+
+    def _take_staged(self, batch: dict):
+        st = getattr(self, '_upload_state', None)
+        slot = st['staged'].pop(id(batch), None) if st else None
+        if slot is None:
+            return batch, None
+        torch.cuda.current_stream().wait_event(slot['ready'])
+        tgt = slot['target'] if isinstance(batch['target'], list) else slot['target'][0]
+        return {'data': slot['data'], 'target': tgt}, slot
+
     def train_step_async(self, batch: dict) -> torch.Tensor:
+        batch, slot = self._take_staged(batch)
+        loss = self._train_step_async(batch)
+        if slot is not None:
+            # inputs have been copied into the step's own buffers (or consumed by its kernels) in stream order
+            slot['consumed'] = torch.cuda.Event()
+            slot['consumed'].record()
+        return loss
+
+    def _train_step_async(self, batch: dict) -> torch.Tensor:
         """the step without the device->host read of the loss (returned as a device scalar).
 
         With ``self.use_cuda_graph`` the whole step (forward, losses, backward, gradient exchange, clip + SGD: a few
@@ -374,6 +442,10 @@ class nnUNetTrainer(object):
         side = st['copy_stream']
         st['data'].copy_(data, non_blocking=True)
         side.wait_event(st['ev_done'])              # the previous step has finished reading the static targets
+        if target and target[0].is_cuda:             # staged device batch: its upload is ordered before `main` only
+            ev = st.setdefault('ev_start', torch.cuda.Event())
+            ev.record(main)
+            side.wait_event(ev)
         with torch.cuda.stream(side):
             for a, b in zip(st['target'], target):
                 a.copy_(b, non_blocking=True)

@@ -377,3 +377,30 @@ def test_cuda_graph_steps_match_eager(dual):
         traj[mode] = [float(tr.train_step(b)['loss']) for b in batches]
     for mode in ('graph', 'split'):
         np.testing.assert_allclose(traj[mode], traj['eager'], rtol=2e-2, atol=2e-3)
+
+
+def test_prefetching_loop_matches_plain_loop():
+    """trainer.prefetching(): same losses, step for step, as handing the host batches to train_step directly (eager and
+    CUDA-graph replay), with distinct batches so that a slot mix-up would show."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    patch = (32, 32, 32)
+    plans, dj = m.make_plans(patch, batch_size=2, n_modalities=2, n_classes=4)
+    strides = plans['configurations']['3d_fullres']['pool_op_kernel_sizes']
+    batches = []
+    for i in range(6):
+        b = oracle.make_batch(2, 2, patch, strides, max_label=3, seed=100 + i, kind='rand')
+        batches.append({'data': b['data'].pin_memory(), 'target': [t.pin_memory() for t in b['target']]})
+    res = {}
+    for mode in ('plain', 'prefetch'):
+        for graph in (False, True):
+            torch.manual_seed(0)
+            tr = m.nnUNetTrainer(plans, '3d_fullres', 0, dj, device=torch.device('cuda:0'))
+            tr.initialize()
+            tr.use_cuda_graph = graph
+            tr.graph_warmup_steps = 1
+            tr.on_train_epoch_start()
+            it = tr.prefetching([dict(b) for b in batches]) if mode == 'prefetch' else batches
+            res[(mode, graph)] = [float(tr.train_step(b)['loss']) for b in it]
+    for graph in (False, True):
+        assert res[('plain', graph)] == res[('prefetch', graph)], (graph, res)
