@@ -706,7 +706,7 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)src, gdim, gstr, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     tc_l2_promotion(kc * 2, ld * 2), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(planes) failed (%d)", who, (int)r); return MVD_ERR_CUDA; }
   }
   if (!tc_encode_w_map(&maps.b, w, (long long)27 * N, K, P.n_tile, kc)) {
@@ -882,7 +882,7 @@ int tc_halo_s2_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
       cuuint32_t box[5] = {(cuuint32_t)S2_KC, (cuuint32_t)(wp ? S2_NW1 : S2_NW0), (cuuint32_t)(hp ? S2_NH1 : S2_NH0), 1, 1};
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
       CUresult r = enc(&maps.a[hp * 2 + wp], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, gdim, gstr, box, es,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, tc_l2_promotion(S2_ROWB, ld * 4),
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(planes) failed (%d)", who, (int)r); return MVD_ERR_CUDA; }
     }

@@ -262,7 +262,7 @@ int tc_subpixel_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
     cuuint32_t box[5] = {KC, HALO_W, HALO_H, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a->y, gdim, gstr, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, tc_l2_promotion(ROWB, ld * 2),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(planes) failed (%d)", who, (int)r); return MVD_ERR_CUDA; }
   }

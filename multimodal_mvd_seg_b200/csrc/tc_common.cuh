@@ -154,6 +154,16 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
+// L2 fetch granularity of an activation map.  Dense rows: 256 B.  When the voxel pitch is wider than the box row (a
+// channel slice of the decoder's concat buffer, or a stride-2 parity lattice) a promoted fetch drags the unused
+// neighbour through DRAM as well -- ncu on the stride-2 forward kernel reading the 32-channel skip out of the 64-channel
+// buffer: 555 MB read for 268 MB of input -- so promotion stops at the row size.
+inline CUtensorMapL2promotion tc_l2_promotion(long long row_bytes, long long pitch_bytes) {
+  if (pitch_bytes <= row_bytes || row_bytes >= 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (row_bytes >= 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (row_bytes >= 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
 // 5-D tensor map (C, W, H, D, B) over a pitched NDHWC bf16 lattice with box (box_c, 8, 16, 1, 1); swizzle 128B when
 // box_c == 64, 64B when box_c == 32.  dims / strides are the W,H,D,B extents and element strides of the lattice.
 bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4], const long long strides_el[4],
