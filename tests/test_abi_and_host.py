@@ -110,3 +110,23 @@ def test_he_init_product(golden_misc):
     torch.nn.Sequential(conv, tconv).apply(m.InitWeights_He(1e-2))
     assert np.array_equal(conv.weight.detach().numpy(), golden_misc['he.conv_w'])
     assert np.array_equal(tconv.weight.detach().numpy(), golden_misc['he.tconv_w'])
+
+
+def test_ds_targets_host_logic_and_cpu_refusal():
+    """shape rule of DownsampleSegForDSTransform2 (deep_supervision_donwsampling.py:46-49: float shape x scale, np.round
+    = half to even) shared with the oracle, argument errors through the C ABI, and no CPU path."""
+    import multimodal_mvd_seg_b200 as m
+    from multimodal_mvd_seg_b200 import ds_targets as prod
+    from oracle import ds_targets as orc
+    for shape, s in [((2, 1, 16, 16, 12), [0.5, 0.5, 0.5]), ((1, 1, 5, 7, 9), [0.5, 0.5, 0.5]),
+                     ((1, 2, 20, 20, 12), [0.25, 0.25, 1]), ((1, 1, 10, 6, 3), [0.25, 0.25, 0.5])]:
+        seg = np.zeros(shape, dtype=np.int16)
+        want = orc.DownsampleSegForDSTransform2([s], 0)(seg=seg)['seg'][0].shape
+        assert prod._new_shape(shape, [2, 3, 4], s) == tuple(want)
+    assert prod._new_shape((1, 1, 5, 7, 9), [2, 3, 4], [0.5] * 3) == (1, 1, 2, 4, 4)      # 2.5 -> 2, 3.5 -> 4, 4.5 -> 4
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.downsample_seg_for_ds(torch.zeros(1, 1, 4, 4, 4), [[0.5, 0.5, 0.5]])
+    with pytest.raises(NotImplementedError):
+        m.DownsampleSegForDSTransform2([[1, 1, 1]], order=3)
+    with pytest.raises(m.MvdError, match='bad arguments'):
+        m.lib.downsample_seg_nearest(None, 1, 4, 4, 4, 1, None, None, None)
