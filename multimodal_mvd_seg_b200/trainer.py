@@ -8,12 +8,14 @@
 ``MVDTrainer`` (the reference's ``ContrastiveTrainer``, MVDTrainer.py:76-985) adds the second modality network, the
 mutual-distillation KL and the topological term with the canonical decisions of SURVEY.md section 8c.
 
-Everything outside the step (dataset unpacking, batchgenerators augmentation, logging, plotting, sliding-window
-validation export) is out of scope; ``plans`` / ``dataset_json`` are read through the two small accessors below, which
+The epoch loop around the step is kept as well (``run_training`` and its ``on_*`` hooks, MVDTrainer.py:808-1127 /
+:1323-1345: loss / pseudo-Dice aggregation, EMA, checkpoint cadence), driven by loaders the caller supplies.  Dataset
+unpacking, batchgenerators augmentation, file logging, plotting and the sliding-window validation export are out of scope; ``plans`` / ``dataset_json`` are read through the two small accessors below, which
 expose the same property names as the reference's ConfigurationManager / LabelManager
 (utilities/plans_handling/plans_handler.py:32-291, utilities/label_handling/label_handling.py:21-234).
 """
 import os
+import time
 from typing import List, Optional, Tuple, Union
 
 import numpy as np
@@ -129,6 +131,53 @@ def make_plans(patch_size, batch_size: int = 2, n_modalities: int = 2, n_classes
     return plans, dataset_json
 
 
+def collate_outputs(outputs: List[dict]) -> dict:
+    """utilities/collate_outputs.py:6-24: scalars -> list, arrays -> stacked along a new first axis, lists -> one list."""
+    collated = {}
+    for k in outputs[0].keys():
+        v0 = outputs[0][k]
+        if np.isscalar(v0):
+            collated[k] = [o[k] for o in outputs]
+        elif isinstance(v0, np.ndarray):
+            collated[k] = np.vstack([o[k][None] for o in outputs])
+        elif isinstance(v0, list):
+            collated[k] = [item for o in outputs for item in o[k]]
+        else:
+            raise ValueError(f'Cannot collate input of type {type(v0)}. Modify collate_outputs to add this functionality')
+    return collated
+
+
+class nnUNetLogger(object):
+    """one value per epoch and key, as training/logging/nnunet_logger.py:9-52 (no plotting: out of scope).  Logging
+    'mean_fg_dice' also logs its exponential moving average 'ema_fg_dice' (0.9 * previous + 0.1 * new)."""
+
+    def __init__(self, verbose: bool = False):
+        self.my_fantastic_logging = {k: list() for k in ('mean_fg_dice', 'ema_fg_dice', 'dice_per_class_or_region',
+                                                         'train_losses', 'val_losses', 'lrs', 'epoch_start_timestamps',
+                                                         'epoch_end_timestamps')}
+        self.verbose = verbose
+
+    def log(self, key, value, epoch: int):
+        log = self.my_fantastic_logging
+        assert key in log and isinstance(log[key], list), 'one list entry per epoch and known key'
+        if self.verbose:
+            print(f'logging {key}: {value} for epoch {epoch}')
+        if len(log[key]) < (epoch + 1):
+            log[key].append(value)
+        else:
+            assert len(log[key]) == (epoch + 1), 'logging list length is off by more than 1'
+            log[key][epoch] = value
+        if key == 'mean_fg_dice':
+            ema = log['ema_fg_dice'][epoch - 1] * 0.9 + 0.1 * value if len(log['ema_fg_dice']) > 0 else value
+            self.log('ema_fg_dice', ema, epoch)
+
+    def get_checkpoint(self):
+        return self.my_fantastic_logging
+
+    def load_checkpoint(self, checkpoint: dict):
+        self.my_fantastic_logging = checkpoint
+
+
 class nnUNetTrainer(object):
     def __init__(self, plans: dict, configuration: str, fold: int, dataset_json: dict, unpack_dataset: bool = True,
                  device: torch.device = torch.device('cuda'), specified_cfg: str = ''):
@@ -163,6 +212,13 @@ class nnUNetTrainer(object):
         self.split_graph = False   # capture forward and (loss + backward + optimiser) as two graphs: the H2D copy of
                                    # the targets then overlaps the forward pass (see train_step_async)
         self.graph_warmup_steps = 2
+        # epoch loop (run_training, MVDTrainer.py:1323-1345): the loaders are set by the caller -- batch production is
+        # outside this package -- and checkpoints are only written when an output folder is given
+        self.logger = nnUNetLogger()
+        self.dataloader_train = self.dataloader_val = None
+        self.output_folder: Optional[str] = None
+        self.save_every = 50
+        self._best_ema = None
         self._arenas: List[GradArena] = []
         self._set_batch_size_and_oversample()
 
@@ -253,6 +309,103 @@ class nnUNetTrainer(object):
         for n in self._networks():
             n.train()
         self.lr_scheduler.step(self.current_epoch)
+        self.logger.log('lrs', self.optimizer.param_groups[0]['lr'], self.current_epoch)
+
+    # ---- epoch-level hooks of the reference loop (MVDTrainer.py:808-1127), minus file / plot / dataloader management
+    def on_train_start(self):
+        if not self.was_initialized:
+            self.initialize()
+        self.set_deep_supervision_enabled(True)
+        if self.dataloader_train is None:
+            raise RuntimeError('run_training: set trainer.dataloader_train (and dataloader_val) to iterators of batch '
+                               'dicts first; data loading / augmentation is outside this package')
+        if self.output_folder is not None:
+            os.makedirs(self.output_folder, exist_ok=True)
+        if self.is_ddp:
+            dist.barrier()
+
+    def on_train_end(self):
+        if self.output_folder is not None:
+            self.save_checkpoint(os.path.join(self.output_folder, 'checkpoint_final.pth'))
+            latest = os.path.join(self.output_folder, 'checkpoint_latest.pth')
+            if self.local_rank == 0 and os.path.isfile(latest):
+                os.remove(latest)
+
+    def on_epoch_start(self):
+        self.logger.log('epoch_start_timestamps', time.time(), self.current_epoch)
+
+    def on_train_epoch_end(self, train_outputs: List[dict]):
+        outputs = collate_outputs(train_outputs)
+        if self.is_ddp:
+            losses_tr = [None for _ in range(dist.get_world_size())]
+            dist.all_gather_object(losses_tr, outputs['loss'])
+            loss_here = np.vstack(losses_tr).mean()
+        else:
+            loss_here = np.mean(outputs['loss'])
+        self.logger.log('train_losses', loss_here, self.current_epoch)
+
+    def on_validation_epoch_start(self):
+        for n in self._networks():
+            n.eval()
+
+    def on_validation_epoch_end(self, val_outputs: List[dict]):
+        outputs_collated = collate_outputs(val_outputs)
+        tp = np.sum(outputs_collated['tp_hard'], 0)
+        fp = np.sum(outputs_collated['fp_hard'], 0)
+        fn = np.sum(outputs_collated['fn_hard'], 0)
+        if self.is_ddp:
+            world_size = dist.get_world_size()
+
+            def gather_sum(v):
+                parts = [None for _ in range(world_size)]
+                dist.all_gather_object(parts, v)
+                return np.vstack([i[None] for i in parts]).sum(0)
+            tp, fp, fn = gather_sum(tp), gather_sum(fp), gather_sum(fn)
+            losses_val = [None for _ in range(world_size)]
+            dist.all_gather_object(losses_val, outputs_collated['loss'])
+            loss_here = np.vstack(losses_val).mean()
+        else:
+            loss_here = np.mean(outputs_collated['loss'])
+        with np.errstate(divide='ignore', invalid='ignore'):      # a class that never occurs: 0 / 0 -> nan, skipped by nanmean
+            global_dc_per_class = [i for i in [2 * i / (2 * i + j + k) for i, j, k in zip(tp, fp, fn)]]
+        mean_fg_dice = np.nanmean(global_dc_per_class)
+        self.logger.log('mean_fg_dice', mean_fg_dice, self.current_epoch)
+        self.logger.log('dice_per_class_or_region', global_dc_per_class, self.current_epoch)
+        self.logger.log('val_losses', loss_here, self.current_epoch)
+
+    def on_epoch_end(self):
+        self.logger.log('epoch_end_timestamps', time.time(), self.current_epoch)
+        current_epoch = self.current_epoch
+        if self.output_folder is not None:
+            if (current_epoch + 1) % self.save_every == 0 and current_epoch != (self.num_epochs - 1):
+                self.save_checkpoint(os.path.join(self.output_folder, 'checkpoint_latest.pth'))
+        ema = self.logger.my_fantastic_logging['ema_fg_dice']
+        if ema and (self._best_ema is None or ema[-1] > self._best_ema):
+            self._best_ema = ema[-1]
+            if self.output_folder is not None:
+                self.save_checkpoint(os.path.join(self.output_folder, 'checkpoint_best.pth'))
+        self.current_epoch += 1
+
+    def run_training(self):
+        """MVDTrainer.py:1323-1345, with the next training batch uploaded underneath the current step."""
+        self.on_train_start()
+        for epoch in range(self.current_epoch, self.num_epochs):
+            self.on_epoch_start()
+            self.on_train_epoch_start()
+            train_outputs = []
+            batches = (next(self.dataloader_train) for _ in range(self.num_iterations_per_epoch))
+            for batch in self.prefetching(batches):
+                train_outputs.append(self.train_step(batch))
+            self.on_train_epoch_end(train_outputs)
+            if self.dataloader_val is not None and self.num_val_iterations_per_epoch > 0:
+                with torch.no_grad():
+                    self.on_validation_epoch_start()
+                    val_outputs = []
+                    for batch_id in range(self.num_val_iterations_per_epoch):
+                        val_outputs.append(self.validation_step(next(self.dataloader_val)))
+                    self.on_validation_epoch_end(val_outputs)
+            self.on_epoch_end()
+        self.on_train_end()
 
     # ------------------------------------------------------------------------------------------------------------
     def _forward(self, data):
@@ -475,8 +628,8 @@ class nnUNetTrainer(object):
             'network_weights': self.network.state_dict(),
             'optimizer_state': self.optimizer.state_dict(),
             'grad_scaler_state': None,
-            'logging': {},
-            '_best_ema': None,
+            'logging': self.logger.get_checkpoint(),
+            '_best_ema': self._best_ema,
             'current_epoch': self.current_epoch + 1,
             'init_args': {'configuration': self.configuration_name, 'fold': self.fold},
             'trainer_name': self.__class__.__name__,
@@ -498,6 +651,9 @@ class nnUNetTrainer(object):
                 key = key[7:]
             new_state_dict[key] = value
         self.current_epoch = ck['current_epoch']
+        if ck.get('logging'):
+            self.logger.load_checkpoint(ck['logging'])
+        self._best_ema = ck.get('_best_ema')
         self.network.load_state_dict(new_state_dict)
         self.optimizer.load_state_dict(ck['optimizer_state'])
 

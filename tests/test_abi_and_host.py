@@ -130,3 +130,111 @@ def test_ds_targets_host_logic_and_cpu_refusal():
         m.DownsampleSegForDSTransform2([[1, 1, 1]], order=3)
     with pytest.raises(m.MvdError, match='bad arguments'):
         m.lib.downsample_seg_nearest(None, 1, 4, 4, 4, 1, None, None, None)
+
+
+def test_epoch_hooks_match_reference_fixture():
+    """collate_outputs, nnUNetLogger.log (incl. the EMA) and the on_train_epoch_end / on_validation_epoch_end aggregation
+    against tests/golden/epoch_hooks.npz, produced by executing the reference's own texts (make_golden_epoch.py).  The
+    hooks only touch self.logger / is_ddp / current_epoch, so they run on a stand-in object (the trainer needs CUDA)."""
+    import importlib.util
+    import multimodal_mvd_seg_b200 as m
+    from multimodal_mvd_seg_b200 import trainer as T
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'epoch_hooks.npz'))
+    spec = importlib.util.spec_from_file_location('mk_epoch', os.path.join(ROOT, 'tests', 'golden', 'make_golden_epoch.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)            # only its synthetic_outputs() is used; nothing under /root/reference is read
+
+    class Stand:
+        is_ddp = False
+    me = Stand()
+    me.logger = T.nnUNetLogger()
+    n_epochs, n_steps, n_fg = (int(v) for v in g['meta'])
+    for ep in range(n_epochs):
+        me.current_epoch = ep
+        train, val = mk.synthetic_outputs(100 + ep, n_steps, n_fg)
+        if ep == 2:
+            for v in val:
+                v['tp_hard'][1] = v['fp_hard'][1] = v['fn_hard'][1] = 0
+        T.nnUNetTrainer.on_train_epoch_end(me, train)
+        T.nnUNetTrainer.on_validation_epoch_end(me, val)
+    log = me.logger.my_fantastic_logging
+    for k in ('train_losses', 'val_losses', 'mean_fg_dice', 'ema_fg_dice'):
+        np.testing.assert_array_equal(np.array(log[k], dtype=np.float64), g[f'log.{k}'])
+    np.testing.assert_array_equal(np.array(log['dice_per_class_or_region'], dtype=np.float64),
+                                  g['log.dice_per_class_or_region'])
+    assert np.isnan(g['log.dice_per_class_or_region'][2, 1])          # the empty class of epoch 2 stays nan
+    mixed = [{'s': 1.5, 'a': np.arange(3.0) + i, 'l': [i, i + 1]} for i in range(3)]
+    c = T.collate_outputs(mixed)
+    np.testing.assert_array_equal(np.array(c['s']), g['collate.s'])
+    np.testing.assert_array_equal(c['a'], g['collate.a'])
+    np.testing.assert_array_equal(np.array(c['l']), g['collate.l'])
+    with pytest.raises(ValueError):
+        T.collate_outputs([{'x': (1, 2)}])
+    # logger contract: one entry per epoch, re-logging an epoch overwrites
+    lg = T.nnUNetLogger()
+    lg.log('mean_fg_dice', 0.5, 0)
+    lg.log('mean_fg_dice', 0.7, 1)
+    assert lg.my_fantastic_logging['ema_fg_dice'] == [0.5, 0.5 * 0.9 + 0.1 * 0.7]
+    lg.log('mean_fg_dice', 0.9, 1)
+    assert lg.my_fantastic_logging['mean_fg_dice'] == [0.5, 0.9]
+    with pytest.raises(AssertionError):
+        lg.log('unknown_key', 1.0, 0)
+
+
+def test_run_training_control_flow(tmp_path):
+    """the epoch loop (MVDTrainer.py:1323-1345) on a stub trainer: step counts, batch order through the generator handed to
+    prefetching(), logger bookkeeping, checkpoint cadence (save_every, best EMA, final)."""
+    from multimodal_mvd_seg_b200 import trainer as T
+
+    class Stub(T.nnUNetTrainer):
+        def __init__(self, out):
+            self.is_ddp, self.local_rank, self.was_initialized = False, 0, True
+            self.num_epochs, self.num_iterations_per_epoch, self.num_val_iterations_per_epoch = 3, 4, 2
+            self.current_epoch, self.save_every, self._best_ema = 0, 2, None
+            self.logger = T.nnUNetLogger()
+            self.output_folder = out
+            self.optimizer = type('O', (), {'param_groups': [{'lr': 0.01}]})()
+            self.lr_scheduler = type('S', (), {'step': lambda self_, e: None})()
+            self.calls, self.saved = [], []
+            self.dataloader_train, self.dataloader_val = iter(range(1000)), iter(range(1000, 2000))
+
+        def _networks(self):
+            return []
+
+        def set_deep_supervision_enabled(self, enabled):
+            self.calls.append(('ds', enabled))
+
+        def prefetching(self, batches):
+            yield from batches
+
+        def train_step(self, b):
+            self.calls.append(('train', b))
+            return {'loss': np.array(1.0 + 0.1 * b, dtype=np.float32)}
+
+        def validation_step(self, b):
+            self.calls.append(('val', b))
+            k = float(self.current_epoch + 1)
+            return {'loss': np.array(0.5, dtype=np.float32), 'tp_hard': np.array([10.0 * k, 5.0]),
+                    'fp_hard': np.array([1.0, 5.0]), 'fn_hard': np.array([1.0, 5.0])}
+
+        def save_checkpoint(self, filename):
+            self.saved.append((self.current_epoch, os.path.basename(filename)))
+
+    tr = Stub(str(tmp_path / 'run'))
+    tr.run_training()
+    assert tr.current_epoch == 3 and os.path.isdir(tr.output_folder)
+    assert [c[1] for c in tr.calls if c[0] == 'train'] == list(range(12))
+    assert [c[1] for c in tr.calls if c[0] == 'val'] == list(range(1000, 1006))
+    assert tr.calls[0] == ('ds', True)
+    log = tr.logger.my_fantastic_logging
+    assert all(len(log[k]) == 3 for k in log)
+    np.testing.assert_allclose(log['train_losses'], [1.15, 1.55, 1.95], rtol=1e-6)
+    d0 = 2 * 20.0 / (2 * 20.0 + 2 + 2)
+    assert abs(log['dice_per_class_or_region'][0][0] - d0) < 1e-12 and abs(log['dice_per_class_or_region'][0][1] - 0.5) < 1e-12
+    # pseudo-Dice rises every epoch -> a new best each time; 'latest' at (epoch + 1) % save_every == 0 except the last epoch
+    assert tr.saved == [(0, 'checkpoint_best.pth'), (1, 'checkpoint_latest.pth'), (1, 'checkpoint_best.pth'),
+                        (2, 'checkpoint_best.pth'), (3, 'checkpoint_final.pth')]
+    tr2 = Stub(None)
+    tr2.dataloader_train = None
+    with pytest.raises(RuntimeError, match='dataloader_train'):
+        tr2.run_training()
