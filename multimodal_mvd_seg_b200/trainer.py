@@ -10,7 +10,8 @@ mutual-distillation KL and the topological term with the canonical decisions of 
 
 The epoch loop around the step is kept as well (``run_training`` and its ``on_*`` hooks, MVDTrainer.py:808-1127 /
 :1323-1345: loss / pseudo-Dice aggregation, EMA, checkpoint cadence), driven by loaders the caller supplies.  Dataset
-unpacking, batchgenerators augmentation, file logging, plotting and the sliding-window validation export are out of scope; ``plans`` / ``dataset_json`` are read through the two small accessors below, which
+unpacking, batchgenerators augmentation, file logging, plotting and the sliding-window validation export are out of
+scope; ``plans`` / ``dataset_json`` are read through the two small accessors below, which
 expose the same property names as the reference's ConfigurationManager / LabelManager
 (utilities/plans_handling/plans_handler.py:32-291, utilities/label_handling/label_handling.py:21-234).
 """
