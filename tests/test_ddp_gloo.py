@@ -62,3 +62,62 @@ def test_grad_arena_allreduce_world2():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _epoch_worker(rank, world, port, q):
+    """every rank aggregates its own step outputs; the logged values must equal the single-process result over the union
+    (MVDTrainer.py:990-993, 1071-1088: all_gather_object of losses and tp / fp / fn)."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from multimodal_mvd_seg_b200 import trainer as T
+
+        def outputs(r):
+            rng = np.random.default_rng(50 + r)
+            tr = [{'loss': np.array(rng.normal(1.0, 0.1), dtype=np.float32)} for _ in range(3)]
+            va = [{'loss': np.array(rng.normal(0.7, 0.1), dtype=np.float32),
+                   'tp_hard': rng.integers(1, 100, 3).astype(np.float64), 'fp_hard': rng.integers(1, 50, 3).astype(np.float64),
+                   'fn_hard': rng.integers(1, 50, 3).astype(np.float64)} for _ in range(3)]
+            return tr, va
+
+        class Stand:
+            pass
+        me = Stand()
+        me.is_ddp, me.current_epoch, me.logger = True, 0, T.nnUNetLogger()
+        tr, va = outputs(rank)
+        T.nnUNetTrainer.on_train_epoch_end(me, tr)
+        T.nnUNetTrainer.on_validation_epoch_end(me, va)
+        ref = Stand()
+        ref.is_ddp, ref.current_epoch, ref.logger = False, 0, T.nnUNetLogger()
+        all_tr, all_va = [], []
+        for r in range(world):
+            a, b = outputs(r)
+            all_tr += a
+            all_va += b
+        T.nnUNetTrainer.on_train_epoch_end(ref, all_tr)
+        T.nnUNetTrainer.on_validation_epoch_end(ref, all_va)
+        ok = True
+        for k in ('train_losses', 'val_losses', 'mean_fg_dice'):
+            ok = ok and abs(float(me.logger.my_fantastic_logging[k][0]) - float(ref.logger.my_fantastic_logging[k][0])) < 1e-6
+        ok = ok and np.allclose(me.logger.my_fantastic_logging['dice_per_class_or_region'][0],
+                                ref.logger.my_fantastic_logging['dice_per_class_or_region'][0], rtol=0, atol=1e-12)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_epoch_end_hooks_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_epoch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res == {0: True, 1: True}
