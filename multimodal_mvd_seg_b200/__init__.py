@@ -5,7 +5,7 @@ libmvdseg.so, hand-written CUDA for sm_100a behind the C ABI of include/mvdseg.h
 from ._lib import LIB_PATH, MvdError, lib
 from . import ops
 from .network import (PlainConvUNet, PlainConvEncoder, UNetDecoder, StackedConvBlocks, ConvDropoutNormReLU,
-                      InitWeights_He, get_network_from_plans)
+                      InitWeights_He, get_network_from_plans, load_pretrained_weights)
 from .losses import (DC_and_CE_loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss, RobustCrossEntropyLoss,
                      get_tp_fp_fn_tn, distill_kl, soft_erode, soft_dilate, soft_open, soft_skel, soft_cldice,
                      softmax_channel, softmax_helper_dim1, deep_supervision_weights)

@@ -325,3 +325,29 @@ def get_network_from_plans(plans_manager, dataset_json, configuration_manager, n
         dropout_op=None, dropout_op_kwargs=None, nonlin=nn.LeakyReLU, nonlin_kwargs={'inplace': True})
     model.apply(InitWeights_He(1e-2))
     return model
+
+
+def load_pretrained_weights(network: nn.Module, fname, verbose: bool = False) -> None:
+    """run/load_pretrained_weights.py:6-64: transfer every tensor whose key and shape match, EXCEPT the segmentation
+    heads (keys containing '.seg_layers.'); all other keys of the network must be present in the checkpoint with the
+    same shape.  ``fname`` is a checkpoint path or an already loaded checkpoint dict with 'network_weights'."""
+    saved_model = fname if isinstance(fname, dict) else torch.load(fname, map_location='cpu', weights_only=False)
+    pretrained_dict = saved_model['network_weights']
+    skip_strings_in_pretrained = ['.seg_layers.']
+    mod = network.module if isinstance(network, nn.parallel.DistributedDataParallel) else network
+    model_dict = mod.state_dict()
+    for key in model_dict:
+        if all(i not in key for i in skip_strings_in_pretrained):
+            assert key in pretrained_dict, \
+                f'Key {key} is missing in the pretrained model weights. The pretrained weights do not seem to be ' \
+                f'compatible with your network.'
+            assert model_dict[key].shape == pretrained_dict[key].shape, \
+                f'The shape of the parameters of key {key} is not the same. Pretrained model: ' \
+                f'{pretrained_dict[key].shape}; your network: {model_dict[key].shape}.'
+    pretrained_dict = {k: v for k, v in pretrained_dict.items()
+                       if k in model_dict and all(i not in k for i in skip_strings_in_pretrained)}
+    model_dict.update(pretrained_dict)
+    if verbose:
+        for key, value in pretrained_dict.items():
+            print(key, 'shape', value.shape)
+    mod.load_state_dict(model_dict)

@@ -238,3 +238,51 @@ def test_run_training_control_flow(tmp_path):
     tr2.dataloader_train = None
     with pytest.raises(RuntimeError, match='dataloader_train'):
         tr2.run_training()
+
+
+def test_load_pretrained_weights_drop_in(tmp_path):
+    """our PlainConvUNet under the REFERENCE's own run/load_pretrained_weights.py (executed from /root/reference when the
+    tree is present: build container only) and under the package's mirror of it: everything but the '.seg_layers.' heads
+    is transferred, a shape mismatch outside the heads is refused."""
+    import importlib.util
+    import multimodal_mvd_seg_b200 as m
+
+    def build(seed, classes=3):
+        torch.manual_seed(seed)
+        net = m.PlainConvUNet(2, 3, [8, 16, 32], kernel_sizes=3, strides=[1, 2, 2], n_conv_per_stage=2, num_classes=classes,
+                              n_conv_per_stage_decoder=2, deep_supervision=True)
+        net.apply(m.InitWeights_He(1e-2))
+        for n, p in net.named_parameters():      # non-default norm parameters and biases
+            if p.dim() == 1:
+                p.data.normal_(0.5, 0.1)
+        return net
+    src = build(0)
+    f = str(tmp_path / 'pre.pth')
+    torch.save({'network_weights': src.state_dict()}, f)
+    loaders = [('mirror', m.load_pretrained_weights)]
+    ref_file = '/root/reference/nnUNet/nnunetv2/run/load_pretrained_weights.py'
+    if os.path.exists(ref_file):
+        spec = importlib.util.spec_from_file_location('ref_lpw', ref_file)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        loaders.append(('reference', mod.load_pretrained_weights))
+    results = {}
+    for name, fn in loaders:
+        dst = build(1)
+        before = {k: v.clone() for k, v in dst.state_dict().items()}
+        fn(dst, f)
+        after = dst.state_dict()
+        for k, v in after.items():
+            if '.seg_layers.' in k:
+                assert torch.equal(v, before[k]), (name, k)
+            else:
+                assert torch.equal(v, src.state_dict()[k]), (name, k)
+        results[name] = {k: v.clone() for k, v in after.items()}
+        # different number of classes: only the heads differ -> still loads
+        fn(build(2, classes=5), f)
+    if 'reference' in results:
+        assert all(torch.equal(results['mirror'][k], results['reference'][k]) for k in results['mirror'])
+    wide = m.PlainConvUNet(2, 3, [8, 16, 48], kernel_sizes=3, strides=[1, 2, 2], n_conv_per_stage=2, num_classes=3,
+                           n_conv_per_stage_decoder=2, deep_supervision=True)
+    with pytest.raises(AssertionError, match='shape'):
+        m.load_pretrained_weights(wide, f)
