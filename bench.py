@@ -336,10 +336,10 @@ def main():
             'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
             'roofline': roofline, 'clocks': clocks, 'loss': loss_val}
     if n_gpus == 1 and not args.no_cpu_baseline:
-        times, frac, threads = reference_step_time(8, 1, dual, topo_iter)
+        times, frac, threads = reference_step_time(30, 1, dual, topo_iter)   # ~10-12 s of host work
         s = sum(times) / len(times)
         line['cpu_baseline'] = {'value': frac / s, 'unit': 'patches/s', 'cores': threads, 'kind': 'port',
-                                'sample': '8 steps of 1 patch, 64^3 crop (1/8 of a 128^3 patch) through the same '
+                                'sample': '30 steps of 1 patch, 64^3 crop (1/8 of a 128^3 patch) through the same '
                                           'network on the host cores (oracle port, fp32)', 'seconds': sum(times)}
     if per_layer:
         rows = sorted(per_layer.items(), key=lambda kv: -kv[1]['ms'])
