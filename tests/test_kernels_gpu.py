@@ -535,4 +535,4 @@ def test_train_step_builds_ds_targets_on_gpu(m):
         else:
             target = full
         losses.append(float(tr.train_step({'data': data, 'target': target})['loss']))
-    assert losses[0] == losses[1]
+    assert abs(losses[0] - losses[1]) <= 1e-5 * max(1.0, abs(losses[0]))    # same targets -> same loss (fp64-atomic order aside)

@@ -402,5 +402,6 @@ def test_prefetching_loop_matches_plain_loop():
             tr.on_train_epoch_start()
             it = tr.prefetching([dict(b) for b in batches]) if mode == 'prefetch' else batches
             res[(mode, graph)] = [float(tr.train_step(b)['loss']) for b in it]
+    # the weight-gradient reductions use fp32 atomics, so two runs agree to rounding, not bit for bit
     for graph in (False, True):
-        assert res[('plain', graph)] == res[('prefetch', graph)], (graph, res)
+        np.testing.assert_allclose(res[('prefetch', graph)], res[('plain', graph)], rtol=2e-3, atol=2e-4)
