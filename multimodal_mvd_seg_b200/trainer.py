@@ -278,6 +278,9 @@ class nnUNetTrainer(object):
                                       deep_supervision=enable_deep_supervision)
 
     def _get_deep_supervision_scales(self):
+        """nnUNetTrainer.py:296-302: one scale per supervised output, None when deep supervision is off."""
+        if not self.enable_deep_supervision:
+            return None
         return list(list(i) for i in 1 / np.cumprod(np.vstack(self.configuration_manager.pool_op_kernel_sizes),
                                                      axis=0))[:-1]
 

@@ -286,3 +286,36 @@ def test_load_pretrained_weights_drop_in(tmp_path):
                            n_conv_per_stage_decoder=2, deep_supervision=True)
     with pytest.raises(AssertionError, match='shape'):
         m.load_pretrained_weights(wide, f)
+
+
+def test_deep_supervision_scales_match_reference_text():
+    """_get_deep_supervision_scales against the reference's own method text (nnUNetTrainer.py:296-302), executed on a
+    stand-in when /root/reference is present; the closed form is asserted either way."""
+    import ast
+    import textwrap
+    import multimodal_mvd_seg_b200 as m
+    from multimodal_mvd_seg_b200 import trainer as T
+
+    class Stand:
+        pass
+    for patch in [(128, 128, 128), (160, 160, 96), (64, 64, 64)]:
+        plans, dj = m.make_plans(patch)
+        me = Stand()
+        me.configuration_manager = T.PlansManager(plans).get_configuration('3d_fullres')
+        me.enable_deep_supervision = True
+        ours = T.nnUNetTrainer._get_deep_supervision_scales(me)
+        pools = np.vstack(me.configuration_manager.pool_op_kernel_sizes)
+        assert len(ours) == len(pools) - 1 and ours[0] == [1.0, 1.0, 1.0]
+        np.testing.assert_array_equal(np.array(ours), (1 / np.cumprod(pools, axis=0))[:-1])
+        ref_file = '/root/reference/nnUNet/nnunetv2/training/nnUNetTrainer/nnUNetTrainer.py'
+        if os.path.exists(ref_file):
+            src = open(ref_file).read()
+            node = next(n for c in ast.parse(src).body if isinstance(c, ast.ClassDef) and c.name == 'nnUNetTrainer'
+                        for n in c.body if isinstance(n, ast.FunctionDef) and n.name == '_get_deep_supervision_scales')
+            ns = dict(np=np)
+            exec(textwrap.dedent(ast.get_source_segment(src, node)), ns)
+            assert ns['_get_deep_supervision_scales'](me) == ours
+            me.enable_deep_supervision = False
+            assert ns['_get_deep_supervision_scales'](me) is None
+        me.enable_deep_supervision = False
+        assert T.nnUNetTrainer._get_deep_supervision_scales(me) is None
