@@ -319,3 +319,50 @@ def test_deep_supervision_scales_match_reference_text():
             assert ns['_get_deep_supervision_scales'](me) is None
         me.enable_deep_supervision = False
         assert T.nnUNetTrainer._get_deep_supervision_scales(me) is None
+
+
+def test_split_batch_for_rank_matches_reference_text():
+    """split_batch_for_rank against ContrastiveTrainer._set_batch_size_and_oversample (MVDTrainer.py:316-361), executed
+    from the reference file with a stand-in torch.distributed (build container only)."""
+    import ast
+    import contextlib
+    import io
+    import textwrap
+    import multimodal_mvd_seg_b200 as m
+    ref_file = '/root/reference/nnUNet/nnunetv2/training/nnUNetTrainer/MVDTrainer.py'
+    if not os.path.exists(ref_file):
+        pytest.skip('reference tree not present')
+    src = open(ref_file).read()
+    node = next(n for c in ast.parse(src).body if isinstance(c, ast.ClassDef) and c.name == 'ContrastiveTrainer'
+                for n in c.body if isinstance(n, ast.FunctionDef) and n.name == '_set_batch_size_and_oversample')
+
+    class Dist:
+        def __init__(self, world, rank):
+            self.world, self.rank = world, rank
+
+        def get_world_size(self):
+            return self.world
+
+        def get_rank(self):
+            return self.rank
+
+    class Stand:
+        pass
+    for global_bs in (2, 5, 8, 16, 17):
+        for world in range(1, min(global_bs, 8) + 1):
+            for over in (0.33, 0.0, 1.0, 0.5):
+                for rank in range(world):
+                    me = Stand()
+                    me.is_ddp = True
+                    me.oversample_foreground_percent = over
+                    me.configuration_manager = Stand()
+                    me.configuration_manager.batch_size = global_bs
+                    ns = dict(np=np, dist=Dist(world, rank))
+                    exec(textwrap.dedent(ast.get_source_segment(src, node)), ns)
+                    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+                        ns['_set_batch_size_and_oversample'](me)
+                        bs, ov = m.split_batch_for_rank(global_bs, world, rank, over)
+                    assert int(bs) == int(me.batch_size), (global_bs, world, rank, over)
+                    ref_ov = float(me.oversample_foreground_percent)
+                    # a rank left without samples (8 over 5 ranks -> 2,2,2,2,0) gets 0/0 in the reference as well
+                    assert (np.isnan(ov) and np.isnan(ref_ov)) or abs(float(ov) - ref_ov) < 1e-12, (global_bs, world, rank, over)
