@@ -34,29 +34,31 @@ def resize_segmentation_closed_form(segmentation: np.ndarray, new_shape) -> np.n
 
 
 class DownsampleSegForDSTransform2:
+    """same constructor and call contract as the reference transform (:13-25, :27-55)."""
+
     def __init__(self, ds_scales, order: int = 0, input_key: str = 'seg', output_key: str = 'seg', axes=None):
-        self.axes, self.output_key, self.input_key, self.order, self.ds_scales = axes, output_key, input_key, order, ds_scales
+        self.ds_scales, self.order, self.input_key, self.output_key, self.axes = ds_scales, order, input_key, output_key, axes
+
+    def _scaled_shape(self, shape, axes, scale):
+        # :46-49 -- float shape, multiplied per listed axis, np.round (half to even), int
+        target = np.asarray(shape, dtype=float)
+        target[list(axes)] *= np.asarray(scale, dtype=float)
+        return tuple(int(v) for v in np.round(target))
 
     def __call__(self, **data_dict):
         seg = data_dict[self.input_key]
-        axes = list(range(2, len(seg.shape))) if self.axes is None else self.axes          # :28-31
-        output = []
-        for s in self.ds_scales:                                                               # :34
-            if not isinstance(s, (tuple, list)):
-                s = [s] * len(axes)
-            else:
-                assert len(s) == len(axes)
-            if all(i == 1 for i in s):                                                         # :43-44
-                output.append(seg)
-            else:
-                new_shape = np.array(seg.shape).astype(float)                                  # :46-49
-                for i, a in enumerate(axes):
-                    new_shape[a] *= s[i]
-                new_shape = np.round(new_shape).astype(int)
-                out_seg = np.zeros(new_shape, dtype=seg.dtype)                                 # :50
-                for b in range(seg.shape[0]):
-                    for c in range(seg.shape[1]):
-                        out_seg[b, c] = resize_segmentation(seg[b, c], new_shape[2:], self.order)   # :51-52
-                output.append(out_seg)
-        data_dict[self.output_key] = output
+        axes = tuple(range(2, seg.ndim)) if self.axes is None else tuple(self.axes)            # :28-31
+        pyramid = []
+        for scale in self.ds_scales:                                                            # :34
+            per_axis = list(scale) if isinstance(scale, (tuple, list)) else [scale] * len(axes)
+            assert len(per_axis) == len(axes), 'one downsampling factor per axis'
+            if all(f == 1 for f in per_axis):                                                   # :43-44: the input itself
+                pyramid.append(seg)
+                continue
+            shape = self._scaled_shape(seg.shape, axes, per_axis)
+            level = np.zeros(shape, dtype=seg.dtype)                                            # :50
+            for b, c in np.ndindex(*seg.shape[:2]):                                             # :51-52: per (sample, channel)
+                level[b, c] = resize_segmentation(seg[b, c], shape[2:], self.order)
+            pyramid.append(level)
+        data_dict[self.output_key] = pyramid
         return data_dict
