@@ -486,8 +486,10 @@ class nnUNetTrainer(object):
             yield cur
 
     def _stage_upload(self, batch: dict) -> None:
-        st = self.__dict__.setdefault('_upload_state', dict(stream=torch.cuda.Stream(device=self.device), slots=[None, None],
-                                                             turn=0, staged={}))
+        st = getattr(self, '_upload_state', None)
+        if st is None:      # one copy stream and two staging slots per trainer, created on first use
+            st = self._upload_state = dict(stream=torch.cuda.Stream(device=self.device), slots=[None, None], turn=0,
+                                           staged={})
         k = st['turn']
         st['turn'] ^= 1
         target = batch['target'] if isinstance(batch['target'], list) else [batch['target']]
