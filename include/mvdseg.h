@@ -78,10 +78,14 @@ typedef struct {
 } mvd_conv3d_args;
 
 /* Sliding-window inference accumulators (inference/predict_from_raw_data.py:703-712):
- *   acc[k][z0+z][y0+y][x0+x] += pred[z][y][x][k] * scale * g[z][y][x];  npred[...] += g  (g = 1 when gaussian == NULL;
- *   npred may be NULL).  pred: bf16 NDHWC tile [d][h][w][K] with voxel pitch ldp; acc fp32 [K][D][H][W]; npred fp32. */
+ *   acc[k][z0+z][y0+y][x0+x] += pred[fz][fy][fx][k] * scale * g[z][y][x];  npred[...] += g  (g = 1 when gaussian ==
+ *   NULL; npred may be NULL).  pred: bf16 NDHWC tile [d][h][w][K] with voxel pitch ldp; acc fp32 [K][D][H][W]; npred
+ *   fp32.  flip_mask (bit 0: z, bit 1: y, bit 2: x) reads the tile mirrored (fz = d-1-z ...): the flip-back of a
+ *   mirrored test-time-augmentation pass (predict_from_raw_data.py:562-589), so that every pass is accumulated in fp32
+ *   with scale = 1/2^n_axes and the averaged prediction is never rounded to 16 bits. */
 int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float scale, float* acc, float* npred, int K,
-                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, mvd_stream_t stream);
+                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, int flip_mask,
+                      mvd_stream_t stream);
 int mvd_sw_finalize(float* acc, const float* npred, int K, long long vol, mvd_stream_t stream);   /* acc /= npred */
 /* Deep-supervision targets on the GPU.  Replaces DownsampleSegForDSTransform2.__call__
  * (training/data_augmentation/custom_transforms/deep_supervision_donwsampling.py:27-55; batchgenerators'
@@ -237,17 +241,6 @@ int mvd_channel_sum(const void* g, int ld, long long NV, int C, float* out, mvd_
 /* out[0] (+)= scale * in[0]: device-side double -> float scalar algebra (keeps the step free of host syncs) */
 int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream);
 int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int C, mvd_stream_t stream); /* dst += src */
-/* hardware probe (tests, DESIGN.md evidence): multiplies a TMA-loaded [256 rows][row_bytes] bf16 tile by an identity
- * with a caller-built UMMA A descriptor (start offset, SBO, LBO, base offset, K- or MN-major) and returns
- * D = float[2][128][16] (second slab: A start advanced by kadv_bytes), i.e. which smem rows/channels were fetched. */
-int mvd_tc_probe(const void* src, const void* ident, int row_bytes, int start_off, int sbo, int lbo, int base_off,
-                 int a_mn_major, int kadv_bytes, float* out, mvd_stream_t stream);
-
-/* hardware probe: cycles for n_mma back-to-back tcgen05.mma (M=128, N=n, K=16) from resident shared memory, round-robin
- * over n_acc accumulators; A start stepped by a_step bytes (mod a_steps_mod steps), 8-row-group pitch a_sbo. */
-int mvd_tc_mma_bench(int n, int n_mma, int n_acc, int a_sbo, int a_step, int a_steps_mod, int row_bytes, int mn_major,
-                     int b_step, int grid, int mode, long long* out_cycles, mvd_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

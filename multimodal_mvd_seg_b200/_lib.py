@@ -53,7 +53,7 @@ _SIGNATURES = {
     'mvd_shutdown': (c_int, []),
     'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, P, I, I, LL, I, S]),
     'mvd_ndhwc_bf16_to_ncdhw_f32': (c_int, [P, I, P, I, I, LL, S]),
-    'mvd_sw_accumulate': (c_int, [P, I, P, F, P, P, I, I, I, I, I, I, I, I, I, I, S]),
+    'mvd_sw_accumulate': (c_int, [P, I, P, F, P, P, I, I, I, I, I, I, I, I, I, I, I, S]),
     'mvd_sw_finalize': (c_int, [P, P, I, LL, S]),
     'mvd_downsample_seg_nearest': (c_int, [P, I, I, I, I, I, P, P, S]),
     'mvd_stem_conv_fprop': (c_int, [P, I, I, I, I, I, P, P, P, I, P, S]),
@@ -95,8 +95,6 @@ _SIGNATURES = {
     'mvd_channel_sum': (c_int, [P, I, LL, I, P, S]),
     'mvd_scalar_axpy': (c_int, [P, F, P, I, S]),
     'mvd_add_bf16': (c_int, [P, I, P, I, LL, I, S]),
-    'mvd_tc_probe': (c_int, [P, P, I, I, I, I, I, I, I, P, S]),
-    'mvd_tc_mma_bench': (c_int, [I, I, I, I, I, I, I, I, I, I, I, P, S]),
     'mvd_im2col_small': (c_int, [P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, S]),
 }
 

@@ -532,7 +532,8 @@ template <int K>
 __global__ void __launch_bounds__(256) sw_accumulate_kernel(const bf16* __restrict__ pred, int ldp,
                                                             const float* __restrict__ g, float scale,
                                                             float* __restrict__ acc, float* __restrict__ npred, int d,
-                                                            int h, int w, int D, int H, int W, int z0, int y0, int x0) {
+                                                            int h, int w, int D, int H, int W, int z0, int y0, int x0,
+                                                            int flip_mask) {
   const long long n = (long long)d * h * w;
   const long long vol = (long long)D * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -541,8 +542,12 @@ __global__ void __launch_bounds__(256) sw_accumulate_kernel(const bf16* __restri
     const int y = (int)(r % h), z = (int)(r / h);
     const float gw = g ? g[i] : 1.f;
     const long long o = ((long long)(z0 + z) * H + (y0 + y)) * W + (x0 + x);
+    // a mirrored test-time-augmentation pass (predict_from_raw_data.py:562-589) is read back through the same flips
+    const int sz = (flip_mask & 1) ? d - 1 - z : z, sy = (flip_mask & 2) ? h - 1 - y : y,
+              sx = (flip_mask & 4) ? w - 1 - x : x;
+    const long long src = ((long long)sz * h + sy) * w + sx;
     float v[K];
-    load_row_k<K>(pred + i * ldp, K == 4 && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 7) == 0), v);
+    load_row_k<K>(pred + src * ldp, K == 4 && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 7) == 0), v);
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[(long long)k * vol + o] += v[k] * scale * gw;
     if (npred) npred[o] += gw;
@@ -603,15 +608,18 @@ int mvd_head_bwd(const void* dlogits, int ldl, const void* z, int ldz, const flo
 }
 
 int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float scale, float* acc, float* npred, int K,
-                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, mvd_stream_t stream) {
-  MVD_REQUIRE(pred && acc && K >= 1 && K <= kMaxHeadK && ldp >= K, "sw_accumulate: bad arguments");
+                      int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, int flip_mask,
+                      mvd_stream_t stream) {
+  MVD_REQUIRE(pred && acc && K >= 1 && K <= kMaxHeadK && ldp >= K && flip_mask >= 0 && flip_mask < 8,
+              "sw_accumulate: bad arguments");
   MVD_REQUIRE(d > 0 && h > 0 && w > 0 && z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + d <= D && y0 + h <= H && x0 + w <= W,
               "sw_accumulate: tile outside the volume");
   const int grid = grid_for((long long)d * h * w, 256, num_sms() * 8);
 #define SW_CASE(KK)                                                                                              \
   case KK:                                                                                                       \
     sw_accumulate_kernel<KK><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, ldp, gaussian, scale, acc, \
-                                                                     npred, d, h, w, D, H, W, z0, y0, x0);         \
+                                                                     npred, d, h, w, D, H, W, z0, y0, x0,          \
+                                                                     flip_mask);                                   \
     break;
   switch (K) {
     SW_CASE(1) SW_CASE(2) SW_CASE(3) SW_CASE(4) SW_CASE(5) SW_CASE(6) SW_CASE(7) SW_CASE(8)

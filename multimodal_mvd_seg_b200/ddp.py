@@ -22,28 +22,69 @@ import torch.distributed as dist
 
 def split_batch_for_rank(global_batch_size: int, world_size: int, rank: int,
                          oversample_foreground_percent: float = 0.33) -> Tuple[int, float]:
-    """(batch_size, oversample_percent) of one rank -- MVDTrainer.py:316-361."""
-    assert global_batch_size >= world_size, \
-        'Cannot run DDP if the batch size is smaller than the number of GPUs... Duh.'
-    batch_size_per_GPU = int(np.ceil(global_batch_size / world_size))
-    batch_sizes, oversample_percents = [], []
-    for r in range(world_size):
-        if (r + 1) * batch_size_per_GPU > global_batch_size:
-            batch_size = batch_size_per_GPU - ((r + 1) * batch_size_per_GPU - global_batch_size)
-        else:
-            batch_size = batch_size_per_GPU
-        batch_sizes.append(batch_size)
-        sample_id_low = 0 if len(batch_sizes) == 0 else np.sum(batch_sizes[:-1])
-        sample_id_high = np.sum(batch_sizes)
-        if sample_id_high / global_batch_size < (1 - oversample_foreground_percent):
-            oversample_percents.append(0.0)
-        elif sample_id_low / global_batch_size > (1 - oversample_foreground_percent):
-            oversample_percents.append(1.0)
-        else:
-            covered = sample_id_high / global_batch_size - sample_id_low / global_batch_size
-            oversample_percents.append(
-                1 - (((1 - oversample_foreground_percent) - sample_id_low / global_batch_size) / covered))
-    return int(batch_sizes[rank]), float(oversample_percents[rank])
+    """(batch_size, oversample_percent) of one rank, the rule of MVDTrainer._set_batch_size_and_oversample
+    (MVDTrainer.py:316-361): every rank takes ceil(global / world) samples, the trailing ranks give back the excess;
+    the foreground-oversampled tail of the GLOBAL batch (its last ``oversample_foreground_percent``) is mapped onto the
+    ranks whose sample range [lo, hi) reaches into it."""
+    if global_batch_size < world_size:
+        raise AssertionError('Cannot run DDP if the batch size is smaller than the number of GPUs... Duh.')
+    per_rank = -(-global_batch_size // world_size)
+    ends = (np.arange(world_size) + 1) * per_rank
+    sizes = per_rank - np.maximum(ends - global_batch_size, 0)
+    hi = np.cumsum(sizes) / global_batch_size
+    lo = hi - sizes / global_batch_size
+    plain_share = 1.0 - oversample_foreground_percent     # leading fraction of the global batch that is NOT oversampled
+    if hi[rank] < plain_share:
+        pct = 0.0
+    elif lo[rank] > plain_share:
+        pct = 1.0
+    else:
+        pct = 1.0 - (plain_share - lo[rank]) / (hi[rank] - lo[rank])
+    return int(sizes[rank]), float(pct)
+
+
+def broadcast_parameters(modules: Sequence[torch.nn.Module], src: int = 0, group=None) -> None:
+    """what the DistributedDataParallel constructor does for the reference (MVDTrainer.py:236-238): every rank starts
+    from rank ``src``'s parameters and buffers.  One flat broadcast per dtype; no-op without an initialised group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return
+    seen, tensors = set(), []
+    for mod in modules:
+        for t in list(mod.parameters()) + list(mod.buffers()):
+            if id(t) not in seen:
+                seen.add(id(t))
+                tensors.append(t.detach())
+    by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for group_tensors in by_dtype.values():
+        flat = torch.cat([t.reshape(-1) for t in group_tensors])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in group_tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+def parameter_checksums(modules: Sequence[torch.nn.Module]) -> torch.Tensor:
+    """[sum, sum of squares] over all parameters in fp64 (replica-consistency check: bench.py, tests)."""
+    acc = None
+    for mod in modules:
+        for p in mod.parameters():
+            v = p.detach().double()
+            cur = torch.stack([v.sum(), (v * v).sum()])
+            acc = cur if acc is None else acc + cur
+    return acc
+
+
+def replicas_identical(modules: Sequence[torch.nn.Module], group=None) -> bool:
+    """all-gathers the parameter checksums; True when every rank holds bit-identical sums."""
+    cs = parameter_checksums(modules)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return True
+    parts = [torch.empty_like(cs) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, cs, group=group)
+    return all(torch.equal(parts[0], q) for q in parts[1:])
 
 
 class GradArena:

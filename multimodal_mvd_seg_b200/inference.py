@@ -7,7 +7,8 @@ Mirrors the pieces of the reference that run at prediction time:
   nnUNetPredictor.predict_sliding_window_return_logits       inference/predict_from_raw_data.py:643-714
 The network forward is the tcgen05 path of this package; the Gaussian-weighted accumulation of every tile into the
 full-volume logits runs in libmvdseg (``mvd_sw_accumulate`` / ``mvd_sw_finalize``).  Accumulators are fp32 (the
-reference keeps them in fp16).  There is no CPU fallback.
+reference keeps them in fp16) and every mirrored pass is added un-averaged with scale 1/2^n, so nothing between the
+network's bf16 logits and the final division is rounded to 16 bits.  There is no CPU fallback.
 """
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -77,17 +78,29 @@ class SlidingWindowPredictor:
                 for sx in steps[0] for sy in steps[1] for sz in steps[2]]
 
     # predict_from_raw_data.py:562-589
-    def _internal_maybe_mirror_and_predict(self, x: torch.Tensor) -> torch.Tensor:
+    def _mirror_passes(self) -> List[Tuple[Tuple[int, ...], int]]:
+        """(flip dims of the [1,c,x,y,z] input, flip_mask of mvd_sw_accumulate) for every test-time-augmentation pass:
+        the identity first, then the reference's order (2,), (3,), (4,), (2,3), (2,4), (3,4), (2,3,4) restricted to the
+        allowed axes."""
+        passes = [((), 0)]
         mirror_axes = self.allowed_mirroring_axes if self.use_mirroring else None
-        prediction = self.network(x).float()
         if mirror_axes is not None:
-            assert max(mirror_axes) <= x.dim() - 3, 'mirror_axes does not match the dimension of the input!'
-            combos = [c for c in ((2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4))
-                      if all((a - 2) in mirror_axes for a in c)]
-            for c in combos:
-                prediction = prediction + torch.flip(self.network(torch.flip(x, c)), c).float()
-            prediction = prediction / (2 ** len(mirror_axes))
-        return prediction
+            assert max(mirror_axes) <= 2, 'mirror_axes does not match the dimension of the input!'
+            for c in ((2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)):
+                if all((a - 2) in mirror_axes for a in c):
+                    passes.append((c, sum(1 << (a - 2) for a in c)))
+        return passes
+
+    def _internal_maybe_mirror_and_predict(self, x: torch.Tensor) -> torch.Tensor:
+        """mean over the mirrored passes as an fp32 [1,K,x,y,z] tensor (the reference's return value; the sliding
+        window below does not go through it: it hands every pass to mvd_sw_accumulate un-averaged)."""
+        passes = self._mirror_passes()
+        prediction = None
+        for dims, _ in passes:
+            p = self.network(torch.flip(x, dims) if dims else x).float()
+            p = torch.flip(p, dims) if dims else p
+            prediction = p if prediction is None else prediction + p
+        return prediction / len(passes)
 
     @torch.no_grad()
     def predict_sliding_window_return_logits(self, input_image: torch.Tensor) -> torch.Tensor:
@@ -118,12 +131,17 @@ class SlidingWindowPredictor:
                                         dtype=torch.float32, device=self.device) if self.use_gaussian else None
             st = torch.cuda.current_stream().cuda_stream
             d, h, w = self.patch_size
+            passes = self._mirror_passes()
+            scale = 1.0 / len(passes)     # = 1 / 2^len(mirror_axes), predict_from_raw_data.py:588
             for sl in slicers:
                 workon = data[sl][None]
-                pred = self._internal_maybe_mirror_and_predict(workon)          # [1, K, d, h, w] fp32
-                pred_cl = pred[0].permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
-                lib.sw_accumulate(pred_cl.data_ptr(), K, ops._ptr(gaussian), 1.0, acc.data_ptr(), npred.data_ptr(), K,
-                                  d, h, w, D, H, W, sl[1].start, sl[2].start, sl[3].start, st)
+                for pi, (dims, mask) in enumerate(passes):
+                    # every pass's bf16 logits go straight into the fp32 accumulator (flipped back by the kernel's
+                    # addressing): the averaged prediction is never rounded to 16 bits
+                    pred_cl = ops.to_cl_view(self.network(torch.flip(workon, dims) if dims else workon))[0]
+                    lib.sw_accumulate(pred_cl.data_ptr(), ops.cl_pitch(pred_cl[None]), ops._ptr(gaussian), scale,
+                                      acc.data_ptr(), npred.data_ptr() if pi == 0 else None, K, d, h, w, D, H, W,
+                                      sl[1].start, sl[2].start, sl[3].start, mask, st)
             lib.sw_finalize(acc.data_ptr(), npred.data_ptr(), K, D * H * W, st)
             return acc[tuple(revert)]
         finally:

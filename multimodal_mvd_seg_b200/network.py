@@ -328,26 +328,23 @@ def get_network_from_plans(plans_manager, dataset_json, configuration_manager, n
 
 
 def load_pretrained_weights(network: nn.Module, fname, verbose: bool = False) -> None:
-    """run/load_pretrained_weights.py:6-64: transfer every tensor whose key and shape match, EXCEPT the segmentation
-    heads (keys containing '.seg_layers.'); all other keys of the network must be present in the checkpoint with the
-    same shape.  ``fname`` is a checkpoint path or an already loaded checkpoint dict with 'network_weights'."""
-    saved_model = fname if isinstance(fname, dict) else torch.load(fname, map_location='cpu', weights_only=False)
-    pretrained_dict = saved_model['network_weights']
-    skip_strings_in_pretrained = ['.seg_layers.']
-    mod = network.module if isinstance(network, nn.parallel.DistributedDataParallel) else network
-    model_dict = mod.state_dict()
-    for key in model_dict:
-        if all(i not in key for i in skip_strings_in_pretrained):
-            assert key in pretrained_dict, \
-                f'Key {key} is missing in the pretrained model weights. The pretrained weights do not seem to be ' \
-                f'compatible with your network.'
-            assert model_dict[key].shape == pretrained_dict[key].shape, \
-                f'The shape of the parameters of key {key} is not the same. Pretrained model: ' \
-                f'{pretrained_dict[key].shape}; your network: {model_dict[key].shape}.'
-    pretrained_dict = {k: v for k, v in pretrained_dict.items()
-                       if k in model_dict and all(i not in k for i in skip_strings_in_pretrained)}
-    model_dict.update(pretrained_dict)
-    if verbose:
-        for key, value in pretrained_dict.items():
-            print(key, 'shape', value.shape)
-    mod.load_state_dict(model_dict)
+    """contract of run/load_pretrained_weights.py:6-64: everything except the segmentation heads (keys containing
+    '.seg_layers.') is taken from the checkpoint's 'network_weights'; each of those keys must exist there with the same
+    shape, otherwise the checkpoint does not belong to this architecture (AssertionError).  ``fname``: a checkpoint
+    path or an already loaded checkpoint dict."""
+    checkpoint = fname if isinstance(fname, dict) else torch.load(fname, map_location='cpu', weights_only=False)
+    source = checkpoint['network_weights']
+    target = network.module if isinstance(network, nn.parallel.DistributedDataParallel) else network
+    state = target.state_dict()
+    wanted = [k for k in state if '.seg_layers.' not in k]
+    absent = [k for k in wanted if k not in source]
+    assert not absent, (f'Key {absent[0]} is missing in the pretrained model weights. The pretrained weights do not '
+                        f'seem to be compatible with your network.')
+    for k in wanted:
+        assert state[k].shape == source[k].shape, \
+            (f'The shape of the parameters of key {k} is not the same. Pretrained model: {source[k].shape}; your '
+             f'network: {state[k].shape}.')
+        if verbose:
+            print(k, 'shape', tuple(source[k].shape))
+        state[k] = source[k]
+    target.load_state_dict(state)

@@ -22,10 +22,34 @@ class SGDNesterovClip(torch.optim.Optimizer):
                  momentum: float = 0.99, nesterov: bool = True, max_norm: Optional[float] = 12.0):
         if not nesterov:
             raise NotImplementedError('the reference trains with nesterov=True (MVDTrainer.py:483)')
-        defaults = dict(lr=lr, weight_decay=weight_decay, momentum=momentum, nesterov=True, max_norm=max_norm)
+        # the groups carry exactly torch.optim.SGD's keys, so `optimizer_state` of a checkpoint interchanges with the
+        # reference's optimiser in both directions (MVDTrainer.py:1138, 1180); the clipping threshold -- an argument
+        # of clip_grad_norm_ in the reference, not optimiser state -- is an attribute
+        defaults = dict(lr=lr, momentum=momentum, dampening=0, weight_decay=weight_decay, nesterov=True,
+                        maximize=False, foreach=None, differentiable=False, fused=None)
         super().__init__(params, defaults)
+        self.max_norm = max_norm
         self._tables = {}      # group index -> cached device tables
         self.last_sqnorm = None  # device double[1]: squared global grad norm of the last step (before clipping)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}      # the momentum buffers were replaced: cached device pointer tables are stale
+        for g in self.param_groups:
+            if not g.get('nesterov', True) or g.get('dampening', 0) != 0 or g.get('maximize', False):
+                raise NotImplementedError('SGDNesterovClip: only nesterov=True, dampening=0, maximize=False is built')
+            g.pop('max_norm', None)      # round-1 checkpoints of this package kept it in the groups
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
+
+    def ensure_state(self):
+        """create the momentum buffers now (first-step laziness must not be captured into a CUDA graph: a captured
+        zero-initialisation would reset the momentum on every replay)."""
+        for g in self.param_groups:
+            for p in g['params']:
+                st = self.state[p]
+                if st.get('momentum_buffer') is None:
+                    st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
 
     def _group_tables(self, gi: int, group) -> dict:
         params = [p for p in group['params']]
@@ -35,8 +59,10 @@ class SGDNesterovClip(torch.optim.Optimizer):
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise MvdError('SGDNesterovClip: parameters must be contiguous fp32')
             st = self.state[p]
-            if 'momentum_buffer' not in st:
+            if st.get('momentum_buffer') is None:
                 st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            elif st['momentum_buffer'].dtype != torch.float32 or not st['momentum_buffer'].is_contiguous():
+                st['momentum_buffer'] = st['momentum_buffer'].float().contiguous()
         sig = []
         for p in params:
             g = p.grad
@@ -77,13 +103,13 @@ class SGDNesterovClip(torch.optim.Optimizer):
         tabs = [self._group_tables(gi, g) for gi, g in enumerate(self.param_groups)]
         dev = self.param_groups[0]['params'][0].device
         sq = torch.zeros((1,), dtype=torch.float64, device=dev)
-        need_norm = any(g['max_norm'] is not None and g['max_norm'] > 0 for g in self.param_groups)
+        need_norm = self.max_norm is not None and self.max_norm > 0
         if need_norm:  # the norm is global over all groups, like clip_grad_norm_(network.parameters())
             for t in tabs:
                 lib.grad_sqnorm(t['ptrs'].data_ptr(), t['numel'].data_ptr(), t['chunk_t'].data_ptr(),
                                 t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), stream)
         for t, g in zip(tabs, self.param_groups):
-            mn = g['max_norm'] if g['max_norm'] is not None else 0.0
+            mn = self.max_norm if need_norm else 0.0
             lib.sgd_nesterov_clip(t['ptrs'].data_ptr(), t['numel'].data_ptr(), t['chunk_t'].data_ptr(),
                                   t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), float(grad_scale), float(mn),
                                   float(g['lr']), float(g['weight_decay']), float(g['momentum']), stream)

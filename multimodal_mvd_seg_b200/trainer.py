@@ -25,7 +25,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import ops
-from .ddp import GradArena, split_batch_for_rank
+from .ddp import GradArena, broadcast_parameters, split_batch_for_rank
 from .ds_targets import downsample_seg_for_ds
 from .losses import (DC_and_CE_loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss, distill_kl, soft_cldice,
                      softmax_channel)
@@ -133,50 +133,70 @@ def make_plans(patch_size, batch_size: int = 2, n_modalities: int = 2, n_classes
 
 
 def collate_outputs(outputs: List[dict]) -> dict:
-    """utilities/collate_outputs.py:6-24: scalars -> list, arrays -> stacked along a new first axis, lists -> one list."""
-    collated = {}
-    for k in outputs[0].keys():
-        v0 = outputs[0][k]
-        if np.isscalar(v0):
-            collated[k] = [o[k] for o in outputs]
-        elif isinstance(v0, np.ndarray):
-            collated[k] = np.vstack([o[k][None] for o in outputs])
-        elif isinstance(v0, list):
-            collated[k] = [item for o in outputs for item in o[k]]
-        else:
-            raise ValueError(f'Cannot collate input of type {type(v0)}. Modify collate_outputs to add this functionality')
-    return collated
+    """merge the per-step result dicts of one epoch (contract of utilities/collate_outputs.py:6-24): python scalars
+    become a list, numpy arrays are stacked along a new leading axis, lists are concatenated."""
+    def merge(values):
+        first = values[0]
+        if np.isscalar(first):
+            return list(values)
+        if isinstance(first, np.ndarray):
+            return np.vstack([v[None] for v in values])
+        if isinstance(first, list):
+            merged = []
+            for v in values:
+                merged.extend(v)
+            return merged
+        raise ValueError(f'Cannot collate input of type {type(first)}. Modify collate_outputs to add this functionality')
+    return {key: merge([o[key] for o in outputs]) for key in outputs[0]}
 
 
 class nnUNetLogger(object):
-    """one value per epoch and key, as training/logging/nnunet_logger.py:9-52 (no plotting: out of scope).  Logging
-    'mean_fg_dice' also logs its exponential moving average 'ema_fg_dice' (0.9 * previous + 0.1 * new)."""
+    """per-epoch series under the key names of training/logging/nnunet_logger.py:18-27 (they are part of the
+    checkpoint, MVDTrainer.py:1140); no plotting.  Writing 'mean_fg_dice' also extends 'ema_fg_dice' with
+    0.9 * previous + 0.1 * value (:49-52)."""
+    KEYS = ('mean_fg_dice', 'ema_fg_dice', 'dice_per_class_or_region', 'train_losses', 'val_losses', 'lrs',
+            'epoch_start_timestamps', 'epoch_end_timestamps')
 
     def __init__(self, verbose: bool = False):
-        self.my_fantastic_logging = {k: list() for k in ('mean_fg_dice', 'ema_fg_dice', 'dice_per_class_or_region',
-                                                         'train_losses', 'val_losses', 'lrs', 'epoch_start_timestamps',
-                                                         'epoch_end_timestamps')}
+        self.my_fantastic_logging = {k: [] for k in self.KEYS}
         self.verbose = verbose
 
     def log(self, key, value, epoch: int):
-        log = self.my_fantastic_logging
-        assert key in log and isinstance(log[key], list), 'one list entry per epoch and known key'
+        series = self.my_fantastic_logging.get(key)
+        assert isinstance(series, list), f'unknown logging key {key}'
         if self.verbose:
             print(f'logging {key}: {value} for epoch {epoch}')
-        if len(log[key]) < (epoch + 1):
-            log[key].append(value)
+        assert len(series) in (epoch, epoch + 1), 'an epoch was skipped: one entry per epoch and key'
+        if len(series) == epoch:
+            series.append(value)
         else:
-            assert len(log[key]) == (epoch + 1), 'logging list length is off by more than 1'
-            log[key][epoch] = value
+            series[epoch] = value
         if key == 'mean_fg_dice':
-            ema = log['ema_fg_dice'][epoch - 1] * 0.9 + 0.1 * value if len(log['ema_fg_dice']) > 0 else value
-            self.log('ema_fg_dice', ema, epoch)
+            ema = self.my_fantastic_logging['ema_fg_dice']
+            self.log('ema_fg_dice', value if not ema else 0.9 * ema[epoch - 1] + 0.1 * value, epoch)
 
     def get_checkpoint(self):
         return self.my_fantastic_logging
 
     def load_checkpoint(self, checkpoint: dict):
         self.my_fantastic_logging = checkpoint
+
+
+def _mean_over_ranks(per_step_values, is_ddp: bool) -> float:
+    """mean of a per-step quantity over all steps of all ranks (MVDTrainer.py:990-993, 1083-1088)."""
+    if not is_ddp:
+        return float(np.mean(per_step_values))
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, per_step_values)
+    return float(np.vstack(gathered).mean())
+
+
+def _sum_over_ranks(counts: np.ndarray, is_ddp: bool) -> np.ndarray:
+    if not is_ddp:
+        return counts
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, counts)
+    return np.sum(np.stack(gathered), axis=0)
 
 
 class nnUNetTrainer(object):
@@ -240,6 +260,7 @@ class nnUNetTrainer(object):
         self.network = self.build_network_architecture(self.plans_manager, self.dataset_json,
                                                        self.configuration_manager, self.num_input_channels,
                                                        enable_deep_supervision=True).to(self.device)
+        self._sync_replicas()
         self.optimizer, self.lr_scheduler = self.configure_optimizers()
         self._setup_grad_arenas()
         self.loss = self._build_loss()
@@ -247,6 +268,12 @@ class nnUNetTrainer(object):
 
     def _networks(self) -> List[nn.Module]:
         return [self.network]
+
+    def _sync_replicas(self):
+        """every rank starts from rank 0's weights, as the DistributedDataParallel constructor guarantees in the
+        reference (MVDTrainer.py:236-238; run_training never seeds, so each rank's He initialisation differs)."""
+        if self.is_ddp:
+            broadcast_parameters(self._networks(), src=0)
 
     def _setup_grad_arenas(self):
         """replaces DDP(self.network, device_ids=[local_rank]) (nnUNetTrainer.py:236-238): gradients live in flat
@@ -339,56 +366,37 @@ class nnUNetTrainer(object):
         self.logger.log('epoch_start_timestamps', time.time(), self.current_epoch)
 
     def on_train_epoch_end(self, train_outputs: List[dict]):
-        outputs = collate_outputs(train_outputs)
-        if self.is_ddp:
-            losses_tr = [None for _ in range(dist.get_world_size())]
-            dist.all_gather_object(losses_tr, outputs['loss'])
-            loss_here = np.vstack(losses_tr).mean()
-        else:
-            loss_here = np.mean(outputs['loss'])
-        self.logger.log('train_losses', loss_here, self.current_epoch)
+        self.logger.log('train_losses', _mean_over_ranks(collate_outputs(train_outputs)['loss'], self.is_ddp), self.current_epoch)
 
     def on_validation_epoch_start(self):
         for n in self._networks():
             n.eval()
 
     def on_validation_epoch_end(self, val_outputs: List[dict]):
-        outputs_collated = collate_outputs(val_outputs)
-        tp = np.sum(outputs_collated['tp_hard'], 0)
-        fp = np.sum(outputs_collated['fp_hard'], 0)
-        fn = np.sum(outputs_collated['fn_hard'], 0)
-        if self.is_ddp:
-            world_size = dist.get_world_size()
-
-            def gather_sum(v):
-                parts = [None for _ in range(world_size)]
-                dist.all_gather_object(parts, v)
-                return np.vstack([i[None] for i in parts]).sum(0)
-            tp, fp, fn = gather_sum(tp), gather_sum(fp), gather_sum(fn)
-            losses_val = [None for _ in range(world_size)]
-            dist.all_gather_object(losses_val, outputs_collated['loss'])
-            loss_here = np.vstack(losses_val).mean()
-        else:
-            loss_here = np.mean(outputs_collated['loss'])
-        with np.errstate(divide='ignore', invalid='ignore'):      # a class that never occurs: 0 / 0 -> nan, skipped by nanmean
-            global_dc_per_class = [i for i in [2 * i / (2 * i + j + k) for i, j, k in zip(tp, fp, fn)]]
-        mean_fg_dice = np.nanmean(global_dc_per_class)
-        self.logger.log('mean_fg_dice', mean_fg_dice, self.current_epoch)
-        self.logger.log('dice_per_class_or_region', global_dc_per_class, self.current_epoch)
-        self.logger.log('val_losses', loss_here, self.current_epoch)
+        """pseudo-Dice of the epoch from the hard tp / fp / fn counts summed over steps and ranks, 2tp / (2tp + fp + fn)
+        per foreground class (MVDTrainer.py:1065-1096); a class that never occurs gives nan and is left out of the mean."""
+        out = collate_outputs(val_outputs)
+        tp, fp, fn = (_sum_over_ranks(np.sum(out[k], axis=0), self.is_ddp) for k in ('tp_hard', 'fp_hard', 'fn_hard'))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            dice = [float(v) for v in 2 * tp / (2 * tp + fp + fn)]
+        e = self.current_epoch
+        self.logger.log('mean_fg_dice', np.nanmean(dice), e)
+        self.logger.log('dice_per_class_or_region', dice, e)
+        self.logger.log('val_losses', _mean_over_ranks(out['loss'], self.is_ddp), e)
 
     def on_epoch_end(self):
-        self.logger.log('epoch_end_timestamps', time.time(), self.current_epoch)
-        current_epoch = self.current_epoch
-        if self.output_folder is not None:
-            if (current_epoch + 1) % self.save_every == 0 and current_epoch != (self.num_epochs - 1):
-                self.save_checkpoint(os.path.join(self.output_folder, 'checkpoint_latest.pth'))
+        """checkpoint cadence of MVDTrainer.py:1101-1127: 'latest' every save_every epochs, 'best' on a new EMA maximum."""
+        e = self.current_epoch
+        self.logger.log('epoch_end_timestamps', time.time(), e)
+        folder = self.output_folder
+        if folder is not None and (e + 1) % self.save_every == 0 and e != self.num_epochs - 1:
+            self.save_checkpoint(os.path.join(folder, 'checkpoint_latest.pth'))
         ema = self.logger.my_fantastic_logging['ema_fg_dice']
         if ema and (self._best_ema is None or ema[-1] > self._best_ema):
             self._best_ema = ema[-1]
-            if self.output_folder is not None:
-                self.save_checkpoint(os.path.join(self.output_folder, 'checkpoint_best.pth'))
-        self.current_epoch += 1
+            if folder is not None:
+                self.save_checkpoint(os.path.join(folder, 'checkpoint_best.pth'))
+        self.current_epoch = e + 1
 
     def run_training(self):
         """MVDTrainer.py:1323-1345, with the next training batch uploaded underneath the current step."""
@@ -561,6 +569,7 @@ class nnUNetTrainer(object):
                tuple(g['lr'] for g in self.optimizer.param_groups))
         if st is None or st['key'] != key:
             self._graph_state = None
+            self.optimizer.ensure_state()    # lazy momentum initialisation must not end up inside the graph
             sd = data.clone()
             stg = [t.clone() for t in target]
             torch.cuda.synchronize()
@@ -626,11 +635,9 @@ class nnUNetTrainer(object):
         return {'loss': l.detach().cpu().numpy(), 'tp_hard': tp_hard, 'fp_hard': fp_hard, 'fn_hard': fn_hard}
 
     # ------------------------------------------------------------------------------------------------------------
-    def save_checkpoint(self, filename: str) -> None:
-        """keys of MVDTrainer.py:1129-1152."""
-        if self.local_rank != 0:
-            return
-        checkpoint = {
+    def _checkpoint_dict(self) -> dict:
+        """keys of MVDTrainer.py:1129-1152 (subclasses extend the dict)."""
+        return {
             'network_weights': self.network.state_dict(),
             'optimizer_state': self.optimizer.state_dict(),
             'grad_scaler_state': None,
@@ -641,27 +648,38 @@ class nnUNetTrainer(object):
             'trainer_name': self.__class__.__name__,
             'inference_allowed_mirroring_axes': None,
         }
-        torch.save(checkpoint, filename)
+
+    def save_checkpoint(self, filename: str) -> None:
+        if self.local_rank != 0:
+            return
+        tmp = filename + '.tmp'
+        torch.save(self._checkpoint_dict(), tmp)      # written once, published atomically
+        os.replace(tmp, filename)
+
+    @staticmethod
+    def _strip_ddp_prefix(weights: dict, own_keys) -> dict:
+        """a checkpoint saved from a DDP-wrapped module carries 'module.' in front of every key (MVDTrainer.py:1162-1167)."""
+        return {(k[7:] if k not in own_keys and k.startswith('module.') else k): v for k, v in weights.items()}
+
+    def _load_networks(self, ck: dict) -> None:
+        self.network.load_state_dict(self._strip_ddp_prefix(ck['network_weights'], self.network.state_dict().keys()))
 
     def load_checkpoint(self, filename_or_checkpoint: Union[dict, str]) -> None:
-        """MVDTrainer.py:1154-1190: strips the DDP 'module.' prefix."""
+        """MVDTrainer.py:1154-1190."""
         if not self.was_initialized:
             self.initialize()
         ck = filename_or_checkpoint
         if isinstance(ck, str):
             ck = torch.load(ck, map_location=self.device, weights_only=False)
-        new_state_dict = {}
-        for k, value in ck['network_weights'].items():
-            key = k
-            if key not in self.network.state_dict().keys() and key.startswith('module.'):
-                key = key[7:]
-            new_state_dict[key] = value
+        self._load_networks(ck)
+        self.optimizer.load_state_dict(ck['optimizer_state'])
         self.current_epoch = ck['current_epoch']
         if ck.get('logging'):
             self.logger.load_checkpoint(ck['logging'])
         self._best_ema = ck.get('_best_ema')
-        self.network.load_state_dict(new_state_dict)
-        self.optimizer.load_state_dict(ck['optimizer_state'])
+        self._sync_replicas()
+        # a captured step holds the addresses of the momentum buffers that load_state_dict just replaced
+        self._graph_state = None
 
 
 class MVDTrainer(nnUNetTrainer):
@@ -689,6 +707,7 @@ class MVDTrainer(nnUNetTrainer):
                                                        self.configuration_manager, 1, True).to(self.device)
         self.network2 = self.build_network_architecture(self.plans_manager, self.dataset_json,
                                                         self.configuration_manager, 1, True).to(self.device)
+        self._sync_replicas()
         self.optimizer, self.lr_scheduler = self.configure_optimizers()
         self._setup_grad_arenas()
         self.loss = self._build_loss()
@@ -717,18 +736,16 @@ class MVDTrainer(nnUNetTrainer):
         self.last_terms = dict(mutual=mutual.detach())
         return l, out1
 
-    def save_checkpoint(self, filename: str) -> None:
-        if self.local_rank != 0:
-            return
-        super().save_checkpoint(filename)
-        ck = torch.load(filename, weights_only=False)
+    def _checkpoint_dict(self) -> dict:
+        ck = super()._checkpoint_dict()
         ck['network2_weights'] = self.network2.state_dict()
-        torch.save(ck, filename)
+        return ck
 
-    def load_checkpoint(self, filename_or_checkpoint):
-        ck = filename_or_checkpoint
-        if isinstance(ck, str):
-            ck = torch.load(ck, map_location=self.device, weights_only=False)
-        super().load_checkpoint(ck)
-        if 'network2_weights' in ck:
-            self.network2.load_state_dict(ck['network2_weights'])
+    def _load_networks(self, ck: dict) -> None:
+        if 'network2_weights' not in ck:
+            raise KeyError("checkpoint has no 'network2_weights': it was not written by MVDTrainer (a single-network or "
+                           'reference-format checkpoint would leave the second modality network at its random '
+                           'initialisation while restoring optimiser momentum for it); load it into nnUNetTrainer, or '
+                           'add the second network\'s state_dict under that key')
+        super()._load_networks(ck)
+        self.network2.load_state_dict(self._strip_ddp_prefix(ck['network2_weights'], self.network2.state_dict().keys()))

@@ -1,13 +1,15 @@
 """tcgen05.mma issue-rate microbenchmark (cycles per M128 x N x K16 MMA) for several operand layouts."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import multimodal_mvd_seg_b200 as m
+from probes import _probe_lib as probe
 dev = torch.device('cuda:0')
 st = torch.cuda.current_stream().cuda_stream
 out = torch.zeros(4, dtype=torch.int64, device=dev)
 def run(n, n_acc, a_sbo, a_step, mod, rb=128, mn=0, b_step=32, grid=1, n_mma=2048, mode=1):
-    m.lib.tc_mma_bench(n, n_mma, n_acc, a_sbo, a_step, mod, rb, mn, b_step, grid, mode, out.data_ptr(), st)
+    probe.tc_mma_bench(n, n_mma, n_acc, a_sbo, a_step, mod, rb, mn, b_step, grid, mode, out.data_ptr(), st)
     torch.cuda.synchronize()
     return float(out[0]) / n_mma
 print('cycles per MMA (M=128, K=16); ideal = N/2')

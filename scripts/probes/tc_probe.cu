@@ -2,6 +2,7 @@
 // evidence): one CTA TMA-loads a [256 rows][C] bf16 tile whose values encode the row (or channel) index, multiplies
 // it by an identity B tile with a caller-specified A descriptor (start offset, SBO, LBO, base offset, layout, major)
 // and returns D, so the host can read off exactly which shared-memory rows / channels the tensor core fetched.
+// Built by `make -C multimodal_mvd_seg_b200/csrc probe` into scripts/probes/libmvdseg_probe.so (not linked into libmvdseg.so).
 #include "conv_common.cuh"
 #include "tc_common.cuh"
 

@@ -1,8 +1,10 @@
 """Runs mvd_tc_probe over descriptor variants and reports which shared-memory rows the tensor core fetched."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import multimodal_mvd_seg_b200 as m
+from probes import _probe_lib as probe
 lib = m.lib
 dev = torch.device('cuda:0')
 st = torch.cuda.current_stream().cuda_stream
@@ -20,7 +22,7 @@ def run(row_bytes, start, sbo, lbo, bo, mn, kadv):
             src = torch.arange(C, dtype=torch.float32)[None, :].expand(256, C)
         src = src.contiguous().to(torch.bfloat16).to(dev)
         out = torch.full((2, 128, 16), -1.0, dtype=torch.float32, device=dev)
-        lib.tc_probe(src.data_ptr(), ident.data_ptr(), row_bytes, start, sbo, lbo, bo, mn, kadv, out.data_ptr(), st)
+        probe.tc_probe(src.data_ptr(), ident.data_ptr(), row_bytes, start, sbo, lbo, bo, mn, kadv, out.data_ptr(), st)
         torch.cuda.synchronize()
         res.append(out.cpu())
     return res  # [row-probe, ch-probe], each [2,128,16]

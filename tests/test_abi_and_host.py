@@ -366,3 +366,33 @@ def test_split_batch_for_rank_matches_reference_text():
                     ref_ov = float(me.oversample_foreground_percent)
                     # a rank left without samples (8 over 5 ranks -> 2,2,2,2,0) gets 0/0 in the reference as well
                     assert (np.isnan(ov) and np.isnan(ref_ov)) or abs(float(ov) - ref_ov) < 1e-12, (global_bs, world, rank, over)
+
+
+def test_optimizer_state_interchanges_with_torch_sgd():
+    """`optimizer_state` of a checkpoint goes both ways between SGDNesterovClip and the reference's
+    torch.optim.SGD(lr, weight_decay=3e-5, momentum=0.99, nesterov=True) (MVDTrainer.py:482-486, 1138, 1180)."""
+    import multimodal_mvd_seg_b200 as m
+    mk = lambda: [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    p_ref, p_mine = mk(), mk()
+    ref = torch.optim.SGD(p_ref, 1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    for p in p_ref:
+        p.grad = torch.randn_like(p)
+    ref.step()                                    # creates the momentum buffers
+    mine = m.SGDNesterovClip(p_mine, 5e-3, weight_decay=3e-5, momentum=0.99, nesterov=True, max_norm=12.0)
+    assert set(mine.param_groups[0]) == set(ref.param_groups[0])          # same group keys: nothing to drop or to miss
+    sd_ref = ref.state_dict()
+    mine.load_state_dict(sd_ref)                  # reference checkpoint -> ours
+    assert mine.max_norm == 12.0 and mine.param_groups[0]['lr'] == 1e-2
+    for a, b in zip(p_mine, p_ref):
+        assert torch.equal(mine.state[a]['momentum_buffer'], ref.state[b]['momentum_buffer'])
+    ref2 = torch.optim.SGD(mk(), 1.0, momentum=0.5)
+    ref2.load_state_dict(mine.state_dict())       # ours -> reference
+    ref2.param_groups[0]['params'][0].grad = torch.zeros(4, 3)
+    ref2.param_groups[0]['params'][1].grad = torch.zeros(5)
+    ref2.step()                                   # would raise KeyError('dampening') on a group with missing keys
+    assert ref2.param_groups[0]['nesterov'] and ref2.param_groups[0]['momentum'] == 0.99
+    # a round-1 checkpoint of this package carried max_norm inside the groups: still loads
+    old = mine.state_dict()
+    old['param_groups'][0]['max_norm'] = 12.0
+    mine.load_state_dict(old)
+    assert 'max_norm' not in mine.param_groups[0]

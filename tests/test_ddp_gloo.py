@@ -121,3 +121,52 @@ def test_epoch_end_hooks_world2():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _broadcast_worker(rank, world, port, q):
+    """ranks seed differently (the reference's run_training never seeds); after the start-up synchronisation every
+    replica holds rank 0's weights, and a few data-parallel SGD steps on the arena's summed gradients keep them equal."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from multimodal_mvd_seg_b200.ddp import GradArena, broadcast_parameters, replicas_identical
+        torch.manual_seed(1000 + rank)
+        nets = [torch.nn.Sequential(torch.nn.Conv3d(2, 4, 3), torch.nn.InstanceNorm3d(4, affine=True)),
+                torch.nn.Linear(5, 3)]
+        before = replicas_identical(nets)
+        broadcast_parameters(nets, src=0)
+        after = replicas_identical(nets)
+        params = [p for n in nets for p in n.parameters()]
+        arena = GradArena(params, bucket_bytes=256)
+        opt = torch.optim.SGD(params, 0.1, momentum=0.9, nesterov=True)
+        for step in range(3):
+            arena.begin_step()
+            g = torch.Generator().manual_seed(7 * rank + step)      # every rank sees different data
+            for p in reversed(params):
+                arena.view_for(p).copy_(torch.randn(p.shape, generator=g))
+                arena.on_params_ready([p])
+            arena.finish()
+            arena.attach_grads()
+            for p in params:
+                p.grad = p.grad / world
+            opt.step()
+        q.put((rank, (bool(before), bool(after), bool(replicas_identical(nets)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_start_and_stay_identical_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_broadcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    # differently seeded before the broadcast, identical after it and after the steps
+    assert res == {0: (False, True, True), 1: (False, True, True)}

@@ -70,8 +70,16 @@ def test_sw_accumulate_kernel_exact():
     want_n[z0:z0 + d, y0:y0 + h, x0:x0 + w] += gw
     st = torch.cuda.current_stream().cuda_stream
     m.lib.sw_accumulate(pred.data_ptr(), K, gw.data_ptr(), 0.5, acc.data_ptr(), npred.data_ptr(), K, d, h, w, D, H, W,
-                        z0, y0, x0, st)
+                        z0, y0, x0, 0, st)
     torch.testing.assert_close(acc, want_acc, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(npred, want_n, rtol=1e-6, atol=1e-6)
+    # mirrored read-back (flip_mask bit 0: z, 1: y, 2: x), no npred update
+    for mask in (1, 2, 4, 3, 5, 6, 7):
+        dims = [i for i in range(3) if mask >> i & 1]
+        want_acc[:, z0:z0 + d, y0:y0 + h, x0:x0 + w] += pred.float().flip(dims).permute(3, 0, 1, 2) * 0.25 * gw
+        m.lib.sw_accumulate(pred.data_ptr(), K, gw.data_ptr(), 0.25, acc.data_ptr(), None, K, d, h, w, D, H, W,
+                            z0, y0, x0, mask, st)
+        torch.testing.assert_close(acc, want_acc, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(npred, want_n, rtol=1e-6, atol=1e-6)
     m.lib.sw_finalize(acc.data_ptr(), npred.data_ptr(), K, D * H * W, st)
     torch.testing.assert_close(acc, want_acc / want_n, rtol=1e-5, atol=1e-6)

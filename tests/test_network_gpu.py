@@ -405,3 +405,28 @@ def test_prefetching_loop_matches_plain_loop():
     # the weight-gradient reductions use fp32 atomics, so two runs agree to rounding, not bit for bit
     for graph in (False, True):
         np.testing.assert_allclose(res[('prefetch', graph)], res[('plain', graph)], rtol=2e-3, atol=2e-4)
+
+
+def test_mvd_checkpoint_roundtrip_and_missing_second_network(tmp_path):
+    """both modality networks travel through one atomically written file; a checkpoint without 'network2_weights' is
+    refused instead of silently leaving net2 at random initialisation; a captured graph is dropped on load."""
+    import multimodal_mvd_seg_b200 as m
+    dev = torch.device('cuda:0')
+    plans, dj = m.make_plans((16, 16, 16), batch_size=1)
+    tr = m.MVDTrainer(plans, '3d_fullres', 0, dj, device=dev, topo_iter=None)
+    tr.initialize()
+    f = str(tmp_path / 'checkpoint_latest.pth')
+    tr.save_checkpoint(f)
+    assert not (tmp_path / 'checkpoint_latest.pth.tmp').exists()
+    tr2 = m.MVDTrainer(plans, '3d_fullres', 0, dj, device=dev, topo_iter=None)
+    tr2.initialize()
+    tr2._graph_state = {'stale': True}
+    tr2.load_checkpoint(f)
+    assert tr2._graph_state is None
+    for a, b in zip(list(tr.network.parameters()) + list(tr.network2.parameters()),
+                    list(tr2.network.parameters()) + list(tr2.network2.parameters())):
+        assert torch.equal(a, b)
+    ck = torch.load(f, weights_only=False)
+    del ck['network2_weights']
+    with pytest.raises(KeyError, match='network2_weights'):
+        tr2.load_checkpoint(ck)
