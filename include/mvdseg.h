@@ -42,6 +42,10 @@ const char* mvd_last_error(void);
 /* number of kernels this library has launched since load / last reset (bench.py's gpu_launches) */
 unsigned long long mvd_launch_count(void);
 void mvd_reset_launch_count(void);
+/* number of convolution calls with algo == 0 (auto) that were NOT covered by a tcgen05 kernel and ran on the CUDA-core
+ * tiles instead (csrc/conv_generic.cu) since load / last reset: bench.py prints it, the benchmark configurations need 0 */
+unsigned long long mvd_fallback_count(void);
+void mvd_reset_fallback_count(void);
 int mvd_shutdown(void);
 
 /* ---- layout at the module edge ---------------------------------------------------------------------------- */

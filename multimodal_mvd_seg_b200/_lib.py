@@ -50,6 +50,8 @@ _SIGNATURES = {
     'mvd_last_error': (c_char_p, []),
     'mvd_launch_count': (c_ulonglong, []),
     'mvd_reset_launch_count': (None, []),
+    'mvd_fallback_count': (c_ulonglong, []),
+    'mvd_reset_fallback_count': (None, []),
     'mvd_shutdown': (c_int, []),
     'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, P, I, I, LL, I, S]),
     'mvd_ndhwc_bf16_to_ncdhw_f32': (c_int, [P, I, P, I, I, LL, S]),
@@ -98,7 +100,8 @@ _SIGNATURES = {
     'mvd_im2col_small': (c_int, [P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, S]),
 }
 
-_UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count',
+_UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count', 'mvd_fallback_count',
+              'mvd_reset_fallback_count',
               'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks'}
 
 

@@ -7,6 +7,7 @@
 namespace mvd {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_fallbacks{0};
 static int g_num_sms = 0;
 
 void set_error(const char* fmt, ...) {
@@ -15,6 +16,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+void count_fallback() { g_fallbacks.fetch_add(1ull, std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 int num_sms() {
   if (g_num_sms == 0) {
@@ -34,5 +36,7 @@ int mvd_version(void) { return 100; }
 const char* mvd_last_error(void) { return mvd::g_err; }
 unsigned long long mvd_launch_count(void) { return mvd::g_launches.load(); }
 void mvd_reset_launch_count(void) { mvd::g_launches.store(0); }
+unsigned long long mvd_fallback_count(void) { return mvd::g_fallbacks.load(); }
+void mvd_reset_fallback_count(void) { mvd::g_fallbacks.store(0); }
 int mvd_shutdown(void) { return MVD_OK; }
 }

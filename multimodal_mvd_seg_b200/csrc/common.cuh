@@ -10,6 +10,7 @@ namespace mvd {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_fallback();   // algo == auto fell through to the CUDA-core kernels (mvd_fallback_count)
 int num_sms();
 
 typedef __nv_bfloat16 bf16;

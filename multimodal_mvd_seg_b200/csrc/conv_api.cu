@@ -33,6 +33,7 @@ int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream) {
   const bool tc = tc_fprop_supported(a);
   if (a->algo == 2 && !tc) { set_error("conv3d_fprop: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
   const bool use_tc = (a->algo != 1 && tc);
+  if (a->algo == 0 && !tc) count_fallback();
   // InstanceNorm statistics: fused into the tcgen05 epilogue where that epilogue has slack (narrow layers, which are
   // also the ones with the most voxels); a separate streaming pass otherwise (measured: for N >= 128 the extra
   // shuffle-reduction per 32-column group makes the epilogue the bottleneck and costs more than the pass it saves)
@@ -53,6 +54,7 @@ int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = tc_dgrad_supported(a);
   if (a->algo == 2 && !tc) { set_error("conv3d_dgrad: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
+  if (a->algo == 0 && !tc) count_fallback();
   return (a->algo != 1 && tc) ? tc_dgrad(a, st) : generic_dgrad(a, st);
 }
 
@@ -63,6 +65,7 @@ int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = tc_wgrad_supported(a);
   if (a->algo == 2 && !tc) { set_error("conv3d_wgrad: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
+  if (a->algo == 0 && !tc) count_fallback();
   return (a->algo != 1 && tc) ? tc_wgrad(a, st) : generic_wgrad(a, st);
 }
 

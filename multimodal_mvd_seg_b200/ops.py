@@ -254,7 +254,19 @@ class ConvTimer:
     ('fprop' | 'dgrad' | 'wgrad') the algorithmic FLOPs 2*B*Vout*Cout*Cin*taps and the event-timed duration."""
 
     def __init__(self):
-        self.records = []   # (pass, flops, start_event, end_event, tag)
+        self.records = []       # (pass, flops, start_event, end_event, tag)
+        self.mem_records = []   # (kernel family, algorithmic bytes, start_event, end_event): the HBM-bound launches
+
+    def mem_summary(self):
+        """per HBM-bound kernel family: algorithmic bytes, event-timed ms, launches."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, nbytes, e0, e1 in self.mem_records:
+            d = out.setdefault(name, dict(bytes=0.0, ms=0.0, launches=0))
+            d['bytes'] += nbytes
+            d['ms'] += e0.elapsed_time(e1)
+            d['launches'] += 1
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
@@ -308,6 +320,18 @@ def _timed_call(kind, flops, tag, fn):
     fn()
     e1.record()
     _conv_timer.records.append((kind, flops, e0, e1, tag))
+
+
+def _timed_mem(name: str, nbytes: float, fn, *a):
+    """CUDA-event bracket around one HBM-bound launch when bench.py's timer is armed (roofline_hbm)."""
+    if _conv_timer is None:
+        return fn(*a)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn(*a)
+    e1.record()
+    _conv_timer.mem_records.append((name, float(nbytes), e0, e1))
+    return r
 
 
 def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None):
@@ -471,11 +495,17 @@ def join_pending():
     _flush_pending(0)
 
 
-def _defer_wgrad(dev, launch, keepalive):
+def _defer_wgrad(dev, launch, keepalive, dw=None):
     """run `launch()` (the wgrad launches) on the side stream after everything enqueued so far on the current stream;
-    returns False (nothing launched) when overlap is off."""
+    returns False (nothing launched) when overlap is off.
+
+    Only gradients that live in the trainer's arena are deferred: those bypass autograd (``_ret`` attaches them as
+    ``p.grad`` itself).  A free-standing ``dw`` is handed to autograd's AccumulateGrad, which -- because the keep-alive
+    list below still references the tensor -- cannot steal it and CLONES it on the compute stream, i.e. possibly before
+    the side stream has written it (found by the full-size block parity test: garbage conv.weight gradients at 128^3,
+    where the wgrad kernels run long enough to lose that race)."""
     global _callback_queued
-    if not (_bwd_overlap and _conv_timer is None):
+    if not (_bwd_overlap and _conv_timer is None) or dw is None or id(dw) not in _arena_ids:
         return False
     main = torch.cuda.current_stream(dev)
     side = side_stream(dev, create=True)
@@ -548,8 +578,8 @@ class ConvNormActFn(torch.autograd.Function):
             wf, wd = _packed_for(weight, True, need_dx)
             conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
         z = out if out is not None else torch.empty_like(y)
-        lib.inorm_lrelu_fwd(y.data_ptr(), cl_pitch(y), z.data_ptr(), cl_pitch(z), stats.data_ptr(), _ptr(gamma),
-                            _ptr(beta), B, V, Cout, eps, slope, _stream())
+        _timed_mem('inorm_lrelu_fwd', 4.0 * B * V * Cout, lib.inorm_lrelu_fwd, y.data_ptr(), cl_pitch(y), z.data_ptr(),
+                   cl_pitch(z), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _stream())
         ctx.geom, ctx.eps, ctx.slope = geom, eps, slope
         ctx.params_for_hook = params_for_hook
         ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta)
@@ -565,17 +595,18 @@ class ConvNormActFn(torch.autograd.Function):
         dev = y.device
         st = _stream()
         bstats = zeros((B, Cout, 2), torch.float64, dev)
-        lib.inorm_lrelu_bwd_stats(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), stats.data_ptr(),
-                                  _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, bstats.data_ptr(), st)
+        _timed_mem('inorm_lrelu_bwd_stats', 4.0 * B * V * Cout, lib.inorm_lrelu_bwd_stats, dz.data_ptr(), cl_pitch(dz),
+                   y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
+                   bstats.data_ptr(), st)
         dy = torch.empty_like(y)
         dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
         dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
         db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
         if db is not None:
             db.zero_()
-        lib.inorm_lrelu_bwd_apply(dz.data_ptr(), cl_pitch(dz), y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy),
-                                  stats.data_ptr(), bstats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
-                                  _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
+        _timed_mem('inorm_lrelu_bwd_apply', 6.0 * B * V * Cout, lib.inorm_lrelu_bwd_apply, dz.data_ptr(), cl_pitch(dz),
+                   y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(), bstats.data_ptr(),
+                   _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
         plain_wgrad = False
         if dw is not None:
@@ -605,7 +636,7 @@ class ConvNormActFn(torch.autograd.Function):
                 dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
                 conv_dgrad(geom, dx, dy, wd)
         if plain_wgrad:   # after the dgrad: deferred onto the side stream (see "Backward overlap"), else right here
-            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, x_cl, dy, dw, None), (x_cl, dy, dw)):
+            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, x_cl, dy, dw, None), (x_cl, dy, dw), dw):
                 conv_wgrad(geom, x_cl, dy, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
@@ -651,7 +682,7 @@ class ConvTransposeFn(torch.autograd.Function):
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
             conv_fprop(geom, dup, dx, wf)
         if dw is not None:
-            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, dup, x_cl, dw, None), (dup, x_cl, dw)):
+            if not _defer_wgrad(dev, lambda: conv_wgrad(geom, dup, x_cl, dw, None), (dup, x_cl, dw), dw):
                 conv_wgrad(geom, dup, x_cl, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
@@ -696,8 +727,8 @@ class HeadFn(torch.autograd.Function):
         w2 = weight.detach().reshape(K, C)
         if w2.dtype != torch.float32 or not w2.is_contiguous():
             w2 = w2.float().contiguous()
-        lib.head_fwd(z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(bias), logits.data_ptr(), K,
-                     B * D * H * W, C, K, _stream())
+        _timed_mem('head_fwd', 2.0 * B * D * H * W * (C + K), lib.head_fwd, z_cl.data_ptr(), cl_pitch(z_cl),
+                   w2.data_ptr(), _ptr(bias), logits.data_ptr(), K, B * D * H * W, C, K, _stream())
         ctx.params_for_hook = params_for_hook
         ctx.save_for_backward(z_cl, weight, bias)
         return logits
@@ -720,8 +751,9 @@ class HeadFn(torch.autograd.Function):
             db = _grad_like(bias) if bias is not None else None
             if db is not None:
                 db.zero_()
-        lib.head_bwd(dl.data_ptr(), cl_pitch(dl), z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(dz),
-                     C if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, _stream())
+        _timed_mem('head_bwd', 2.0 * B * D * H * W * (K + C + (C if dz is not None else 0)), lib.head_bwd,
+                   dl.data_ptr(), cl_pitch(dl), z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(dz),
+                   C if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, _stream())
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dz, _ret(dw, weight), _ret(db, bias), None
@@ -762,7 +794,8 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
             V = D * H * W
             tg = _target_f32(targets[i])
             acc = zeros((B * C * 3 + 1,), torch.float64, dev)
-            lib.dice_ce_fwd(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, V, C, acc.data_ptr(), st)
+            _timed_mem('dice_ce_fwd', B * V * (2.0 * C + 4), lib.dice_ce_fwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
+                       B, V, C, acc.data_ptr(), st)
             gscale = 1.0
             if cfg['batch_dice'] and cfg['ddp'] and torch.distributed.is_available() and torch.distributed.is_initialized():
                 torch.distributed.all_reduce(acc[:B * C * 3])  # AllGatherGrad(...).sum(0), ddp_allgather.py:35-48
@@ -796,8 +829,9 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
             j += 3
             B, V, C, shp = meta[i]
             dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
-            lib.dice_ce_bwd(lg.data_ptr(), cl_pitch(lg), tg.data_ptr(), B, V, C, coef.data_ptr(), cfg['weight_ce'],
-                            float(cfg['weights'][i]), gout.data_ptr(), dl.data_ptr(), C, st)
+            _timed_mem('dice_ce_bwd', B * V * (4.0 * C + 4), lib.dice_ce_bwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
+                       B, V, C, coef.data_ptr(), cfg['weight_ce'], float(cfg['weights'][i]), gout.data_ptr(),
+                       dl.data_ptr(), C, st)
             grads.append(ncdhw_view(dl))
         return (None, *grads, *([None] * n))
 
@@ -815,7 +849,8 @@ class KLFn(torch.autograd.Function):
         width = 2 if C == 1 else C
         st = _stream()
         acc = torch.zeros((1,), dtype=torch.float64, device=a.device)
-        lib.kl_fwd(a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, float(T), acc.data_ptr(), st)
+        _timed_mem('kl_fwd', 4.0 * NV * C, lib.kl_fwd, a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C,
+                   float(T), acc.data_ptr(), st)
         loss = torch.empty((), dtype=torch.float32, device=a.device)
         scale = float(T) ** 2 / float(NV * width)
         lib.scalar_axpy(acc.data_ptr(), scale, loss.data_ptr(), 0, st)
@@ -832,8 +867,9 @@ class KLFn(torch.autograd.Function):
         da = torch.empty(a.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[0] else None
         db = torch.empty(b.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[1] else None
         if da is not None or db is not None:
-            lib.kl_bwd(a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, ctx.T, ctx.scale, gout.data_ptr(),
-                       _ptr(da), C, _ptr(db), C, _stream())
+            _timed_mem('kl_bwd', 2.0 * NV * C * (2 + (da is not None) + (db is not None)), lib.kl_bwd, a.data_ptr(),
+                       cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, ctx.T, ctx.scale, gout.data_ptr(), _ptr(da), C,
+                       _ptr(db), C, _stream())
         return (None if da is None else ncdhw_view(da)), (None if db is None else ncdhw_view(db)), None
 
 

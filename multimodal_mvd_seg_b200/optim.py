@@ -14,6 +14,11 @@ import torch
 
 from ._lib import MvdError, lib
 
+
+def _timed_mem(name, nbytes, fn, *a):
+    from . import ops      # bench.py's per-kernel event timer (no-op unless armed)
+    return ops._timed_mem(name, nbytes, fn, *a)
+
 _CHUNK = 4096
 
 
@@ -91,7 +96,7 @@ class SGDNesterovClip(torch.optim.Optimizer):
                       numel=torch.tensor(numel, dtype=torch.int64, device=dev),
                       chunk_t=torch.tensor(chunk_t, dtype=torch.int32, device=dev),
                       chunk_o=torch.tensor(chunk_o, dtype=torch.int64, device=dev),
-                      n_chunks=len(chunk_t))
+                      n_chunks=len(chunk_t), n_elems=int(sum(numel)))
         self._tables[gi] = cached
         return cached
 
@@ -106,13 +111,14 @@ class SGDNesterovClip(torch.optim.Optimizer):
         need_norm = self.max_norm is not None and self.max_norm > 0
         if need_norm:  # the norm is global over all groups, like clip_grad_norm_(network.parameters())
             for t in tabs:
-                lib.grad_sqnorm(t['ptrs'].data_ptr(), t['numel'].data_ptr(), t['chunk_t'].data_ptr(),
-                                t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), stream)
+                _timed_mem('grad_sqnorm', 4.0 * t['n_elems'], lib.grad_sqnorm, t['ptrs'].data_ptr(), t['numel'].data_ptr(),
+                           t['chunk_t'].data_ptr(), t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), stream)
         for t, g in zip(tabs, self.param_groups):
             mn = self.max_norm if need_norm else 0.0
-            lib.sgd_nesterov_clip(t['ptrs'].data_ptr(), t['numel'].data_ptr(), t['chunk_t'].data_ptr(),
-                                  t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), float(grad_scale), float(mn),
-                                  float(g['lr']), float(g['weight_decay']), float(g['momentum']), stream)
+            _timed_mem('sgd_nesterov_clip', 20.0 * t['n_elems'], lib.sgd_nesterov_clip, t['ptrs'].data_ptr(),
+                       t['numel'].data_ptr(), t['chunk_t'].data_ptr(), t['chunk_o'].data_ptr(), t['n_chunks'],
+                       sq.data_ptr(), float(grad_scale), float(mn), float(g['lr']), float(g['weight_decay']),
+                       float(g['momentum']), stream)
         self.last_sqnorm = sq
         return None
 

@@ -278,7 +278,7 @@ class nnUNetTrainer(object):
     def _setup_grad_arenas(self):
         """replaces DDP(self.network, device_ids=[local_rank]) (nnUNetTrainer.py:236-238): gradients live in flat
         arenas, buckets are all-reduced as backward produces them."""
-        self._arenas = [GradArena(list(n.parameters())) for n in self._networks()]
+        self._arenas = [GradArena(list(n.parameters()), world_size=None if self.is_ddp else 1) for n in self._networks()]
         lookup = {}
         for a in self._arenas:
             for p in a.params:

@@ -129,3 +129,141 @@ def test_morphology_scaling_is_exact_at_cfg4_size():
     sk = m.soft_skel(x, 3)
     assert float(sk.min()) >= 0.0 and float(sk.max()) <= 1.0 and tuple(sk.shape) == tuple(x.shape)
     assert torch.equal(m.soft_skel(x.flip(2), 3), sk.flip(2))        # mirror equivariance along D
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Backward parity at BASELINE.json's sizes, against the oracle run on the GPU under bf16 autocast (external check of
+# dgrad / wgrad / InstanceNorm-backward / head-backward at the sizes the benchmark is quoted on)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('patch,cin', [((128, 128, 128), 2), ((160, 160, 96), 1)], ids=['cfg2', 'cfg4'])
+def test_blockwise_teacher_forced_parity_full_size(patch, cin):
+    """cfg-2: 2 x 2 x 128^3 (6 stages, bottleneck 4^3); cfg-3/4 network: 2 x 1 x 160 x 160 x 96 (last stride (2,2,1),
+    bottleneck 5 x 5 x 6).  Output, input gradient and all parameter gradients of all 27 blocks <= 2e-2."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    from _parity import blockwise_teacher_forced
+    m.lib.reset_fallback_count()
+    checked, errs = blockwise_teacher_forced(m, oracle, patch, cin, 2)
+    bad = [f'{k}: {e:.4f}' for k, e in errs.items() if not e < 2e-2]
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(f'{patch}: {checked} blocks, {len(errs)} tensors, worst {worst[0]} = {worst[1]:.4f}')
+    assert checked >= 26, checked
+    assert not bad, bad
+    # every layer of the benchmark configurations is covered by a tcgen05 kernel: no silent CUDA-core fallback
+    assert m.lib.fallback_count() == 0, m.lib.fallback_count()
+
+
+@pytest.mark.parametrize('topo_iter', [3, 10])
+def test_cfg4_dual_net_losses_and_dlogits_match_oracle(topo_iter):
+    """cfg-4: two 1-channel networks at 2 x 160 x 160 x 96, L(out1) + L(out2) + 0.5 KL + 1.0 clDice(iter).
+    Logits of both networks <= 2e-2 against the oracle networks under bf16 autocast; then, ON IDENTICAL LOGITS, the
+    total loss and its `seg` / `mutual` / `topo` terms <= 1e-5 (fp32 reductions) and d(term)/d(logits) <= 2e-2 for the
+    deep-supervision loss (all active scales), the KL (both networks) and the clDice term."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    patch, B, c = (160, 160, 96), 2, 2
+    topo = oracle.topology_for_patch(patch)
+    assert tuple(topo['strides'][-1]) == (2, 2, 1)
+    refs = [oracle.build_plain_conv_unet(1, 4, patch, seed=s).to(DEV) for s in (0, 1)]
+    nets = []
+    for r in refs:
+        n = m.PlainConvUNet(1, num_classes=4, **topo).to(DEV)
+        n.load_state_dict(r.state_dict())
+        nets.append(n)
+    batch = oracle.make_batch(B, 2, patch, topo['strides'], kind='structured')
+    data = batch['data'].to(DEV)
+    target = [t.to(DEV) for t in batch['target']]
+    m.lib.reset_fallback_count()
+    with torch.no_grad():
+        outs = [nets[i](data[:, i:i + 1]) for i in range(2)]
+        with torch.autocast('cuda', dtype=BF):
+            outs_ref = [refs[i](data[:, i:i + 1]) for i in range(2)]
+    assert m.lib.fallback_count() == 0
+    for o, orf in zip(outs, outs_ref):
+        assert len(o) == len(orf) == 5
+        for a, b in zip(o, orf):
+            assert tuple(a.shape) == tuple(b.shape)
+            assert rel_err(a.float(), b.float()) < 2e-2
+    del outs_ref, refs
+    n_sc = len(outs[0])
+
+    def terms(mod, L1, L2, f32):
+        ds = mod.DeepSupervisionWrapper(
+            mod.DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, weight_ce=1,
+                               weight_dice=1, ignore_label=None, dice_class=mod.MemoryEfficientSoftDiceLoss),
+            mod.deep_supervision_weights(n_sc))
+        seg = ds(L1, target) + ds(L2, target)
+        mutual = mod.distill_kl(L1[0], L2[0], 1.0)
+        gt = (target[0].long() == c).float()
+        if f32:
+            prob = torch.softmax(L1[0], 1)[:, c:c + 1]
+        else:
+            prob = mod.softmax_channel(L1[0], c)
+        topo_l = mod.soft_cldice(iter_=topo_iter, smooth=1.)(gt, prob)
+        return seg, mutual, topo_l
+
+    leaves = lambda f32: [[(o.detach().float() if f32 else o.detach().clone()).requires_grad_() for o in outs[i]]
+                          for i in range(2)]
+    ours, want = leaves(False), leaves(True)
+    got_terms, want_terms = terms(m, ours[0], ours[1], False), terms(oracle, want[0], want[1], True)
+    for name, g, w in zip(('seg', 'mutual', 'topo'), got_terms, want_terms):
+        assert abs(float(g) - float(w)) <= 1e-5 * max(1.0, abs(float(w))), (name, float(g), float(w))
+    tot_g = got_terms[0] + 0.5 * got_terms[1] + 1.0 * got_terms[2]
+    tot_w = want_terms[0] + 0.5 * want_terms[1] + 1.0 * want_terms[2]
+    assert abs(float(tot_g) - float(tot_w)) <= 1e-5 * max(1.0, abs(float(tot_w)))
+    report = {}
+    for ti, name in enumerate(('seg', 'mutual', 'topo')):
+        for L in ours + want:
+            for t in L:
+                t.grad = None
+        got_terms[ti].backward(retain_graph=True)
+        want_terms[ti].backward(retain_graph=True)
+        for ni in range(2):
+            for si in range(n_sc):
+                gw = want[ni][si].grad
+                gg = ours[ni][si].grad
+                if gw is None or float(gw.abs().max()) == 0.0:
+                    assert gg is None or float(gg.float().abs().max()) == 0.0, (name, ni, si)
+                    continue
+                assert gg is not None, (name, ni, si)
+                report[f'{name}.net{ni + 1}.scale{si}'] = rel_err(gg.float(), gw)
+    print(f'cfg-4 iter {topo_iter}: total {float(tot_g):.6f} vs {float(tot_w):.6f}; dlogits ' +
+          ', '.join(f'{k} {v:.4f}' for k, v in report.items()))
+    assert {'seg.net1.scale0', 'seg.net2.scale3', 'mutual.net1.scale0', 'mutual.net2.scale0', 'topo.net1.scale0'} <= set(report)
+    bad = {k: v for k, v in report.items() if not v < 2e-2}
+    assert not bad, bad
+
+
+def test_cfg2_argmax_agreement_after_training_full_size():
+    """north_star: argmax masks identical on >= 99.9 % of voxels -- asserted RAW (no decisiveness filter) at cfg-2's
+    size on weights that have been trained for a while (at random initialisation the four logits are near-tied and the
+    reference itself in bf16 disagrees with its own fp32 run on ~1 % of voxels)."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    dev = torch.device(DEV)
+    patch = (128, 128, 128)
+    plans, dj = m.make_plans(patch, batch_size=2, n_modalities=2, n_classes=4)
+    tr = m.nnUNetTrainer(plans, '3d_fullres', 0, dj, device=dev)
+    torch.manual_seed(0)
+    tr.initialize()
+    topo = oracle.topology_for_patch(patch)
+    batch = oracle.make_batch(2, 2, patch, topo['strides'], kind='structured')
+    lab = batch['target'][0]
+    batch['data'] = batch['data'] * 0.3 + torch.cat([(lab == 2).float() * 2 + (lab == 1).float(),
+                                                      (lab == 3).float() * 2 - (lab == 1).float()], 1)
+    tr.on_train_epoch_start()
+    first = float(tr.train_step(batch)['loss'])
+    for _ in range(60):
+        last = float(tr.train_step(batch)['loss'])
+    assert last < first - 0.3, (first, last)
+    ref = oracle.build_plain_conv_unet(2, 4, patch, seed=0).to(dev)
+    ref.load_state_dict(tr.network.state_dict())
+    data = batch['data'].to(dev)
+    with torch.no_grad():
+        out = tr.network(data)
+        with torch.autocast('cuda', dtype=BF):
+            out_ref = ref(data)
+    assert rel_err(out[0].float(), out_ref[0].float()) < 2e-2
+    agree = float((out[0].argmax(1) == out_ref[0].argmax(1)).float().mean())
+    print(f'cfg-2 full size after 61 steps: loss {first:.3f} -> {last:.3f}; raw argmax agreement {agree:.5f}')
+    assert agree >= 0.999, agree

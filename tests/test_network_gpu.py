@@ -169,79 +169,13 @@ def test_argmax_agreement_after_training():
 def test_blockwise_teacher_forced_parity():
     """Every block of the network (ConvDropoutNormReLU, ConvTranspose3d, seg head) is fed the ORACLE's own bf16 input
     and output-gradient tensors, captured with hooks during an autocast fwd/bwd of the whole oracle network, and must
-    reproduce the oracle's output, input gradient and parameter gradients within 2e-2 (norm-wise)."""
+    reproduce the oracle's output, input gradient and parameter gradients within 2e-2 (norm-wise).  The same check at
+    BASELINE.json's sizes lives in test_fullsize_gpu.py."""
     import multimodal_mvd_seg_b200 as m
     import oracle
-    from multimodal_mvd_seg_b200 import ops
-    dev = 'cuda:0'
-    patch = (40, 40, 24)
-    net, ref, topo = _build_pair(m, oracle, 2, patch)
-    batch = oracle.make_batch(2, 2, patch, topo['strides'], kind='structured')
-    data = batch['data'].to(dev)
-    target = [t.to(dev) for t in batch['target']]
-    rec = {}
-
-    def hook(name):
-        def f(mod, inp, out):
-            r = rec.setdefault(name, {})
-            r['x'] = inp[0].detach()
-            r['y'] = out.detach().clone()
-            out.register_hook(lambda g: r.__setitem__('gy', g.detach().clone()))
-            if inp[0].requires_grad:
-                inp[0].register_hook(lambda g: r.__setitem__('gx', g.detach().clone()))
-        return f
-
-    handles = []
-    for name, mod in ref.named_modules():
-        if name.startswith('decoder.encoder'):
-            continue
-        if isinstance(mod, (oracle.ConvDropoutNormReLU, torch.nn.ConvTranspose3d)) or '.seg_layers.' in name:
-            handles.append(mod.register_forward_hook(hook(name)))
-    with torch.autocast('cuda', dtype=torch.bfloat16):
-        out_ref = ref(data)
-        l_ref = _ds_loss(oracle, len(out_ref))(out_ref, target)
-    l_ref.backward()
-    for h in handles:
-        h.remove()
-    ref_mods = dict(ref.named_modules())
-    ours = dict(net.named_modules())
-    checked = 0
-    bad = []
-    for name, r in rec.items():
-        if 'gy' not in r:      # zero-weighted deep-supervision head: no gradient reaches it
-            continue
-        mod, rmod = ours[name], ref_mods[name]
-        # a tensor hook reports the TOTAL gradient of a tensor; where the block's input has other consumers too
-        # (stage outputs feeding both the next stage and the skip / a head and the next up-convolution) the block's
-        # own input gradient cannot be isolated here -- those dgrads are covered by test_kernels_gpu.py
-        multi = ('.seg_layers.' in name or '.transpconvs.' in name or
-                 (name.startswith('encoder.stages.') and name.endswith('.convs.0') and not name.startswith('encoder.stages.0.')))
-        if multi:
-            r.pop('gx', None)
-        x = ops.to_cl_view(r['x'].to(torch.bfloat16)).detach().requires_grad_('gx' in r)
-        gy = ops.to_cl_view(r['gy'].to(torch.bfloat16))
-        for p in mod.parameters():
-            p.grad = None
-        if isinstance(mod, m.ConvDropoutNormReLU):
-            y = mod.forward_cl(x)
-            plist = [('conv.weight', mod.conv.weight, rmod.conv.weight), ('norm.weight', mod.norm.weight, rmod.norm.weight),
-                     ('norm.bias', mod.norm.bias, rmod.norm.bias)]
-        elif isinstance(mod, torch.nn.ConvTranspose3d):
-            y = ops.ConvTransposeFn.apply(x, mod.weight, mod.bias, tuple(mod.stride), None, None)
-            plist = [('weight', mod.weight, rmod.weight), ('bias', mod.bias, rmod.bias)]
-        else:
-            y = ops.HeadFn.apply(x, mod.weight, mod.bias, None)
-            plist = [('weight', mod.weight, rmod.weight), ('bias', mod.bias, rmod.bias)]
-        y.backward(gy)
-        errs = {'out': rel_err(ops.ncdhw_view(y).float(), r['y'].float())}
-        if 'gx' in r:
-            errs['gx'] = rel_err(ops.ncdhw_view(x.grad).float(), r['gx'].float())
-        for pn, p, rp in plist:
-            errs[pn] = rel_err(p.grad, rp.grad)
-        checked += 1
-        for k, e in errs.items():
-            if not e < TOL:
-                bad.append(f'{name}.{k}: {e:.4f}')
+    from _parity import blockwise_teacher_forced
+    checked, errs = blockwise_teacher_forced(m, oracle, (40, 40, 24), 2, 2)
+    bad = [f'{k}: {e:.4f}' for k, e in errs.items() if not e < TOL]
     assert checked >= 20
     assert not bad, bad
 
