@@ -170,6 +170,31 @@ int mvd_dice_ce_finalize(const double* acc, int B, long long V, int C, float smo
 /* dlogits (bf16, pitch ldd) = gout[0] * weight * d(w_ce*CE + w_dice*Dice)/dlogits */
 int mvd_dice_ce_bwd(const void* logits, int ld, const float* target, int B, long long V, int C, const float* coef,
                     float w_ce, float weight, const float* gout, void* dlogits, int ldd, mvd_stream_t stream);
+/* The deep-supervision loss of a whole step in three launches (csrc/losses_multi.cu).  One segment per (network,
+ * active scale); production shape only: C = 4, dense logits [B][V][4] (pitch 4), fp32 targets [B][V], V % 4 == 0,
+ * 16-byte aligned pointers (anything else: the per-scale entry points above).  The table is a HOST array.
+ *   fwd      : acc [n_seg][B*4*3 + 1] doubles (caller zeroes) <- per-(b,c) sums and the CE sum of every segment; when
+ *              `counter` (device unsigned, zero before the first call; the kernel leaves it zero) is given, the last
+ *              block to finish also writes coef [n_seg][B][4][2] and loss_out[0] = sum_seg weight * (w_ce CE + w_dice Dice)
+ *   finalize : the same scalar algebra as its own launch (data-parallel batch_dice: the sums are all-reduced first)
+ *   bwd      : dlogits of every segment = gout[0] * weight * d(w_ce CE + w_dice Dice)/dlogits; coef_scale multiplies
+ *              the Dice coefficients (world size under AllGatherGrad, ddp_allgather.py:35-48; else 1) */
+#define MVD_DICE_CE_MAX_SEGMENTS 16
+typedef struct {
+  const void* logits;    /* bf16 [B][V][4]                    */
+  const float* target;   /* fp32 [B][V] class ids             */
+  void* dlogits;         /* bf16 [B][V][4] (bwd only)         */
+  long long V;           /* voxels per sample                 */
+  float weight;          /* deep-supervision weight of the scale */
+} mvd_dice_ce_segment;
+int mvd_dice_ce_multi_fwd(const mvd_dice_ce_segment* segs, int n_seg, int B, int C, float smooth, int do_bg,
+                          int batch_dice, float w_ce, float w_dice, double* acc, float* coef, float* loss_out,
+                          unsigned* counter, mvd_stream_t stream);
+int mvd_dice_ce_multi_finalize(const mvd_dice_ce_segment* segs, int n_seg, int B, int C, float smooth, int do_bg,
+                               int batch_dice, float w_ce, float w_dice, const double* acc, float* coef,
+                               float* loss_out, mvd_stream_t stream);
+int mvd_dice_ce_multi_bwd(const mvd_dice_ce_segment* segs, int n_seg, int B, int C, const float* coef, float w_ce,
+                          float coef_scale, const float* gout, mvd_stream_t stream);
 /* validation_step's online tp/fp/fn of the argmax segmentation (nnUNetTrainer.py:973-1004): out = [C][3] doubles */
 int mvd_argmax_tp_fp_fn(const void* logits, int ld, const float* target, int B, long long V, int C, double* out,
                         mvd_stream_t stream);
@@ -182,6 +207,14 @@ int mvd_kl_fwd(const void* ys, int lds, const void* yt, int ldt, long long NV, i
 /* dys/dyt (bf16) = gout[0]*scale * dKL/dy ; scale = T^2/numel supplied by the caller; either may be NULL */
 int mvd_kl_bwd(const void* ys, int lds, const void* yt, int ldt, long long NV, int C, float T, float scale,
                const float* gout, void* dys, int ldds, void* dyt, int lddt, mvd_stream_t stream);
+
+/* distill_kl in ONE pass (dense C = 4 logits, NV % 4 == 0): loss_sum[0] (double, caller zeroes) += sum p_t (log p_t -
+ * log p_s), and dys / dyt (bf16, either may be NULL) = gscale * dKL/dy with gscale = assumed upstream gradient * T^2 / numel
+ * supplied by the caller.  mvd_rescale_bf16_pair multiplies both gradient tensors (n_elems bf16 each) by
+ * gout[0] / assumed on the device and returns at once when that ratio is 1: exact autograd without a host sync. */
+int mvd_kl_fused(const void* ys, const void* yt, long long NV, int C, float T, float gscale, double* loss_sum,
+                 void* dys, void* dyt, mvd_stream_t stream);
+int mvd_rescale_bf16_pair(void* a, void* b, long long n_elems, const float* gout, float assumed, mvd_stream_t stream);
 
 /* ---- soft skeleton / clDice (training/loss/soft_skeleton.py:6-37) ------------------------------------------ */
 /* fp32 volumes [B][D][H][W] */

@@ -38,6 +38,12 @@ class ConvArgs(Structure):
     ]
 
 
+class DiceCESegment(Structure):
+    """mirror of mvd_dice_ce_segment (include/mvdseg.h)."""
+    _fields_ = [('logits', c_void_p), ('target', c_void_p), ('dlogits', c_void_p), ('V', c_longlong),
+                ('weight', c_float)]
+
+
 P = c_void_p
 I = c_int
 LL = c_longlong
@@ -72,6 +78,11 @@ _SIGNATURES = {
     'mvd_inorm_lrelu_bwd_apply': (c_int, [P, I, P, I, P, I, P, P, P, P, I, LL, I, F, F, P, P, P, S]),
     'mvd_head_fwd': (c_int, [P, I, P, P, P, I, LL, I, I, S]),
     'mvd_head_bwd': (c_int, [P, I, P, I, P, P, I, P, P, LL, I, I, S]),
+    'mvd_dice_ce_multi_fwd': (c_int, [P, I, I, I, F, I, I, F, F, P, P, P, P, S]),
+    'mvd_dice_ce_multi_finalize': (c_int, [P, I, I, I, F, I, I, F, F, P, P, P, S]),
+    'mvd_dice_ce_multi_bwd': (c_int, [P, I, I, I, P, F, F, P, S]),
+    'mvd_kl_fused': (c_int, [P, P, LL, I, F, F, P, P, P, S]),
+    'mvd_rescale_bf16_pair': (c_int, [P, P, LL, P, F, S]),
     'mvd_dice_ce_fwd': (c_int, [P, I, P, I, LL, I, P, S]),
     'mvd_dice_ce_finalize': (c_int, [P, I, LL, I, F, I, I, F, F, F, P, P, S]),
     'mvd_dice_ce_bwd': (c_int, [P, I, P, I, LL, I, P, F, F, P, P, I, S]),
@@ -142,6 +153,7 @@ class _Lib:
 
 
 lib = _Lib(_cdll)
+lib.DICE_CE_MAX_SEGMENTS = 16   # MVD_DICE_CE_MAX_SEGMENTS (include/mvdseg.h)
 
 
 def exported_symbols():

@@ -27,15 +27,23 @@ def softmax_helper_dim1(x: torch.Tensor) -> torch.Tensor:
     return torch.softmax(x, 1)
 
 
-def _dice_ce(logits, target, *, w_ce, w_dice, smooth, do_bg, batch_dice, ddp, weights=None):
-    single = not isinstance(logits, (list, tuple))
-    if single:
-        logits, target = [logits], [target]
+def _dice_ce(logits, target, *, w_ce, w_dice, smooth, do_bg, batch_dice, ddp, weights=None, networks=None):
+    """logits / target: one tensor, or one list over the deep-supervision scales.  ``networks``: a list of such logits
+    lists (several networks supervised by the same targets): everything goes through one autograd node."""
+    if networks is None:
+        single = not isinstance(logits, (list, tuple))
+        if single:
+            logits, target = [logits], [target]
+        networks = [list(logits)]
+    target = list(target)
+    n = len(target)
+    assert all(len(net) == n for net in networks), 'every network needs one output per target scale'
     if weights is None:
-        weights = [1.0] * len(logits)
+        weights = [1.0] * n
     cfg = dict(weights=[float(w) for w in weights], weight_ce=float(w_ce), weight_dice=float(w_dice),
-               smooth=float(smooth), do_bg=bool(do_bg), batch_dice=bool(batch_dice), ddp=bool(ddp))
-    return ops.DiceCEMultiScaleFn.apply(cfg, *logits, *target)
+               smooth=float(smooth), do_bg=bool(do_bg), batch_dice=bool(batch_dice), ddp=bool(ddp),
+               n_nets=len(networks))
+    return ops.DiceCEMultiScaleFn.apply(cfg, *[t for net in networks for t in net], *target)
 
 
 class MemoryEfficientSoftDiceLoss(nn.Module):
@@ -106,6 +114,19 @@ class DeepSupervisionWrapper(nn.Module):
                 l = l + weights[i] * self.loss(*inputs)
         return l
 
+    def forward_networks(self, outputs_per_network, targets):
+        """sum over several networks of ``self(outputs_k, targets)`` -- ``loss(out1, tgt) + loss(out2, tgt)`` of the
+        mutual-distillation step (MVDTrainer.py:925) -- in one fused forward and one fused backward launch."""
+        weights = [1] * len(targets) if self.weight_factors is None else self.weight_factors
+        if isinstance(self.loss, DC_and_CE_loss):
+            return _dice_ce(None, list(targets), weights=weights, networks=[list(o) for o in outputs_per_network],
+                            **self.loss._kw())
+        total = None
+        for o in outputs_per_network:
+            l = self(o, targets)
+            total = l if total is None else total + l
+        return total
+
 
 def deep_supervision_weights(n_scales: int) -> np.ndarray:
     """nnUNetTrainer.py:366-372."""
@@ -125,8 +146,11 @@ def get_tp_fp_fn_tn(net_output, gt, axes=None, mask=None, square=False):
     return tp, fp, fn, tn
 
 
-def distill_kl(y_s, y_t, T=1):
-    return ops.KLFn.apply(y_s, y_t, float(T))
+def distill_kl(y_s, y_t, T=1, upstream_grad=None):
+    """other_loss.py:51-64.  ``upstream_grad`` (optional, not in the reference signature): the constant the caller
+    multiplies the result with before adding it to the loss (lambda1, MVDTrainer.py:925); lets the kernel produce loss
+    and gradients in a single pass (ops.KLFn)."""
+    return ops.KLFn.apply(y_s, y_t, float(T), upstream_grad)
 
 
 def soft_erode(img):

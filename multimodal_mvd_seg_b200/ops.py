@@ -10,7 +10,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import ConvArgs, MvdError, lib
+from ._lib import ConvArgs, DiceCESegment, MvdError, lib
 
 BF16 = torch.bfloat16
 
@@ -772,75 +772,150 @@ def _target_f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+_counters = {}    # device -> persistent zero-initialised uint32 ticket counter of the fused loss kernel
+
+
+def _ticket_counter(dev):
+    c = _counters.get(dev)
+    if c is None:
+        c = _counters[dev] = torch.zeros((1,), dtype=torch.int32, device=dev)
+    return c
+
+
+def _quad_ok(lg: torch.Tensor, tg: torch.Tensor) -> bool:
+    """the production shape of the fused loss kernels: C = 4 dense logits, V % 4 == 0, 16-byte aligned."""
+    B, D, H, W, C = lg.shape
+    return (C == 4 and cl_pitch(lg) == 4 and (D * H * W) % 4 == 0 and lg.data_ptr() % 16 == 0
+            and tg.data_ptr() % 16 == 0)
+
+
 class DiceCEMultiScaleFn(torch.autograd.Function):
-    """sum_i weight_i * (w_ce*CE + w_dice*SoftDice)(logits_i, target_i) -- DeepSupervisionWrapper(DC_and_CE_loss)."""
+    """sum over networks n and scales i of weight_i * (w_ce*CE + w_dice*SoftDice)(logits_n_i, target_i) --
+    DeepSupervisionWrapper(DC_and_CE_loss) for one or several networks that share the targets.
+
+    tensors = logits of network 0 (all scales), logits of network 1, ..., then the targets (one per scale).
+    Production shape: ONE forward launch for everything (sums + last-block-done scalar algebra) and ONE backward launch
+    (csrc/losses_multi.cu); other shapes run scale by scale (csrc/losses.cu)."""
 
     @staticmethod
     def forward(ctx, cfg: dict, *tensors):
-        n = len(tensors) // 2
-        logits, targets = tensors[:n], tensors[n:]
+        n_nets = int(cfg.get('n_nets', 1))
+        n = len(tensors) // (n_nets + 1)
+        targets = tensors[n_nets * n:]
         weights = cfg['weights']
-        dev = logits[0].device
-        require_cuda(logits[0], 'DC_and_CE_loss')
+        dev = tensors[0].device
+        require_cuda(tensors[0], 'DC_and_CE_loss')
         st = _stream()
-        loss = torch.zeros((), dtype=torch.float32, device=dev)
-        saved, meta = [], []
-        for i in range(n):
-            if weights[i] == 0:
-                meta.append(None)
-                continue
-            lg = to_cl_view(logits[i])
-            B, D, H, W, C = lg.shape
+        items = []      # (tensor slot, scale, logits NDHWC, target fp32)
+        tg_cache = {}
+        for k in range(n_nets):
+            for i in range(n):
+                if weights[i] == 0:
+                    continue
+                if i not in tg_cache:
+                    tg_cache[i] = _target_f32(targets[i])
+                items.append((k * n + i, i, to_cl_view(tensors[k * n + i]), tg_cache[i]))
+        ddp_bd = bool(cfg['batch_dice'] and cfg['ddp'] and torch.distributed.is_available()
+                      and torch.distributed.is_initialized())
+        gscale = float(torch.distributed.get_world_size()) if ddp_bd else 1.0
+        B = items[0][2].shape[0]
+        C = items[0][2].shape[-1]
+        fused = (len(items) <= lib.DICE_CE_MAX_SEGMENTS and all(it[2].shape[0] == B and _quad_ok(it[2], it[3]) for it in items))
+        ctx.cfg, ctx.items_meta, ctx.n_tensors, ctx.fused, ctx.gscale = cfg, [(it[0], it[1]) for it in items], len(tensors), fused, gscale
+        if fused:
+            ns = len(items)
+            segs = (DiceCESegment * ns)()
+            for j, (_, i, lg, tg) in enumerate(items):
+                V = lg.shape[1] * lg.shape[2] * lg.shape[3]
+                segs[j].logits, segs[j].target, segs[j].dlogits, segs[j].V, segs[j].weight = \
+                    lg.data_ptr(), tg.data_ptr(), None, V, float(weights[i])
+            stride = B * C * 3 + 1
+            acc = zeros((ns, stride), torch.float64, dev)
+            coef = torch.empty((ns, B, C, 2), dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            nbytes = sum(B * s.V * (2.0 * C + 4) for s in segs)
+            args = (segs, ns, B, C, cfg['smooth'], int(cfg['do_bg']), int(cfg['batch_dice']), cfg['weight_ce'],
+                    cfg['weight_dice'], acc.data_ptr(), coef.data_ptr(), loss.data_ptr())
+            if not ddp_bd:
+                _timed_mem('dice_ce_fwd', nbytes, lib.dice_ce_multi_fwd, *args, _ticket_counter(dev).data_ptr(), st)
+            else:
+                _timed_mem('dice_ce_fwd', nbytes, lib.dice_ce_multi_fwd, *args, None, st)
+                ce = acc[:, stride - 1].clone()          # the CE mean stays per rank; only the Dice sums are gathered
+                torch.distributed.all_reduce(acc)        # AllGatherGrad(...).sum(0), ddp_allgather.py:35-48
+                acc[:, stride - 1] = ce
+                lib.dice_ce_multi_finalize(*args, st)
+            ctx.save_for_backward(coef, *[it[2] for it in items], *[it[3] for it in items])
+            return loss
+        # ---- generic shapes: scale by scale
+        loss = zeros((1,), torch.float32, dev)[0]
+        saved = []
+        for (_, i, lg, tg) in items:
+            Bi, D, H, W, Ci = lg.shape
             V = D * H * W
-            tg = _target_f32(targets[i])
-            acc = zeros((B * C * 3 + 1,), torch.float64, dev)
-            _timed_mem('dice_ce_fwd', B * V * (2.0 * C + 4), lib.dice_ce_fwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
-                       B, V, C, acc.data_ptr(), st)
-            gscale = 1.0
-            if cfg['batch_dice'] and cfg['ddp'] and torch.distributed.is_available() and torch.distributed.is_initialized():
-                torch.distributed.all_reduce(acc[:B * C * 3])  # AllGatherGrad(...).sum(0), ddp_allgather.py:35-48
-                gscale = float(torch.distributed.get_world_size())
-            coef = torch.empty((B, C, 2), dtype=torch.float32, device=dev)
-            lib.dice_ce_finalize(acc.data_ptr(), B, V, C, cfg['smooth'], int(cfg['do_bg']), int(cfg['batch_dice']),
+            acc = zeros((Bi * Ci * 3 + 1,), torch.float64, dev)
+            _timed_mem('dice_ce_fwd', Bi * V * (2.0 * Ci + 4), lib.dice_ce_fwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
+                       Bi, V, Ci, acc.data_ptr(), st)
+            if ddp_bd:
+                torch.distributed.all_reduce(acc[:Bi * Ci * 3])
+            coef = torch.empty((Bi, Ci, 2), dtype=torch.float32, device=dev)
+            lib.dice_ce_finalize(acc.data_ptr(), Bi, V, Ci, cfg['smooth'], int(cfg['do_bg']), int(cfg['batch_dice']),
                                  cfg['weight_ce'], cfg['weight_dice'], float(weights[i]), coef.data_ptr(),
                                  loss.data_ptr(), st)
             if gscale != 1.0:
                 coef.mul_(gscale)
             saved += [lg, tg, coef]
-            meta.append((B, V, C, tuple(logits[i].shape)))
-        ctx.cfg, ctx.meta, ctx.n = cfg, meta, n
         ctx.save_for_backward(*saved)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        cfg, meta, n = ctx.cfg, ctx.meta, ctx.n
+        cfg = ctx.cfg
         saved = ctx.saved_tensors
         st = _stream()
         gout = gout.contiguous().float()
-        grads, j = [], 0
-        for i in range(n):
-            if meta[i] is None or not ctx.needs_input_grad[1 + i]:
-                grads.append(None)
-                if meta[i] is not None:
-                    j += 3
+        grads = [None] * ctx.n_tensors
+        weights = cfg['weights']
+        if ctx.fused:
+            ns = len(ctx.items_meta)
+            coef, lgs, tgs = saved[0], saved[1:1 + ns], saved[1 + ns:]
+            B, C = lgs[0].shape[0], lgs[0].shape[-1]
+            segs = (DiceCESegment * ns)()
+            outs = []
+            for j, ((slot, i), lg, tg) in enumerate(zip(ctx.items_meta, lgs, tgs)):
+                dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
+                outs.append(dl)
+                segs[j].logits, segs[j].target, segs[j].dlogits = lg.data_ptr(), tg.data_ptr(), dl.data_ptr()
+                segs[j].V, segs[j].weight = lg.shape[1] * lg.shape[2] * lg.shape[3], float(weights[i])
+                if ctx.needs_input_grad[1 + slot]:
+                    grads[slot] = ncdhw_view(dl)
+            nbytes = sum(B * s.V * (4.0 * C + 4) for s in segs)
+            _timed_mem('dice_ce_bwd', nbytes, lib.dice_ce_multi_bwd, segs, ns, B, C, coef.data_ptr(), cfg['weight_ce'],
+                       ctx.gscale, gout.data_ptr(), st)
+            return (None, *grads)
+        for j, (slot, i) in enumerate(ctx.items_meta):
+            if not ctx.needs_input_grad[1 + slot]:
                 continue
-            lg, tg, coef = saved[j:j + 3]
-            j += 3
-            B, V, C, shp = meta[i]
+            lg, tg, coef = saved[3 * j:3 * j + 3]
+            B, D, H, W, C = lg.shape
+            V = D * H * W
             dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
             _timed_mem('dice_ce_bwd', B * V * (4.0 * C + 4), lib.dice_ce_bwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
-                       B, V, C, coef.data_ptr(), cfg['weight_ce'], float(cfg['weights'][i]), gout.data_ptr(),
+                       B, V, C, coef.data_ptr(), cfg['weight_ce'], float(weights[i]), gout.data_ptr(),
                        dl.data_ptr(), C, st)
-            grads.append(ncdhw_view(dl))
-        return (None, *grads, *([None] * n))
+            grads[slot] = ncdhw_view(dl)
+        return (None, *grads)
 
 
 class KLFn(torch.autograd.Function):
-    """distill_kl(y_s, y_t, T) of other_loss.py:51-64 on logits of logical shape [B,C,...]."""
+    """distill_kl(y_s, y_t, T) of other_loss.py:51-64 on logits of logical shape [B,C,...].
+
+    ``upstream``: the factor the caller is going to multiply the result with before it enters the total loss (lambda1 in
+    MVDTrainer.py:925).  When given (and the logits have the production shape) the forward pass is ONE kernel that also
+    writes both gradients, scaled for an upstream gradient of exactly ``upstream``; backward then only launches a rescale
+    by gout / upstream, which returns immediately on the device when that ratio is 1."""
 
     @staticmethod
-    def forward(ctx, ys, yt, T: float):
+    def forward(ctx, ys, yt, T: float, upstream=None):
         require_cuda(ys, 'distill_kl')
         a, b = to_cl_view(ys), to_cl_view(yt)
         assert a.shape == b.shape
@@ -848,29 +923,49 @@ class KLFn(torch.autograd.Function):
         NV = B * D * H * W
         width = 2 if C == 1 else C
         st = _stream()
-        acc = torch.zeros((1,), dtype=torch.float64, device=a.device)
+        dev = a.device
+        acc = zeros((1,), torch.float64, dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scale = float(T) ** 2 / float(NV * width)
+        ctx.T, ctx.scale = float(T), scale
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ctx.fused = (upstream is not None and float(upstream) != 0.0 and (need_a or need_b) and C == 4
+                     and cl_pitch(a) == 4 and cl_pitch(b) == 4 and NV % 4 == 0
+                     and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+        if ctx.fused:
+            da = torch.empty(a.shape, dtype=BF16, device=dev) if need_a else None
+            db = torch.empty(b.shape, dtype=BF16, device=dev) if need_b else None
+            ctx.upstream = float(upstream)
+            _timed_mem('kl_fwd_bwd', 2.0 * NV * C * (2 + need_a + need_b), lib.kl_fused, a.data_ptr(), b.data_ptr(), NV, C,
+                       float(T), ctx.upstream * scale, acc.data_ptr(), _ptr(da), _ptr(db), st)
+            lib.scalar_axpy(acc.data_ptr(), scale, loss.data_ptr(), 0, st)
+            ctx.grads = (da, db)
+            return loss
         _timed_mem('kl_fwd', 4.0 * NV * C, lib.kl_fwd, a.data_ptr(), cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C,
                    float(T), acc.data_ptr(), st)
-        loss = torch.empty((), dtype=torch.float32, device=a.device)
-        scale = float(T) ** 2 / float(NV * width)
         lib.scalar_axpy(acc.data_ptr(), scale, loss.data_ptr(), 0, st)
-        ctx.T, ctx.scale = float(T), scale
         ctx.save_for_backward(a, b)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
+        gout = gout.contiguous().float()
+        if ctx.fused:
+            da, db = ctx.grads
+            ctx.grads = None
+            n = (da if da is not None else db).numel()
+            lib.rescale_bf16_pair(_ptr(da), _ptr(db), n, gout.data_ptr(), ctx.upstream, _stream())
+            return (None if da is None else ncdhw_view(da)), (None if db is None else ncdhw_view(db)), None, None
         a, b = ctx.saved_tensors
         B, D, H, W, C = a.shape
         NV = B * D * H * W
-        gout = gout.contiguous().float()
         da = torch.empty(a.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[0] else None
         db = torch.empty(b.shape, dtype=BF16, device=a.device) if ctx.needs_input_grad[1] else None
         if da is not None or db is not None:
             _timed_mem('kl_bwd', 2.0 * NV * C * (2 + (da is not None) + (db is not None)), lib.kl_bwd, a.data_ptr(),
                        cl_pitch(a), b.data_ptr(), cl_pitch(b), NV, C, ctx.T, ctx.scale, gout.data_ptr(), _ptr(da), C,
                        _ptr(db), C, _stream())
-        return (None if da is None else ncdhw_view(da)), (None if db is None else ncdhw_view(db)), None
+        return (None if da is None else ncdhw_view(da)), (None if db is None else ncdhw_view(db)), None, None
 
 
 class SoftmaxChannelFn(torch.autograd.Function):

@@ -722,12 +722,15 @@ class MVDTrainer(nnUNetTrainer):
 
     def _loss(self, output, target):
         out1, out2 = output
-        l = self.loss(out1, target) + self.loss(out2, target)
+        if hasattr(self.loss, 'forward_networks'):      # loss(out1, tgt) + loss(out2, tgt) through one fused node
+            l = self.loss.forward_networks([out1, out2], target)
+        else:
+            l = self.loss(out1, target) + self.loss(out2, target)
         c = self.vessel_class
         if self.kl_vessel_only:
             mutual = distill_kl(out1[0][:, c:c + 1], out2[0][:, c:c + 1], self.kl_T)
         else:
-            mutual = distill_kl(out1[0], out2[0], self.kl_T)
+            mutual = distill_kl(out1[0], out2[0], self.kl_T, upstream_grad=self.lambda1)
         l = l + self.lambda1 * mutual
         if self.topo is not None:
             prob = softmax_channel(out1[0], c)

@@ -69,7 +69,8 @@ def blockwise_teacher_forced(m, oracle, patch, cin, B, dev='cuda:0', seed=0):
     del out_ref, l_ref
     ref_mods = dict(ref.named_modules())
     ours = dict(net.named_modules())
-    checked, errs_all = 0, {}
+    ref_grads = {n: p.grad.detach().clone() for n, p in ref.named_parameters() if p.grad is not None}
+    checked, errs_all, floors = 0, {}, {}
     for name in list(rec):
         r = rec.pop(name)
         if 'gy' not in r:      # zero-weighted deep-supervision head: no gradient reaches it
@@ -88,20 +89,52 @@ def blockwise_teacher_forced(m, oracle, patch, cin, B, dev='cuda:0', seed=0):
             p.grad = None
         if isinstance(mod, m.ConvDropoutNormReLU):
             y = mod.forward_cl(x)
-            plist = [('conv.weight', mod.conv.weight, rmod.conv.weight), ('norm.weight', mod.norm.weight, rmod.norm.weight),
-                     ('norm.bias', mod.norm.bias, rmod.norm.bias)]
+            pnames = ['conv.weight', 'norm.weight', 'norm.bias']
         elif isinstance(mod, torch.nn.ConvTranspose3d):
             y = ops.ConvTransposeFn.apply(x, mod.weight, mod.bias, tuple(mod.stride), None, None)
-            plist = [('weight', mod.weight, rmod.weight), ('bias', mod.bias, rmod.bias)]
+            pnames = ['weight', 'bias']
         else:
             y = ops.HeadFn.apply(x, mod.weight, mod.bias, None)
-            plist = [('weight', mod.weight, rmod.weight), ('bias', mod.bias, rmod.bias)]
+            pnames = ['weight', 'bias']
         y.backward(gy)
-        errs_all[f'{name}.out'] = rel_err(ops.ncdhw_view(y).float(), r['y'].float())
+        got = {'out': ops.ncdhw_view(y).float()}
+        want = {'out': r['y'].float()}
         if 'gx' in r:
-            errs_all[f'{name}.gx'] = rel_err(ops.ncdhw_view(x.grad).float(), r['gx'].float())
-        for pn, p, rp in plist:
-            errs_all[f'{name}.{pn}'] = rel_err(p.grad, rp.grad)
+            got['gx'], want['gx'] = ops.ncdhw_view(x.grad).float(), r['gx'].float()
+        own, rown = dict(mod.named_parameters()), dict(rmod.named_parameters())
+        for pn in pnames:
+            got[pn], want[pn] = own[pn].grad.float(), ref_grads[f'{name}.{pn}'].float()
+        # the same block of the ORACLE evaluated in fp32 on the identical (bf16-valued) inputs: how far the reference's
+        # own bf16-autocast evaluation is from exact arithmetic for each of these tensors (its rounding-noise floor)
+        for p in rmod.parameters():
+            p.grad = None
+        x32 = r['x'].float().detach().requires_grad_('gx' in r)
+        y32 = rmod(x32)
+        y32.backward(r['gy'].float())
+        truth = {'out': y32.detach()}
+        if 'gx' in r:
+            truth['gx'] = x32.grad
+        for pn in pnames:
+            truth[pn] = rown[pn].grad.float()
+        for k in got:
+            errs_all[f'{name}.{k}'] = rel_err(got[k], want[k])
+            floors[f'{name}.{k}'] = (rel_err(got[k], truth[k]), rel_err(want[k], truth[k]))
         checked += 1
-        del x, gy, y, r
-    return checked, errs_all
+        del x, gy, y, r, x32, y32, got, want, truth
+    return checked, errs_all, floors
+
+
+def out_of_tolerance(errs, floors, tol=TOL):
+    """tensors that miss the tolerance against the bf16-autocast oracle AND are further from the oracle's exact (fp32)
+    evaluation of the same block on the same inputs than the bf16 oracle itself is (+10 %): i.e. genuinely worse than
+    the reference's own rounding noise.  A weight gradient that sums millions of cancelling bf16-rounded products (the
+    last decoder convolution in front of the rank-4 head gradient) carries a few per cent of such noise in BOTH
+    implementations."""
+    bad = []
+    for k, e in errs.items():
+        if e < tol:
+            continue
+        ours32, ref32 = floors[k]
+        if not ours32 <= 1.1 * ref32:
+            bad.append(f'{k}: {e:.4f} vs bf16 oracle; {ours32:.4f} vs fp32 oracle (bf16 oracle itself: {ref32:.4f})')
+    return bad

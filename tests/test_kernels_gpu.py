@@ -354,6 +354,74 @@ def test_deep_supervision_wrapper_matches_oracle(m):
     assert xs[3].grad is None and float(xr[3].grad.abs().max()) == 0.0   # zero-weighted scale
 
 
+@pytest.mark.parametrize('batch_dice', [False, True])
+def test_deep_supervision_two_networks_one_launch(m, batch_dice):
+    """loss(out1, tgt) + loss(out2, tgt) of the mutual-distillation step through DeepSupervisionWrapper.forward_networks:
+    one fused forward launch (all scales of both networks, last-block-done scalar algebra) and one backward launch;
+    value 1e-5 and gradients against the oracle, and identical to the two separate calls."""
+    import oracle
+    outs1, tgts = _logits_targets(2, 4, (16, 20, 12), 43, scales=4)
+    outs2, _ = _logits_targets(2, 4, (16, 20, 12), 47, scales=4)
+    w = m.deep_supervision_weights(4)
+    mk = lambda mod: mod.DeepSupervisionWrapper(
+        mod.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, weight_ce=1,
+                           weight_dice=1, ignore_label=None, dice_class=mod.MemoryEfficientSoftDiceLoss), w)
+    x1 = [m.ops.ncdhw_view(o).requires_grad_(True) for o in outs1]
+    x2 = [m.ops.ncdhw_view(o).requires_grad_(True) for o in outs2]
+    before = m.lib.launch_count()
+    l = mk(m).forward_networks([x1, x2], tgts)
+    fwd_launches = m.lib.launch_count() - before
+    r1 = [o.float().permute(0, 4, 1, 2, 3).requires_grad_(True) for o in outs1]
+    r2 = [o.float().permute(0, 4, 1, 2, 3).requires_grad_(True) for o in outs2]
+    lr = mk(oracle)(r1, tgts) + mk(oracle)(r2, tgts)
+    assert abs(float(l) - float(lr)) <= 1e-5 * max(1.0, abs(float(lr)))
+    before = m.lib.launch_count()
+    (l * 2.0).backward()
+    bwd_launches = m.lib.launch_count() - before
+    (lr * 2.0).backward()
+    assert fwd_launches == 1 and bwd_launches == 1, (fwd_launches, bwd_launches)
+    for xs, rs in ((x1, r1), (x2, r2)):
+        for i in range(3):
+            assert rel_err(xs[i].grad.float(), rs[i].grad) < 6e-3
+        assert xs[3].grad is None
+    # same numbers as two separate wrapper calls
+    y1 = [m.ops.ncdhw_view(o).requires_grad_(True) for o in outs1]
+    l1 = mk(m)(y1, tgts)
+    l2 = mk(m)([m.ops.ncdhw_view(o) for o in outs2], tgts)
+    assert abs(float(l1) + float(l2) - float(l)) <= 1e-6 * max(1.0, abs(float(l)))
+    (l1 * 2.0).backward()
+    assert torch.equal(y1[0].grad, x1[0].grad)
+    # repeated calls: the ticket counter is left at zero
+    l_again = mk(m).forward_networks([x1, x2], tgts)
+    assert float(l_again) == float(l)
+
+
+@pytest.mark.parametrize('T', [1.0, 2.0])
+def test_distill_kl_single_pass_with_upstream_factor(m, T):
+    """distill_kl(..., upstream_grad=lambda1): loss and both gradients from ONE kernel; exact for the announced upstream
+    factor (backward = a rescale launch that exits on the device) and for any other one (rescaled)."""
+    import oracle
+    (a,), _ = _logits_targets(2, 4, (36, 40, 44), 51)
+    (b,), _ = _logits_targets(2, 4, (36, 40, 44), 52)
+    ar, br = (t.float().permute(0, 4, 1, 2, 3).detach().clone().requires_grad_(True) for t in (a, b))
+    lr = oracle.distill_kl(ar, br, T)
+    (0.5 * lr).backward()
+    for actual in (0.5, 1.25):
+        av, bv = (m.ops.ncdhw_view(t).detach().requires_grad_(True) for t in (a, b))
+        before = m.lib.launch_count()
+        l = m.distill_kl(av, bv, T, upstream_grad=0.5)
+        assert m.lib.launch_count() - before == 2          # the fused pass + the scalar scaling
+        assert abs(float(l) - float(lr)) <= 1e-5 * max(abs(float(lr)), 1e-3)
+        (actual * l).backward()
+        assert rel_err(av.grad.float(), ar.grad * (actual / 0.5)) < 8e-3
+        assert rel_err(bv.grad.float(), br.grad * (actual / 0.5)) < 8e-3
+    # only one side needs a gradient (a detached teacher)
+    av = m.ops.ncdhw_view(a).detach().requires_grad_(True)
+    l = m.distill_kl(av, m.ops.ncdhw_view(b), T, upstream_grad=0.5)
+    (0.5 * l).backward()
+    assert rel_err(av.grad.float(), ar.grad) < 8e-3
+
+
 def test_argmax_tp_fp_fn(m):
     import oracle
     (lg,), (tg,) = _logits_targets(2, 4, (7, 8, 9), 44)

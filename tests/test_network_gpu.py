@@ -174,7 +174,7 @@ def test_blockwise_teacher_forced_parity():
     import multimodal_mvd_seg_b200 as m
     import oracle
     from _parity import blockwise_teacher_forced
-    checked, errs = blockwise_teacher_forced(m, oracle, (40, 40, 24), 2, 2)
+    checked, errs, floors = blockwise_teacher_forced(m, oracle, (40, 40, 24), 2, 2)
     bad = [f'{k}: {e:.4f}' for k, e in errs.items() if not e < TOL]
     assert checked >= 20
     assert not bad, bad
