@@ -49,9 +49,11 @@ void mvd_reset_fallback_count(void);
 int mvd_shutdown(void);
 
 /* ---- layout at the module edge ---------------------------------------------------------------------------- */
-/* data.to(device) then network(data): fp32 NCDHW batch -> bf16 NDHWC (nnUNetTrainer.py:895,907) */
-int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int B, int C, long long V, int ld_dst,
-                                mvd_stream_t stream);
+/* data.to(device) then network(data): fp32 NCDHW batch -> bf16 NDHWC (nnUNetTrainer.py:895,907).  src_batch_stride
+ * (elements; 0 = dense C*V) lets a channel slice of a wider batch be read in place: the per-modality split data[:, 0:1] /
+ * data[:, 1:2] of the mutual-distillation step (selfattnNet.py:588-589) */
+int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, long long src_batch_stride, void* dst, int B, int C, long long V,
+                                int ld_dst, mvd_stream_t stream);
 /* logits back to fp32 NCDHW for callers that want the reference's memory format */
 int mvd_ndhwc_bf16_to_ncdhw_f32(const void* src, int ld_src, float* dst, int B, int C, long long V,
                                 mvd_stream_t stream);
@@ -103,11 +105,12 @@ int mvd_downsample_seg_nearest(const float* seg, int BC, int Di, int Hi, int Wi,
  * get_network_from_plans.py:75-77 for the first block.
  *   x     : DENSE bf16 NDHWC input [B][D][H][W][Cin]
  *   wcol  : bf16 [32][KPAD], KPAD = 32*Cin, column k = tap*Cin + ci (tap = (kd*3 + kh)*3 + kw), zero padded
+ *           (mvd_pack_conv_weights_multi writes it: mvd_pack_desc.stem_kpad)
  *   fprop : y (pitch ldy) = conv + bias (bf16), optional InstanceNorm sums stats [B][32][2] accumulated
- *   wgrad : dw_col fp32 [32][KPAD] = sum_v dy[v][co] * col[v][k] (overwritten) */
+ *   wgrad : dw fp32 [32][Cin][27] (the torch layout of the weight) = sum_v dy[v][co] * x[v + tap - 1][ci] (overwritten) */
 int mvd_stem_conv_fprop(const void* x, int B, int D, int H, int W, int Cin, const void* wcol, const float* bias,
                         void* y, int ldy, double* stats, mvd_stream_t stream);
-int mvd_stem_conv_wgrad(const void* x, int B, int D, int H, int W, int Cin, const void* dy, int lddy, float* dw_col,
+int mvd_stem_conv_wgrad(const void* x, int B, int D, int H, int W, int Cin, const void* dy, int lddy, float* dw,
                         mvd_stream_t stream);
 /* pack fp32 torch-layout weights [Cout][Cin][kd][kh][kw] into the two bf16 GEMM layouts:
  *   w_fprop [tap][Cout][Cin]  (B operand of fprop:  N = Cout rows, K = Cin contiguous)
@@ -119,6 +122,9 @@ typedef struct mvd_pack_desc {
   void* w_dgrad;          /* bf16 [tap][Cin][Cout] or NULL                                                  */
   int Cout, Cin, taps;    /* taps <= 27                                                                     */
   int block_begin;        /* first thread block of this layer: running sum of mvd_pack_blocks() over the table */
+  int stem_kpad;          /* 0: the two layouts above.  > 0 (Cin <= 16): w_fprop receives the stem layout instead,
+                             bf16 [Cout][stem_kpad] with column k = tap*Cin + ci, zero padded (mvd_stem_conv_fprop)   */
+  int reserved;
 } mvd_pack_desc;
 /* packs a whole table of layers (device memory, n entries, ascending block_begin) in one launch of total_blocks blocks */
 int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int total_blocks, mvd_stream_t stream);
@@ -153,9 +159,10 @@ int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, 
 /* ---- 1x1x1 segmentation heads (UNetDecoder.py:67-70) ------------------------------------------------------- */
 int mvd_head_fwd(const void* z, int ldz, const float* w /*[K][C] fp32*/, const float* bias /*[K]*/, void* logits,
                  int ldl, long long NV /*B*V*/, int C, int K, mvd_stream_t stream);
-/* dz (bf16) = dlogits * w ; dw [K][C], dbias [K] fp32 accumulated (caller zeroes) */
+/* dz (bf16) = dlogits * w (accumulate_dz: += , the gradient another consumer of z already left there);
+ * dw [K][C], dbias [K] fp32 accumulated (caller zeroes) */
 int mvd_head_bwd(const void* dlogits, int ldl, const void* z, int ldz, const float* w, void* dz, int lddz,
-                 float* dw, float* dbias, long long NV, int C, int K, mvd_stream_t stream);
+                 float* dw, float* dbias, long long NV, int C, int K, int accumulate_dz, mvd_stream_t stream);
 
 /* ---- deep-supervision Dice + CE (nnUNetTrainer.py:359-374; robust_ce_loss.py:12-16) ----------------------- */
 /* acc = [B][C][3] doubles (intersect, sum_pred, sum_gt) followed by 1 double (sum of -log p[target]); caller zeroes.
@@ -275,6 +282,11 @@ int mvd_sgd_nesterov_clip(const uint64_t* ptrs, const long long* numel, const in
 /* ---- utility ----------------------------------------------------------------------------------------------- */
 /* out[c] = sum over NV voxels of g[v][c] (fp32; bias gradient of ConvTranspose3d) */
 int mvd_channel_sum(const void* g, int ld, long long NV, int C, float* out, mvd_stream_t stream);
+/* zero n regions of one fp32 buffer in a single launch: table (device) = n x (element offset, element count) int64.
+ * The trainer clears the accumulate-type gradients of a step (conv biases in front of InstanceNorm, head weights) with it. */
+int mvd_zero_regions(float* base, const long long* table_device, int n, mvd_stream_t stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream: the per-step scratch pool */
+int mvd_zero_bytes(void* ptr, size_t bytes, mvd_stream_t stream);
 /* out[0] (+)= scale * in[0]: device-side double -> float scalar algebra (keeps the step free of host syncs) */
 int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream);
 int mvd_add_bf16(void* dst, int ldd, const void* src, int lds, long long NV, int C, mvd_stream_t stream); /* dst += src */

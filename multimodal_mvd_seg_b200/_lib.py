@@ -59,7 +59,7 @@ _SIGNATURES = {
     'mvd_fallback_count': (c_ulonglong, []),
     'mvd_reset_fallback_count': (None, []),
     'mvd_shutdown': (c_int, []),
-    'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, P, I, I, LL, I, S]),
+    'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, LL, P, I, I, LL, I, S]),
     'mvd_ndhwc_bf16_to_ncdhw_f32': (c_int, [P, I, P, I, I, LL, S]),
     'mvd_sw_accumulate': (c_int, [P, I, P, F, P, P, I, I, I, I, I, I, I, I, I, I, I, S]),
     'mvd_sw_finalize': (c_int, [P, P, I, LL, S]),
@@ -77,7 +77,7 @@ _SIGNATURES = {
     'mvd_inorm_lrelu_bwd_stats': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, P, S]),
     'mvd_inorm_lrelu_bwd_apply': (c_int, [P, I, P, I, P, I, P, P, P, P, I, LL, I, F, F, P, P, P, S]),
     'mvd_head_fwd': (c_int, [P, I, P, P, P, I, LL, I, I, S]),
-    'mvd_head_bwd': (c_int, [P, I, P, I, P, P, I, P, P, LL, I, I, S]),
+    'mvd_head_bwd': (c_int, [P, I, P, I, P, P, I, P, P, LL, I, I, I, S]),
     'mvd_dice_ce_multi_fwd': (c_int, [P, I, I, I, F, I, I, F, F, P, P, P, P, S]),
     'mvd_dice_ce_multi_finalize': (c_int, [P, I, I, I, F, I, I, F, F, P, P, P, S]),
     'mvd_dice_ce_multi_bwd': (c_int, [P, I, I, I, P, F, F, P, S]),
@@ -105,6 +105,8 @@ _SIGNATURES = {
     'mvd_cldice_finalize': (c_int, [P, F, P, S]),
     'mvd_grad_sqnorm': (c_int, [P, P, P, P, I, P, S]),
     'mvd_sgd_nesterov_clip': (c_int, [P, P, P, P, I, P, F, F, F, F, F, S]),
+    'mvd_zero_regions': (c_int, [P, P, I, S]),
+    'mvd_zero_bytes': (c_int, [P, c_size_t, S]),
     'mvd_channel_sum': (c_int, [P, I, LL, I, P, S]),
     'mvd_scalar_axpy': (c_int, [P, F, P, I, S]),
     'mvd_add_bf16': (c_int, [P, I, P, I, LL, I, S]),

@@ -365,7 +365,7 @@ int generic_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   P.dst = (bf16*)a->y; P.ldd = a->ldy; P.N = a->Cout; P.Dm = a->Do; P.Hm = a->Ho; P.Wm = a->Wo;
   P.w = (const bf16*)a->w; P.bias = a->bias; P.B = a->B;
   P.kd = a->kd; P.kh = a->kh; P.kw = a->kw; P.sd = a->sd; P.sh = a->sh; P.sw = a->sw;
-  P.pd = a->pd; P.ph = a->ph; P.pw = a->pw; P.accumulate = 0;
+  P.pd = a->pd; P.ph = a->ph; P.pw = a->pw; P.accumulate = a->accumulate;
   P.flatK = (a->Cin % 4 != 0) || (a->ldx % 4 != 0) || (((uintptr_t)a->x) & 7) || (((uintptr_t)a->w) & 7);
   const long long M = (long long)a->B * a->Do * a->Ho * a->Wo;
   if (a->Cout <= 32) {

@@ -419,6 +419,10 @@ static bool is_k3s1p1(const mvd_conv3d_args* a) {
 }
 
 int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
+  if (a->accumulate && ((is_k3s1p1(a) && tc_halo_enabled()) || tc_halo_s2_fprop_supported(a))) {
+    set_error("conv3d_fprop(tcgen05): accumulate is built for the tap-by-tap kernel (up-convolution adjoints) only");
+    return MVD_ERR_UNSUPPORTED;
+  }
   if (is_k3s1p1(a) && tc_halo_enabled()) {
     int wrow[27];
     for (int i = 0; i < 27; ++i) wrow[i] = i * a->Cout;
@@ -470,7 +474,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   P.out = (bf16*)a->y;
   P.sw = a->ldy; P.sh = (long long)a->ldy * a->Wo; P.sd = P.sh * a->Ho; P.sb = P.sd * a->Do;
   P.bias = a->bias;
-  P.accumulate = 0;
+  P.accumulate = a->accumulate;     // the adjoint of an up-convolution adds into the gradient a segmentation head left
   P.stats = a->stats; P.Ntot = a->Cout;
   P.nbias = a->Cout;
   if (P.stats && (P.n_tile != a->Cout || (a->Cout != 32 && a->Cout != 64))) {

@@ -4,6 +4,20 @@
 #include "common.cuh"
 
 namespace mvd {
+// dz store of the head backward; `accumulate`: add to what another consumer of the same activation already wrote there
+// (the up-convolution that also reads a decoder stage output: folds autograd's two-consumer sum into this kernel)
+__device__ __forceinline__ void store_dz(bf16* p, const float* o, bool accumulate) {
+  if (accumulate) {
+    float old[8], s[8];
+    unpack8(ldg16(p), old);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = o[j] + old[j];
+    stg16(p, pack8(s));
+  } else {
+    stg16(p, pack8(o));
+  }
+}
+
 
 constexpr int kMaxHeadK = 8;
 
@@ -39,7 +53,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
 template <int K>
 __global__ void __launch_bounds__(256) head_bwd_data_kernel(const bf16* __restrict__ dl, int ldl,
                                                             const float* __restrict__ w, bf16* __restrict__ dz,
-                                                            int lddz, long long NV, int C) {
+                                                            int lddz, long long NV, int C, bool acc_dz) {
   extern __shared__ float sw[];
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = round_bf(w[i]);
   __syncthreads();
@@ -59,7 +73,7 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const bf16* __restri
       for (int k = 0; k < K; ++k) a = fmaf(g[k], sw[k * C + cg * 8 + j], a);
       o[j] = a;
     }
-    stg16(dz + v * lddz + cg * 8, pack8(o));
+    store_dz(dz + v * lddz + cg * 8, o, acc_dz);
   }
 }
 
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ z, int ldz,
                                                           const float* __restrict__ w, bf16* __restrict__ dz, int lddz,
                                                           float* __restrict__ dw, float* __restrict__ dbias,
-                                                          long long NV, int vec) {
+                                                          long long NV, int vec, bool acc_dz) {
   constexpr int C = CG * 8, ROWS = 256 / CG, U = 4;
   __shared__ float sacc[K * C + K];
   for (int i = threadIdx.x; i < K * C + K; i += 256) sacc[i] = 0.f;
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(256) head_bwd_cg_kernel(const bf16* __restrict
           for (int k = 0; k < K; ++k) a = fmaf(g[u][k], wr[k][j], a);
           o[j] = a;
         }
-        stg16(dz + v * lddz + cg * 8, pack8(o));
+        store_dz(dz + v * lddz + cg * 8, o, acc_dz);
       }
       if (dw) {
         float f[8];
@@ -336,7 +350,8 @@ __global__ void __launch_bounds__(256, 2) head_bwd_cg4_staged_kernel(const bf16*
                                                                      const bf16* __restrict__ z, int ldz,
                                                                      const float* __restrict__ w, bf16* __restrict__ dz,
                                                                      int lddz, float* __restrict__ dw,
-                                                                     float* __restrict__ dbias, long long NV) {
+                                                                     float* __restrict__ dbias, long long NV,
+                                                                     bool acc_dz) {
   constexpr int K = 4, C = CG * 8, ROWS = 256 / CG;
   extern __shared__ __align__(16) uint4 hring[];     // [stage][256] z vectors, then [stage][256] 8-byte logit-gradient rows
   __shared__ float sacc[K * C + K];
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(256, 2) head_bwd_cg4_staged_kernel(const bf16*
         for (int k = 0; k < K; ++k) a = fmaf(g[k], wr[k][j], a);
         o[j] = a;
       }
-      stg16(dz + v * lddz + cg * 8, pack8(o));
+      store_dz(dz + v * lddz + cg * 8, o, acc_dz);
     }
     if (need_z) {
       const uint4 u = mine[st * 256];
@@ -461,7 +476,7 @@ static int head_fwd_cg_launch(const bf16* z, int ldz, const float* w, const floa
 
 template <int K, int CG>
 static int head_bwd_cg_launch(const bf16* dl, int ldl, const bf16* z, int ldz, const float* w, bf16* dz, int lddz,
-                              float* dw, float* db, long long NV, cudaStream_t st) {
+                              float* dw, float* db, long long NV, bool acc_dz, cudaStream_t st) {
   const int vec = (K == 4 && ldl % 4 == 0 && ((uintptr_t)dl & 7) == 0) ? 1 : 0;
   if constexpr (K == 4) {
     if (vec && ldz % 8 == 0 && ((uintptr_t)z & 15) == 0 && (!dz || (lddz % 8 == 0 && ((uintptr_t)dz & 15) == 0))) {
@@ -472,13 +487,13 @@ static int head_bwd_cg_launch(const bf16* dl, int ldl, const bf16* z, int ldz, c
         attr_done = true;
       }
       const int grid = head_staged_grid(head_bwd_cg4_staged_kernel<CG>, smem, NV, 256 / CG);
-      head_bwd_cg4_staged_kernel<CG><<<grid, 256, smem, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV);
+      head_bwd_cg4_staged_kernel<CG><<<grid, 256, smem, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, acc_dz);
       MVD_LAUNCH_CHECK("head_bwd");
       return MVD_OK;
     }
   }
   const int grid = head_wave_grid(head_bwd_cg_kernel<K, CG>, NV, 256 / CG);
-  head_bwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, vec);
+  head_bwd_cg_kernel<K, CG><<<grid, 256, 0, st>>>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, vec, acc_dz);
   MVD_LAUNCH_CHECK("head_bwd");
   return MVD_OK;
 }
@@ -498,14 +513,14 @@ static int head_fwd_launch(const bf16* z, int ldz, const float* w, const float* 
 
 template <int K>
 static int head_bwd_launch(const bf16* dl, int ldl, const bf16* z, int ldz, const float* w, bf16* dz, int lddz,
-                           float* dw, float* db, long long NV, int C, cudaStream_t st) {
-  if (C == 32) return head_bwd_cg_launch<K, 4>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
-  if (C == 64) return head_bwd_cg_launch<K, 8>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
-  if (C == 128) return head_bwd_cg_launch<K, 16>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
-  if (C == 256) return head_bwd_cg_launch<K, 32>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, st);
+                           float* dw, float* db, long long NV, int C, bool acc_dz, cudaStream_t st) {
+  if (C == 32) return head_bwd_cg_launch<K, 4>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, acc_dz, st);
+  if (C == 64) return head_bwd_cg_launch<K, 8>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, acc_dz, st);
+  if (C == 128) return head_bwd_cg_launch<K, 16>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, acc_dz, st);
+  if (C == 256) return head_bwd_cg_launch<K, 32>(dl, ldl, z, ldz, w, dz, lddz, dw, db, NV, acc_dz, st);
   if (dz) {
     int grid = grid_for(NV * (C / 8), 256 * 2, num_sms() * 8);
-    head_bwd_data_kernel<K><<<grid, 256, K * C * sizeof(float), st>>>(dl, ldl, w, dz, lddz, NV, C);
+    head_bwd_data_kernel<K><<<grid, 256, K * C * sizeof(float), st>>>(dl, ldl, w, dz, lddz, NV, C, acc_dz);
     MVD_LAUNCH_CHECK("head_bwd_data");
   }
   if (dw) {
@@ -594,14 +609,14 @@ int mvd_head_fwd(const void* z, int ldz, const float* w, const float* bias, void
 }
 
 int mvd_head_bwd(const void* dlogits, int ldl, const void* z, int ldz, const float* w, void* dz, int lddz,
-                 float* dw, float* dbias, long long NV, int C, int K, mvd_stream_t stream) {
+                 float* dw, float* dbias, long long NV, int C, int K, int accumulate_dz, mvd_stream_t stream) {
   MVD_REQUIRE(dlogits && z && w && NV > 0, "head_bwd: bad arguments");
   MVD_REQUIRE(K >= 1 && K <= kMaxHeadK, "head_bwd: num_classes must be in 1..8 (got %d)", K);
   MVD_REQUIRE(C % 8 == 0 && ldz % 8 == 0 && ((uintptr_t)z & 15) == 0 && C <= 1024, "head_bwd: C/alignment");
   MVD_REQUIRE(!dz || (lddz % 8 == 0 && ((uintptr_t)dz & 15) == 0), "head_bwd: dz alignment");
 #define CALL(KK)                                                                                               \
   head_bwd_launch<KK>((const bf16*)dlogits, ldl, (const bf16*)z, ldz, w, (bf16*)dz, lddz, dw, dbias, NV, C, \
-                      (cudaStream_t)stream)
+                      accumulate_dz != 0, (cudaStream_t)stream)
   HEAD_DISPATCH(K, CALL)
 #undef CALL
   return MVD_ERR_UNSUPPORTED;

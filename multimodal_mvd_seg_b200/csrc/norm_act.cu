@@ -13,10 +13,10 @@ namespace mvd {
 // layout
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void ncdhw_to_ndhwc_small_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long V,
-                                            int ld) {
+__global__ void ncdhw_to_ndhwc_small_kernel(const float* __restrict__ src, long long sb, bf16* __restrict__ dst,
+                                            long long V, int ld) {
   const int b = blockIdx.y;
-  const float* s = src + (long long)b * C * V;
+  const float* s = src + (long long)b * sb;
   bf16* d = dst + (long long)b * V * ld;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
 #pragma unroll
@@ -24,10 +24,10 @@ __global__ void ncdhw_to_ndhwc_small_kernel(const float* __restrict__ src, bf16*
   }
 }
 
-__global__ void ncdhw_to_ndhwc_generic_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C,
+__global__ void ncdhw_to_ndhwc_generic_kernel(const float* __restrict__ src, long long sb, bf16* __restrict__ dst, int C,
                                               long long V, int ld) {
   const int b = blockIdx.y;
-  const float* s = src + (long long)b * C * V;
+  const float* s = src + (long long)b * sb;
   bf16* d = dst + (long long)b * V * ld;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x)
     for (int c = 0; c < C; ++c) d[v * ld + c] = f2bf(__ldg(s + (long long)c * V + v));
@@ -484,16 +484,18 @@ using namespace mvd;
 
 extern "C" {
 
-int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int B, int C, long long V, int ld_dst,
+int mvd_ncdhw_f32_to_ndhwc_bf16(const float* src, long long src_batch_stride, void* dst, int B, int C, long long V,
+                                int ld_dst,
                                 mvd_stream_t stream) {
   MVD_REQUIRE(src && dst && B > 0 && C > 0 && V > 0 && ld_dst >= C, "ncdhw_to_ndhwc: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(grid_for(V, 256, num_sms() * 8), B);
   bf16* d = (bf16*)dst;
-  if (C == 1) ncdhw_to_ndhwc_small_kernel<1><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
-  else if (C == 2) ncdhw_to_ndhwc_small_kernel<2><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
-  else if (C == 4) ncdhw_to_ndhwc_small_kernel<4><<<grid, 256, 0, st>>>(src, d, V, ld_dst);
-  else ncdhw_to_ndhwc_generic_kernel<<<grid, 256, 0, st>>>(src, d, C, V, ld_dst);
+  const long long sb = src_batch_stride > 0 ? src_batch_stride : (long long)C * V;
+  if (C == 1) ncdhw_to_ndhwc_small_kernel<1><<<grid, 256, 0, st>>>(src, sb, d, V, ld_dst);
+  else if (C == 2) ncdhw_to_ndhwc_small_kernel<2><<<grid, 256, 0, st>>>(src, sb, d, V, ld_dst);
+  else if (C == 4) ncdhw_to_ndhwc_small_kernel<4><<<grid, 256, 0, st>>>(src, sb, d, V, ld_dst);
+  else ncdhw_to_ndhwc_generic_kernel<<<grid, 256, 0, st>>>(src, sb, d, C, V, ld_dst);
   MVD_LAUNCH_CHECK("ncdhw_to_ndhwc");
   return MVD_OK;
 }

@@ -97,6 +97,16 @@ __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const mvd_pack_d
   const int a = threadIdx.x >> 4, b = threadIdx.x & 15;
   bf16* wf = (bf16*)d.w_fprop;
   bf16* wd = (bf16*)d.w_dgrad;
+  if (d.stem_kpad > 0) {                   // stem layout [Cout][kpad], k = tap*Cin + ci (Cin <= 16: one ci tile)
+    const int kpad = d.stem_kpad;
+    if (wf)
+      for (int i = threadIdx.x; i < nco * kpad; i += 256) {
+        const int r = i / kpad, k = i - r * kpad;
+        const int t = k / Cin, ci = k - t * Cin;
+        wf[(long long)(co0 + r) * kpad + k] = f2bf(k < taps * Cin ? tile[r][ci * taps + t] : 0.f);
+      }
+    return;
+  }
   if (wf && a < nco && b < nci) {          // a = co, b = ci (fastest)
 #pragma unroll 9
     for (int t = 0; t < taps; ++t)
@@ -107,6 +117,11 @@ __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const mvd_pack_d
     for (int t = 0; t < taps; ++t)
       wd[((long long)t * Cin + ci0 + a) * Cout + co0 + b] = f2bf(tile[b][a * taps + t]);
   }
+}
+
+__global__ void __launch_bounds__(128) zero_regions_kernel(float* __restrict__ base, const long long* __restrict__ table) {
+  const long long off = table[2 * blockIdx.x], n = table[2 * blockIdx.x + 1];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) base[off + i] = 0.f;
 }
 
 __global__ void scalar_axpy_kernel(const double* __restrict__ in, float scale, float* __restrict__ out, int accumulate) {
@@ -147,6 +162,19 @@ int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int to
 
 int mvd_pack_blocks(int Cout, int Cin) {
   return ((Cout + kPackTile - 1) / kPackTile) * ((Cin + kPackTile - 1) / kPackTile);
+}
+
+int mvd_zero_regions(float* base, const long long* table_device, int n, mvd_stream_t stream) {
+  MVD_REQUIRE(base && table_device && n > 0, "zero_regions: bad arguments");
+  zero_regions_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(base, table_device);
+  MVD_LAUNCH_CHECK("zero_regions");
+  return MVD_OK;
+}
+
+int mvd_zero_bytes(void* ptr, size_t bytes, mvd_stream_t stream) {
+  MVD_REQUIRE(ptr && bytes > 0, "zero_bytes: bad arguments");
+  MVD_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+  return MVD_OK;
 }
 
 int mvd_scalar_axpy(const double* in, float scale, float* out, int accumulate, mvd_stream_t stream) {

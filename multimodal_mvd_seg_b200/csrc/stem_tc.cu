@@ -43,7 +43,7 @@ struct StemParams {
   const float* bias;
   double* stats;
   // wgrad
-  float* dw_col;                  // [32][KPAD] fp32, accumulated with atomics (caller zeroes)
+  float* dw_col;                  // [32][CIN][27] fp32 (torch layout), accumulated with atomics (zeroed by the entry point)
 };
 
 struct alignas(64) StemMaps {
@@ -391,9 +391,10 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) stem_wgrad_kernel(const __gr
     uint32_t v[32];
     tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16), v);
     tmem_ld_wait();
-    if (m < KPAD) {
+    if (m < 27 * CIN) {      // row m = tap * CIN + ci  ->  torch layout dw[co][ci][tap]
+      const int tap = m / CIN, ci = m - tap * CIN;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(&P.dw_col[e * KPAD + m], __uint_as_float(v[e]));
+      for (int e = 0; e < 32; ++e) atomicAdd(&P.dw_col[(e * CIN + ci) * 27 + tap], __uint_as_float(v[e]));
     }
   }
   tcgen05_fence_before();
@@ -495,7 +496,7 @@ int mvd_stem_conv_wgrad(const void* x, int B, int D, int H, int W, int Cin, cons
     maps.w = maps.dy;
   }
   P.dw_col = dw_col;
-  MVD_CUDA(cudaMemsetAsync(dw_col, 0, sizeof(float) * NOUT * kpad, (cudaStream_t)stream));
+  MVD_CUDA(cudaMemsetAsync(dw_col, 0, sizeof(float) * NOUT * Cin * 27, (cudaStream_t)stream));
   // tiles + slack for the junk M blocks of the last stage (M = 128 rows = 128 / KPAD tile-sized blocks)
   const size_t tile_bytes = (size_t)128 * kpad * 2;
   const size_t smem = (size_t)3 * 128 * 64 + (size_t)(kStages + 128 / kpad) * tile_bytes + 1024;

@@ -128,11 +128,38 @@ class GradArena:
     def view_for(self, p: torch.Tensor) -> Optional[torch.Tensor]:
         return self._views.get(id(p))
 
+    def prezero(self, params) -> List[torch.Tensor]:
+        """register parameters whose gradient region is cleared at the top of every step (kernels accumulate into them,
+        or they may receive no gradient at all); returns their arena views.  One launch clears all of them."""
+        seen, rows, views = set(), [], []
+        for p in params:
+            ent = self.offset.get(id(p))
+            if ent is None or id(p) in seen:
+                continue
+            seen.add(id(p))
+            rows.append(ent)
+            views.append(self._views[id(p)])
+        self._prezero_ids = seen
+        self._prezero_rows = rows
+        self._prezero_table = None
+        if rows and self.flat.is_cuda:
+            self._prezero_table = torch.tensor([v for r in rows for v in r], dtype=torch.int64, device=self.flat.device)
+        return views
+
     # -- step protocol ------------------------------------------------------------------------------------------
     def begin_step(self):
         self._ready = [set() for _ in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        rows = getattr(self, '_prezero_rows', None)
+        if rows:
+            if self._prezero_table is not None:
+                from ._lib import lib
+                lib.zero_regions(self.flat.data_ptr(), self._prezero_table.data_ptr(), len(rows),
+                                 torch.cuda.current_stream(self.flat.device).cuda_stream)
+            else:
+                for o, n in rows:
+                    self.flat[o:o + n].zero_()
 
     def on_params_ready(self, params):
         """called from backward (autograd thread) when the gradients of `params` have been enqueued."""
@@ -174,7 +201,7 @@ class GradArena:
         """after backward: zero the regions of parameters that received no gradient, flush the remaining buckets and
         make the compute stream wait for the exchange."""
         for b, bk in enumerate(self.buckets):
-            missing = bk['ids'] - self._ready[b]
+            missing = bk['ids'] - self._ready[b] - getattr(self, '_prezero_ids', set())
             if missing:
                 for p in self.params:
                     if id(p) in missing:

@@ -178,6 +178,10 @@ class soft_cldice(nn.Module):
         return ops.SoftClDiceFn.apply(y_true, y_pred, int(self.iter), float(self.smooth))
 
 
-def softmax_channel(logits, channel: int):
-    """softmax(logits, 1)[:, channel:channel+1] in fp32 (input of the topological term, MVDTrainer.py:907)."""
-    return ops.SoftmaxChannelFn.apply(logits, int(channel))
+def softmax_channel(logits, channel: int, target=None):
+    """softmax(logits, 1)[:, channel:channel+1] in fp32 (input of the topological term, MVDTrainer.py:907).  With
+    ``target`` ([B,1,D,H,W] class ids) returns (prob, onehot) where onehot = (target == channel).float() -- the ground
+    truth channel of MVDTrainer.py:904-905 -- produced by the same kernel."""
+    if target is None:
+        return ops.SoftmaxChannelFn.apply(logits, int(channel))
+    return ops.SoftmaxChannelFn.apply(logits, int(channel), target)

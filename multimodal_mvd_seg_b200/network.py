@@ -261,16 +261,21 @@ class PlainConvUNet(nn.Module):
     def _weight_packer(self):
         """one launch refreshes the bf16 GEMM layouts of every conv / transposed-conv weight (ops.WeightPacker);
         rebuilt when a weight's storage moved (``.to(device)``)."""
-        ws = [m.conv.weight for m in self.modules() if isinstance(m, ConvDropoutNormReLU) and m.conv.weight.shape[1] > 4]
-        ws += [t.weight for t in self.decoder.transpconvs]
+        ws = []
+        for m in self.modules():
+            if isinstance(m, ConvDropoutNormReLU):
+                kpad = ops.stem_kpad_for(m.conv.weight, m.stride)
+                if kpad or m.conv.weight.shape[1] > 4:
+                    ws.append((m.conv.weight, kpad))
+        ws += [(t.weight, 0) for t in self.decoder.transpconvs]
         seen, uniq = set(), []
-        for w in ws:   # decoder.encoder aliases the encoder modules
+        for w, kpad in ws:   # decoder.encoder aliases the encoder modules
             if id(w) not in seen:
                 seen.add(id(w))
-                uniq.append(w)
-        sig = tuple(w.data_ptr() for w in uniq)
+                uniq.append((w, kpad))
+        sig = tuple(w.data_ptr() for w, _ in uniq)
         if getattr(self, '_packer_sig', None) != sig:
-            self._packer = ops.WeightPacker([(w, True, True) for w in uniq])
+            self._packer = ops.WeightPacker([(w, True, not kpad, kpad) for w, kpad in uniq])
             self._packer_sig = sig
         return self._packer
 

@@ -87,12 +87,20 @@ def to_cl_view(t: torch.Tensor) -> torch.Tensor:
 # layout at the module edge
 # ---------------------------------------------------------------------------------------------------------------
 def input_to_cl(x: torch.Tensor) -> torch.Tensor:
-    """fp32 NCDHW batch -> bf16 NDHWC (no gradient: the network input is data)."""
+    """fp32 NCDHW batch -> bf16 NDHWC (no gradient: the network input is data).  A channel slice of a wider batch
+    (data[:, 0:1]: dense [C][D][H][W] per sample, larger batch stride) is read in place."""
     require_cuda(x, 'input_to_cl')
-    x = x.contiguous().float()
+    if x.dtype != torch.float32:
+        x = x.float()
     B, C, D, H, W = x.shape
+    V = D * H * W
+    st = x.stride()
+    per_sample_dense = st[4] == 1 and st[3] == W and st[2] == H * W and (C == 1 or st[1] == V)
+    if not per_sample_dense or (B > 1 and st[0] < C * V):
+        x = x.contiguous()
+        st = x.stride()
     out = torch.empty((B, D, H, W, C), dtype=BF16, device=x.device)
-    lib.ncdhw_f32_to_ndhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, D * H * W, C, _stream())
+    lib.ncdhw_f32_to_ndhwc_bf16(x.data_ptr(), st[0] if B > 1 else 0, out.data_ptr(), B, C, V, C, _stream())
     return out
 
 
@@ -179,7 +187,7 @@ class WeightPacker:
     (CUDA-graph friendly); ``run()`` re-reads the current weight values."""
 
     _DESC = np.dtype([('w', '<u8'), ('wf', '<u8'), ('wd', '<u8'), ('Cout', '<i4'), ('Cin', '<i4'), ('taps', '<i4'),
-                      ('block_begin', '<i4')])
+                      ('block_begin', '<i4'), ('stem_kpad', '<i4'), ('reserved', '<i4')])
 
     def __init__(self, entries):
         entries = list(entries)
@@ -188,7 +196,9 @@ class WeightPacker:
         rows = np.zeros(len(entries), dtype=self._DESC)
         blocks = 0
         self._keep = []
-        for i, (w, want_f, want_d) in enumerate(entries):
+        for i, ent in enumerate(entries):
+            w, want_f, want_d = ent[:3]
+            stem_kpad = int(ent[3]) if len(ent) > 3 else 0
             require_cuda(w, 'WeightPacker')
             wd_ = w.detach()
             if wd_.dtype != torch.float32 or not wd_.is_contiguous():
@@ -197,11 +207,16 @@ class WeightPacker:
             taps = int(np.prod(wd_.shape[2:]))
             if taps > 27:
                 raise MvdError('WeightPacker: at most 27 taps')
-            wf = torch.empty((taps, Cout, Cin), dtype=BF16, device=w.device) if want_f else None
-            wdg = torch.empty((taps, Cin, Cout), dtype=BF16, device=w.device) if want_d else None
-            rows[i] = (wd_.data_ptr(), _ptr(wf) or 0, _ptr(wdg) or 0, Cout, Cin, taps, blocks)
+            if stem_kpad:      # the stem's [1][Cout][kpad] im2col-column layout (mvd_stem_conv_fprop), no dgrad layout
+                if Cin > 16 or taps * Cin > stem_kpad:
+                    raise MvdError('WeightPacker: stem layout needs Cin <= 16 and taps * Cin <= kpad')
+                wf, wdg = torch.empty((1, Cout, stem_kpad), dtype=BF16, device=w.device), None
+            else:
+                wf = torch.empty((taps, Cout, Cin), dtype=BF16, device=w.device) if want_f else None
+                wdg = torch.empty((taps, Cin, Cout), dtype=BF16, device=w.device) if want_d else None
+            rows[i] = (wd_.data_ptr(), _ptr(wf) or 0, _ptr(wdg) or 0, Cout, Cin, taps, blocks, stem_kpad, 0)
             blocks += lib.pack_blocks(Cout, Cin)
-            self.packed[id(w)] = (wf, wdg)
+            self.packed[(id(w), stem_kpad)] = (wf, wdg)
             self._keep.append(w)
         self.n, self.blocks = len(entries), blocks
         self.table = torch.from_numpy(rows.view(np.uint8).copy()).to(entries[0][0].device)
@@ -209,8 +224,8 @@ class WeightPacker:
     def run(self):
         lib.pack_conv_weights_multi(self.table.data_ptr(), self.n, self.blocks, _stream())
 
-    def get(self, w):
-        return self.packed[id(w)]
+    def get(self, w, stem_kpad=0):
+        return self.packed[(id(w), stem_kpad)]
 
 
 _single_packers = {}
@@ -222,31 +237,42 @@ def set_active_packer(pk: Optional[WeightPacker]):
     _active_packer = pk
 
 
-def _packed_for(weight, want_fprop=True, want_dgrad=True):
+def _packed_for(weight, want_fprop=True, want_dgrad=True, stem_kpad=0):
     """the bf16 layouts of `weight`: from the network-wide packer when a forward pass armed one (already refreshed by
     its single launch), else packed here."""
     if _active_packer is not None:
-        hit = _active_packer.packed.get(id(weight))
+        hit = _active_packer.packed.get((id(weight), int(stem_kpad)))
         if hit is not None:
             return hit
-    return pack_weights(weight, want_fprop, want_dgrad)
+    return pack_weights(weight, want_fprop, want_dgrad, stem_kpad)
 
 
-def pack_weights(w: torch.Tensor, want_fprop=True, want_dgrad=True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """fp32 [Cout][Cin][kd][kh][kw] -> bf16 [tap][Cout][Cin] and [tap][Cin][Cout] for ONE layer.  The packed buffers are
-    cached per (storage address, shape): repeated calls refresh and return the same tensors."""
+def pack_weights(w: torch.Tensor, want_fprop=True, want_dgrad=True, stem_kpad=0) \
+        -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """fp32 [Cout][Cin][kd][kh][kw] -> bf16 [tap][Cout][Cin] and [tap][Cin][Cout] for ONE layer (stem_kpad > 0: the
+    stem's [1][Cout][kpad] layout instead).  The packed buffers are cached per (storage address, shape): repeated calls
+    refresh and return the same tensors."""
     require_cuda(w, 'pack_weights')
     w = w.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    key = (w.data_ptr(), tuple(w.shape), bool(want_fprop), bool(want_dgrad), w.device)
+    key = (w.data_ptr(), tuple(w.shape), bool(want_fprop), bool(want_dgrad), int(stem_kpad), w.device)
     pk = _single_packers.get(key)
     if pk is None:
         if len(_single_packers) > 512:
             _single_packers.clear()
-        pk = _single_packers[key] = (WeightPacker([(w, want_fprop, want_dgrad)]), w)
+        pk = _single_packers[key] = (WeightPacker([(w, want_fprop, want_dgrad, stem_kpad)]), w)
     pk[0].run()
     return next(iter(pk[0].packed.values()))
+
+
+def stem_kpad_for(weight: torch.Tensor, stride) -> int:
+    """> 0 when a conv with this weight is run by the stem kernels (csrc/stem_tc.cu: 1 or 2 input modalities -> 32
+    features, 3x3x3, stride 1); the value is the zero-padded im2col width its packed weight uses."""
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    if Cin in (1, 2) and Cout == 32 and tuple(weight.shape[2:]) == (3, 3, 3) and tuple(stride) == (1, 1, 1):
+        return 32 * Cin
+    return 0
 
 
 class ConvTimer:
@@ -362,6 +388,7 @@ def set_grad_allocator(fn):
     global _grad_alloc
     _grad_alloc = fn
     _arena_ids.clear()
+    _prezeroed_ids.clear()
 
 
 _arena_ids = set()
@@ -377,7 +404,7 @@ def begin_step(device):
     ent = _zero_pool.get(device)
     if ent is None:
         ent = _zero_pool[device] = [torch.empty((_ZERO_POOL_BYTES,), dtype=torch.uint8, device=device), 0]
-    ent[0].zero_()
+    lib.zero_bytes(ent[0].data_ptr(), _ZERO_POOL_BYTES, torch.cuda.current_stream(device).cuda_stream)   # a memset node
     ent[1] = 0
 
 
@@ -391,13 +418,24 @@ def zeros(shape, dtype, device):
     return ent[0][off:off + n].view(dtype).view(shape)
 
 
-def _grad_like(p: torch.Tensor) -> torch.Tensor:
+_prezeroed_ids = set()   # arena views the trainer clears at the top of every step (GradArena.prezero): no fill here
+
+
+def set_prezeroed(views):
+    _prezeroed_ids.clear()
+    _prezeroed_ids.update(id(v) for v in views)
+
+
+def _grad_like(p: torch.Tensor, zero: bool = False) -> torch.Tensor:
+    """destination of a parameter gradient; ``zero``: the kernel accumulates into it (bias / head sums)."""
     if _grad_alloc is not None:
         g = _grad_alloc(p)
         if g is not None:
             _arena_ids.add(id(g))   # the arena's views are persistent objects
+            if zero and id(g) not in _prezeroed_ids:
+                g.zero_()
             return g
-    return torch.empty(p.shape, dtype=torch.float32, device=p.device)
+    return (torch.zeros if zero else torch.empty)(p.shape, dtype=torch.float32, device=p.device)
 
 
 def _ret(g: Optional[torch.Tensor], p: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -445,6 +483,21 @@ _pending_skip = {}     # data_ptr -> decoder-side gradient view, between ConcatV
 def reset_skip_registry():
     _dx_consumers.clear()
     _pending_skip.clear()
+    _head_inputs.clear()
+    _pair_pending.clear()      # entries whose head never ran backward (zero-weighted scale) must not pile up
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Decoder stage outputs have TWO consumers: the stage's segmentation head and the next up-convolution
+# (UNetDecoder.py:104-121), so autograd would sum the two gradients with an elementwise kernel.  In backward the
+# up-convolution runs first (it was created later); it hands its gradient to autograd as usual and leaves a reference
+# here, and the head's backward then ADDS its share into that very tensor inside its own kernel (mvd_head_bwd
+# accumulate_dz) and reports no gradient of its own.  If the head runs first, or never (zero-weighted scale), nothing
+# is parked and autograd's own accumulation applies: correct in every order, fused in the usual one.
+# ---------------------------------------------------------------------------------------------------------------
+_head_inputs = {}      # data_ptr of a head's input (this forward) -> the HeadFn ctx
+_pair_pending = {}     # pair key -> gradient tensor the up-convolution's backward already returned
+_pair_seq = [0]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -559,9 +612,8 @@ class ConvNormActFn(torch.autograd.Function):
             taps = geom.k[0] * geom.k[1] * geom.k[2]
             kpad = 32 * Cin if fused_stem else (32 if taps * Cin <= 32 else 64)
             assert taps * Cin <= kpad
-            # [Cout][Cin][taps] -> [1 tap][Cout][(tap, ci) zero-padded]: a 1.7k-element reshuffle, host-side plumbing
-            wcol = torch.zeros((1, Cout, kpad), dtype=BF16, device=dev)
-            wcol[0, :, :taps * Cin] = weight.detach().reshape(Cout, Cin, taps).permute(0, 2, 1).reshape(Cout, taps * Cin)
+            # [Cout][Cin][taps] -> [1 tap][Cout][(tap, ci) zero-padded]: written by the weight-pack launch
+            wcol, _ = _packed_for(weight, True, False, stem_kpad=kpad)
             if fused_stem:
                 _timed_call('fprop', 2.0 * B * V * Cout * Cin * taps, f'stem {Cin}->{Cout} k333 out{Do}x{Ho}x{Wo}',
                             lambda: lib.stem_conv_fprop(x_cl.data_ptr(), B, Di, Hi, Wi, Cin, wcol.data_ptr(), _ptr(bias),
@@ -601,9 +653,7 @@ class ConvNormActFn(torch.autograd.Function):
         dy = torch.empty_like(y)
         dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
         dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
-        db = _grad_like(bias) if bias is not None and ctx.needs_input_grad[2] else None
-        if db is not None:
-            db.zero_()
+        db = _grad_like(bias, zero=True) if bias is not None and ctx.needs_input_grad[2] else None
         _timed_mem('inorm_lrelu_bwd_apply', 6.0 * B * V * Cout, lib.inorm_lrelu_bwd_apply, dz.data_ptr(), cl_pitch(dz),
                    y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(), bstats.data_ptr(),
                    _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
@@ -612,18 +662,18 @@ class ConvNormActFn(torch.autograd.Function):
         if dw is not None:
             if ctx.stem:
                 Cin_w, taps = weight.shape[1], weight.shape[2] * weight.shape[3] * weight.shape[4]
-                kpad = 32 * Cin_w if ctx.fused_stem else x_cl.shape[-1]
-                dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
-                if ctx.fused_stem:
+                if ctx.fused_stem:       # writes dw in the torch layout [Cout][Cin][27] itself
                     Bx, Dx, Hx, Wx, _ = x_cl.shape
                     _timed_call('wgrad', 2.0 * Bx * Dx * Hx * Wx * Cout * Cin_w * taps,
                                 f'stem {Cin_w}->{Cout} k333 out{Dx}x{Hx}x{Wx}',
                                 lambda: lib.stem_conv_wgrad(x_cl.data_ptr(), Bx, Dx, Hx, Wx, Cin_w, dy.data_ptr(),
-                                                            cl_pitch(dy), dw_col.data_ptr(), st))
+                                                            cl_pitch(dy), dw.data_ptr(), st))
                 else:
+                    kpad = x_cl.shape[-1]
+                    dw_col = torch.empty((Cout, kpad, 1, 1, 1), dtype=torch.float32, device=dev)
                     conv_wgrad(geom, x_cl, dy, dw_col, None)
-                dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
-                         .reshape(weight.shape))
+                    dw.copy_(dw_col.reshape(Cout, kpad)[:, :taps * Cin_w].reshape(Cout, taps, Cin_w).permute(0, 2, 1)
+                             .reshape(weight.shape))
             else:
                 plain_wgrad = True
         dx = None
@@ -662,6 +712,11 @@ class ConvTransposeFn(torch.autograd.Function):
         conv_dgrad(geom, up, x_cl, wd, bias=bias)
         ctx.geom = geom
         ctx.params_for_hook = params_for_hook
+        ctx.pair_key = None
+        head = _head_inputs.get(x_cl.data_ptr())
+        if head is not None and ctx.needs_input_grad[0] and head[1] == tuple(x_cl.shape) and head[0].pair_key is None:
+            _pair_seq[0] += 1
+            ctx.pair_key = head[0].pair_key = _pair_seq[0]
         ctx.save_for_backward(x_cl, wf, weight, bias)
         return up
 
@@ -681,6 +736,8 @@ class ConvTransposeFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
             conv_fprop(geom, dup, dx, wf)
+            if ctx.pair_key is not None:
+                _pair_pending[ctx.pair_key] = dx     # the stage's head adds its share in place (see _head_inputs)
         if dw is not None:
             if not _defer_wgrad(dev, lambda: conv_wgrad(geom, dup, x_cl, dw, None), (dup, x_cl, dw), dw):
                 conv_wgrad(geom, dup, x_cl, dw, None)
@@ -730,6 +787,9 @@ class HeadFn(torch.autograd.Function):
         _timed_mem('head_fwd', 2.0 * B * D * H * W * (C + K), lib.head_fwd, z_cl.data_ptr(), cl_pitch(z_cl),
                    w2.data_ptr(), _ptr(bias), logits.data_ptr(), K, B * D * H * W, C, K, _stream())
         ctx.params_for_hook = params_for_hook
+        ctx.pair_key = None
+        if ctx.needs_input_grad[0]:
+            _head_inputs[z_cl.data_ptr()] = (ctx, tuple(z_cl.shape))
         ctx.save_for_backward(z_cl, weight, bias)
         return logits
 
@@ -743,17 +803,22 @@ class HeadFn(torch.autograd.Function):
         w2 = weight.detach().reshape(K, C)
         if w2.dtype != torch.float32 or not w2.is_contiguous():
             w2 = w2.float().contiguous()
-        dz = torch.empty((B, D, H, W, C), dtype=BF16, device=dev) if ctx.needs_input_grad[0] else None
+        parked = _pair_pending.pop(ctx.pair_key, None) if ctx.pair_key is not None else None
+        acc_dz = parked is not None and ctx.needs_input_grad[0] and tuple(parked.shape) == (B, D, H, W, C) \
+            and cl_pitch_ok(parked)
+        if acc_dz:
+            dz = parked        # the up-convolution's share, already in autograd's hands: add ours in the kernel
+        else:
+            dz = torch.empty((B, D, H, W, C), dtype=BF16, device=dev) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1]:
-            dw = _grad_like(weight)
-            dw.zero_()
-            db = _grad_like(bias) if bias is not None else None
-            if db is not None:
-                db.zero_()
-        _timed_mem('head_bwd', 2.0 * B * D * H * W * (K + C + (C if dz is not None else 0)), lib.head_bwd,
-                   dl.data_ptr(), cl_pitch(dl), z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(dz),
-                   C if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, _stream())
+            dw = _grad_like(weight, zero=True)
+            db = _grad_like(bias, zero=True) if bias is not None else None
+        _timed_mem('head_bwd', 2.0 * B * D * H * W * (K + C + (C if dz is not None else 0) + (C if acc_dz else 0)),
+                   lib.head_bwd, dl.data_ptr(), cl_pitch(dl), z_cl.data_ptr(), cl_pitch(z_cl), w2.data_ptr(), _ptr(dz),
+                   cl_pitch(dz) if dz is not None else 0, _ptr(dw), _ptr(db), B * D * H * W, C, K, int(acc_dz), _stream())
+        if acc_dz:
+            dz = None          # reported through the parked tensor
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return dz, _ret(dw, weight), _ret(db, bias), None
@@ -969,29 +1034,37 @@ class KLFn(torch.autograd.Function):
 
 
 class SoftmaxChannelFn(torch.autograd.Function):
-    """softmax(logits, 1)[:, ch:ch+1] as fp32 [B,1,D,H,W] (the clDice term's prediction, MVDTrainer.py:904-908)."""
+    """softmax(logits, 1)[:, ch:ch+1] as fp32 [B,1,D,H,W] (the clDice term's prediction, MVDTrainer.py:904-908); with a
+    ``target`` also the one-hot ground-truth channel (target == ch) as fp32, from the same launch (:904-905)."""
 
     @staticmethod
-    def forward(ctx, logits, channel: int):
+    def forward(ctx, logits, channel: int, target=None):
         require_cuda(logits, 'softmax_channel')
         lg = to_cl_view(logits)
         B, D, H, W, C = lg.shape
         prob = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=lg.device)
-        lib.softmax_channel_fwd(lg.data_ptr(), cl_pitch(lg), None, B * D * H * W, C, channel, prob.data_ptr(), None,
-                                _stream())
+        onehot = tg = None
+        if target is not None:
+            tg = _target_f32(target)
+            onehot = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=lg.device)
+        lib.softmax_channel_fwd(lg.data_ptr(), cl_pitch(lg), _ptr(tg), B * D * H * W, C, channel, prob.data_ptr(),
+                                _ptr(onehot), _stream())
         ctx.channel = channel
         ctx.save_for_backward(lg)
-        return prob
+        if onehot is None:
+            return prob
+        ctx.mark_non_differentiable(onehot)
+        return prob, onehot
 
     @staticmethod
-    def backward(ctx, dprob):
+    def backward(ctx, dprob, *unused):
         (lg,) = ctx.saved_tensors
         B, D, H, W, C = lg.shape
         dprob = dprob.contiguous().float()
         dl = torch.empty(lg.shape, dtype=BF16, device=lg.device)
         lib.softmax_channel_bwd(lg.data_ptr(), cl_pitch(lg), dprob.data_ptr(), B * D * H * W, C, ctx.channel,
                                 dl.data_ptr(), C, _stream())
-        return ncdhw_view(dl), None
+        return ncdhw_view(dl), None, None
 
 
 def _vol_dims(t: torch.Tensor):
@@ -1140,7 +1213,7 @@ class SoftClDiceFn(torch.autograd.Function):
         need = ctx.needs_input_grad[1]
         sp, E, delta, skel = _skel_forward(y_pred, iters, need)
         stv, _, _, _ = _skel_forward(y_true, iters, False)
-        sums = torch.zeros((4,), dtype=torch.float64, device=dev)
+        sums = zeros((4,), torch.float64, dev)
         lib.dot_sum(sp.data_ptr(), y_true.data_ptr(), N, sums.data_ptr(), st)
         lib.dot_sum(stv.data_ptr(), y_pred.data_ptr(), N, sums[2:].data_ptr(), st)
         out4 = torch.empty((4,), dtype=torch.float32, device=dev)

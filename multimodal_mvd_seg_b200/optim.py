@@ -107,7 +107,8 @@ class SGDNesterovClip(torch.optim.Optimizer):
         stream = torch.cuda.current_stream().cuda_stream
         tabs = [self._group_tables(gi, g) for gi, g in enumerate(self.param_groups)]
         dev = self.param_groups[0]['params'][0].device
-        sq = torch.zeros((1,), dtype=torch.float64, device=dev)
+        from . import ops
+        sq = ops.zeros((1,), torch.float64, dev)      # from the per-step zero pool (no fill kernel)
         need_norm = self.max_norm is not None and self.max_norm > 0
         if need_norm:  # the norm is global over all groups, like clip_grad_norm_(network.parameters())
             for t in tabs:

@@ -297,6 +297,15 @@ class nnUNetTrainer(object):
         ops.set_grad_allocator(alloc)
         ops.clear_param_grad_ready_hooks()
         ops.add_param_grad_ready_hook(ready)
+        # gradients the kernels ACCUMULATE into (conv biases in front of InstanceNorm, head weights / biases) and those
+        # of a head that may receive no gradient at all (zero-weighted scale): cleared by one launch per arena at the
+        # top of every step instead of a fill per tensor
+        views = []
+        for net, a in zip(self._networks(), self._arenas):
+            acc_params = [m.bias for m in net.modules() if isinstance(m, nn.Conv3d) and m.bias is not None]
+            acc_params += [m.weight for m in net.decoder.seg_layers]
+            views += a.prezero(acc_params)
+        ops.set_prezeroed(views)
 
     @staticmethod
     def build_network_architecture(plans_manager, dataset_json, configuration_manager, num_input_channels,
@@ -733,8 +742,7 @@ class MVDTrainer(nnUNetTrainer):
             mutual = distill_kl(out1[0], out2[0], self.kl_T, upstream_grad=self.lambda1)
         l = l + self.lambda1 * mutual
         if self.topo is not None:
-            prob = softmax_channel(out1[0], c)
-            gt = (target[0] == c).float()
+            prob, gt = softmax_channel(out1[0], c, target[0])      # softmax channel c and (target == c), one launch
             l = l + self.lambda3 * self.topo(gt, prob)
         self.last_terms = dict(mutual=mutual.detach())
         return l, out1

@@ -390,10 +390,10 @@ def test_deep_supervision_two_networks_one_launch(m, batch_dice):
     l2 = mk(m)([m.ops.ncdhw_view(o) for o in outs2], tgts)
     assert abs(float(l1) + float(l2) - float(l)) <= 1e-6 * max(1.0, abs(float(l)))
     (l1 * 2.0).backward()
-    assert torch.equal(y1[0].grad, x1[0].grad)
+    assert rel_err(y1[0].grad.float(), x1[0].grad.float()) < 1e-3
     # repeated calls: the ticket counter is left at zero
     l_again = mk(m).forward_networks([x1, x2], tgts)
-    assert float(l_again) == float(l)
+    assert abs(float(l_again) - float(l)) <= 1e-6 * max(1.0, abs(float(l)))
 
 
 @pytest.mark.parametrize('T', [1.0, 2.0])
