@@ -78,7 +78,9 @@ typedef struct {
                                  accumulated (caller zeroes); InstanceNorm statistics, fprop only           */
   float* dw;                  /* wgrad out, fp32 in torch layout [Cout][Cin][kd][kh][kw]                    */
   float* dbias;               /* wgrad out, fp32 [Cout]; may be NULL                                        */
-  void* workspace; size_t workspace_bytes; /* scratch (wgrad split-K partials); see mvd_conv3d_workspace_bytes */
+  void* workspace; size_t workspace_bytes; /* scratch (wgrad partials; fprop / dgrad split-K partials of small layers:
+                                              optional there, without it the unsplit kernel runs); see
+                                              mvd_conv3d_workspace_bytes */
   int algo;                   /* 0 auto, 1 CUDA-core tiles, 2 tcgen05 implicit GEMM                          */
   int accumulate;             /* dgrad: add into the output instead of overwriting it                       */
 } mvd_conv3d_args;

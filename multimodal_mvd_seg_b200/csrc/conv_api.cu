@@ -22,6 +22,7 @@ extern "C" {
 size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass) {
   if (!a) return 0;
   if (pass == 2 && a->algo != 1 && tc_wgrad_supported(a)) return tc_wgrad_workspace_bytes(a);
+  if ((pass == 0 || pass == 1) && a->algo != 1 && a->x && a->y && a->w) return tc_splitk_workspace_bytes(a, pass);
   return 0;
 }
 

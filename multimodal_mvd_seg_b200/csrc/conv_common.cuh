@@ -15,6 +15,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);   // fp32 scratch [taps][Cin][Cout]
+size_t tc_splitk_workspace_bytes(const mvd_conv3d_args* a, int pass);   // fprop (0) / dgrad (1): split-K partials, 0 = not split
 int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch);   // validates + zeroes the workspace
 int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st);                   // scratch -> dw[co][ci][tap] (+ dbias)
 // sub-pixel data gradient of the stride-2 3x3x3 conv with 32 input channels (conv_tc_subpixel.cu)

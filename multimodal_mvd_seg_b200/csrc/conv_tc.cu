@@ -35,6 +35,8 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+static bool tc_splitk_wanted(const mvd_conv3d_args* a, int pass);
+
 namespace {
 
 using namespace tc;
@@ -85,6 +87,12 @@ struct TcParams {
   // n % scatter_c of the voxel displaced by par_off[n / scatter_c]
   int scatter_c;
   long long par_off[8];
+  // split-K (small produced lattices: 8^3 / 4^3 layers whose few tiles would leave most SMs idle while every tile
+  // re-streams the whole weight set): a work unit is (tile, slice s of the tap x channel-chunk loop); the epilogue adds
+  // its fp32 partial into `scratch` (same element offsets as `out`) with vector reductions, splitk_finish_kernel then
+  // applies bias / rounding / accumulate
+  int ksplit;
+  float* scratch;
   TcClass cls[kMaxClasses];
   TcTap taps[kMaxTaps];
 };
@@ -107,7 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int stage_bytes = A_BYTES + b_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = P.stages;
-  const int total_tiles = P.num_m_tiles * P.num_n_tiles;
+  const int ksplit = P.ksplit;
+  const int total_tiles = P.num_m_tiles * P.num_n_tiles * ksplit;   // work units: (tile, K slice)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -128,7 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = s_tmem_base;
 
   // tile -> (class, n0, b, d, h0, w0)
-  auto decode_tile = [&](int tile, int& c, int& n0, int& b, int& d, int& h0, int& w0) {
+  auto decode_tile = [&](int unit, int& c, int& n0, int& b, int& d, int& h0, int& w0) {
+    const int tile = unit / ksplit;
     const int nt = tile % P.num_n_tiles;
     int m = tile / P.num_n_tiles;
     n0 = nt * P.n_tile;
@@ -154,17 +164,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int c, n0, b, d, h0, w0;
         decode_tile(tile, c, n0, b, d, h0, w0);
-        const int t0 = P.cls[c].tap_begin, t1 = t0 + P.cls[c].ntaps;
-        for (int t = t0; t < t1; ++t) {
+        const int t0 = P.cls[c].tap_begin;
+        const int kit = P.cls[c].ntaps * P.kchunks, sl = tile % ksplit;
+        const int it0 = (int)((long long)kit * sl / ksplit), it1 = (int)((long long)kit * (sl + 1) / ksplit);
+        int t = t0 + it0 / P.kchunks, kc = it0 % P.kchunks;
+        for (int it = it0; it < it1; ++it) {
           const TcTap tap = P.taps[t];
-          for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(&bar_empty[stage], phase ^ 1, 1);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)stage_bytes);
-            tma_load_5d(&maps.a[tap.map], sa, &bar_full[stage], kc * KC, w0 + tap.dx, h0 + tap.dy, d + tap.dz, b);
-            tma_load_2d(&maps.b, sa + A_BYTES, &bar_full[stage], kc * KC, tap.wrow + n0);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(&bar_empty[stage], phase ^ 1, 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)stage_bytes);
+          tma_load_5d(&maps.a[tap.map], sa, &bar_full[stage], kc * KC, w0 + tap.dx, h0 + tap.dy, d + tap.dz, b);
+          tma_load_2d(&maps.b, sa + A_BYTES, &bar_full[stage], kc * KC, tap.wrow + n0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++kc == P.kchunks) { kc = 0; ++t; }
         }
       }
     }
@@ -180,10 +192,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t phase = 0, accphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int c = 0;
-        const int m = tile / num_n_tiles;
+        const int m = (tile / ksplit) / num_n_tiles;
         for (int i = 1; i < nclasses; ++i)
           if (m >= P.cls[i].tile_begin) c = i;
-        const int kiters = P.cls[c].ntaps * kchunks;
+        const int kit = P.cls[c].ntaps * kchunks, sl = tile % ksplit;
+        const int kiters = (int)((long long)kit * (sl + 1) / ksplit) - (int)((long long)kit * sl / ksplit);
         mbar_wait(&bar_tempty[acc], accphase ^ 1, 2);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_tile);
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
           return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
         };
-        const bool accum = P.accumulate != 0;
+        const bool accum = P.accumulate != 0 && ksplit == 1;
         bf16x8 old[4];
         bool has[4] = {false, false, false, false};
         if (accum && 32 * half < P.n_tile) {   // old values of the first chunk fly while the MMAs of this tile finish
@@ -257,6 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
           tmem_ld_wait();
+          if (ksplit > 1) {      // fp32 partial of this K slice: 8 vector reductions per row and 32-column chunk
+            if (ok) {
+              float* dst = P.scratch + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd +
+                           (long long)(h0 + (rr0 >> 3)) * sh + (long long)(w0 + (rr0 & 7)) * sw + n0 + cc;
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+            }
+            continue;
+          }
           const long long col_off = col_offset(cc);
           int n = n0 + cc;          // bias index: channel within the parity in scatter mode
           if (P.scatter_c) n -= (n / P.scatter_c) * P.scatter_c;
@@ -291,6 +313,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// split-K tail: out[v][n] = bf16(scratch[v][n] + bias[n]) (+ out[v][n] when accumulating), voxels dense with pitch ld
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ scratch, bf16* __restrict__ out,
+                                                            const float* __restrict__ bias, long long nvox, int N,
+                                                            int ld, int accumulate) {
+  const int CG = N >> 3;
+  const long long total = nvox * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / CG;
+    const int cg = (int)(i - v * CG);
+    const long long off = v * ld + cg * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(scratch + off), a1 = *reinterpret_cast<const float4*>(scratch + off + 4);
+    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += round_bf(__ldg(bias + cg * 8 + j));
+    }
+    bf16x8 r = pack8(f);
+    if (accumulate) {      // same two roundings as the in-kernel accumulate path: bf16(new), then bf16(new + old)
+      float n[8], o[8];
+      unpack8(r, n);
+      unpack8(ldg16(out + off), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) n[j] += o[j];
+      r = pack8(n);
+    }
+    stg16(out + off, r);
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -345,8 +396,34 @@ bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn,
   return true;
 }
 
-int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* who) {
+// produced lattices this small go through the split-K form when the caller supplies a workspace (conv3d_workspace_bytes)
+constexpr long long kSplitKMaxVoxels = 4096;
+
+struct SplitK {
+  float* scratch = nullptr;     // caller's workspace, >= nvox * ld floats
+  long long nvox = 0;           // voxels of the produced lattice (all samples)
+  int ld = 0, N = 0;            // pitch / channels of the produced tensor
+};
+
+int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* who, const SplitK* sk = nullptr) {
   if (P.nbias > kMaxBias) { set_error("%s: more than %d produced channels", who, kMaxBias); return MVD_ERR_UNSUPPORTED; }
+  P.ksplit = 1;
+  P.scratch = nullptr;
+  if (sk && sk->scratch && !P.scatter_c && !P.stats && sk->nvox <= kSplitKMaxVoxels) {
+    const int tiles = P.num_m_tiles * P.num_n_tiles;
+    int min_kit = 1 << 30;
+    for (int c = 0; c < P.nclasses; ++c) min_kit = P.cls[c].ntaps * P.kchunks < min_kit ? P.cls[c].ntaps * P.kchunks : min_kit;
+    int S = num_sms() / (tiles > 0 ? tiles : 1);
+    if (S > min_kit / 2) S = min_kit / 2;      // at least two pipeline stages of work per unit
+    if (S > 1) {
+      P.ksplit = S;
+      P.scratch = sk->scratch;
+      MVD_CUDA(cudaMemsetAsync(sk->scratch, 0, (size_t)sk->nvox * sk->ld * sizeof(float), st));
+    }
+  }
+  float* const bias_keep = const_cast<float*>(P.bias);
+  const int acc_keep = P.accumulate;
+  if (P.ksplit > 1) P.stats = nullptr;        // statistics of a split layer: the caller's streaming pass
   const int a_bytes = 128 * kc * 2, b_bytes = P.n_tile * kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
   int stages = (192 * 1024) / stage_bytes;   // + 21 KB of static shared memory (epilogue stages, bias)
@@ -371,12 +448,18 @@ int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* wh
     }
     attr_done[ki] = true;
   }
-  const int total = P.num_m_tiles * P.num_n_tiles;
+  const int total = P.num_m_tiles * P.num_n_tiles * P.ksplit;
   int grid = num_sms();
   if (grid > total) grid = total;
   if (kc == 64) conv_tc_kernel<64><<<grid, kThreads, smem, st>>>(maps, P);
   else conv_tc_kernel<32><<<grid, kThreads, smem, st>>>(maps, P);
   MVD_LAUNCH_CHECK(who);
+  if (P.ksplit > 1) {
+    const long long vecs = sk->nvox * (sk->N / 8);
+    splitk_finish_kernel<<<grid_for(vecs, 256, num_sms() * 4), 256, 0, st>>>(sk->scratch, P.out, bias_keep, sk->nvox, sk->N,
+                                                                            sk->ld, acc_keep);
+    MVD_LAUNCH_CHECK(who);
+  }
   return MVD_OK;
 }
 
@@ -401,6 +484,33 @@ bool add_class(TcParams& P, int Dt, int Ht, int Wt, int tap_begin, int ntaps, lo
 // fprop: produced = y (conv output lattice), gathered = x.  Input coordinate o*s - p + t = s*(o + q) + r with
 // r = (t - p) mod s, q = floor((t - p)/s): tap -> (parity map r, shift q).
 // ---------------------------------------------------------------------------------------------------------------
+// split-K is taken when the produced lattice is small, the reduction is long enough to slice, no statistics are fused
+// into the epilogue (Cout 32 / 64) and the caller handed over the workspace mvd_conv3d_workspace_bytes asked for
+static size_t splitk_bytes(const mvd_conv3d_args* a, int pass) {
+  const long long nvox = pass == 0 ? (long long)a->B * a->Do * a->Ho * a->Wo : (long long)a->B * a->Di * a->Hi * a->Wi;
+  const int ld = pass == 0 ? a->ldy : a->ldx, K = pass == 0 ? a->Cin : a->Cout, N = pass == 0 ? a->Cout : a->Cin;
+  const int taps = a->kd * a->kh * a->kw;
+  const bool scatter = pass == 1 && a->kd == a->sd && a->kh == a->sh && a->kw == a->sw && a->pd == 0 && a->ph == 0 && a->pw == 0;
+  if (nvox > kSplitKMaxVoxels || (long long)taps * K < 1024 || scatter || N % 8) return 0;
+  if (pass == 0 && a->stats && (a->Cout == 32 || a->Cout == 64)) return 0;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MVD_NO_SPLITK");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  return enabled ? (size_t)nvox * ld * sizeof(float) : 0;
+}
+size_t tc_splitk_workspace_bytes(const mvd_conv3d_args* a, int pass) {
+  if (pass == 0 ? !tc_fprop_supported(a) : !tc_dgrad_supported(a)) return 0;
+  if (pass == 1 && tc_subpixel_dgrad_supported(a)) return 0;
+  if (pass == 0 && tc_halo_s2_fprop_supported(a)) return 0;
+  return splitk_bytes(a, pass);
+}
+static bool tc_splitk_wanted(const mvd_conv3d_args* a, int pass) {
+  const size_t need = splitk_bytes(a, pass);
+  return need > 0 && a->workspace && a->workspace_bytes >= need && (((uintptr_t)a->workspace) & 15) == 0;
+}
+
 bool tc_fprop_supported(const mvd_conv3d_args* a) {
   const int taps = a->kd * a->kh * a->kw;
   if (!tc_shape_ok(a->Cin, a->Cout, a->ldx, a->ldy, a->x, a->y, a->w, taps)) return false;
@@ -419,11 +529,11 @@ static bool is_k3s1p1(const mvd_conv3d_args* a) {
 }
 
 int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
-  if (a->accumulate && ((is_k3s1p1(a) && tc_halo_enabled()) || tc_halo_s2_fprop_supported(a))) {
+  if (a->accumulate && ((is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 0)) || tc_halo_s2_fprop_supported(a))) {
     set_error("conv3d_fprop(tcgen05): accumulate is built for the tap-by-tap kernel (up-convolution adjoints) only");
     return MVD_ERR_UNSUPPORTED;
   }
-  if (is_k3s1p1(a) && tc_halo_enabled()) {
+  if (is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 0)) {
     int wrow[27];
     for (int i = 0; i < 27; ++i) wrow[i] = i * a->Cout;
     return tc_halo_conv((const bf16*)a->x, a->ldx, a->Cin, (bf16*)a->y, a->ldy, a->Cout, (const bf16*)a->w, wrow,
@@ -481,7 +591,10 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
     set_error("conv3d_fprop(tcgen05): fused InstanceNorm sums need Cout = 32 or 64");
     return MVD_ERR_UNSUPPORTED;
   }
-  return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)");
+  SplitK sk;
+  sk.scratch = tc_splitk_wanted(a, 0) ? (float*)a->workspace : nullptr;
+  sk.nvox = (long long)a->B * a->Do * a->Ho * a->Wo; sk.ld = a->ldy; sk.N = a->Cout;
+  return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)", &sk);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -502,7 +615,7 @@ bool tc_dgrad_supported(const mvd_conv3d_args* a) {
 
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (tc_subpixel_dgrad_supported(a)) return tc_subpixel_dgrad(a, st);
-  if (is_k3s1p1(a) && tc_halo_enabled()) {
+  if (is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 1)) {
     int wrow[27];   // produced voxel i gathers y[i + 1 - t]: halo offset o = 2 - t per axis, i.e. tap 26 - idx
     for (int i = 0; i < 27; ++i) wrow[i] = (26 - i) * a->Cin;
     return tc_halo_conv((const bf16*)a->y, a->ldy, a->Cout, (bf16*)a->x, a->ldx, a->Cin, (const bf16*)a->w, wrow,
@@ -588,7 +701,10 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
                   ((long long)rd * a->Hi * a->Wi + (long long)rh * a->Wi + rw) * ldx);
       }
   if (P.nclasses == 0) return MVD_OK;
-  return launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)");
+  SplitK sk;
+  sk.scratch = tc_splitk_wanted(a, 1) ? (float*)a->workspace : nullptr;
+  sk.nvox = (long long)a->B * a->Di * a->Hi * a->Wi; sk.ld = a->ldx; sk.N = a->Cin;
+  return launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)", &sk);
 }
 
 }  // namespace mvd

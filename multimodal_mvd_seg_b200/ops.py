@@ -360,14 +360,28 @@ def _timed_mem(name: str, nbytes: float, fn, *a):
     return r
 
 
-def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None):
-    a = _conv_args(geom, x_cl, y_cl, w_packed=wf, bias=bias, stats=stats)
+def _maybe_workspace(a: ConvArgs, which: int, dev):
+    """fprop / dgrad of layers with a small produced lattice run split-K when given scratch for the fp32 partials."""
+    nbytes = lib.conv3d_workspace_bytes(ctypes.byref(a), which)
+    if not nbytes:
+        return None
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    return ws
+
+
+def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None, accumulate=False):
+    a = _conv_args(geom, x_cl, y_cl, w_packed=wf, bias=bias, stats=stats, accumulate=accumulate)
+    ws = _maybe_workspace(a, 0, x_cl.device)
     _timed('fprop', a, lib.conv3d_fprop)
+    del ws
 
 
 def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False):
     a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd, bias=bias, accumulate=accumulate)
+    ws = _maybe_workspace(a, 1, y_cl.device)
     _timed('dgrad', a, lib.conv3d_dgrad)
+    del ws
 
 
 def conv_wgrad(geom, x_cl, y_cl, dw, dbias=None):
