@@ -245,6 +245,16 @@ int mvd_skel_update(const float* Ej, const float* Ej1, const float* skel_in, flo
  * Bit-identical to mvd_soft_erode + mvd_skel_update level by level.  (soft_skeleton.py:29-37) */
 int mvd_soft_skel_fused(const float* E_in, const float* skel_in, int n_levels, float* const* E_next,
                         float* const* delta, float* const* skel, int B, int D, int H, int W, mvd_stream_t stream);
+/* Fused backward of n_levels (1..2) consecutive soft_skel levels a .. a+n-1 with all scatter-adds in shared memory (no
+ * global atomics) and delta recomputed from the E volumes:
+ *   E[0..n]        : E_a ... E_{a+n} (E_0 = the input of soft_skel, E_{j+1} = erode(E_j): what mvd_soft_skel_fused stores)
+ *   skel_prev[l]   : skeleton after level a+l-1; skel_prev[0] == NULL and first_is_level0 != 0 when a == 0
+ *   G_in           : d loss / d skeleton entering level a+n-1 (the upstream gradient for the topmost launch)
+ *   gE_top_in      : partial gradient of E_{a+n} written by the launch above (NULL for the topmost launch)
+ *   gE_out, G_out  : gradient of E_a (the final input gradient when a == 0) and the chain state for the launch below */
+int mvd_soft_skel_bwd_fused(const float* const* E, const float* const* skel_prev, int n_levels, int first_is_level0,
+                            const float* G_in, const float* gE_top_in, float* gE_out, float* G_out, int B, int D, int H,
+                            int W, mvd_stream_t stream);
 int mvd_skel_chain_bwd(const float* delta, const float* skel, const float* g_skel, float* g_delta, int L,
                        long long N, mvd_stream_t stream);
 /* gE_j += g_delta_j * [delta_j > 0];  gE_j1 (via dilate backward) -= same   (one level) */

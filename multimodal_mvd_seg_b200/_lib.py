@@ -95,6 +95,7 @@ _SIGNATURES = {
     'mvd_soft_dilate_bwd': (c_int, [P, P, F, P, I, I, I, I, S]),
     'mvd_skel_update': (c_int, [P, P, P, P, P, I, I, I, I, I, S]),
     'mvd_soft_skel_fused': (c_int, [P, P, I, P, P, P, I, I, I, I, S]),
+    'mvd_soft_skel_bwd_fused': (c_int, [P, P, I, I, P, P, P, P, I, I, I, I, S]),
     'mvd_skel_chain_bwd': (c_int, [P, P, P, P, I, LL, S]),
     'mvd_skel_level_bwd': (c_int, [P, P, P, P, P, I, I, I, I, S]),
     'mvd_dot_sum': (c_int, [P, P, LL, P, S]),

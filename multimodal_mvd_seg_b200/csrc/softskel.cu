@@ -340,6 +340,175 @@ __global__ void __launch_bounds__(kSkelThreads) skel_fused_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused BACKWARD: up to kSkelBwdLevels consecutive soft_skel levels j = a+n-1 ... a per launch, all scatter-adds in
+// SHARED memory (no global atomics, no per-level volume passes), delta_j recomputed from the E volumes (no delta stack).
+//
+// Per level j the backward of   delta_j = relu(E_j - dilate(E_{j+1})),   E_{j+1} = erode(E_j),
+//                               skel_j = skel_{j-1} + relu(delta_j - skel_{j-1} * delta_j)      (soft_skeleton.py:29-37)
+// is  (chain)   m = delta_j - skel_{j-1}*delta_j > 0;  g_delta = m ? G (1 - skel_{j-1}) : 0;  G <- m ? G (1 - delta_j) : G
+//               (j = 0: g_delta = G),   gd = delta_j > 0 ? g_delta : 0
+//     (A)       gE_j[v] += gd;   gE_{j+1}[argmax27 E_{j+1} around v] -= gd        (first maximum in scan order)
+//     (B)       gE_j[first minima of the three axis windows of E_j around w] += gE_{j+1}[w] * (1, .5/.5 on ties)
+// A CTA owns a 32 x 16 x 8 tile.  For the tile's gE_a to be complete, gE_{a+l} must be complete on the tile grown by l
+// voxels, gd_{a+l} is needed on the tile grown by l + 2 and the chain state G on the tile grown by n + 1: three gradient
+// boxes (G, gE upper, gE lower) with halo n + 1 plus one E box with halo n + 2 live in shared memory; the E box is
+// refilled per phase (E_{j+1} for A, E_j for B).  Between launches only G and the upper gE travel through HBM.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSkelBwdLevels = 2, kBwdTX = 32, kBwdTY = 16, kBwdTZ = 8, kBwdThreads = 512;
+
+struct SkelBwdPass {
+  const float* E[kSkelBwdLevels + 1];        // E_a ... E_{a+n}
+  const float* skel_prev[kSkelBwdLevels];    // skeleton after level a+l-1 (l = 0..n-1); [0] is NULL when a == 0
+  const float* G_in;                         // d/d skel entering level a+n-1
+  const float* gE_top_in;                    // partial gE_{a+n} from the launch above, NULL = zero
+  float* gE_out;                             // gE_a (final gradient of the input when a == 0)
+  float* G_out;                              // chain state below level a (NULL when a == 0)
+  int n, first_is_level0;
+  Vol s;
+  int tiles_x, tiles_y, tiles_z;
+};
+
+struct Box {   // a halo'd box around the tile: cell (x, y, z) in tile coordinates -halo .. T+halo-1
+  int halo, nx, ny, nz;
+  __device__ __forceinline__ int idx(int x, int y, int z) const { return ((z + halo) * ny + (y + halo)) * nx + (x + halo); }
+  __device__ __forceinline__ int cells() const { return nx * ny * nz; }
+};
+
+__global__ void __launch_bounds__(kBwdThreads) skel_bwd_fused_kernel(const __grid_constant__ SkelBwdPass P) {
+  extern __shared__ float sb_smem[];
+  const int n = P.n, R = n + 1;
+  Box gb{R, kBwdTX + 2 * R, kBwdTY + 2 * R, kBwdTZ + 2 * R};
+  Box eb{R + 1, kBwdTX + 2 * R + 2, kBwdTY + 2 * R + 2, kBwdTZ + 2 * R + 2};
+  float* G = sb_smem;
+  float* gUp = G + gb.cells();
+  float* gLo = gUp + gb.cells();
+  float* Eb = gLo + gb.cells();
+  const float INF = __int_as_float(0x7f800000);
+  int t = blockIdx.x;
+  const int tx = t % P.tiles_x; t /= P.tiles_x;
+  const int ty = t % P.tiles_y; t /= P.tiles_y;
+  const int tz = t % P.tiles_z;
+  const int b = t / P.tiles_z;
+  const int x0 = tx * kBwdTX, y0 = ty * kBwdTY, z0 = tz * kBwdTZ;
+  const int W = P.s.W, H = P.s.H, D = P.s.D;
+  const long long vol = (long long)D * H * W;
+  const long long boff = (long long)b * vol;
+  auto inside = [&](int x, int y, int z) { return x0 + x >= 0 && x0 + x < W && y0 + y >= 0 && y0 + y < H && z0 + z >= 0 && z0 + z < D; };
+  auto gidx = [&](int x, int y, int z) { return boff + ((long long)(z0 + z) * H + (y0 + y)) * W + (x0 + x); };
+  // fill a box region (tile grown by `h`) from a global volume, `oob` outside the volume (src == nullptr: all `oob`)
+  auto load_box = [&](float* dst, const Box& bx, const float* src, int h, float oob) {
+    const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
+    for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
+      const int x = c % ex - h, r = c / ex;
+      const int y = r % ey - h, z = r / ey - h;
+      dst[bx.idx(x, y, z)] = (src && inside(x, y, z)) ? __ldg(src + gidx(x, y, z)) : oob;
+    }
+  };
+  load_box(G, gb, P.G_in, R, 0.f);
+  load_box(gUp, gb, P.gE_top_in, R, 0.f);
+  load_box(gLo, gb, nullptr, R, 0.f);
+  for (int l = n - 1; l >= 0; --l) {
+    const bool level0 = (l == 0) && P.first_is_level0;
+    // ---------------- phase A: chain, pointwise part, dilate routing (E box = E_{j+1} on the tile grown by l + 3)
+    __syncthreads();
+    load_box(Eb, eb, P.E[l + 1], l + 3, INF);
+    __syncthreads();
+    {
+      const int h = l + 2;
+      const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
+      const float* Ej = P.E[l];
+      const float* skp = P.skel_prev[l];
+      for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
+        const int x = c % ex - h, r = c / ex;
+        const int y = r % ey - h, z = r / ey - h;
+        if (!inside(x, y, z)) continue;
+        // opened = max27(E_{j+1}) with the FIRST maximum in (z, y, x) scan order; out-of-volume cells hold +inf: skipped
+        float best = 0.f;
+        int bo = -1;
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int o = eb.idx(x + dx, y + dy, z + dz);
+              const float v = Eb[o];
+              if (v != INF && (bo < 0 || v > best)) { best = v; bo = ((dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1); }
+            }
+        const long long g = gidx(x, y, z);
+        const float delta = fmaxf(__ldg(Ej + g) - best, 0.f);
+        const int gi = gb.idx(x, y, z);
+        float Gv = G[gi], gdel;
+        if (level0) {
+          gdel = Gv;
+        } else {
+          const float sk = __ldg(skp + g);
+          const bool m = __fsub_rn(delta, __fmul_rn(sk, delta)) > 0.f;
+          gdel = m ? Gv * (1.f - sk) : 0.f;
+          if (m) G[gi] = Gv * (1.f - delta);
+        }
+        if (!(delta > 0.f) || gdel == 0.f) continue;
+        if (x >= -l && x < kBwdTX + l && y >= -l && y < kBwdTY + l && z >= -l && z < kBwdTZ + l) atomicAdd(&gLo[gi], gdel);
+        const int dz = bo / 9 - 1, dy = (bo / 3) % 3 - 1, dx = bo % 3 - 1;
+        const int ux = x + dx, uy = y + dy, uz = z + dz;
+        if (ux >= -(l + 1) && ux < kBwdTX + l + 1 && uy >= -(l + 1) && uy < kBwdTY + l + 1 && uz >= -(l + 1) && uz < kBwdTZ + l + 1)
+          atomicAdd(&gUp[gb.idx(ux, uy, uz)], -gdel);
+      }
+    }
+    // ---------------- phase B: erosion routing gE_{j+1} -> gE_j (E box = E_j on the tile grown by l + 2)
+    __syncthreads();
+    load_box(Eb, eb, P.E[l], l + 2, INF);
+    __syncthreads();
+    {
+      const int h = l + 1;
+      const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
+      for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
+        const int x = c % ex - h, r = c / ex;
+        const int y = r % ey - h, z = r / ey - h;
+        const float g = gUp[gb.idx(x, y, z)];
+        if (g == 0.f || !inside(x, y, z)) continue;
+        // first minimum of each axis window (out-of-volume taps hold +inf and can never win: the centre is finite)
+        auto min3 = [&](int sx, int sy, int sz, int& off) {
+          float best = Eb[eb.idx(x - sx, y - sy, z - sz)];
+          off = -1;
+          const float c0 = Eb[eb.idx(x, y, z)], c1 = Eb[eb.idx(x + sx, y + sy, z + sz)];
+          if (c0 < best) { best = c0; off = 0; }
+          if (c1 < best) { best = c1; off = 1; }
+          return best;
+        };
+        int o1, o2, o3;
+        const float p1 = min3(0, 0, 1, o1), p2 = min3(0, 1, 0, o2), p3 = min3(1, 0, 0, o3);
+        const float m12 = fminf(p1, p2);
+        const float w12 = (m12 < p3) ? 1.f : ((m12 == p3) ? 0.5f : 0.f);
+        const float w3 = 1.f - w12;
+        const float w1 = w12 * ((p1 < p2) ? 1.f : ((p1 == p2) ? 0.5f : 0.f));
+        const float w2 = w12 - w1;
+        auto put = [&](int ux, int uy, int uz, float v) {
+          if (v != 0.f && ux >= -l && ux < kBwdTX + l && uy >= -l && uy < kBwdTY + l && uz >= -l && uz < kBwdTZ + l)
+            atomicAdd(&gLo[gb.idx(ux, uy, uz)], v);
+        };
+        put(x, y, z + o1, g * w1);
+        put(x, y + o2, z, g * w2);
+        put(x + o3, y, z, g * w3);
+      }
+    }
+    __syncthreads();
+    // gE_j becomes the upper gradient of the next level; the other box is cleared for gE_{j-1}
+    float* tmp = gUp; gUp = gLo; gLo = tmp;
+    if (l > 0) load_box(gLo, gb, nullptr, R, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kBwdTX * kBwdTY * kBwdTZ; c += kBwdThreads) {
+    const int x = c % kBwdTX, r = c / kBwdTX;
+    const int y = r % kBwdTY, z = r / kBwdTY;
+    if (!inside(x, y, z)) continue;
+    const long long g = gidx(x, y, z);
+    P.gE_out[g] = gUp[gb.idx(x, y, z)];
+    if (P.G_out) P.G_out[g] = G[gb.idx(x, y, z)];
+  }
+}
+
 static int vol_grid(long long N) { return grid_for(N, 256 * 2, num_sms() * 16); }
 
 }  // namespace mvd
@@ -436,6 +605,44 @@ int mvd_soft_skel_fused(const float* E_in, const float* skel_in, int n_levels, f
   }
   skel_fused_kernel<<<(unsigned)tiles, kSkelThreads, smem, (cudaStream_t)stream>>>(P);
   MVD_LAUNCH_CHECK("soft_skel_fused");
+  return MVD_OK;
+}
+
+int mvd_soft_skel_bwd_fused(const float* const* E, const float* const* skel_prev, int n_levels, int first_is_level0,
+                            const float* G_in, const float* gE_top_in, float* gE_out, float* G_out, int B, int D, int H,
+                            int W, mvd_stream_t stream) {
+  MVD_REQUIRE(E && skel_prev && G_in && gE_out && n_levels >= 1 && n_levels <= kSkelBwdLevels,
+              "soft_skel_bwd_fused: 1..%d levels per launch", kSkelBwdLevels);
+  VOL_CHECK("soft_skel_bwd_fused");
+  MVD_REQUIRE(first_is_level0 || G_out, "soft_skel_bwd_fused: G_out is required unless the launch ends at level 0");
+  SkelBwdPass P;
+  memset(&P, 0, sizeof(P));
+  for (int l = 0; l <= n_levels; ++l) {
+    MVD_REQUIRE(E[l] != nullptr, "soft_skel_bwd_fused: missing E volume %d", l);
+    P.E[l] = E[l];
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    MVD_REQUIRE(skel_prev[l] != nullptr || (l == 0 && first_is_level0), "soft_skel_bwd_fused: missing skeleton %d", l);
+    P.skel_prev[l] = skel_prev[l];
+  }
+  P.G_in = G_in; P.gE_top_in = gE_top_in; P.gE_out = gE_out; P.G_out = first_is_level0 ? nullptr : G_out;
+  P.n = n_levels; P.first_is_level0 = first_is_level0 ? 1 : 0;
+  P.s = Vol{B, D, H, W};
+  P.tiles_x = (W + kBwdTX - 1) / kBwdTX; P.tiles_y = (H + kBwdTY - 1) / kBwdTY; P.tiles_z = (D + kBwdTZ - 1) / kBwdTZ;
+  const long long tiles = (long long)B * P.tiles_x * P.tiles_y * P.tiles_z;
+  MVD_REQUIRE(tiles < (1LL << 31), "soft_skel_bwd_fused: too many tiles");
+  const int R = n_levels + 1;
+  const size_t gcells = (size_t)(kBwdTX + 2 * R) * (kBwdTY + 2 * R) * (kBwdTZ + 2 * R);
+  const size_t ecells = (size_t)(kBwdTX + 2 * R + 2) * (kBwdTY + 2 * R + 2) * (kBwdTZ + 2 * R + 2);
+  const size_t smem = (3 * gcells + ecells) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MVD_CUDA(cudaFuncSetAttribute(skel_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_done = true;
+  }
+  MVD_REQUIRE(smem <= 210 * 1024, "soft_skel_bwd_fused: boxes do not fit shared memory");
+  skel_bwd_fused_kernel<<<(unsigned)tiles, kBwdThreads, smem, (cudaStream_t)stream>>>(P);
+  MVD_LAUNCH_CHECK("soft_skel_bwd_fused");
   return MVD_OK;
 }
 

@@ -1134,7 +1134,8 @@ _SKEL_LEVELS_PER_PASS = 4   # levels kept on chip per launch (csrc/softskel.cu: 
 
 def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
     """runs soft_skel's iters + 1 levels with the fused on-chip kernel (<= 4 levels per launch); returns
-    (skel, E stack [L+1], delta stack [L], skel stack [L]) -- the stacks (what the backward needs) only if ``keep``."""
+    (skel, E stack [L] = E_1..E_L, skel stack [L]) -- the stacks (what the backward needs; E_0 is the input itself and
+    the deltas are recomputed there) only if ``keep``."""
     dims = _vol_dims(img)
     N = img.numel()
     L = iters + 1
@@ -1142,16 +1143,14 @@ def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
     dev = img.device
     flat = img.reshape(-1)
     if keep:
-        E = torch.empty((L + 1, N), dtype=torch.float32, device=dev)
-        E[0].copy_(flat)
-        delta = torch.empty((L, N), dtype=torch.float32, device=dev)
+        E = torch.empty((L, N), dtype=torch.float32, device=dev)
         skel = torch.empty((L, N), dtype=torch.float32, device=dev)
     else:
-        E = delta = skel = None
+        E = skel = None
         tmpE = [torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(2 if L > _SKEL_LEVELS_PER_PASS else 0)]
         tmpS = [torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(2 if L > _SKEL_LEVELS_PER_PASS else 1)]
     PtrArr = ctypes.c_void_p * _SKEL_LEVELS_PER_PASS
-    e_in, s_in, last = (E[0] if keep else flat), None, None
+    e_in, s_in, last = flat, None, None
     for pi, j0 in enumerate(range(0, L, _SKEL_LEVELS_PER_PASS)):
         n = min(_SKEL_LEVELS_PER_PASS, L - j0)
         more = j0 + n < L
@@ -1159,7 +1158,7 @@ def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
         e_out = None
         for l in range(n):
             if keep:
-                en[l], dl[l], sk[l] = E[j0 + l + 1].data_ptr(), delta[j0 + l].data_ptr(), skel[j0 + l].data_ptr()
+                en[l], sk[l] = E[j0 + l].data_ptr(), skel[j0 + l].data_ptr()
             elif l == n - 1:
                 last = tmpS[pi % len(tmpS)]
                 sk[l] = last.data_ptr()
@@ -1168,27 +1167,40 @@ def _skel_forward(img: torch.Tensor, iters: int, keep: bool):
                     en[l] = e_out.data_ptr()
         lib.soft_skel_fused(e_in.data_ptr(), _ptr(s_in), n, en, dl, sk, *dims, st)
         if keep:
-            e_in, s_in = E[j0 + n], skel[j0 + n - 1]
+            e_in, s_in = E[j0 + n - 1], skel[j0 + n - 1]
         else:
             e_in, s_in = e_out, last
     out = skel[L - 1] if keep else last
-    return out.view(img.shape), E, delta, skel
+    return out.view(img.shape), E, skel
 
 
-def _skel_backward(g_skel: torch.Tensor, E, delta, skel, dims):
-    """gradient of soft_skel w.r.t. its input, given d/d(skel)."""
-    L, N = delta.shape
+_SKEL_BWD_LEVELS = 2     # levels per backward launch (csrc/softskel.cu: kSkelBwdLevels)
+
+
+def _skel_backward(g_skel: torch.Tensor, img_flat: torch.Tensor, E, skel, dims):
+    """gradient of soft_skel w.r.t. its input, given d/d(skel): fused launches of <= 2 levels from the deepest level
+    down, scatter-adds in shared memory; between launches only the chain state G and the partial gradient of the
+    topmost E volume of the next launch travel through HBM."""
+    L, N = E.shape
     st = _stream()
     dev = g_skel.device
-    g_delta = torch.empty((L, N), dtype=torch.float32, device=dev)
-    lib.skel_chain_bwd(delta.data_ptr(), skel.data_ptr(), g_skel.data_ptr(), g_delta.data_ptr(), L, N, st)
-    gE = torch.zeros((L + 1, N), dtype=torch.float32, device=dev)
-    for j in range(L):
-        lib.skel_level_bwd(E[j + 1].data_ptr(), delta[j].data_ptr(), g_delta[j].data_ptr(), gE[j].data_ptr(),
-                           gE[j + 1].data_ptr(), *dims, st)
-    for lvl in range(L, 0, -1):
-        lib.soft_erode_bwd(E[lvl - 1].data_ptr(), gE[lvl].data_ptr(), gE[lvl - 1].data_ptr(), *dims, st)
-    return gE[0]
+    Ev = [img_flat] + [E[j] for j in range(L)]          # E_0 .. E_L
+    PtrE = ctypes.c_void_p * (_SKEL_BWD_LEVELS + 1)
+    PtrS = ctypes.c_void_p * _SKEL_BWD_LEVELS
+    G, g_top, hi = g_skel, None, L
+    while hi > 0:
+        n = min(_SKEL_BWD_LEVELS, hi)
+        a = hi - n
+        pe, ps = PtrE(), PtrS()
+        for l in range(n + 1):
+            pe[l] = Ev[a + l].data_ptr()
+        for l in range(n):
+            ps[l] = skel[a + l - 1].data_ptr() if a + l >= 1 else None
+        g_out = torch.empty((N,), dtype=torch.float32, device=dev)
+        G_out = torch.empty((N,), dtype=torch.float32, device=dev) if a > 0 else None
+        lib.soft_skel_bwd_fused(pe, ps, n, int(a == 0), G.data_ptr(), _ptr(g_top), g_out.data_ptr(), _ptr(G_out), *dims, st)
+        G, g_top, hi = G_out, g_out, a
+    return g_top
 
 
 class SoftSkelFn(torch.autograd.Function):
@@ -1199,17 +1211,17 @@ class SoftSkelFn(torch.autograd.Function):
         require_cuda(img, 'soft_skel')
         img = _f32c(img)
         need = ctx.needs_input_grad[0]
-        sk, E, delta, skel = _skel_forward(img, iters, need)
+        sk, E, skel = _skel_forward(img, iters, need)
         ctx.dims, ctx.shape = _vol_dims(img), img.shape
         if need:
-            ctx.save_for_backward(E, delta, skel)
+            ctx.save_for_backward(img, E, skel)
         return sk.clone() if need else sk
 
     @staticmethod
     def backward(ctx, g):
-        E, delta, skel = ctx.saved_tensors
+        img, E, skel = ctx.saved_tensors
         g = _f32c(g).reshape(-1)
-        return _skel_backward(g, E, delta, skel, ctx.dims).view(ctx.shape), None
+        return _skel_backward(g, img.reshape(-1), E, skel, ctx.dims).view(ctx.shape), None
 
 
 class SoftClDiceFn(torch.autograd.Function):
@@ -1225,8 +1237,8 @@ class SoftClDiceFn(torch.autograd.Function):
         st = _stream()
         N = y_pred.numel()
         need = ctx.needs_input_grad[1]
-        sp, E, delta, skel = _skel_forward(y_pred, iters, need)
-        stv, _, _, _ = _skel_forward(y_true, iters, False)
+        sp, E, skel = _skel_forward(y_pred, iters, need)
+        stv, _, _ = _skel_forward(y_true, iters, False)
         sums = zeros((4,), torch.float64, dev)
         lib.dot_sum(sp.data_ptr(), y_true.data_ptr(), N, sums.data_ptr(), st)
         lib.dot_sum(stv.data_ptr(), y_pred.data_ptr(), N, sums[2:].data_ptr(), st)
@@ -1234,18 +1246,18 @@ class SoftClDiceFn(torch.autograd.Function):
         lib.cldice_finalize(sums.data_ptr(), float(smooth), out4.data_ptr(), st)
         ctx.dims, ctx.shape = _vol_dims(y_pred), y_pred.shape
         if need:
-            ctx.save_for_backward(E, delta, skel, y_true, stv.reshape(-1).clone(), out4)
-        return out4[0].clone()
+            ctx.save_for_backward(y_pred, E, skel, y_true, stv.reshape(-1), out4)
+        return out4[0]
 
     @staticmethod
     def backward(ctx, gout):
-        E, delta, skel, y_true, stv, out4 = ctx.saved_tensors
+        y_pred, E, skel, y_true, stv, out4 = ctx.saved_tensors
         st = _stream()
         N = y_true.numel()
         gout = gout.contiguous().float()
         g_skel = torch.empty((N,), dtype=torch.float32, device=y_true.device)
         lib.cldice_seed(y_true.data_ptr(), out4.data_ptr(), gout.data_ptr(), g_skel.data_ptr(), N, st)
-        gE0 = _skel_backward(g_skel, E, delta, skel, ctx.dims)
+        gE0 = _skel_backward(g_skel, y_pred.reshape(-1), E, skel, ctx.dims)
         dp = torch.empty((N,), dtype=torch.float32, device=y_true.device)
         lib.cldice_combine(gE0.data_ptr(), stv.data_ptr(), out4.data_ptr(), gout.data_ptr(), dp.data_ptr(), N, st)
         return None, dp.view(ctx.shape), None, None

@@ -491,23 +491,55 @@ def test_soft_skel_golden(m, golden_skel, vol, it):
 @pytest.mark.parametrize('shape,it', [((2, 37, 21, 45), 3), ((1, 9, 40, 70), 10), ((1, 3, 5, 4), 6)])
 def test_soft_skel_fused_equals_level_by_level(m, shape, it):
     """the on-chip multi-level kernel (<= 4 levels per launch, tiles with halos, volume borders) against the
-    level-by-level kernels (mvd_soft_erode + mvd_skel_update): bit-identical skeleton, E, delta and skeleton stacks."""
+    level-by-level kernels (mvd_soft_erode + mvd_skel_update): bit-identical skeleton, E and skeleton stacks; and the
+    fused shared-memory backward (<= 2 levels per launch, delta recomputed) against the level-by-level backward kernels
+    with global atomics (chain + dilate / erosion routing per level)."""
     g = torch.Generator().manual_seed(17)
     x = torch.rand(shape, generator=g).to(dev())
     x[x < 0.3] = 0.0            # plateaus -> ties
     B, D, H, W = shape
     N, L, st = x.numel(), it + 1, torch.cuda.current_stream().cuda_stream
     x5 = x.unsqueeze(1)
-    sk, E, delta, skel = m.ops._skel_forward(x5, it, True)
-    sk2, _, _, _ = m.ops._skel_forward(x5, it, False)
+    sk, E, skel = m.ops._skel_forward(x5, it, True)
+    sk2, _, _ = m.ops._skel_forward(x5, it, False)
     Er = torch.empty((L + 1, N), device=dev()); Er[0] = x.reshape(-1)
     dr = torch.empty((L, N), device=dev()); sr = torch.empty((L, N), device=dev())
     for j in range(L):
         m.lib.soft_erode(Er[j].data_ptr(), Er[j + 1].data_ptr(), B, D, H, W, st)
         m.lib.skel_update(Er[j].data_ptr(), Er[j + 1].data_ptr(), sr[j - 1].data_ptr() if j else None,
                           dr[j].data_ptr(), sr[j].data_ptr(), 1 if j == 0 else 0, B, D, H, W, st)
-    assert torch.equal(E, Er) and torch.equal(delta, dr) and torch.equal(skel, sr)
+    assert torch.equal(E, Er[1:]) and torch.equal(skel, sr)
     assert torch.equal(sk.reshape(-1), sr[L - 1]) and torch.equal(sk2.reshape(-1), sr[L - 1])
+    # backward: fused vs level by level
+    g_skel = torch.randn((N,), generator=g).to(dev())
+    got = m.ops._skel_backward(g_skel, x.reshape(-1), E, skel, (B, D, H, W))
+    g_delta = torch.empty((L, N), device=dev())
+    m.lib.skel_chain_bwd(dr.data_ptr(), sr.data_ptr(), g_skel.data_ptr(), g_delta.data_ptr(), L, N, st)
+    gE = torch.zeros((L + 1, N), device=dev())
+    for j in range(L):
+        m.lib.skel_level_bwd(Er[j + 1].data_ptr(), dr[j].data_ptr(), g_delta[j].data_ptr(), gE[j].data_ptr(),
+                             gE[j + 1].data_ptr(), B, D, H, W, st)
+    for lvl in range(L, 0, -1):
+        m.lib.soft_erode_bwd(Er[lvl - 1].data_ptr(), gE[lvl].data_ptr(), gE[lvl - 1].data_ptr(), B, D, H, W, st)
+    torch.testing.assert_close(got, gE[0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('shape,it', [((2, 37, 21, 45), 3), ((1, 20, 40, 35), 10), ((1, 3, 5, 4), 2), ((1, 12, 18, 33), 0)])
+def test_soft_skel_backward_matches_reference_autograd(m, shape, it):
+    """gradient of soft_skel through the fused backward against PyTorch autograd of the reference formulation
+    (soft_skeleton.py:6-37 as restated in oracle/losses.py; tie rules of max_pool3d / torch.min / relu): several tiles,
+    volume borders, plateaus, odd and even level counts (1- and 2-level launches)."""
+    import oracle
+    g = torch.Generator().manual_seed(23)
+    x = torch.rand((shape[0], 1, *shape[1:]), generator=g)
+    x[x < 0.25] = 0.0
+    x[x > 0.9] = 1.0
+    w = torch.randn(x.shape, generator=g).to(dev())
+    xa = x.to(dev()).requires_grad_(True)
+    (m.soft_skel(xa, it) * w).sum().backward()
+    xr = x.to(dev()).requires_grad_(True)
+    (oracle.soft_skel(xr, it) * w).sum().backward()
+    torch.testing.assert_close(xa.grad, xr.grad, rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize('it', [3, 10])
