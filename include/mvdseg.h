@@ -131,6 +131,12 @@ typedef struct mvd_pack_desc {
 /* packs a whole table of layers (device memory, n entries, ascending block_begin) in one launch of total_blocks blocks */
 int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int total_blocks, mvd_stream_t stream);
 int mvd_pack_blocks(int Cout, int Cin);   /* thread blocks one layer occupies in the table */
+/* Weight-gradient reduction mode.  1 (default): deterministic two-stage reduction -- every split of the voxel range
+ * stores its partial dw into its own workspace slice, a finishing kernel adds the slices in a fixed order (bit-
+ * reproducible, no atomics).  0: one slice, red.global.add.v4.f32 (order-dependent last bits).  Process-wide; changes the
+ * answer of mvd_conv3d_workspace_bytes(pass 2).  Env MVD_WGRAD_ATOMICS=1 selects 0 at load. */
+int mvd_set_deterministic(int on);
+int mvd_get_deterministic(void);
 size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass /*0 fprop,1 dgrad,2 wgrad*/);
 int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream); /* y = conv(x, w) + bias  (w = w_fprop) */
 int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* x = conv^T(y, w)       (w = w_dgrad) */

@@ -57,6 +57,8 @@ _SIGNATURES = {
     'mvd_launch_count': (c_ulonglong, []),
     'mvd_reset_launch_count': (None, []),
     'mvd_fallback_count': (c_ulonglong, []),
+    'mvd_set_deterministic': (c_int, [I]),
+    'mvd_get_deterministic': (c_int, []),
     'mvd_reset_fallback_count': (None, []),
     'mvd_shutdown': (c_int, []),
     'mvd_ncdhw_f32_to_ndhwc_bf16': (c_int, [P, LL, P, I, I, LL, I, S]),
@@ -115,7 +117,7 @@ _SIGNATURES = {
 }
 
 _UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count', 'mvd_fallback_count',
-              'mvd_reset_fallback_count',
+              'mvd_reset_fallback_count', 'mvd_get_deterministic',
               'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks'}
 
 

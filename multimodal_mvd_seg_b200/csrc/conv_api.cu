@@ -19,6 +19,12 @@ static int check_geom(const mvd_conv3d_args* a, const char* who) {
 
 extern "C" {
 
+int mvd_set_deterministic(int on) {
+  set_wgrad_deterministic(on);
+  return MVD_OK;
+}
+int mvd_get_deterministic(void) { return wgrad_deterministic() ? 1 : 0; }
+
 size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass) {
   if (!a) return 0;
   if (pass == 2 && a->algo != 1 && tc_wgrad_supported(a)) return tc_wgrad_workspace_bytes(a);

@@ -26,5 +26,8 @@ bool tc_halo_s2_fprop_supported(const mvd_conv3d_args* a);
 int tc_halo_s2_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 // sliding-window halo variant for 3x3x3 / stride 1 (conv_tc_wgrad_halo.cu)
 bool tc_wgrad_halo_supported(const mvd_conv3d_args* a);
+int tc_wgrad_halo_splits(const mvd_conv3d_args* a);     // CTAs per (ci, co) set = slices of the deterministic reduction
+bool wgrad_deterministic();
+void set_wgrad_deterministic(int on);
 int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st);
 }  // namespace mvd

@@ -92,7 +92,8 @@ struct TcParams {
   // its fp32 partial into `scratch` (same element offsets as `out`) with vector reductions, splitk_finish_kernel then
   // applies bias / rounding / accumulate
   int ksplit;
-  float* scratch;
+  float* scratch;              // [ksplit][out-shaped fp32]: slice s holds the partial of K slice s (plain stores, no atomics:
+  long long slice_stride;      //  the finishing kernel adds the slices in a fixed order -> bit-reproducible results)
   TcClass cls[kMaxClasses];
   TcTap taps[kMaxTaps];
 };
@@ -270,12 +271,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
           tmem_ld_wait();
-          if (ksplit > 1) {      // fp32 partial of this K slice: 8 vector reductions per row and 32-column chunk
+          if (ksplit > 1) {      // fp32 partial of this K slice -> its own scratch slice (8 x 16-byte stores per row chunk)
             if (ok) {
-              float* dst = P.scratch + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd +
-                           (long long)(h0 + (rr0 >> 3)) * sh + (long long)(w0 + (rr0 & 7)) * sw + n0 + cc;
+              const int sl = tile % ksplit;
+              const int kit = P.cls[c].ntaps * P.kchunks;
+              const bool empty = (int)((long long)kit * (sl + 1) / ksplit) == (int)((long long)kit * sl / ksplit);
+              float* dst = P.scratch + (long long)sl * P.slice_stride + P.cls[c].out_off + (long long)b * P.sb +
+                           (long long)d * P.sd + (long long)(h0 + (rr0 >> 3)) * sh + (long long)(w0 + (rr0 & 7)) * sw + n0 + cc;
 #pragma unroll
-              for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+              for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<uint4*>(dst + e) = empty ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
             }
             continue;
           }
@@ -316,7 +321,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 // split-K tail: out[v][n] = bf16(scratch[v][n] + bias[n]) (+ out[v][n] when accumulating), voxels dense with pitch ld
-__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ scratch, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ scratch, long long slice_stride,
+                                                            int nslices, bf16* __restrict__ out,
                                                             const float* __restrict__ bias, long long nvox, int N,
                                                             int ld, int accumulate) {
   const int CG = N >> 3;
@@ -325,8 +331,12 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     const long long v = i / CG;
     const int cg = (int)(i - v * CG);
     const long long off = v * ld + cg * 8;
-    const float4 a0 = *reinterpret_cast<const float4*>(scratch + off), a1 = *reinterpret_cast<const float4*>(scratch + off + 4);
-    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sl = 0; sl < nslices; ++sl) {      // fixed order: reproducible bit for bit
+      const float* p = scratch + (long long)sl * slice_stride + off;
+      const float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
     if (bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += round_bf(__ldg(bias + cg * 8 + j));
@@ -398,9 +408,11 @@ bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn,
 
 // produced lattices this small go through the split-K form when the caller supplies a workspace (conv3d_workspace_bytes)
 constexpr long long kSplitKMaxVoxels = 4096;
+constexpr int kSplitKMaxSlices = 16;      // workspace is sized for this many K slices
 
 struct SplitK {
-  float* scratch = nullptr;     // caller's workspace, >= nvox * ld floats
+  float* scratch = nullptr;     // caller's workspace
+  size_t bytes = 0;             // its size: bounds the number of K slices
   long long nvox = 0;           // voxels of the produced lattice (all samples)
   int ld = 0, N = 0;            // pitch / channels of the produced tensor
 };
@@ -409,16 +421,20 @@ int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* wh
   if (P.nbias > kMaxBias) { set_error("%s: more than %d produced channels", who, kMaxBias); return MVD_ERR_UNSUPPORTED; }
   P.ksplit = 1;
   P.scratch = nullptr;
+  P.slice_stride = 0;
   if (sk && sk->scratch && !P.scatter_c && !P.stats && sk->nvox <= kSplitKMaxVoxels) {
     const int tiles = P.num_m_tiles * P.num_n_tiles;
-    int min_kit = 1 << 30;
-    for (int c = 0; c < P.nclasses; ++c) min_kit = P.cls[c].ntaps * P.kchunks < min_kit ? P.cls[c].ntaps * P.kchunks : min_kit;
+    int max_kit = 0;
+    for (int c = 0; c < P.nclasses; ++c) max_kit = P.cls[c].ntaps * P.kchunks > max_kit ? P.cls[c].ntaps * P.kchunks : max_kit;
+    const long long slice = sk->nvox * sk->ld;                 // floats per slice: the produced tensor's own offsets
     int S = num_sms() / (tiles > 0 ? tiles : 1);
-    if (S > min_kit / 2) S = min_kit / 2;      // at least two pipeline stages of work per unit
+    if (S > max_kit / 2) S = max_kit / 2;                      // at least two pipeline stages of work per unit
+    const long long fit = (long long)(sk->bytes / sizeof(float)) / slice;
+    if (S > fit) S = (int)fit;
     if (S > 1) {
       P.ksplit = S;
       P.scratch = sk->scratch;
-      MVD_CUDA(cudaMemsetAsync(sk->scratch, 0, (size_t)sk->nvox * sk->ld * sizeof(float), st));
+      P.slice_stride = slice;
     }
   }
   float* const bias_keep = const_cast<float*>(P.bias);
@@ -456,8 +472,8 @@ int launch_tc(TcMaps& maps, TcParams& P, int kc, cudaStream_t st, const char* wh
   MVD_LAUNCH_CHECK(who);
   if (P.ksplit > 1) {
     const long long vecs = sk->nvox * (sk->N / 8);
-    splitk_finish_kernel<<<grid_for(vecs, 256, num_sms() * 4), 256, 0, st>>>(sk->scratch, P.out, bias_keep, sk->nvox, sk->N,
-                                                                            sk->ld, acc_keep);
+    splitk_finish_kernel<<<grid_for(vecs, 256, num_sms() * 4), 256, 0, st>>>(sk->scratch, P.slice_stride, P.ksplit, P.out,
+                                                                            bias_keep, sk->nvox, sk->N, sk->ld, acc_keep);
     MVD_LAUNCH_CHECK(who);
   }
   return MVD_OK;
@@ -498,7 +514,7 @@ static size_t splitk_bytes(const mvd_conv3d_args* a, int pass) {
     const char* e = getenv("MVD_NO_SPLITK");
     enabled = (e && e[0] == '1') ? 0 : 1;
   }
-  return enabled ? (size_t)nvox * ld * sizeof(float) : 0;
+  return enabled ? (size_t)kSplitKMaxSlices * nvox * ld * sizeof(float) : 0;
 }
 size_t tc_splitk_workspace_bytes(const mvd_conv3d_args* a, int pass) {
   if (pass == 0 ? !tc_fprop_supported(a) : !tc_dgrad_supported(a)) return 0;
@@ -508,7 +524,7 @@ size_t tc_splitk_workspace_bytes(const mvd_conv3d_args* a, int pass) {
 }
 static bool tc_splitk_wanted(const mvd_conv3d_args* a, int pass) {
   const size_t need = splitk_bytes(a, pass);
-  return need > 0 && a->workspace && a->workspace_bytes >= need && (((uintptr_t)a->workspace) & 15) == 0;
+  return need > 0 && a->workspace && a->workspace_bytes >= need / kSplitKMaxSlices * 2 && (((uintptr_t)a->workspace) & 15) == 0;
 }
 
 bool tc_fprop_supported(const mvd_conv3d_args* a) {
@@ -593,6 +609,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   }
   SplitK sk;
   sk.scratch = tc_splitk_wanted(a, 0) ? (float*)a->workspace : nullptr;
+  sk.bytes = a->workspace_bytes;
   sk.nvox = (long long)a->B * a->Do * a->Ho * a->Wo; sk.ld = a->ldy; sk.N = a->Cout;
   return launch_tc(maps, P, kc, st, "conv3d_fprop(tcgen05)", &sk);
 }
@@ -703,6 +720,7 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (P.nclasses == 0) return MVD_OK;
   SplitK sk;
   sk.scratch = tc_splitk_wanted(a, 1) ? (float*)a->workspace : nullptr;
+  sk.bytes = a->workspace_bytes;
   sk.nvox = (long long)a->B * a->Di * a->Hi * a->Wi; sk.ld = a->ldx; sk.N = a->Cin;
   return launch_tc(maps, P, kc, st, "conv3d_dgrad(tcgen05)", &sk);
 }

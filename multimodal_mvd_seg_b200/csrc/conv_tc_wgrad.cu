@@ -42,7 +42,8 @@ struct WgParams {
   int n_tile, num_n_tiles, ksplit;
   int a_stages;
   uint32_t idesc, tmem_cols;
-  float* dw;                                           // scratch [taps][Cin][Cout]
+  float* dw;                                           // scratch [slices][taps][Cin][Cout]
+  long long slice_stride;                              // 0: all splits reduce into slice 0 with red.global.add (atomics)
   WgTap tap[kMaxTaps];
 };
 
@@ -177,10 +178,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        if (valid) {   // scratch [tap][ci][co]: this row's 32 columns are 128 contiguous bytes -> 8 vector reductions
-          float* dst = P.dw + ((long long)tp * P.Cin + ci) * P.Cout + n0 + c;
+        if (valid) {   // scratch [tap][ci][co]: this row's 32 columns are 128 contiguous bytes
+          float* dst = P.dw + (long long)split * P.slice_stride + ((long long)tp * P.Cin + ci) * P.Cout + n0 + c;
+          if (P.slice_stride) {          // deterministic: plain stores into this split's own slice
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+            for (int e = 0; e < 32; e += 4) *reinterpret_cast<uint4*>(dst + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else {                       // 8 vector reductions
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
         }
       }
     }
@@ -191,14 +197,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 }
 
 // scratch [taps][Cin][Cout] -> dw [Cout][Cin][taps]; block = (ci, 64 output channels), transposed through smem
+// (nslices > 1: the deterministic two-stage reduction -- the slices are added here in a fixed order)
 __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
-                                                           int taps, int Cin, int Cout) {
+                                                           int taps, int Cin, int Cout, int nslices,
+                                                           long long slice_stride) {
   __shared__ float tile[27][65];
   const int ci = blockIdx.x, co0 = blockIdx.y * 64;
   const int nco = min(64, Cout - co0);
   for (int i = threadIdx.x; i < taps * 64; i += 128) {
     const int t = i >> 6, c = i & 63;
-    if (c < nco) tile[t][c] = scratch[((long long)t * Cin + ci) * Cout + co0 + c];
+    if (c < nco) {
+      const float* p = scratch + ((long long)t * Cin + ci) * Cout + co0 + c;
+      float a = 0.f;
+      for (int sl = 0; sl < nslices; ++sl) a += p[(long long)sl * slice_stride];
+      tile[t][c] = a;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nco * taps; i += 128) {
@@ -249,8 +262,39 @@ bool tc_wgrad_supported(const mvd_conv3d_args* a) {
   return get_encode_tiled() != nullptr;
 }
 
+// ---- reduction mode ---------------------------------------------------------------------------------------------
+// deterministic (default): every split of the voxel range writes its partial dw into its OWN slice of the workspace with
+// plain stores and wgrad_finish_kernel adds the slices in a fixed order -> dw is reproducible bit for bit, no zero-fill,
+// no atomics.  MVD_WGRAD_ATOMICS=1 (or mvd_set_deterministic(0)) restores the single-slice red.global.add form.
+static int g_deterministic = -1;
+bool wgrad_deterministic() {
+  if (g_deterministic < 0) {
+    const char* e = getenv("MVD_WGRAD_ATOMICS");
+    g_deterministic = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_deterministic == 1;
+}
+void set_wgrad_deterministic(int on) { g_deterministic = on ? 1 : 0; }
+
+// number of splits of the voxel range each kernel uses for this layer (= slices in deterministic mode)
+static int wgrad_tc_splits(const mvd_conv3d_args* a) {
+  const int SW = (a->Cin % 64 == 0) ? 64 : 32;
+  const int taps = a->kd * a->kh * a->kw;
+  const int total_groups = cdiv(taps * (a->Cin / SW), 128 / SW);
+  const int n_tile = pick_wg_n_tile(a->Cout);
+  const int gmax = 512 / n_tile;
+  const int units = cdiv(total_groups, gmax) * (a->Cout / n_tile);
+  const int v_tiles = a->B * a->Do * cdiv(a->Ho, TILE_H) * cdiv(a->Wo, TILE_W);
+  int ksplit = cdiv(num_sms(), units);
+  if (ksplit > v_tiles) ksplit = v_tiles;
+  return ksplit < 1 ? 1 : ksplit;
+}
+int tc_wgrad_halo_splits(const mvd_conv3d_args* a);   // conv_tc_wgrad_halo.cu
+
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a) {
-  return sizeof(float) * (size_t)a->Cout * a->Cin * a->kd * a->kh * a->kw;
+  const size_t one = sizeof(float) * (size_t)a->Cout * a->Cin * a->kd * a->kh * a->kw;
+  if (!wgrad_deterministic()) return one;
+  return one * (size_t)(tc_wgrad_halo_supported(a) ? tc_wgrad_halo_splits(a) : wgrad_tc_splits(a));
 }
 
 int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
@@ -259,7 +303,9 @@ int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
     set_error("conv3d_wgrad(tcgen05): needs a 16-byte aligned workspace of %zu bytes (mvd_conv3d_workspace_bytes)", need);
     return MVD_ERR_INVALID;
   }
-  MVD_CUDA(cudaMemsetAsync(a->workspace, 0, need, st));
+  // atomics accumulate into a zeroed scratch; in deterministic mode only the tap-by-tap kernel can leave holes (splits or
+  // slot groups without work), the halo kernel overwrites every element of every slice
+  if (!wgrad_deterministic() || !tc_wgrad_halo_supported(a)) MVD_CUDA(cudaMemsetAsync(a->workspace, 0, need, st));
   *scratch = (float*)a->workspace;
   return MVD_OK;
 }
@@ -267,7 +313,9 @@ int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
 int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st) {
   const int taps = a->kd * a->kh * a->kw;
   dim3 grid(a->Cin, (a->Cout + 63) / 64);
-  wgrad_finish_kernel<<<grid, 128, 0, st>>>((const float*)a->workspace, a->dw, taps, a->Cin, a->Cout);
+  const long long one = (long long)a->Cout * a->Cin * taps;
+  const int nslices = wgrad_deterministic() ? (int)(tc_wgrad_workspace_bytes(a) / (sizeof(float) * (size_t)one)) : 1;
+  wgrad_finish_kernel<<<grid, 128, 0, st>>>((const float*)a->workspace, a->dw, taps, a->Cin, a->Cout, nslices, one);
   MVD_LAUNCH_CHECK("conv3d_wgrad(finish)");
   if (a->dbias)
     return mvd_channel_sum(a->y, a->ldy, (long long)a->B * a->Do * a->Ho * a->Wo, a->Cout, a->dbias, (mvd_stream_t)st);
@@ -340,6 +388,7 @@ int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (ksplit < 1) ksplit = 1;
   P.ksplit = ksplit;
   P.dw = scratch;
+  P.slice_stride = wgrad_deterministic() ? (long long)a->Cout * a->Cin * taps : 0;
   const int b_bytes = P.n_tile * 128 * 2;
   const int a_stage = 32 * 1024;
   int a_stages = (196 * 1024 - 2 * b_bytes) / a_stage;

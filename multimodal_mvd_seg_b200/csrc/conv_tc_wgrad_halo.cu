@@ -45,6 +45,7 @@ struct WhParams {
   int dchunk, dchunks;                  // d planes per work item
   int items_per_set, ctas_per_set;
   float* dw;
+  long long slice_stride;   // deterministic mode: CTA `rank` of every set stores into slice `rank`; 0 = one slice, red.add
 };
 
 __device__ __forceinline__ void tmem_st_zero_32x32b_x32(uint32_t taddr) {
@@ -204,9 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
       tmem_ld_wait();
       if (ox < 3) {   // scratch [tap][ci][co]: 128 contiguous bytes per row -> 8 vector reductions
         const int tap = (oz * 3 + oy) * 3 + ox;
-        float* dst = P.dw + ((long long)tap * P.Cin + ci) * P.Cout + nb * 32;
+        float* dst = P.dw + (long long)rank * P.slice_stride + ((long long)tap * P.Cin + ci) * P.Cout + nb * 32;
+        if (P.slice_stride) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+          for (int e = 0; e < 32; e += 4) *reinterpret_cast<uint4*>(dst + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
       }
     }
   }
@@ -253,17 +259,10 @@ bool tc_wgrad_halo_supported(const mvd_conv3d_args* a) {
   return enabled == 1 && get_encode_tiled() != nullptr;
 }
 
-int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st) {
-  float* scratch = nullptr;
-  if (int rc0 = tc_wgrad_begin(a, st, &scratch)) return rc0;
-  WhMaps maps;
-  WhParams P;
-  memset(&P, 0, sizeof(P));
-  if (!encode5(&maps.x, (const bf16*)a->x, a->Cin, a->ldx, a->Wi, a->Hi, a->Di, a->B, HALO_W, HALO_H) ||
-      !encode5(&maps.y, (const bf16*)a->y, a->Cout, a->ldy, a->Wo, a->Ho, a->Do, a->B, TILE_W, TILE_H)) {
-    set_error("conv3d_wgrad(tcgen05 halo): cuTensorMapEncodeTiled failed");
-    return MVD_ERR_CUDA;
-  }
+bool wgrad_deterministic();   // conv_tc_wgrad.cu
+
+// work decomposition shared by the launch and by the workspace query: sets of (32 ci, 32 co), CTAs per set, depth chunks
+static void wgrad_halo_plan(const mvd_conv3d_args* a, WhParams& P) {
   P.B = a->B; P.D = a->Do; P.H = a->Ho; P.W = a->Wo;
   P.tiles_w = cdiv(P.W, TILE_W); P.tiles_h = cdiv(P.H, TILE_H);
   P.Cin = a->Cin; P.Cout = a->Cout; P.cblocks = a->Cin / 32; P.nblocks = a->Cout / 32;
@@ -281,6 +280,30 @@ int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st) {
   P.items_per_set = columns * dchunks;
   if (ctas_per_set > P.items_per_set) ctas_per_set = P.items_per_set;
   P.ctas_per_set = ctas_per_set;
+}
+
+int tc_wgrad_halo_splits(const mvd_conv3d_args* a) {
+  WhParams P;
+  memset(&P, 0, sizeof(P));
+  wgrad_halo_plan(a, P);
+  return P.ctas_per_set;
+}
+
+int tc_wgrad_halo(const mvd_conv3d_args* a, cudaStream_t st) {
+  float* scratch = nullptr;
+  if (int rc0 = tc_wgrad_begin(a, st, &scratch)) return rc0;
+  WhMaps maps;
+  WhParams P;
+  memset(&P, 0, sizeof(P));
+  if (!encode5(&maps.x, (const bf16*)a->x, a->Cin, a->ldx, a->Wi, a->Hi, a->Di, a->B, HALO_W, HALO_H) ||
+      !encode5(&maps.y, (const bf16*)a->y, a->Cout, a->ldy, a->Wo, a->Ho, a->Do, a->B, TILE_W, TILE_H)) {
+    set_error("conv3d_wgrad(tcgen05 halo): cuTensorMapEncodeTiled failed");
+    return MVD_ERR_CUDA;
+  }
+  wgrad_halo_plan(a, P);
+  const int sets = P.cblocks * P.nblocks;
+  const int ctas_per_set = P.ctas_per_set;
+  P.slice_stride = wgrad_deterministic() ? (long long)a->Cout * a->Cin * 27 : 0;
   P.dw = scratch;
   const size_t smem = (size_t)kPlaneRing * PLANE_BYTES + (size_t)(kBrickRing + 2) * BRICK_BYTES + 1024;
   static bool attr_done = false;

@@ -123,6 +123,75 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
         ops.set_conv_algo('auto')
 
 
+@pytest.mark.parametrize('cin,cout,E,s,k', [(32, 32, 40, 1, 3), (64, 64, 24, 1, 3), (32, 64, 24, 2, 3), (320, 320, 8, 1, 3),
+                                            (64, 32, 16, 2, 2)])
+def test_wgrad_deterministic_two_stage_reduction(m, cin, cout, E, s, k):
+    """default reduction mode: every split of the voxel range stores its partial into its own workspace slice and the
+    finishing kernel adds the slices in a fixed order -> dw is bit-reproducible from run to run (and equals the atomics
+    mode up to fp32 summation order)."""
+    ops = m.ops
+    g = torch.Generator().manual_seed(5)
+    p = (k - 1) // 2 if k == 3 else 0
+    geom = ops.ConvGeom((k,) * 3, (s,) * 3, (p,) * 3)
+    Eo = geom.out_size((E, E, E))[0]
+    x = torch.randn((2, E, E, E, cin), generator=g).to(BF).to(dev())
+    dy = torch.randn((2, Eo, Eo, Eo, cout), generator=g).to(BF).to(dev())
+    assert m.lib.get_deterministic() == 1
+    runs = []
+    for _ in range(3):
+        dw = torch.empty((cout, cin, k, k, k), dtype=torch.float32, device=dev())
+        ops.conv_wgrad(geom, x, dy, dw)
+        runs.append(dw)
+        torch.randn((1 << 22,), device=dev()).sum()     # perturb the timing between the runs
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    m.lib.set_deterministic(0)
+    try:
+        dwa = torch.empty_like(runs[0])
+        ops.conv_wgrad(geom, x, dy, dwa)
+    finally:
+        m.lib.set_deterministic(1)
+    assert rel_err(dwa, runs[0]) < 1e-5
+    ref = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (cout, cin, k, k, k),
+                                      dy.float().permute(0, 4, 1, 2, 3), stride=s, padding=p)
+    assert rel_err(runs[0], ref) < 1e-3
+
+
+@pytest.mark.parametrize('cin,cout,shape,s', [(320, 320, (2, 8, 8, 8), 1), (320, 320, (2, 4, 4, 4), 1), (256, 320, (2, 16, 16, 16), 2),
+                                             (640, 320, (1, 5, 5, 6), 1), (320, 320, (2, 10, 10, 6), 1)])
+def test_small_lattice_split_k_is_reproducible_and_matches_torch(m, cin, cout, shape, s):
+    """layers whose produced lattice is small run split-K (K-sliced work units, sliced fp32 partials, ordered finishing
+    sum): fprop / dgrad bit-reproducible, equal to the unsplit kernel up to fp32 summation order, and to fp32 F.conv3d."""
+    import torch.nn.functional as F
+    ops = m.ops
+    g = torch.Generator().manual_seed(6)
+    geom = ops.ConvGeom((3,) * 3, (s,) * 3, (1,) * 3)
+    B, D, H, W = shape
+    Do, Ho, Wo = geom.out_size((D, H, W))
+    x = torch.randn((B, D, H, W, cin), generator=g).to(BF).to(dev())
+    dy = torch.randn((B, Do, Ho, Wo, cout), generator=g).to(BF).to(dev())
+    w = (torch.randn((cout, cin, 3, 3, 3), generator=g) / np.sqrt(cin * 27)).to(dev())
+    bias = torch.randn((cout,), generator=g).to(dev())
+    wf, wd = ops.pack_weights(w)
+    ys = [torch.empty_like(dy) for _ in range(2)]
+    for y in ys:
+        ops.conv_fprop(geom, x, y, wf, bias=bias)
+    assert torch.equal(ys[0], ys[1])
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.to(BF).float(), bias.to(BF).float(), stride=s, padding=1)
+    assert rel_err(ys[0].float().permute(0, 4, 1, 2, 3), ref) < 1e-2
+    dxs = [torch.empty_like(x) for _ in range(2)]
+    for dx in dxs:
+        ops.conv_dgrad(geom, dx, dy, wd)
+    assert torch.equal(dxs[0], dxs[1])
+    refdx = torch.nn.grad.conv3d_input(x.float().permute(0, 4, 1, 2, 3).shape, w.to(BF).float(),
+                                       dy.float().permute(0, 4, 1, 2, 3), stride=s, padding=1)
+    assert rel_err(dxs[0].float().permute(0, 4, 1, 2, 3), refdx) < 1e-2
+    # accumulate into an existing gradient (the skip-connection fold)
+    base = torch.randn(x.shape, generator=g).to(BF).to(dev())
+    acc = base.clone()
+    ops.conv_dgrad(geom, acc, dy, wd, accumulate=True)
+    assert rel_err(acc.float(), (dxs[0].float() + base.float())) < 1e-2
+
+
 @pytest.mark.parametrize('cout', [64, 32])
 @pytest.mark.parametrize('shape', [(2, 7, 9, 11), (1, 18, 34, 20), (1, 2, 2, 2), (1, 9, 40, 16)])
 def test_conv_s2_halo_fprop_pitched(m, shape, cout):
