@@ -75,7 +75,8 @@ typedef struct {
   const void* w;              /* bf16 packed weights, see mvd_pack_conv_weights                             */
   const float* bias;          /* fp32 [Cout] (fprop) / [Cin] (transposed fprop); may be NULL                */
   double* stats;              /* optional [B][C][2] running (sum, sum of squares) of the bf16-rounded output,
-                                 accumulated (caller zeroes); InstanceNorm statistics, fprop only           */
+                                 accumulated (caller zeroes): InstanceNorm statistics (fprop, C = Cout); for
+                                 dgrad the sums of the produced gradient (C = Cin, ignored with accumulate)  */
   float* dw;                  /* wgrad out, fp32 in torch layout [Cout][Cin][kd][kh][kw]                    */
   float* dbias;               /* wgrad out, fp32 [Cout]; may be NULL                                        */
   void* workspace; size_t workspace_bytes; /* scratch (wgrad partials; fprop / dgrad split-K partials of small layers:
@@ -300,6 +301,10 @@ int mvd_sgd_nesterov_clip(const uint64_t* ptrs, const long long* numel, const in
 /* ---- utility ----------------------------------------------------------------------------------------------- */
 /* out[c] = sum over NV voxels of g[v][c] (fp32; bias gradient of ConvTranspose3d) */
 int mvd_channel_sum(const void* g, int ld, long long NV, int C, float* out, mvd_stream_t stream);
+/* out[c] = sum_b stats[b][c0 + c][0] for c < n: turns the statistics a conv epilogue produced (mvd_conv3d_args.stats,
+ * [B][C][2] doubles) into a per-channel sum, e.g. the bias gradient of a ConvTranspose3d from the sums of the gradient
+ * tensor its consumer's dgrad just wrote (replaces a full pass of mvd_channel_sum over that tensor) */
+int mvd_stats_channel_sum(const double* stats, int B, int C, int c0, int n, float* out, mvd_stream_t stream);
 /* zero n regions of one fp32 buffer in a single launch: table (device) = n x (element offset, element count) int64.
  * The trainer clears the accumulate-type gradients of a step (conv biases in front of InstanceNorm, head weights) with it. */
 int mvd_zero_regions(float* base, const long long* table_device, int n, mvd_stream_t stream);

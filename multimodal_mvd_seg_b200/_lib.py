@@ -108,6 +108,7 @@ _SIGNATURES = {
     'mvd_cldice_finalize': (c_int, [P, F, P, S]),
     'mvd_grad_sqnorm': (c_int, [P, P, P, P, I, P, S]),
     'mvd_sgd_nesterov_clip': (c_int, [P, P, P, P, I, P, F, F, F, F, F, S]),
+    'mvd_stats_channel_sum': (c_int, [P, I, I, I, I, P, S]),
     'mvd_zero_regions': (c_int, [P, P, I, S]),
     'mvd_zero_bytes': (c_int, [P, c_size_t, S]),
     'mvd_channel_sum': (c_int, [P, I, LL, I, P, S]),

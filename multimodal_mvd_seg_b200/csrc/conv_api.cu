@@ -62,7 +62,19 @@ int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
   const bool tc = tc_dgrad_supported(a);
   if (a->algo == 2 && !tc) { set_error("conv3d_dgrad: shape not covered by the tcgen05 kernel"); return MVD_ERR_UNSUPPORTED; }
   if (a->algo == 0 && !tc) count_fallback();
-  return (a->algo != 1 && tc) ? tc_dgrad(a, st) : generic_dgrad(a, st);
+  // optional sums of the produced gradient (stats = [B][Cin][2]: sum, sum of squares): fused into the halo kernel's
+  // epilogue for 3x3x3 / stride-1 layers with 32 or 64 input channels, a streaming pass otherwise
+  const bool k3s1p1 = a->kd == 3 && a->kh == 3 && a->kw == 3 && a->sd == 1 && a->sh == 1 && a->sw == 1 && a->pd == 1 &&
+                      a->ph == 1 && a->pw == 1;
+  const bool fuse = a->stats && tc && a->algo != 1 && k3s1p1 && !a->accumulate && (a->Cin == 32 || a->Cin == 64) &&
+                    tc_splitk_workspace_bytes(a, 1) == 0;
+  mvd_conv3d_args b = *a;
+  if (!fuse) b.stats = nullptr;
+  rc = (a->algo != 1 && tc) ? tc_dgrad(&b, st) : generic_dgrad(&b, st);
+  if (rc) return rc;
+  if (a->stats && !fuse)
+    return mvd_inorm_stats(a->x, a->ldx, a->B, (long long)a->Di * a->Hi * a->Wi, a->Cin, a->stats, stream);
+  return MVD_OK;
 }
 
 int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {

@@ -635,8 +635,10 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 1)) {
     int wrow[27];   // produced voxel i gathers y[i + 1 - t]: halo offset o = 2 - t per axis, i.e. tap 26 - idx
     for (int i = 0; i < 27; ++i) wrow[i] = (26 - i) * a->Cin;
+    // a->stats (conv_api passes it only for Cin = 32 / 64 without accumulate): per-(sample, channel) sums of the produced
+    // gradient from the epilogue -- the bias gradient of the up-convolution that produced half of this tensor
     return tc_halo_conv((const bf16*)a->y, a->ldy, a->Cout, (bf16*)a->x, a->ldx, a->Cin, (const bf16*)a->w, wrow,
-                        a->bias, a->accumulate, nullptr, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
+                        a->bias, a->accumulate, a->stats, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
   }
   const int kc = (a->Cout % 64 == 0) ? 64 : 32;
   TcMaps maps;

@@ -124,6 +124,15 @@ __global__ void __launch_bounds__(128) zero_regions_kernel(float* __restrict__ b
   for (long long i = threadIdx.x; i < n; i += blockDim.x) base[off + i] = 0.f;
 }
 
+// out[c] = sum_b stats[b][c0 + c][0]   (the channel sums a conv epilogue left in its statistics buffer)
+__global__ void stats_channel_sum_kernel(const double* __restrict__ stats, int B, int C, int c0, int n, float* __restrict__ out) {
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    double a = 0.0;
+    for (int b = 0; b < B; ++b) a += stats[((long long)b * C + c0 + c) * 2];
+    out[c] = (float)a;
+  }
+}
+
 __global__ void scalar_axpy_kernel(const double* __restrict__ in, float scale, float* __restrict__ out, int accumulate) {
   if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + (float)((double)scale * in[0]);
 }
@@ -162,6 +171,13 @@ int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int to
 
 int mvd_pack_blocks(int Cout, int Cin) {
   return ((Cout + kPackTile - 1) / kPackTile) * ((Cin + kPackTile - 1) / kPackTile);
+}
+
+int mvd_stats_channel_sum(const double* stats, int B, int C, int c0, int n, float* out, mvd_stream_t stream) {
+  MVD_REQUIRE(stats && out && B > 0 && c0 >= 0 && n > 0 && c0 + n <= C, "stats_channel_sum: bad arguments");
+  stats_channel_sum_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stats, B, C, c0, n, out);
+  MVD_LAUNCH_CHECK("stats_channel_sum");
+  return MVD_OK;
 }
 
 int mvd_zero_regions(float* base, const long long* table_device, int n, mvd_stream_t stream) {

@@ -377,8 +377,8 @@ def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None, accumulate=False):
     del ws
 
 
-def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False):
-    a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd, bias=bias, accumulate=accumulate)
+def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False, stats=None):
+    a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd, bias=bias, accumulate=accumulate, stats=stats)
     ws = _maybe_workspace(a, 1, y_cl.device)
     _timed('dgrad', a, lib.conv3d_dgrad)
     del ws
@@ -498,6 +498,8 @@ def reset_skip_registry():
     _dx_consumers.clear()
     _pending_skip.clear()
     _head_inputs.clear()
+    _concat_bufs.clear()
+    _dx_colsum.clear()
     _pair_pending.clear()      # entries whose head never ran backward (zero-weighted scale) must not pile up
 
 
@@ -509,6 +511,18 @@ def reset_skip_registry():
 # accumulate_dz) and reports no gradient of its own.  If the head runs first, or never (zero-weighted scale), nothing
 # is parked and autograd's own accumulation applies: correct in every order, fused in the usual one.
 # ---------------------------------------------------------------------------------------------------------------
+_concat_bufs = set()   # data_ptr of the decoder's concat buffers (this forward): their gradient's first half is the
+                       # gradient of an up-convolution's output, whose bias gradient is its per-channel sum
+_dx_colsum = {}        # data_ptr of such a gradient tensor -> (statistics buffer its dgrad epilogue filled, channels)
+_colsum_fusion = True
+
+
+def set_colsum_fusion(on: bool):
+    """A/B and test hook: take the up-convolution's bias gradient from the consumer's dgrad epilogue sums (default) or
+    from a streaming pass over the gradient tensor."""
+    global _colsum_fusion
+    _colsum_fusion = bool(on)
+
 _head_inputs = {}      # data_ptr of a head's input (this forward) -> the HeadFn ctx
 _pair_pending = {}     # pair key -> gradient tensor the up-convolution's backward already returned
 _pair_seq = [0]
@@ -613,6 +627,8 @@ class ConvNormActFn(torch.autograd.Function):
         if need_dx:
             _dx_consumers[x_cl.data_ptr()] = _dx_consumers.get(x_cl.data_ptr(), 0) + 1
         ctx.x_ptr = x_cl.data_ptr()
+        ctx.want_colsum = _colsum_fusion and need_dx and x_cl.data_ptr() in _concat_bufs and Cin in (32, 64) and geom.k == (3, 3, 3) \
+            and geom.s == (1, 1, 1) and geom.p == (1, 1, 1)
         y = torch.empty((B, Do, Ho, Wo, Cout), dtype=BF16, device=dev)
         stats = zeros((B, Cout, 2), torch.float64, dev)
         V = Do * Ho * Wo
@@ -698,7 +714,11 @@ class ConvNormActFn(torch.autograd.Function):
                 conv_dgrad(geom, dx, dy, wd, accumulate=True)
             else:
                 dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
-                conv_dgrad(geom, dx, dy, wd)
+                colsum = None
+                if ctx.want_colsum:      # channel sums of dx out of the dgrad epilogue: the up-convolution's bias gradient
+                    colsum = zeros((x_cl.shape[0], x_cl.shape[-1], 2), torch.float64, dev)
+                    _dx_colsum[dx.data_ptr()] = (colsum, x_cl.shape[-1])
+                conv_dgrad(geom, dx, dy, wd, stats=colsum)
         if plain_wgrad:   # after the dgrad: deferred onto the side stream (see "Backward overlap"), else right here
             if not _defer_wgrad(dev, lambda: conv_wgrad(geom, x_cl, dy, dw, None), (x_cl, dy, dw), dw):
                 conv_wgrad(geom, x_cl, dy, dw, None)
@@ -745,7 +765,11 @@ class ConvTransposeFn(torch.autograd.Function):
         if bias is not None and ctx.needs_input_grad[2]:
             db = _grad_like(bias)
             B, D, H, W, C = dup.shape
-            lib.channel_sum(dup.data_ptr(), cl_pitch(dup), B * D * H * W, C, db.data_ptr(), _stream())
+            ent = _dx_colsum.pop(dup.data_ptr(), None)
+            if ent is not None and ent[1] >= C:    # the producer of `dup` left its channel sums: no pass over the tensor
+                lib.stats_channel_sum(ent[0].data_ptr(), B, ent[1], 0, C, db.data_ptr(), _stream())
+            else:
+                lib.channel_sum(dup.data_ptr(), cl_pitch(dup), B * D * H * W, C, db.data_ptr(), _stream())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x_cl.shape, dtype=BF16, device=dev)
@@ -774,6 +798,8 @@ class ConcatViewFn(torch.autograd.Function):
         ctx.skip_ptr = skip.data_ptr()
         # exactly one conv takes a gradient w.r.t. the skip tensor (the next encoder stage): it will fold our share in
         ctx.defer = ctx.needs_input_grad[1] and _dx_consumers.get(ctx.skip_ptr, 0) == 1
+        if ctx.needs_input_grad[0]:
+            _concat_bufs.add(buf.data_ptr())
         return buf.view(buf.shape)  # a fresh tensor object aliasing the buffer
 
     @staticmethod

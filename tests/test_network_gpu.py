@@ -364,3 +364,30 @@ def test_mvd_checkpoint_roundtrip_and_missing_second_network(tmp_path):
     del ck['network2_weights']
     with pytest.raises(KeyError, match='network2_weights'):
         tr2.load_checkpoint(ck)
+
+
+def test_upconv_bias_gradient_from_dgrad_epilogue_sums():
+    """the bias gradient of the full-resolution up-convolution comes out of the channel sums the consuming conv's dgrad
+    epilogue produced (no pass over the gradient tensor); must equal the streaming channel_sum it replaces."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    from multimodal_mvd_seg_b200 import ops
+    from _parity import build_pair, ds_loss
+    patch = (32, 32, 32)
+    net, ref, topo = build_pair(m, oracle, 2, patch)
+    batch = oracle.make_batch(2, 2, patch, topo['strides'], kind='structured')
+    data = batch['data'].to('cuda:0')
+    target = [t.to('cuda:0') for t in batch['target']]
+    grads = {}
+    try:
+        for mode in (True, False):
+            ops.set_colsum_fusion(mode)
+            for p in net.parameters():
+                p.grad = None
+            out = net(data)
+            ds_loss(m, len(out))(out, target).backward()
+            grads[mode] = [t.bias.grad.detach().clone() for t in net.decoder.transpconvs]
+    finally:
+        ops.set_colsum_fusion(True)
+    for a, b in zip(grads[True], grads[False]):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-6)
