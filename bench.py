@@ -243,10 +243,34 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
     barrier()
     launches_per_step = m.lib.launch_count() / n_instr
     fallbacks = int(m.lib.fallback_count())
+    # ---- gradient exchange timeline (N > 1): eager steps with the overlap ON (no per-kernel timer), CUDA events around
+    # every bucket's all-reduce on the comm stream and around the compute stream's final wait for the exchange
+    ddp_timeline = None
+    if world > 1:
+        m.ops.set_conv_timer(None)
+        for a in tr._arenas:
+            a.arm_timeline(True)
+        for _ in range(3):
+            tr.train_step_async(resident)
+        barrier()
+        per_arena = [a.timeline_summary() for a in tr._arenas]
+        for a in tr._arenas:
+            a.arm_timeline(False)
+        steps_rec = [list(x) for x in zip(*[p for p in per_arena if p])]
+        if steps_rec:
+            last = steps_rec[-1]       # the last recorded step, all arenas (networks)
+            ddp_timeline = dict(arenas=len(last), buckets=sum(r['buckets'] for r in last),
+                                bytes_per_step=sum(r['bytes'] for r in last),
+                                allreduce_ms_sum=sum(r['allreduce_ms_sum'] for r in last),
+                                exposed_ms=sum(r['exposed_ms'] for r in last),
+                                first_allreduce_after_step_start_ms=min(r['first_allreduce_after_step_start_ms'] for r in last),
+                                note='eager step with backward overlap on; exposed = compute stream waiting for the '
+                                     'exchange after backward (rank 0)')
+        m.ops.set_conv_timer(timer)
+    m.ops.set_conv_timer(None)
     conv = timer.summary()
     mem = timer.mem_summary()
     per_layer = timer.per_layer() if args.per_layer else None
-    m.ops.set_conv_timer(None)
     for d in list(conv.values()) + list(mem.values()):
         for k in d:
             d[k] /= n_instr
@@ -302,7 +326,7 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
     res = dict(name=name, patch=patch, dual=dual, ms_per_step=ms_total / steps, steps=steps, e2e_s=e2e_s,
                e2e_steps=e2e_steps, h2d=h2d, launches_per_step=launches_per_step, fallbacks=fallbacks, conv=conv,
                mem=mem, per_layer=per_layer, clocks=clocks, loss=loss_val, cuda_graph=bool(tr.use_cuda_graph),
-               ddp_weights_identical=identical)
+               ddp_weights_identical=identical, ddp_timeline=ddp_timeline)
     # release this workload's device memory before the next one is built
     del tr, resident, host
     m.ops.set_grad_allocator(None)
@@ -483,6 +507,7 @@ def main():
             'roofline': roofline, 'roofline_hbm': hbm_roofline(r, peaks), 'clocks': r['clocks'], 'loss': r['loss']}
     if n_gpus > 1:
         line['ddp_weights_identical'] = r['ddp_weights_identical']
+        line['ddp_exchange'] = r['ddp_timeline']
     if extras:
         ex = {}
         for n, e in extras.items():
@@ -503,6 +528,7 @@ def main():
                        'loss': e['loss']}
             if n_gpus > 1:
                 ex[key]['ddp_weights_identical'] = e['ddp_weights_identical']
+                ex[key]['ddp_exchange'] = e['ddp_timeline']
         line['extra_workloads'] = ex
     if n_gpus == 1 and not args.no_extra:
         line['gpu_torch_context'] = gpu_torch_context(patch, dual, topo_iter, dev)

@@ -132,6 +132,18 @@ typedef struct mvd_pack_desc {
 /* packs a whole table of layers (device memory, n entries, ascending block_begin) in one launch of total_blocks blocks */
 int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int total_blocks, mvd_stream_t stream);
 int mvd_pack_blocks(int Cout, int Cin);   /* thread blocks one layer occupies in the table */
+/* The optimiser update of the conv weights fused with the refresh of their packed layouts: for every table entry
+ * (p = pack.w, grad, momentum: fp32, same shape)  g = grad*coef + wd*p; buf = mom*buf + g; p -= lr*(g + mom*buf)  with
+ * the clip coefficient of mvd_sgd_nesterov_clip, then pack.w_fprop / pack.w_dgrad are rewritten from the new weights.
+ * The next forward pass needs no mvd_pack_conv_weights_multi (MVDTrainer.py:978-979 + autocast's weight casts, :894). */
+typedef struct mvd_sgd_pack_desc {
+  mvd_pack_desc pack;
+  const float* grad;
+  float* momentum;
+} mvd_sgd_pack_desc;
+int mvd_sgd_pack_conv_weights(const mvd_sgd_pack_desc* descs_device, int n, int total_blocks, const double* sqnorm,
+                               float gscale, float max_norm, float lr, float weight_decay, float momentum,
+                               mvd_stream_t stream);
 /* Weight-gradient reduction mode.  1 (default): deterministic two-stage reduction -- every split of the voxel range
  * stores its partial dw into its own workspace slice, a finishing kernel adds the slices in a fixed order (bit-
  * reproducible, no atomics).  0: one slice, red.global.add.v4.f32 (order-dependent last bits).  Process-wide; changes the
@@ -164,6 +176,24 @@ int mvd_inorm_lrelu_bwd_apply(const void* dz, int lddz, const void* y, int ldy, 
                               const double* stats, const double* bstats, const float* gamma, const float* beta,
                               int B, long long V, int C, float eps, float slope, float* dgamma, float* dbeta,
                               float* dsum, mvd_stream_t stream);
+
+/* InstanceNorm + LeakyReLU of the last decoder block folded into its only consumer, the 1x1x1 head (csrc/norm_head.cu;
+ * C = 32 features, K = 4 classes -- mvd_inorm_lrelu_head_supported): the normalised activation and the head's data
+ * gradient never touch HBM.
+ *   fwd       : logits [B][V][4] (dense bf16) = head(lrelu(IN(y)))            y: raw conv output, stats as above
+ *   bwd_stats : bstats (caller zeroes) from dz = dlogits W recomputed per voxel; head dw [4][32] / dbias [4] accumulated
+ *   bwd_apply : dy (pitch lddy), dgamma / dbeta / dsum as mvd_inorm_lrelu_bwd_apply */
+int mvd_inorm_lrelu_head_supported(int C, int K);
+int mvd_inorm_lrelu_head_fwd(const void* y, int ldy, const double* stats, const float* gamma, const float* beta,
+                             const float* w, const float* bias, void* logits, int B, long long V, int C, int K,
+                             float eps, float slope, mvd_stream_t stream);
+int mvd_inorm_lrelu_head_bwd_stats(const void* dlogits, const void* y, int ldy, const double* stats, const float* gamma,
+                                   const float* beta, const float* w, int B, long long V, int C, int K, float eps,
+                                   float slope, double* bstats, float* dw, float* dbias, mvd_stream_t stream);
+int mvd_inorm_lrelu_head_bwd_apply(const void* dlogits, const void* y, int ldy, void* dy, int lddy, const double* stats,
+                                   const double* bstats, const float* gamma, const float* beta, const float* w, int B,
+                                   long long V, int C, int K, float eps, float slope, float* dgamma, float* dbeta,
+                                   float* dsum, mvd_stream_t stream);
 
 /* ---- 1x1x1 segmentation heads (UNetDecoder.py:67-70) ------------------------------------------------------- */
 int mvd_head_fwd(const void* z, int ldz, const float* w /*[K][C] fp32*/, const float* bias /*[K]*/, void* logits,

@@ -78,6 +78,10 @@ _SIGNATURES = {
     'mvd_inorm_lrelu_fwd': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, S]),
     'mvd_inorm_lrelu_bwd_stats': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, P, S]),
     'mvd_inorm_lrelu_bwd_apply': (c_int, [P, I, P, I, P, I, P, P, P, P, I, LL, I, F, F, P, P, P, S]),
+    'mvd_inorm_lrelu_head_supported': (c_int, [I, I]),
+    'mvd_inorm_lrelu_head_fwd': (c_int, [P, I, P, P, P, P, P, P, I, LL, I, I, F, F, S]),
+    'mvd_inorm_lrelu_head_bwd_stats': (c_int, [P, P, I, P, P, P, P, I, LL, I, I, F, F, P, P, P, S]),
+    'mvd_inorm_lrelu_head_bwd_apply': (c_int, [P, P, I, P, I, P, P, P, P, P, I, LL, I, I, F, F, P, P, P, S]),
     'mvd_head_fwd': (c_int, [P, I, P, P, P, I, LL, I, I, S]),
     'mvd_head_bwd': (c_int, [P, I, P, I, P, P, I, P, P, LL, I, I, I, S]),
     'mvd_dice_ce_multi_fwd': (c_int, [P, I, I, I, F, I, I, F, F, P, P, P, P, S]),
@@ -107,6 +111,7 @@ _SIGNATURES = {
     'mvd_cldice_combine': (c_int, [P, P, P, P, P, LL, S]),
     'mvd_cldice_finalize': (c_int, [P, F, P, S]),
     'mvd_grad_sqnorm': (c_int, [P, P, P, P, I, P, S]),
+    'mvd_sgd_pack_conv_weights': (c_int, [P, I, I, P, F, F, F, F, F, S]),
     'mvd_sgd_nesterov_clip': (c_int, [P, P, P, P, I, P, F, F, F, F, F, S]),
     'mvd_stats_channel_sum': (c_int, [P, I, I, I, I, P, S]),
     'mvd_zero_regions': (c_int, [P, P, I, S]),
@@ -118,7 +123,7 @@ _SIGNATURES = {
 }
 
 _UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count', 'mvd_fallback_count',
-              'mvd_reset_fallback_count', 'mvd_get_deterministic',
+              'mvd_reset_fallback_count', 'mvd_get_deterministic', 'mvd_inorm_lrelu_head_supported',
               'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks'}
 
 

@@ -197,6 +197,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 }
 
 // scratch [taps][Cin][Cout] -> dw [Cout][Cin][taps]; block = (ci, 64 output channels), transposed through smem
+// deterministic mode, first level: the splits' slices are added in kSliceGroups interleaved groups (fixed order inside a
+// group), one thread per element and group, so that the 16 MB of partials of a 148-way split are swept by the whole
+// machine instead of by the finishing kernel's Cin x Cout/64 blocks; the groups land behind the slices
+constexpr int kSliceGroups = 8;
+__global__ void __launch_bounds__(256) wgrad_slice_reduce_kernel(const float* __restrict__ scratch, long long E,
+                                                                 int nslices, float* __restrict__ groups) {
+  const int g = blockIdx.y;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int sl = g; sl < nslices; sl += kSliceGroups) a += scratch[(long long)sl * E + e];
+    groups[(long long)g * E + e] = a;
+  }
+}
+
 // (nslices > 1: the deterministic two-stage reduction -- the slices are added here in a fixed order)
 __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            int taps, int Cin, int Cout, int nslices,
@@ -294,7 +308,11 @@ int tc_wgrad_halo_splits(const mvd_conv3d_args* a);   // conv_tc_wgrad_halo.cu
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a) {
   const size_t one = sizeof(float) * (size_t)a->Cout * a->Cin * a->kd * a->kh * a->kw;
   if (!wgrad_deterministic()) return one;
-  return one * (size_t)(tc_wgrad_halo_supported(a) ? tc_wgrad_halo_splits(a) : wgrad_tc_splits(a));
+  const int splits = tc_wgrad_halo_supported(a) ? tc_wgrad_halo_splits(a) : wgrad_tc_splits(a);
+  return one * (size_t)(splits + (splits > kSliceGroups ? kSliceGroups : 0));     // slices (+ the first-level group sums)
+}
+static int wgrad_slices(const mvd_conv3d_args* a) {
+  return tc_wgrad_halo_supported(a) ? tc_wgrad_halo_splits(a) : wgrad_tc_splits(a);
 }
 
 int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
@@ -305,7 +323,10 @@ int tc_wgrad_begin(const mvd_conv3d_args* a, cudaStream_t st, float** scratch) {
   }
   // atomics accumulate into a zeroed scratch; in deterministic mode only the tap-by-tap kernel can leave holes (splits or
   // slot groups without work), the halo kernel overwrites every element of every slice
-  if (!wgrad_deterministic() || !tc_wgrad_halo_supported(a)) MVD_CUDA(cudaMemsetAsync(a->workspace, 0, need, st));
+  if (!wgrad_deterministic())
+    MVD_CUDA(cudaMemsetAsync(a->workspace, 0, need, st));
+  else if (!tc_wgrad_halo_supported(a))
+    MVD_CUDA(cudaMemsetAsync(a->workspace, 0, sizeof(float) * (size_t)a->Cout * a->Cin * a->kd * a->kh * a->kw * wgrad_slices(a), st));
   *scratch = (float*)a->workspace;
   return MVD_OK;
 }
@@ -314,8 +335,17 @@ int tc_wgrad_finish(const mvd_conv3d_args* a, cudaStream_t st) {
   const int taps = a->kd * a->kh * a->kw;
   dim3 grid(a->Cin, (a->Cout + 63) / 64);
   const long long one = (long long)a->Cout * a->Cin * taps;
-  const int nslices = wgrad_deterministic() ? (int)(tc_wgrad_workspace_bytes(a) / (sizeof(float) * (size_t)one)) : 1;
-  wgrad_finish_kernel<<<grid, 128, 0, st>>>((const float*)a->workspace, a->dw, taps, a->Cin, a->Cout, nslices, one);
+  int nslices = wgrad_deterministic() ? wgrad_slices(a) : 1;
+  const float* src = (const float*)a->workspace;
+  if (nslices > kSliceGroups) {      // first level of the fixed-order reduction
+    float* groups = (float*)a->workspace + (long long)nslices * one;
+    wgrad_slice_reduce_kernel<<<dim3((unsigned)grid_for(one, 256, num_sms() * 2), kSliceGroups), 256, 0, st>>>(src, one, nslices,
+                                                                                                          groups);
+    MVD_LAUNCH_CHECK("conv3d_wgrad(slice reduce)");
+    src = groups;
+    nslices = kSliceGroups;
+  }
+  wgrad_finish_kernel<<<grid, 128, 0, st>>>(src, a->dw, taps, a->Cin, a->Cout, nslices, one);
   MVD_LAUNCH_CHECK("conv3d_wgrad(finish)");
   if (a->dbias)
     return mvd_channel_sum(a->y, a->ldy, (long long)a->B * a->Do * a->Ho * a->Wo, a->Cout, a->dbias, (mvd_stream_t)st);

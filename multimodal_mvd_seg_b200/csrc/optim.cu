@@ -133,6 +133,66 @@ __global__ void stats_channel_sum_kernel(const double* __restrict__ stats, int B
   }
 }
 
+// SGD update of the conv weights FUSED with the refresh of their bf16 GEMM layouts (mvd_sgd_pack_desc): a block owns a
+// 16 (co) x 16 (ci) x taps tile of one layer, applies  g = grad*coef + wd*p;  buf = mom*buf + g;  p -= lr*(g + mom*buf)
+// on it (rows of 16*taps contiguous floats: coalesced reads / writes of p, grad, buf) and writes the two packed layouts
+// of the UPDATED weights from the same tile -- the next forward pass finds them ready, the separate pack pass (a read of
+// all fp32 weights per step) disappears.
+__global__ void __launch_bounds__(256) sgd_pack_kernel(const mvd_sgd_pack_desc* __restrict__ descs, int n,
+                                                       const double* __restrict__ sqnorm, float gscale, float max_norm,
+                                                       float lr, float wd_, float mom) {
+  __shared__ float tile[kPackTile][kPackTile * kPackMaxTaps + 1];
+  int li = 0;
+  while (li + 1 < n && (int)blockIdx.x >= descs[li + 1].pack.block_begin) ++li;
+  const mvd_sgd_pack_desc d = descs[li];
+  const int Cout = d.pack.Cout, Cin = d.pack.Cin, taps = d.pack.taps;
+  const int tiles_ci = (Cin + kPackTile - 1) / kPackTile;
+  const int tb = (int)blockIdx.x - d.pack.block_begin;
+  const int ci0 = (tb % tiles_ci) * kPackTile, co0 = (tb / tiles_ci) * kPackTile;
+  const int nci = min(kPackTile, Cin - ci0), nco = min(kPackTile, Cout - co0);
+  const int rowlen = nci * taps;
+  float coef = gscale;
+  if (max_norm > 0.f) {
+    const float total = (float)sqrt(sqnorm[0]) * gscale;
+    const float c = max_norm / (total + 1e-6f);
+    coef *= (c < 1.f ? c : 1.f);
+  }
+  float* w = const_cast<float*>(d.pack.w);
+  for (int i = threadIdx.x; i < nco * rowlen; i += 256) {
+    const int r = i / rowlen, c = i - r * rowlen;
+    const long long o = ((long long)(co0 + r) * Cin + ci0) * taps + c;
+    const float pv = w[o];
+    const float gv = fmaf(wd_, pv, d.grad[o] * coef);
+    const float bv = fmaf(mom, d.momentum[o], gv);
+    d.momentum[o] = bv;
+    const float pn = pv - lr * fmaf(mom, bv, gv);
+    w[o] = pn;
+    tile[r][c] = pn;
+  }
+  __syncthreads();
+  const int a = threadIdx.x >> 4, b = threadIdx.x & 15;
+  bf16* wf = (bf16*)d.pack.w_fprop;
+  bf16* wdg = (bf16*)d.pack.w_dgrad;
+  if (d.pack.stem_kpad > 0) {
+    const int kpad = d.pack.stem_kpad;
+    if (wf)
+      for (int i = threadIdx.x; i < nco * kpad; i += 256) {
+        const int r = i / kpad, k = i - r * kpad;
+        const int t = k / Cin, ci = k - t * Cin;
+        wf[(long long)(co0 + r) * kpad + k] = f2bf(k < taps * Cin ? tile[r][ci * taps + t] : 0.f);
+      }
+    return;
+  }
+  if (wf && a < nco && b < nci) {
+#pragma unroll 9
+    for (int t = 0; t < taps; ++t) wf[((long long)t * Cout + co0 + a) * Cin + ci0 + b] = f2bf(tile[a][b * taps + t]);
+  }
+  if (wdg && a < nci && b < nco) {
+#pragma unroll 9
+    for (int t = 0; t < taps; ++t) wdg[((long long)t * Cin + ci0 + a) * Cout + co0 + b] = f2bf(tile[b][a * taps + t]);
+  }
+}
+
 __global__ void scalar_axpy_kernel(const double* __restrict__ in, float scale, float* __restrict__ out, int accumulate) {
   if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + (float)((double)scale * in[0]);
 }
@@ -166,6 +226,17 @@ int mvd_pack_conv_weights_multi(const mvd_pack_desc* descs_device, int n, int to
   MVD_REQUIRE(descs_device && n > 0 && total_blocks > 0, "pack_conv_weights_multi: bad arguments");
   pack_conv_weights_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_device, n);
   MVD_LAUNCH_CHECK("pack_conv_weights");
+  return MVD_OK;
+}
+
+int mvd_sgd_pack_conv_weights(const mvd_sgd_pack_desc* descs_device, int n, int total_blocks, const double* sqnorm,
+                               float gscale, float max_norm, float lr, float weight_decay, float momentum,
+                               mvd_stream_t stream) {
+  MVD_REQUIRE(descs_device && n > 0 && total_blocks > 0, "sgd_pack_conv_weights: bad arguments");
+  MVD_REQUIRE(max_norm <= 0.f || sqnorm, "sgd_pack_conv_weights: clipping needs the squared norm");
+  sgd_pack_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_device, n, sqnorm, gscale, max_norm, lr,
+                                                                  weight_decay, momentum);
+  MVD_LAUNCH_CHECK("sgd_pack_conv_weights");
   return MVD_OK;
 }
 

@@ -122,7 +122,32 @@ class GradArena:
         self.bucket_of = {i: b for b, bk in enumerate(self.buckets) for i in bk['ids']}
         self._views = {id(p): self.flat[o:o + n].view(p.shape) for p in self.params for (o, n) in [self.offset[id(p)]]}
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        # exchange timeline (bench.py / profiles): when armed, CUDA events bracket every bucket's all-reduce on the comm
+        # stream and the compute stream's wait for the exchange in finish(); eager steps only (events are not captured)
+        self.timeline: Optional[list] = None
         self.begin_step()
+
+    def arm_timeline(self, on: bool = True):
+        self.timeline = [] if on else None
+
+    def timeline_summary(self):
+        """per recorded step: bytes, bucket count, summed all-reduce time on the comm stream, span from the first
+        all-reduce start to the last end, and the EXPOSED part = how long the compute stream sat in finish() waiting
+        for the exchange after backward had been enqueued."""
+        if not self.timeline:
+            return None
+        torch.cuda.synchronize()
+        out = []
+        for rec in self.timeline:
+            if not rec['buckets'] or 'wait0' not in rec:
+                continue
+            ar = [a.elapsed_time(b) for (a, b, _) in rec['buckets']]
+            first, last = rec['buckets'][0][0], rec['buckets'][-1][1]
+            out.append(dict(buckets=len(ar), bytes=int(sum(n for (_, _, n) in rec['buckets'])), allreduce_ms_sum=float(sum(ar)),
+                            allreduce_span_ms=float(first.elapsed_time(last)),
+                            exposed_ms=float(rec['wait0'].elapsed_time(rec['wait1'])),
+                            first_allreduce_after_step_start_ms=float(rec['t0'].elapsed_time(first))))
+        return out
 
     # -- allocator handed to ops.set_grad_allocator ---------------------------------------------------------------
     def view_for(self, p: torch.Tensor) -> Optional[torch.Tensor]:
@@ -151,6 +176,10 @@ class GradArena:
         self._ready = [set() for _ in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        if self.timeline is not None and self.comm_stream is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self.timeline.append(dict(t0=t0, buckets=[]))
         rows = getattr(self, '_prezero_rows', None)
         if rows:
             if self._prezero_table is not None:
@@ -193,7 +222,14 @@ class GradArena:
                 self.comm_stream.wait_event(ev)
                 if ev_side is not None:
                     self.comm_stream.wait_event(ev_side)
+                if self.timeline:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(self.comm_stream)
                 self._handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                if self.timeline:
+                    self._handles[-1].wait()          # stream-side wait: orders e1 behind the collective on comm_stream
+                    e1.record(self.comm_stream)
+                    self.timeline[-1]['buckets'].append((e0, e1, chunk.numel() * 4))
         else:
             self._handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -209,10 +245,17 @@ class GradArena:
                         self.flat[o:o + n].zero_()
             if self.distributed and not self._launched[b]:
                 self._launch(b)
+        rec = self.timeline[-1] if self.timeline else None
+        if rec is not None and self.comm_stream is not None:
+            rec['wait0'] = torch.cuda.Event(enable_timing=True)
+            rec['wait0'].record()
         for h in self._handles:
             h.wait()
         if self.comm_stream is not None and self._handles:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if rec is not None and self.comm_stream is not None:
+            rec['wait1'] = torch.cuda.Event(enable_timing=True)
+            rec['wait1'].record()
         self._handles = []
 
     def attach_grads(self):

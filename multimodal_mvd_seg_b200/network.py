@@ -59,8 +59,16 @@ class ConvDropoutNormReLU(nn.Module):
         self.all_modules = nn.Sequential(self.conv, self.norm, self.nonlin)
         self._geom = ConvGeom(k, s, [(i - 1) // 2 for i in k])
 
-    def forward_cl(self, x_cl: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_cl(self, x_cl: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   head: Optional[nn.Conv3d] = None) -> torch.Tensor:
+        """``head``: the 1x1x1 segmentation layer that is the only consumer of this block's output -- the call then
+        returns the head's logits (InstanceNorm + LeakyReLU folded into the head, ops.ConvNormActFn)."""
         params = [p for p in (self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias) if p is not None]
+        if head is not None:
+            params = params + [p for p in (head.weight, head.bias) if p is not None]
+            return ops.ConvNormActFn.apply(x_cl, self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias,
+                                           self._geom, float(self.norm.eps), float(self.nonlin.negative_slope), None,
+                                           params, head.weight, head.bias)
         return ops.ConvNormActFn.apply(x_cl, self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias,
                                        self._geom, float(self.norm.eps), float(self.nonlin.negative_slope),
                                        Slot(out) if out is not None else None, params)
@@ -92,10 +100,10 @@ class StackedConvBlocks(nn.Module):
         self.output_channels = output_channels[-1]
         self.initial_stride = _t3(initial_stride)
 
-    def forward_cl(self, x_cl, out: Optional[torch.Tensor] = None):
+    def forward_cl(self, x_cl, out: Optional[torch.Tensor] = None, head: Optional[nn.Conv3d] = None):
         n = len(self.convs)
         for i, blk in enumerate(self.convs):
-            x_cl = blk.forward_cl(x_cl, out if i == n - 1 else None)
+            x_cl = blk.forward_cl(x_cl, out if i == n - 1 else None, head if i == n - 1 else None)
         return x_cl
 
     def forward(self, x):
@@ -211,9 +219,16 @@ class UNetDecoder(nn.Module):
             else:
                 up = ops.ConvTransposeFn.apply(lres, tc.weight, tc.bias, tuple(tc.stride), None, tparams)
                 x = torch.cat((up, skip), -1)
+            last = s == len(self.stages) - 1
+            head = (self.seg_layers[s] if self.deep_supervision else self.seg_layers[-1]) \
+                if (self.deep_supervision or last) else None
+            if last and ops.head_fusion_ok(self.stages[s].output_channels, head):
+                # nothing but the head reads the full-resolution stage output: InstanceNorm + LeakyReLU of its last
+                # block run inside the head kernels, the activation itself is never written
+                seg.append(self.stages[s].forward_cl(x, head=head))
+                break
             x = self.stages[s].forward_cl(x)
-            if self.deep_supervision or s == len(self.stages) - 1:
-                head = self.seg_layers[s] if self.deep_supervision else self.seg_layers[-1]
+            if head is not None:
                 seg.append(ops.HeadFn.apply(x, head.weight, head.bias, [head.weight, head.bias]))
             lres = x
         seg = seg[::-1]
@@ -284,7 +299,8 @@ class PlainConvUNet(nn.Module):
         ops.reset_skip_registry()
         if x_cl.is_cuda and ops._default_algo != 1:
             pk = self._weight_packer()
-            pk.run()
+            if not pk.is_fresh():      # the fused optimiser kernel keeps the layouts current between steps
+                pk.run()
             ops.set_active_packer(pk)
         try:
             return self._forward_impl(x_cl)

@@ -219,10 +219,27 @@ class WeightPacker:
             self.packed[(id(w), stem_kpad)] = (wf, wdg)
             self._keep.append(w)
         self.n, self.blocks = len(entries), blocks
+        self.rows = rows          # host copy of the table (the fused optimiser kernel extends it, optim.SGDNesterovClip)
         self.table = torch.from_numpy(rows.view(np.uint8).copy()).to(entries[0][0].device)
+        self._fresh_versions = None
 
     def run(self):
         lib.pack_conv_weights_multi(self.table.data_ptr(), self.n, self.blocks, _stream())
+        self.mark_fresh()
+
+    # The packed layouts stay valid across steps when the optimiser refreshes them itself (mvd_sgd_pack_conv_weights):
+    # it calls mark_fresh() after its update.  Any other in-place change of a weight (load_state_dict, broadcast, a torch
+    # optimiser) bumps the tensor's version counter and is noticed here; raw-pointer updates that do NOT refresh the
+    # layouts must call invalidate().
+    def mark_fresh(self):
+        self._fresh_versions = [w._version for w in self._keep]
+
+    def invalidate(self):
+        self._fresh_versions = None
+
+    def is_fresh(self) -> bool:
+        fv = self._fresh_versions
+        return fv is not None and all(w._version == v for w, v in zip(self._keep, fv))
 
     def get(self, w, stem_kpad=0):
         return self.packed[(id(w), stem_kpad)]
@@ -517,6 +534,28 @@ _dx_colsum = {}        # data_ptr of such a gradient tensor -> (statistics buffe
 _colsum_fusion = True
 
 
+import os as _os
+_head_fusion = False
+
+
+def set_head_fusion(on: bool):
+    """fold InstanceNorm + LeakyReLU of the last decoder block into its segmentation head (csrc/norm_head.cu).  OFF by
+    default: measured on the B200 at 2 x 128^3 the fused kernels move 40 % fewer bytes but are issue-bound (the per-voxel
+    recomputation of the head's data gradient and of the activation adds ~12 % instructions to kernels that already
+    keep the issue slots 74 % busy): forward 0.120 ms vs 0.159 ms unfused, backward 0.407 ms vs 0.362 ms -- no net gain
+    (profiles/r2_norm_head_fusion.txt).  MVD_HEAD_FUSION=1 or this switch turns it on."""
+    global _head_fusion
+    _head_fusion = bool(on)
+
+
+_head_fusion = _os.environ.get('MVD_HEAD_FUSION', '0') == '1'
+
+
+def head_fusion_ok(channels: int, head) -> bool:
+    return (_head_fusion and head is not None and _default_algo != 1 and head.weight.is_cuda
+            and bool(lib.inorm_lrelu_head_supported(int(channels), int(head.weight.shape[0]))))
+
+
 def set_colsum_fusion(on: bool):
     """A/B and test hook: take the up-convolution's bias gradient from the consumer's dgrad epilogue sums (default) or
     from a streaming pass over the gradient tensor."""
@@ -615,7 +654,10 @@ def _defer_wgrad(dev, launch, keepalive, dw=None):
 class ConvNormActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_cl, weight, bias, gamma, beta, geom: ConvGeom, eps: float, slope: float,
-                out_slot: Optional['Slot'], params_for_hook):
+                out_slot: Optional['Slot'], params_for_hook, head_w=None, head_b=None):
+        """head_w / head_b: the 1x1x1 segmentation head that is the ONLY consumer of this block's output (last decoder
+        stage): the function then returns the head's logits and the normalised activation never exists in HBM
+        (csrc/norm_head.cu)."""
         require_cuda(x_cl, 'ConvNormAct')
         out = out_slot.t if out_slot is not None else None
         x_cl = as_cl(x_cl)
@@ -659,34 +701,64 @@ class ConvNormActFn(torch.autograd.Function):
         else:
             wf, wd = _packed_for(weight, True, need_dx)
             conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
+        ctx.geom, ctx.eps, ctx.slope = geom, eps, slope
+        ctx.params_for_hook = params_for_hook
+        ctx.has_head = head_w is not None
+        if ctx.has_head:
+            K = head_w.shape[0]
+            assert not stem and out is None and lib.inorm_lrelu_head_supported(Cout, K)
+            hw = head_w.detach().reshape(K, Cout)
+            logits = torch.empty((B, Do, Ho, Wo, K), dtype=BF16, device=dev)
+            _timed_mem('inorm_lrelu_head_fwd', B * V * (2.0 * Cout + 2.0 * K), lib.inorm_lrelu_head_fwd, y.data_ptr(),
+                       cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), hw.data_ptr(), _ptr(head_b),
+                       logits.data_ptr(), B, V, Cout, K, eps, slope, _stream())
+            ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta, head_w, head_b)
+            return logits
         z = out if out is not None else torch.empty_like(y)
         _timed_mem('inorm_lrelu_fwd', 4.0 * B * V * Cout, lib.inorm_lrelu_fwd, y.data_ptr(), cl_pitch(y), z.data_ptr(),
                    cl_pitch(z), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _stream())
-        ctx.geom, ctx.eps, ctx.slope = geom, eps, slope
-        ctx.params_for_hook = params_for_hook
-        ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta)
+        ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta, None, None)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x_cl, y, stats, wd, weight, bias, gamma, beta = ctx.saved_tensors
+        x_cl, y, stats, wd, weight, bias, gamma, beta, head_w, head_b = ctx.saved_tensors
         geom, eps, slope = ctx.geom, ctx.eps, ctx.slope
-        dz = as_cl(dz)
         B, Do, Ho, Wo, Cout = y.shape
         V = Do * Ho * Wo
         dev = y.device
         st = _stream()
         bstats = zeros((B, Cout, 2), torch.float64, dev)
-        _timed_mem('inorm_lrelu_bwd_stats', 4.0 * B * V * Cout, lib.inorm_lrelu_bwd_stats, dz.data_ptr(), cl_pitch(dz),
-                   y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
-                   bstats.data_ptr(), st)
         dy = torch.empty_like(y)
         dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
         dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
         db = _grad_like(bias, zero=True) if bias is not None and ctx.needs_input_grad[2] else None
-        _timed_mem('inorm_lrelu_bwd_apply', 6.0 * B * V * Cout, lib.inorm_lrelu_bwd_apply, dz.data_ptr(), cl_pitch(dz),
-                   y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(), bstats.data_ptr(),
-                   _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
+        dhw = dhb = None
+        if ctx.has_head:
+            # the incoming gradient is d loss / d logits: the head's data gradient dz = dlogits W is recomputed per voxel
+            # inside both InstanceNorm-backward passes, the head's own dW / db come out of the first one
+            dl = as_cl(dz)
+            K = head_w.shape[0]
+            if cl_pitch(dl) != K or dl.data_ptr() % 8:
+                dl = dl.contiguous()
+            hw = head_w.detach().reshape(K, Cout)
+            dhw = _grad_like(head_w, zero=True) if ctx.needs_input_grad[10] else None
+            dhb = _grad_like(head_b, zero=True) if head_b is not None and ctx.needs_input_grad[11] else None
+            _timed_mem('inorm_lrelu_head_bwd_stats', B * V * (2.0 * Cout + 2.0 * K), lib.inorm_lrelu_head_bwd_stats,
+                       dl.data_ptr(), y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), hw.data_ptr(),
+                       B, V, Cout, K, eps, slope, bstats.data_ptr(), _ptr(dhw), _ptr(dhb), st)
+            _timed_mem('inorm_lrelu_head_bwd_apply', B * V * (4.0 * Cout + 2.0 * K), lib.inorm_lrelu_head_bwd_apply,
+                       dl.data_ptr(), y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(),
+                       bstats.data_ptr(), _ptr(gamma), _ptr(beta), hw.data_ptr(), B, V, Cout, K, eps, slope, _ptr(dgamma),
+                       _ptr(dbeta), _ptr(db), st)
+        else:
+            dz = as_cl(dz)
+            _timed_mem('inorm_lrelu_bwd_stats', 4.0 * B * V * Cout, lib.inorm_lrelu_bwd_stats, dz.data_ptr(), cl_pitch(dz),
+                       y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
+                       bstats.data_ptr(), st)
+            _timed_mem('inorm_lrelu_bwd_apply', 6.0 * B * V * Cout, lib.inorm_lrelu_bwd_apply, dz.data_ptr(), cl_pitch(dz),
+                       y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(), bstats.data_ptr(),
+                       _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
         dw = _grad_like(weight) if ctx.needs_input_grad[1] else None
         plain_wgrad = False
         if dw is not None:
@@ -724,7 +796,8 @@ class ConvNormActFn(torch.autograd.Function):
                 conv_wgrad(geom, x_cl, dy, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
-        return dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None
+        return (dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None,
+                _ret(dhw, head_w), _ret(dhb, head_b))
 
 
 # ---------------------------------------------------------------------------------------------------------------

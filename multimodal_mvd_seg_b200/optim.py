@@ -36,6 +36,13 @@ class SGDNesterovClip(torch.optim.Optimizer):
         self.max_norm = max_norm
         self._tables = {}      # group index -> cached device tables
         self.last_sqnorm = None  # device double[1]: squared global grad norm of the last step (before clipping)
+        self._packers = []     # ops.WeightPacker objects whose weights are updated AND re-packed by one fused kernel
+
+    def attach_weight_packers(self, packers):
+        """conv weights that live in these packers are updated by mvd_sgd_pack_conv_weights, which also rewrites their
+        bf16 GEMM layouts: the next forward pass skips its weight-pack launch."""
+        self._packers = [p for p in packers if p is not None]
+        self._tables = {}
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -79,24 +86,59 @@ class SGDNesterovClip(torch.optim.Optimizer):
             elif g.dtype != torch.float32 or not g.is_contiguous():
                 p.grad = g = g.float().contiguous()
             sig.append((p.data_ptr(), g.data_ptr(), self.state[p]['momentum_buffer'].data_ptr()))
+        psig = tuple(id(pk) for pk in self._packers)
         cached = self._tables.get(gi)
-        if cached is not None and cached['sig'] == sig:
+        if cached is not None and cached['sig'] == sig and cached['psig'] == psig:
             return cached
         dev = params[0].device
         numel = [p.numel() for p in params]
-        chunk_t, chunk_o = [], []
-        for i, n in enumerate(numel):
-            for off in range(0, n, _CHUNK):
-                chunk_t.append(i)
-                chunk_o.append(off)
+        # conv weights owned by an attached packer: their update is fused with the re-pack (one table row each)
+        import numpy as np
+        from .ops import WeightPacker
+        fused_rows, fused_idx, blocks = [], set(), 0
+        index_of = {id(p): i for i, p in enumerate(params)}
+        for pk in self._packers:
+            for w, row in zip(pk._keep, pk.rows):
+                i = index_of.get(id(w))
+                if i is None:
+                    continue
+                r = row.copy()
+                r['block_begin'] = blocks
+                blocks += lib.pack_blocks(int(r['Cout']), int(r['Cin']))
+                fused_rows.append((r, sig[i][1], sig[i][2]))
+                fused_idx.add(i)
+        if any(not pk_all for pk_all in [all(id(w) in index_of for w in pk._keep) for pk in self._packers]):
+            fused_rows, fused_idx, blocks = [], set(), 0      # a packer with foreign weights cannot be kept fresh
+        fused_table = None
+        if fused_rows:
+            dt = np.dtype(WeightPacker._DESC.descr + [('grad', '<u8'), ('mom', '<u8')])
+            arr = np.zeros(len(fused_rows), dtype=dt)
+            for j, (r, gptr, mptr) in enumerate(fused_rows):
+                for name in WeightPacker._DESC.names:
+                    arr[j][name] = r[name]
+                arr[j]['grad'], arr[j]['mom'] = gptr, mptr
+            fused_table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+
+        def chunks(indices):
+            ct, co = [], []
+            for i in indices:
+                for off in range(0, numel[i], _CHUNK):
+                    ct.append(i)
+                    co.append(off)
+            return (torch.tensor(ct, dtype=torch.int32, device=dev), torch.tensor(co, dtype=torch.int64, device=dev), len(ct))
+        all_ct, all_co, all_n = chunks(range(len(params)))
+        plain = [i for i in range(len(params)) if i not in fused_idx]
+        pl_ct, pl_co, pl_n = chunks(plain) if fused_idx else (all_ct, all_co, all_n)
         # uint64 pointers stored as int64 bit patterns
         flat = [v - (1 << 64) if v >= (1 << 63) else v for row in sig for v in row]
-        cached = dict(sig=sig,
+        cached = dict(sig=sig, psig=psig,
                       ptrs=torch.tensor(flat, dtype=torch.int64, device=dev),
                       numel=torch.tensor(numel, dtype=torch.int64, device=dev),
-                      chunk_t=torch.tensor(chunk_t, dtype=torch.int32, device=dev),
-                      chunk_o=torch.tensor(chunk_o, dtype=torch.int64, device=dev),
-                      n_chunks=len(chunk_t), n_elems=int(sum(numel)))
+                      chunk_t=all_ct, chunk_o=all_co, n_chunks=all_n, n_elems=int(sum(numel)),
+                      plain_chunk_t=pl_ct, plain_chunk_o=pl_co, plain_n_chunks=pl_n,
+                      plain_elems=int(sum(numel[i] for i in plain)),
+                      fused_table=fused_table, fused_n=len(fused_rows), fused_blocks=blocks,
+                      fused_elems=int(sum(numel[i] for i in fused_idx)))
         self._tables[gi] = cached
         return cached
 
@@ -114,12 +156,24 @@ class SGDNesterovClip(torch.optim.Optimizer):
             for t in tabs:
                 _timed_mem('grad_sqnorm', 4.0 * t['n_elems'], lib.grad_sqnorm, t['ptrs'].data_ptr(), t['numel'].data_ptr(),
                            t['chunk_t'].data_ptr(), t['chunk_o'].data_ptr(), t['n_chunks'], sq.data_ptr(), stream)
+        fused_any = False
         for t, g in zip(tabs, self.param_groups):
             mn = self.max_norm if need_norm else 0.0
-            _timed_mem('sgd_nesterov_clip', 20.0 * t['n_elems'], lib.sgd_nesterov_clip, t['ptrs'].data_ptr(),
-                       t['numel'].data_ptr(), t['chunk_t'].data_ptr(), t['chunk_o'].data_ptr(), t['n_chunks'],
-                       sq.data_ptr(), float(grad_scale), float(mn), float(g['lr']), float(g['weight_decay']),
-                       float(g['momentum']), stream)
+            if t['plain_n_chunks']:
+                _timed_mem('sgd_nesterov_clip', 20.0 * t['plain_elems'], lib.sgd_nesterov_clip, t['ptrs'].data_ptr(),
+                           t['numel'].data_ptr(), t['plain_chunk_t'].data_ptr(), t['plain_chunk_o'].data_ptr(),
+                           t['plain_n_chunks'], sq.data_ptr(), float(grad_scale), float(mn), float(g['lr']),
+                           float(g['weight_decay']), float(g['momentum']), stream)
+            if t['fused_table'] is not None:     # conv weights: update + refresh of the bf16 GEMM layouts in one kernel
+                _timed_mem('sgd_pack_conv_weights', 24.0 * t['fused_elems'], lib.sgd_pack_conv_weights,
+                           t['fused_table'].data_ptr(), t['fused_n'], t['fused_blocks'], sq.data_ptr(), float(grad_scale),
+                           float(mn), float(g['lr']), float(g['weight_decay']), float(g['momentum']), stream)
+                fused_any = True
+        for pk in self._packers:
+            if fused_any:
+                pk.mark_fresh()
+            else:
+                pk.invalidate()
         self.last_sqnorm = sq
         return None
 

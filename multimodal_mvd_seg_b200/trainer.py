@@ -306,6 +306,10 @@ class nnUNetTrainer(object):
             acc_params += [m.weight for m in net.decoder.seg_layers]
             views += a.prezero(acc_params)
         ops.set_prezeroed(views)
+        # conv weights: optimiser update and refresh of their packed bf16 layouts in one kernel (no pack pass per step)
+        if hasattr(self.optimizer, 'attach_weight_packers'):
+            self.optimizer.attach_weight_packers([n._weight_packer() for n in self._networks()
+                                                  if hasattr(n, '_weight_packer')])
 
     @staticmethod
     def build_network_architecture(plans_manager, dataset_json, configuration_manager, num_input_channels,

@@ -71,6 +71,12 @@ def blockwise_teacher_forced(m, oracle, patch, cin, B, dev='cuda:0', seed=0):
     ours = dict(net.named_modules())
     ref_grads = {n: p.grad.detach().clone() for n, p in ref.named_parameters() if p.grad is not None}
     checked, errs_all, floors = 0, {}, {}
+    # the last decoder block and its head also run FUSED in the product (InstanceNorm + LeakyReLU folded into the head,
+    # csrc/norm_head.cu): keep their records for a second, joint check below
+    n_dec = len(net.decoder.stages)
+    last_blk = f'decoder.stages.{n_dec - 1}.convs.{len(net.decoder.stages[-1].convs) - 1}'
+    last_head = f'decoder.seg_layers.{n_dec - 1}'
+    fused_rec = (dict(rec[last_blk]), dict(rec[last_head])) if last_blk in rec and 'gy' in rec.get(last_head, {}) else None
     for name in list(rec):
         r = rec.pop(name)
         if 'gy' not in r:      # zero-weighted deep-supervision head: no gradient reaches it
@@ -121,6 +127,34 @@ def blockwise_teacher_forced(m, oracle, patch, cin, B, dev='cuda:0', seed=0):
             floors[f'{name}.{k}'] = (rel_err(got[k], truth[k]), rel_err(want[k], truth[k]))
         checked += 1
         del x, gy, y, r, x32, y32, got, want, truth
+    if fused_rec is not None and ops.head_fusion_ok(net.decoder.stages[-1].output_channels, ours[last_head]):
+        rb, rh = fused_rec
+        blk, head, rblk, rhead = ours[last_blk], ours[last_head], ref_mods[last_blk], ref_mods[last_head]
+        for p in list(blk.parameters()) + list(head.parameters()):
+            p.grad = None
+        x = ops.to_cl_view(rb['x'].to(torch.bfloat16)).detach().requires_grad_(True)
+        logits = blk.forward_cl(x, head=head)
+        logits.backward(ops.to_cl_view(rh['gy'].to(torch.bfloat16)))
+        got = {'out': ops.ncdhw_view(logits).float(), 'gx': ops.ncdhw_view(x.grad).float(),
+               'conv.weight': blk.conv.weight.grad.float(), 'norm.weight': blk.norm.weight.grad.float(),
+               'norm.bias': blk.norm.bias.grad.float(), 'head.weight': head.weight.grad.float(),
+               'head.bias': head.bias.grad.float()}
+        want = {'out': rh['y'].float(), 'gx': rb['gx'].float(),
+                'conv.weight': ref_grads[f'{last_blk}.conv.weight'].float(), 'norm.weight': ref_grads[f'{last_blk}.norm.weight'].float(),
+                'norm.bias': ref_grads[f'{last_blk}.norm.bias'].float(), 'head.weight': ref_grads[f'{last_head}.weight'].float(),
+                'head.bias': ref_grads[f'{last_head}.bias'].float()}
+        for p in list(rblk.parameters()) + list(rhead.parameters()):
+            p.grad = None
+        x32 = rb['x'].float().detach().requires_grad_(True)
+        y32 = rhead(rblk(x32))
+        y32.backward(rh['gy'].float())
+        truth = {'out': y32.detach(), 'gx': x32.grad, 'conv.weight': rblk.conv.weight.grad.float(),
+                 'norm.weight': rblk.norm.weight.grad.float(), 'norm.bias': rblk.norm.bias.grad.float(),
+                 'head.weight': rhead.weight.grad.float(), 'head.bias': rhead.bias.grad.float()}
+        for k in got:
+            errs_all[f'fused[{last_blk}+head].{k}'] = rel_err(got[k], want[k])
+            floors[f'fused[{last_blk}+head].{k}'] = (rel_err(got[k], truth[k]), rel_err(want[k], truth[k]))
+        checked += 1
     return checked, errs_all, floors
 
 

@@ -389,5 +389,34 @@ def test_upconv_bias_gradient_from_dgrad_epilogue_sums():
             grads[mode] = [t.bias.grad.detach().clone() for t in net.decoder.transpconvs]
     finally:
         ops.set_colsum_fusion(True)
-    for a, b in zip(grads[True], grads[False]):
-        torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-6)
+    # both are fp32 sums of the same bf16 values in different orders: compare norm-wise, against the scale of the summands
+    errs = [rel_err(a, b) for a, b in zip(grads[True], grads[False])]
+    print('up-convolution bias gradients, fused vs streamed:', ['%.2e' % e for e in errs],
+          [float(a.abs().max()) for a in grads[True]])
+    assert max(errs) < 5e-3, errs
+
+
+def test_norm_head_fusion_matches_oracle_blockwise():
+    """InstanceNorm + LeakyReLU of the last decoder block folded into the segmentation head (csrc/norm_head.cu; an opt-in
+    variant, ops.set_head_fusion): logits, input gradient and all parameter gradients (conv, norm, head) of the fused
+    block against the oracle's tensors, and the whole-network logits against the unfused path."""
+    import multimodal_mvd_seg_b200 as m
+    import oracle
+    from multimodal_mvd_seg_b200 import ops
+    from _parity import blockwise_teacher_forced, build_pair
+    try:
+        ops.set_head_fusion(True)
+        checked, errs, floors = blockwise_teacher_forced(m, oracle, (40, 40, 24), 2, 2)
+        fused = {k: e for k, e in errs.items() if k.startswith('fused[')}
+        assert len(fused) == 7, fused
+        bad = [f'{k}: {e:.4f}' for k, e in fused.items() if not e < TOL]
+        assert not bad, bad
+        net, ref, topo = build_pair(m, oracle, 2, (32, 32, 32))
+        x = torch.randn(2, 2, 32, 32, 32, device='cuda:0')
+        with torch.no_grad():
+            y_fused = net(x)
+            ops.set_head_fusion(False)
+            y_plain = net(x)
+        assert torch.equal(y_fused[0], y_plain[0])      # same rounding points: bit-identical logits
+    finally:
+        ops.set_head_fusion(False)
