@@ -233,6 +233,9 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
     for _ in range(2):
         tr.train_step_async(resident)
     barrier()
+    conc = getattr(tr, 'concurrent_networks', None)
+    if conc:       # per-kernel event timing wants one stream: the two networks run back to back in this pass only
+        tr.concurrent_networks = False
     timer = m.ops.ConvTimer()
     m.ops.set_conv_timer(timer)
     m.lib.reset_launch_count()
@@ -279,6 +282,8 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
             d['ms'] /= n_instr
             d['flops'] /= n_instr
 
+    if conc:
+        tr.concurrent_networks = True
     # ---- warm-up of the timed configuration (CUDA-graph capture happens here)
     tr.use_cuda_graph = not args.no_graph
     tr.split_graph = bool(args.split_graph)

@@ -709,6 +709,11 @@ class MVDTrainer(nnUNetTrainer):
         self.kl_T = kl_T
         self.kl_vessel_only = kl_vessel_only
         self.network2 = None
+        # the two modality networks are independent until the loss: run network 2 on a second stream so that its
+        # latency-bound low-resolution layers (grids smaller than the machine) and its HBM-bound passes fill in under
+        # network 1's kernels.  MVD_CONCURRENT_NETS=0 runs them back to back on one stream.
+        self.concurrent_networks = os.environ.get('MVD_CONCURRENT_NETS', '1') != '0'
+        self._net2_stream = None
 
     def initialize(self):
         if self.was_initialized:
@@ -731,7 +736,34 @@ class MVDTrainer(nnUNetTrainer):
         return [self.network, self.network2]
 
     def _forward(self, data):
-        return self.network(data[:, 0:1]), self.network2(data[:, 1:2])
+        if not self.concurrent_networks:
+            return self.network(data[:, 0:1]), self.network2(data[:, 1:2])
+        main = torch.cuda.current_stream()
+        if self._net2_stream is None:
+            self._net2_stream = torch.cuda.Stream(device=self.device)
+        side = self._net2_stream
+        side.wait_stream(main)                 # input, zero pool and weights are ready on the compute stream
+        with torch.cuda.stream(side):
+            out2 = self.network2(data[:, 1:2])
+        out1 = self.network(data[:, 0:1])
+        main.wait_stream(side)
+        return out1, out2
+
+    def _step_backward(self, output, target) -> torch.Tensor:
+        if not self.concurrent_networks or self._net2_stream is None:
+            return super()._step_backward(output, target)
+        l, _ = self._loss(output, target)
+        l.backward()
+        # network 2's backward ran on its own stream (autograd keeps every node on its forward stream); parameter
+        # gradients bypass AccumulateGrad here, so the engine has no leaf stream to join: do it explicitly
+        torch.cuda.current_stream().wait_stream(self._net2_stream)
+        world = 1
+        for a in self._arenas:
+            a.finish()
+            a.attach_grads()
+            world = a.world_size
+        self.optimizer.step(grad_scale=1.0 / world)
+        return l.detach()
 
     def _loss(self, output, target):
         out1, out2 = output
