@@ -144,10 +144,11 @@ typedef struct mvd_sgd_pack_desc {
 int mvd_sgd_pack_conv_weights(const mvd_sgd_pack_desc* descs_device, int n, int total_blocks, const double* sqnorm,
                                float gscale, float max_norm, float lr, float weight_decay, float momentum,
                                mvd_stream_t stream);
-/* Weight-gradient reduction mode.  1 (default): deterministic two-stage reduction -- every split of the voxel range
- * stores its partial dw into its own workspace slice, a finishing kernel adds the slices in a fixed order (bit-
- * reproducible, no atomics).  0: one slice, red.global.add.v4.f32 (order-dependent last bits).  Process-wide; changes the
- * answer of mvd_conv3d_workspace_bytes(pass 2).  Env MVD_WGRAD_ATOMICS=1 selects 0 at load. */
+/* Weight-gradient reduction mode.  0 (default): the splits of the voxel range reduce into one scratch with
+ * red.global.add.v4.f32 (order-dependent last bits).  1: deterministic two-stage reduction -- every split stores its
+ * partial dw into its own workspace slice and the slices are added in a fixed order (bit-reproducible; +1.2 % step time
+ * at cfg-2).  Process-wide; changes the answer of mvd_conv3d_workspace_bytes(pass 2).  Env MVD_DETERMINISTIC=1 selects 1
+ * at load.  (The split-K partials of small fprop / dgrad layers are always reduced in a fixed order.) */
 int mvd_set_deterministic(int on);
 int mvd_get_deterministic(void);
 size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass /*0 fprop,1 dgrad,2 wgrad*/);

@@ -126,9 +126,9 @@ def test_conv_fprop_dgrad_wgrad(m, case, algo):
 @pytest.mark.parametrize('cin,cout,E,s,k', [(32, 32, 40, 1, 3), (64, 64, 24, 1, 3), (32, 64, 24, 2, 3), (320, 320, 8, 1, 3),
                                             (64, 32, 16, 2, 2)])
 def test_wgrad_deterministic_two_stage_reduction(m, cin, cout, E, s, k):
-    """default reduction mode: every split of the voxel range stores its partial into its own workspace slice and the
-    finishing kernel adds the slices in a fixed order -> dw is bit-reproducible from run to run (and equals the atomics
-    mode up to fp32 summation order)."""
+    """deterministic reduction mode (mvd_set_deterministic(1)): every split of the voxel range stores its partial into its
+    own workspace slice and the slices are added in a fixed order -> dw is bit-reproducible from run to run (and equals
+    the default atomics mode up to fp32 summation order)."""
     ops = m.ops
     g = torch.Generator().manual_seed(5)
     p = (k - 1) // 2 if k == 3 else 0
@@ -136,20 +136,20 @@ def test_wgrad_deterministic_two_stage_reduction(m, cin, cout, E, s, k):
     Eo = geom.out_size((E, E, E))[0]
     x = torch.randn((2, E, E, E, cin), generator=g).to(BF).to(dev())
     dy = torch.randn((2, Eo, Eo, Eo, cout), generator=g).to(BF).to(dev())
-    assert m.lib.get_deterministic() == 1
     runs = []
-    for _ in range(3):
-        dw = torch.empty((cout, cin, k, k, k), dtype=torch.float32, device=dev())
-        ops.conv_wgrad(geom, x, dy, dw)
-        runs.append(dw)
-        torch.randn((1 << 22,), device=dev()).sum()     # perturb the timing between the runs
-    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
-    m.lib.set_deterministic(0)
+    m.lib.set_deterministic(1)
     try:
-        dwa = torch.empty_like(runs[0])
-        ops.conv_wgrad(geom, x, dy, dwa)
+        assert m.lib.get_deterministic() == 1
+        for _ in range(3):
+            dw = torch.empty((cout, cin, k, k, k), dtype=torch.float32, device=dev())
+            ops.conv_wgrad(geom, x, dy, dw)
+            runs.append(dw)
+            torch.randn((1 << 22,), device=dev()).sum()     # perturb the timing between the runs
     finally:
-        m.lib.set_deterministic(1)
+        m.lib.set_deterministic(0)
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    dwa = torch.empty_like(runs[0])
+    ops.conv_wgrad(geom, x, dy, dwa)                        # default mode: vector atomics
     assert rel_err(dwa, runs[0]) < 1e-5
     ref = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (cout, cin, k, k, k),
                                       dy.float().permute(0, 4, 1, 2, 3), stride=s, padding=p)
