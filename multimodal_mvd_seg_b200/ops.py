@@ -1008,7 +1008,10 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
                 segs[j].logits, segs[j].target, segs[j].dlogits, segs[j].V, segs[j].weight = \
                     lg.data_ptr(), tg.data_ptr(), None, V, float(weights[i])
             stride = B * C * 3 + 1
-            acc = zeros((ns, stride), torch.float64, dev)
+            # (the data-parallel batch_dice branch all-reduces and edits `acc` with in-place torch ops: those bump the
+            # version counter of the whole tensor they alias, so it must not be a view of the shared zero pool, whose
+            # other views are saved for backward elsewhere)
+            acc = torch.zeros((ns, stride), dtype=torch.float64, device=dev) if ddp_bd else zeros((ns, stride), torch.float64, dev)
             coef = torch.empty((ns, B, C, 2), dtype=torch.float32, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             nbytes = sum(B * s.V * (2.0 * C + 4) for s in segs)
@@ -1030,7 +1033,8 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
         for (_, i, lg, tg) in items:
             Bi, D, H, W, Ci = lg.shape
             V = D * H * W
-            acc = zeros((Bi * Ci * 3 + 1,), torch.float64, dev)
+            acc = torch.zeros((Bi * Ci * 3 + 1,), dtype=torch.float64, device=dev) if ddp_bd else \
+                zeros((Bi * Ci * 3 + 1,), torch.float64, dev)
             _timed_mem('dice_ce_fwd', Bi * V * (2.0 * Ci + 4), lib.dice_ce_fwd, lg.data_ptr(), cl_pitch(lg), tg.data_ptr(),
                        Bi, V, Ci, acc.data_ptr(), st)
             if ddp_bd:

@@ -25,4 +25,4 @@ def test_split_step_equals_union_step_and_replicas_stay_identical(workload, batc
     assert p.returncode == 0 and lines, (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
     res = json.loads(lines[-1])
     assert res['ok'] and res['identical_after_initialize'] and res['identical_after_steps'], res
-    assert res['split_vs_union_update_rel_err'] < 2e-2, res
+    assert res['split_vs_emulated_update_rel_err'] < 5e-3 and res['split_vs_union_update_rel_err'] < 0.15, res
