@@ -364,7 +364,7 @@ def conv_roofline(r, peaks, clocks):
             'peak_burst': burst, 'peak_sustained': sustained,
             'kernel': 'conv3d fprop+dgrad+wgrad (all conv launches of the step)',
             'conv_share_of_step': tot_ms / r['ms_per_step'],
-            'timing': 'CUDA events around every conv launch in an instrumented eager pass of the same step',
+            'timing': 'CUDA events around every conv launch in an instrumented eager pass of the same step; a 0.1 ms busy-wait kernel queued ahead of each bracket keeps the host launch path out of the interval',
             'per_pass': {k: {'tflops': d['flops'] / (d['ms'] / 1e3) / 1e12, 'ms_per_step': d['ms'],
                              'launches_per_step': d['launches']} for k, d in conv.items()},
             'algorithmic_conv_gflop_per_step': conv_flops_per_step(r['patch'], PER_GPU_BATCH, 1 if r['dual'] else 2,
@@ -382,8 +382,8 @@ def hbm_roofline(r, peaks):
                      'algorithmic_mb_per_step': d['bytes'] / 1e6}
     return {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s',
             'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback of B200_PROFILING.md',
-            'timing': 'CUDA events around every launch of the family in the instrumented eager pass (short launches '
-                      'include their launch latency and pipeline fill)', 'kernels': out}
+            'timing': 'CUDA events around every launch of the family in the instrumented eager pass, each behind a 0.1 ms '
+                      'busy-wait kernel (device time only; short launches still include their pipeline fill)', 'kernels': out}
 
 
 def main():

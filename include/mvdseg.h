@@ -47,6 +47,8 @@ void mvd_reset_launch_count(void);
 unsigned long long mvd_fallback_count(void);
 void mvd_reset_fallback_count(void);
 int mvd_shutdown(void);
+/* measurement aid: one thread busy-waits `cycles` SM clocks on `stream` (not counted in mvd_launch_count) */
+int mvd_spin(long long cycles, mvd_stream_t stream);
 
 /* ---- layout at the module edge ---------------------------------------------------------------------------- */
 /* data.to(device) then network(data): fp32 NCDHW batch -> bf16 NDHWC (nnUNetTrainer.py:895,907).  src_batch_stride

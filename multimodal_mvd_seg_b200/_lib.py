@@ -54,6 +54,7 @@ S = c_void_p  # stream
 _SIGNATURES = {
     'mvd_version': (c_int, []),
     'mvd_last_error': (c_char_p, []),
+    'mvd_spin': (c_int, [LL, S]),
     'mvd_launch_count': (c_ulonglong, []),
     'mvd_reset_launch_count': (None, []),
     'mvd_fallback_count': (c_ulonglong, []),

@@ -31,7 +31,21 @@ int num_sms() {
 }
 }  // namespace mvd
 
+// busy-wait of `cycles` SM clocks on one thread: measurement aid (bench.py queues it in front of an event-timed launch so
+// that the host has enqueued the whole bracket before the GPU reaches it -- otherwise the events also measure how long
+// the GPU waited for the Python / ctypes launch path)
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+
 extern "C" {
+int mvd_spin(long long cycles, mvd_stream_t stream) {
+  if (cycles <= 0) return MVD_OK;
+  spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(cycles);
+  return cudaGetLastError() == cudaSuccess ? MVD_OK : MVD_ERR_CUDA;
+}
 int mvd_version(void) { return 100; }
 const char* mvd_last_error(void) { return mvd::g_err; }
 unsigned long long mvd_launch_count(void) { return mvd::g_launches.load(); }
