@@ -595,7 +595,7 @@ _bwd_overlap = _os.environ.get('MVD_NO_BWD_OVERLAP', '0') != '1'
 _side_streams = {}
 _pending = []            # (completion event on the side stream, main stream, tensors kept alive)
 _callback_queued = False
-_MAX_PENDING = int(_os.environ.get('MVD_MAX_PENDING_WGRAD', '2'))   # deferred wgrads in flight before the main stream waits for the oldest
+_MAX_PENDING = int(_os.environ.get('MVD_MAX_PENDING_WGRAD', '64'))   # deferred wgrads in flight before the main stream waits for the oldest
 
 
 def set_backward_overlap(on: bool):
@@ -610,7 +610,7 @@ def side_stream(dev, create: bool = False):
         key = torch.device('cuda', torch.cuda.current_device())
     st = _side_streams.get(key)
     if st is None and create:
-        st = _side_streams[key] = torch.cuda.Stream(device=key)
+        st = _side_streams[key] = torch.cuda.Stream(device=key, priority=0)    # lowest: the weight gradients fill gaps
     return st
 
 

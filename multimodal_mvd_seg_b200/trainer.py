@@ -591,9 +591,9 @@ class nnUNetTrainer(object):
                 # the targets (36 % of the batch bytes) can run on a copy stream underneath it
                 pool = torch.cuda.graph_pool_handle()
                 g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1, pool=pool):
+                with torch.cuda.graph(g1, pool=pool, stream=self._capture_stream()):
                     outs = self._step_forward(sd)
-                with torch.cuda.graph(g2, pool=pool):
+                with torch.cuda.graph(g2, pool=pool, stream=self._capture_stream()):
                     loss = self._step_backward(outs, stg)
                 st = self._graph_state = dict(key=key, graph=g1, graph2=g2, data=sd, target=stg, loss=loss, outs=outs,
                                               copy_stream=torch.cuda.Stream(device=sd.device),
@@ -601,7 +601,7 @@ class nnUNetTrainer(object):
                 st['ev_done'].record()
             else:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._capture_stream()):
                     loss = self._step_body(sd, stg)
                 st = self._graph_state = dict(key=key, graph=g, graph2=None, data=sd, target=stg, loss=loss)
             st['graph'].replay()
@@ -610,6 +610,17 @@ class nnUNetTrainer(object):
                 st['ev_done'].record()
             return st['loss']
         return self._replay(st, data, target)
+
+    def _capture_stream(self):
+        """the step is captured on a HIGH-priority stream: its kernel nodes (the dependency chain of the step) are
+        scheduled ahead of the deferred weight-gradient kernels, which run on a lowest-priority side stream and fill the
+        SMs the chain leaves free.  MVD_STREAM_PRIORITY=0 captures on a normal stream."""
+        if os.environ.get('MVD_STREAM_PRIORITY', '1') == '0':
+            return None
+        s = getattr(self, '_hp_stream', None)
+        if s is None:
+            s = self._hp_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return s
 
     def _replay(self, st, data, target) -> torch.Tensor:
         """copy a batch (host or device tensors) into the graph's static inputs and replay."""
@@ -740,7 +751,7 @@ class MVDTrainer(nnUNetTrainer):
             return self.network(data[:, 0:1]), self.network2(data[:, 1:2])
         main = torch.cuda.current_stream()
         if self._net2_stream is None:
-            self._net2_stream = torch.cuda.Stream(device=self.device)
+            self._net2_stream = torch.cuda.Stream(device=self.device, priority=-1)
         side = self._net2_stream
         side.wait_stream(main)                 # input, zero pool and weights are ready on the compute stream
         with torch.cuda.stream(side):
