@@ -91,7 +91,7 @@ class GradArena:
     """flat fp32 gradient storage + bucketed, backward-overlapped all-reduce."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter], bucket_bytes: int = 32 << 20,
-                 process_group=None, world_size: Optional[int] = None):
+                 process_group=None, world_size: Optional[int] = None, tail_bytes: int = 2 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.distributed = dist.is_available() and dist.is_initialized() and \
@@ -106,15 +106,28 @@ class GradArena:
             self.offset[id(p)] = (off, n)
             off += (n + 3) // 4 * 4  # keep every view 16-byte aligned
         self.flat = torch.zeros((off,), dtype=torch.float32, device=dev)
-        # buckets: contiguous ranges of ~bucket_bytes in backward order
+        # buckets: contiguous ranges of ~bucket_bytes in backward order, except the LAST one: the parameters whose
+        # gradients arrive at the very end of backward (the first encoder stages: a few hundred KB) form a small tail
+        # bucket of >= tail_bytes, so that the only all-reduce that cannot hide behind remaining backward work is
+        # latency-sized instead of up to bucket_bytes long
         self.buckets: List[dict] = []
-        cur = dict(start=0, end=0, ids=set())
         limit = max(1, bucket_bytes // 4)
-        for p in order:
+        tail_limit = max(1, min(tail_bytes, bucket_bytes) // 4)
+        split, acc = len(order), 0
+        while split > 1 and acc < tail_limit:
+            split -= 1
+            acc += (order[split].numel() + 3) // 4 * 4
+        if acc >= limit or split <= 0:
+            split = len(order)           # everything is tiny anyway: no separate tail
+        cur = dict(start=0, end=0, ids=set())
+        for k, p in enumerate(order):
+            if k == split and cur['ids']:
+                self.buckets.append(cur)
+                cur = dict(start=cur['end'], end=cur['end'], ids=set())
             o, n = self.offset[id(p)]
             cur['ids'].add(id(p))
             cur['end'] = o + (n + 3) // 4 * 4
-            if cur['end'] - cur['start'] >= limit:
+            if k < split and cur['end'] - cur['start'] >= limit:
                 self.buckets.append(cur)
                 cur = dict(start=cur['end'], end=cur['end'], ids=set())
         if cur['ids']:
