@@ -58,7 +58,7 @@ struct TcTap {
 // the output strides (the parity classes of a strided dgrad).  Plain convolutions have one class.
 struct TcClass {
   int tap_begin, ntaps;
-  int Dt, Ht, Wt, tiles_w, tiles_h;
+  int Dt, Ht, Wt, tiles_w, tiles_h, tiles_d;
   int tile_begin;                // first (m) tile index of this class
   long long out_off;             // element offset of the class lattice origin inside `out`
 };
@@ -91,6 +91,10 @@ struct TcParams {
   // re-streams the whole weight set): a work unit is (tile, slice s of the tap x channel-chunk loop); the epilogue adds
   // its fp32 partial into `scratch` (same element offsets as `out`) with vector reductions, splitk_finish_kernel then
   // applies bias / rounding / accumulate
+  // shape of the 128-voxel brick (M tile) in the produced lattice: (8 w, 16 h, 1 d, 1 sample) for the large layers; small
+  // lattices (8^3, 4^3, 5x5x6 ...) use bricks that reach over planes and samples -- (8,8,2,1), (4,4,4,2) -- so that all
+  // 128 MMA rows are real voxels and the layer's weights are streamed once per 128 voxels, not once per half-empty plane
+  int bw, bh, bd, bb, tiles_b;
   int ksplit;
   float* scratch;              // [ksplit][out-shaped fp32]: slice s holds the partial of K slice s (plain stores, no atomics:
   long long slice_stride;      //  the finishing kernel adds the slices in a fixed order -> bit-reproducible results)
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  // tile -> (class, n0, b, d, h0, w0)
+  // work unit -> (class, n0, brick origin b, d, h0, w0)
+  const bool generic_brick = !(P.bw == 8 && P.bh == 16);
   auto decode_tile = [&](int unit, int& c, int& n0, int& b, int& d, int& h0, int& w0) {
     const int tile = unit / ksplit;
     const int nt = tile % P.num_n_tiles;
@@ -147,13 +152,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int i = 1; i < P.nclasses; ++i)
       if (m >= P.cls[i].tile_begin) c = i;
     m -= P.cls[c].tile_begin;
-    const int tw = P.cls[c].tiles_w, th = P.cls[c].tiles_h, Dt = P.cls[c].Dt;
-    w0 = (m % tw) * TILE_W;
+    const int tw = P.cls[c].tiles_w, th = P.cls[c].tiles_h, td = P.cls[c].tiles_d;
+    w0 = (m % tw) * P.bw;
     m /= tw;
-    h0 = (m % th) * TILE_H;
+    h0 = (m % th) * P.bh;
     m /= th;
-    d = m % Dt;
-    b = m / Dt;
+    d = (m % td) * P.bd;
+    b = (m / td) * P.bb;
+  };
+  // row of the brick (0..127) -> voxel offsets inside it
+  auto row_coords = [&](int rr, int& rw, int& rh, int& rd, int& rb) {
+    if (!generic_brick) { rw = rr & 7; rh = rr >> 3; rd = 0; rb = 0; return; }
+    rw = rr % P.bw; rr /= P.bw;
+    rh = rr % P.bh; rr /= P.bh;
+    rd = rr % P.bd;
+    rb = rr / P.bd;
   };
 
   if (warp == 0) {
@@ -238,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (st.b >= 0) st.flush(P.stats, P.Ntot, lane);
           st.reset(b);
         }
-        const int Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
+        const int Dt = P.cls[c].Dt, Ht = P.cls[c].Ht, Wt = P.cls[c].Wt;
         bf16* tile_base = P.out + P.cls[c].out_off + (long long)b * P.sb + (long long)d * P.sd;
         const long long sh = P.sh, sw = P.sw;
         // destination of channel 0 of the 32-column group starting at produced column n0 + cc, for row R of this warp
@@ -250,10 +263,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           return n;
         };
+        // element offset of row rr of the brick relative to tile_base, or -1 when that voxel is outside the lattice
+        auto row_off = [&](int rr) -> long long {
+          int rw, rh, rd, rb;
+          row_coords(rr, rw, rh, rd, rb);
+          const int h = h0 + rh, w = w0 + rw;
+          if (h >= Ht || w >= Wt || d + rd >= Dt || b + rb >= P.B) return -1;
+          return (long long)rb * P.sb + (long long)rd * P.sd + (long long)h * sh + (long long)w * sw;
+        };
         auto row_ptr_at = [&](int R, long long col_off) -> bf16* {
-          const int rr = q * 32 + R;
-          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
-          return (h < Ht && w < Wt) ? tile_base + (long long)h * sh + (long long)w * sw + col_off : nullptr;
+          const long long o = row_off(q * 32 + R);
+          return o >= 0 ? tile_base + o + col_off : nullptr;
         };
         const bool accum = P.accumulate != 0 && ksplit == 1;
         bf16x8 old[4];
@@ -266,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.n_tile);
         const int rr0 = q * 32 + lane;
-        const bool ok = (h0 + (rr0 >> 3) < Ht) && (w0 + (rr0 & 7) < Wt);
+        const long long own_off = row_off(rr0);
+        const bool ok = own_off >= 0;
         for (int cc = 32 * half; cc < P.n_tile; cc += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cc, v);
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const int kit = P.cls[c].ntaps * P.kchunks;
               const bool empty = (int)((long long)kit * (sl + 1) / ksplit) == (int)((long long)kit * sl / ksplit);
               float* dst = P.scratch + (long long)sl * P.slice_stride + P.cls[c].out_off + (long long)b * P.sb +
-                           (long long)d * P.sd + (long long)(h0 + (rr0 >> 3)) * sh + (long long)(w0 + (rr0 & 7)) * sw + n0 + cc;
+                           (long long)d * P.sd + own_off + n0 + cc;
 #pragma unroll
               for (int e = 0; e < 32; e += 4)
                 *reinterpret_cast<uint4*>(dst + e) = empty ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
@@ -368,13 +389,14 @@ int pick_n_tile(int N) {
 }  // namespace
 
 bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4] /*W,H,D,B extents*/,
-                       const long long strides_el[4] /*W,H,D,B strides in elements*/, int kc) {
+                       const long long strides_el[4] /*W,H,D,B strides in elements*/, int kc, const int* brick) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2], (cuuint64_t)dims[3]};
   cuuint64_t gstr[4] = {(cuuint64_t)strides_el[0] * 2, (cuuint64_t)strides_el[1] * 2, (cuuint64_t)strides_el[2] * 2,
                         (cuuint64_t)strides_el[3] * 2};
   cuuint32_t box[5] = {(cuuint32_t)kc, TILE_W, TILE_H, 1, 1};
+  if (brick) { box[1] = brick[0]; box[2] = brick[1]; box[3] = brick[2]; box[4] = brick[3]; }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -404,6 +426,19 @@ bool tc_shape_ok(int K, int N, int ldk, int ldn, const void* pk, const void* pn,
   if (((uintptr_t)pk & 15) || ((uintptr_t)pn & 15) || ((uintptr_t)w & 15)) return false;
   if (taps > kMaxTaps) return false;
   return true;
+}
+
+// brick (M tile) shape for a produced lattice [B][D][H][W]: the default 8 x 16 plane brick, or -- for small lattices --
+// a brick that reaches over planes / samples so that its 128 rows are real voxels
+static void pick_brick(int B, int D, int H, int W, long long nvox_limit, int brick[4]) {
+  brick[0] = 8; brick[1] = 16; brick[2] = 1; brick[3] = 1;
+  if ((long long)B * D * H * W > nvox_limit || H > 8) return;
+  const int bw = W > 4 ? 8 : 4;
+  const int bh = H > 4 ? 8 : 4;
+  int rest = 128 / (bw * bh);            // 2, 4 or 8 rows of (d, b) left
+  int bd = 1;
+  while (bd < rest && bd < D) bd <<= 1;
+  brick[0] = bw; brick[1] = bh; brick[2] = bd; brick[3] = rest / bd;
 }
 
 // produced lattices this small go through the split-K form when the caller supplies a workspace (conv3d_workspace_bytes)
@@ -487,10 +522,11 @@ bool add_class(TcParams& P, int Dt, int Ht, int Wt, int tap_begin, int ntaps, lo
   TcClass& c = P.cls[P.nclasses++];
   c.tap_begin = tap_begin; c.ntaps = ntaps;
   c.Dt = Dt; c.Ht = Ht; c.Wt = Wt;
-  c.tiles_w = cdiv(Wt, TILE_W); c.tiles_h = cdiv(Ht, TILE_H);
+  c.tiles_w = cdiv(Wt, P.bw); c.tiles_h = cdiv(Ht, P.bh); c.tiles_d = cdiv(Dt, P.bd);
+  P.tiles_b = cdiv(P.B, P.bb);
   c.tile_begin = P.num_m_tiles;
   c.out_off = out_off;
-  P.num_m_tiles += P.B * Dt * c.tiles_h * c.tiles_w;
+  P.num_m_tiles += P.tiles_b * c.tiles_d * c.tiles_h * c.tiles_w;
   return true;
 }
 
@@ -560,6 +596,9 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
   TcMaps maps;
   TcParams P;
   memset(&P, 0, sizeof(P));
+  int brick[4];
+  pick_brick(a->B, a->Do, a->Ho, a->Wo, (a->stats && (a->Cout == 32 || a->Cout == 64)) ? 0 : kSplitKMaxVoxels, brick);
+  P.bw = brick[0]; P.bh = brick[1]; P.bd = brick[2]; P.bb = brick[3];
   const bf16* x = (const bf16*)a->x;
   const long long ld = a->ldx;
   bool ok = true;
@@ -574,7 +613,7 @@ int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st) {
         if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) { dims[0] = dims[1] = dims[2] = 1; base = x; }
         const long long strides[4] = {ld * a->sw, ld * a->Wi * a->sh, ld * a->Wi * a->Hi * a->sd,
                                       ld * a->Wi * a->Hi * a->Di};
-        ok = tc_encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc);
+        ok = tc_encode_act_map(&maps.a[mi], base, a->Cin, a->ldx, dims, strides, kc, brick);
       }
   const int taps = a->kd * a->kh * a->kw;
   P.n_tile = pick_n_tile(a->Cout);
@@ -644,11 +683,17 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   TcMaps maps;
   TcParams P;
   memset(&P, 0, sizeof(P));
+  int brick[4];
+  {   // bricks live on the parity sub-lattices of the produced tensor; the transposed-conv scatter keeps the default
+    const bool scatter = a->kd == a->sd && a->kh == a->sh && a->kw == a->sw && a->pd == 0 && a->ph == 0 && a->pw == 0;
+    pick_brick(a->B, cdiv(a->Di, a->sd), cdiv(a->Hi, a->sh), cdiv(a->Wi, a->sw), scatter ? 0 : kSplitKMaxVoxels, brick);
+  }
+  P.bw = brick[0]; P.bh = brick[1]; P.bd = brick[2]; P.bb = brick[3];
   const bf16* y = (const bf16*)a->y;
   const long long ldy = a->ldy;
   const int dims[4] = {a->Wo, a->Ho, a->Do, a->B};
   const long long strides[4] = {ldy, ldy * a->Wo, ldy * a->Wo * a->Ho, ldy * a->Wo * a->Ho * a->Do};
-  if (!tc_encode_act_map(&maps.a[0], y, a->Cout, a->ldy, dims, strides, kc)) {
+  if (!tc_encode_act_map(&maps.a[0], y, a->Cout, a->ldy, dims, strides, kc, brick)) {
     set_error("conv3d_dgrad(tcgen05): cuTensorMapEncodeTiled(A) failed");
     return MVD_ERR_CUDA;
   }

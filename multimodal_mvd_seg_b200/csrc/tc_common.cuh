@@ -167,7 +167,7 @@ inline CUtensorMapL2promotion tc_l2_promotion(long long row_bytes, long long pit
 // 5-D tensor map (C, W, H, D, B) over a pitched NDHWC bf16 lattice with box (box_c, 8, 16, 1, 1); swizzle 128B when
 // box_c == 64, 64B when box_c == 32.  dims / strides are the W,H,D,B extents and element strides of the lattice.
 bool tc_encode_act_map(CUtensorMap* m, const bf16* base, int C, int ld, const int dims[4], const long long strides_el[4],
-                       int box_c);
+                       int box_c, const int* brick = nullptr /* {w, h, d, b} box, default {8, 16, 1, 1} */);
 // 2-D map over packed weights [rows][K] with box (kc, n_tile)
 bool tc_encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n_tile, int kc);
 // halo-plane kernel for 3x3x3 / stride 1 / pad 1 (conv_tc_halo.cu): dst[v][n] = sum_{o in {0,1,2}^3} sum_k
