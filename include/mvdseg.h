@@ -65,6 +65,19 @@ int mvd_ndhwc_bf16_to_ncdhw_f32(const void* src, int ld_src, float* dst, int B, 
  * utilities/get_network_from_plans.py:70-83 and training/my_network/UNetDecoder.py:55-65.
  * One geometry struct serves all six entry points; (Di,Hi,Wi,Cin) is always the conv INPUT side
  * (for a transposed conv the "conv" is its adjoint, i.e. Cin = the ConvTranspose3d's out_channels). */
+/* InstanceNorm + LeakyReLU that sits in FRONT of the tensor a data gradient is produced for (the block whose output the
+ * conv consumed): with it mvd_conv3d_dgrad also returns that block's backward statistics, so the separate pass
+ * mvd_inorm_lrelu_bwd_stats over the gradient it just wrote is not needed (get_network_from_plans.py:41-44: conv -> norm ->
+ * nonlin blocks back to back). */
+typedef struct {
+  const void* y; int ldy;     /* bf16 raw output of the conv in front of that norm, dense voxel order, pitch ldy      */
+  const double* stats;        /* its forward statistics [B][Cin][2] (sum, sum of squares)                             */
+  const float* gamma;         /* affine weight / bias, fp32 [Cin]; may be NULL (1 / 0)                                */
+  const float* beta;
+  float eps, slope;
+  double* bstats;             /* out, accumulated (caller zeroes): [B][Cin][2] exactly as mvd_inorm_lrelu_bwd_stats   */
+} mvd_norm_bwd_stats_args;
+
 typedef struct {
   int B;
   int Di, Hi, Wi, Cin;   /* conv input  [B,Di,Hi,Wi,Cin]  */
@@ -86,6 +99,10 @@ typedef struct {
                                               mvd_conv3d_workspace_bytes */
   int algo;                   /* 0 auto, 1 CUDA-core tiles, 2 tcgen05 implicit GEMM                          */
   int accumulate;             /* dgrad: add into the output instead of overwriting it                       */
+  const mvd_norm_bwd_stats_args* norm_bwd; /* dgrad only, optional: also produce the backward statistics of the
+                                 InstanceNorm + LeakyReLU in front of x from the FINAL values written to x (after
+                                 accumulate).  Computed in the conv epilogue where mvd_conv3d_dgrad_fuses_norm_bwd says so,
+                                 by a pass over x otherwise. */
 } mvd_conv3d_args;
 
 /* Sliding-window inference accumulators (inference/predict_from_raw_data.py:703-712):
@@ -157,6 +174,8 @@ size_t mvd_conv3d_workspace_bytes(const mvd_conv3d_args* a, int pass /*0 fprop,1
 int mvd_conv3d_fprop(const mvd_conv3d_args* a, mvd_stream_t stream); /* y = conv(x, w) + bias  (w = w_fprop) */
 int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* x = conv^T(y, w)       (w = w_dgrad) */
 int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream); /* dw = x (*) y, dbias = sum y          */
+/* 1 when mvd_conv3d_dgrad(a) folds a->norm_bwd into its epilogue (no extra pass over the produced gradient) */
+int mvd_conv3d_dgrad_fuses_norm_bwd(const mvd_conv3d_args* a);
 
 /* stem (Cin = 1 or 2 input modalities): explicit im2col, X_col[v][tap*Cin + ci] (stride 1), zero-padded to Kpad columns
  * (a multiple of 8); the stem's fprop / wgrad then run as single-tap tensor-core GEMMs over X_col. */

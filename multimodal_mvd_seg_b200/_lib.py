@@ -35,7 +35,14 @@ class ConvArgs(Structure):
         ('workspace', c_void_p), ('workspace_bytes', c_size_t),
         ('algo', c_int),
         ('accumulate', c_int),
+        ('norm_bwd', c_void_p),
     ]
+
+
+class NormBwdStatsArgs(Structure):
+    """mirror of mvd_norm_bwd_stats_args (include/mvdseg.h)."""
+    _fields_ = [('y', c_void_p), ('ldy', c_int), ('stats', c_void_p), ('gamma', c_void_p), ('beta', c_void_p),
+                ('eps', c_float), ('slope', c_float), ('bstats', c_void_p)]
 
 
 class DiceCESegment(Structure):
@@ -75,6 +82,7 @@ _SIGNATURES = {
     'mvd_conv3d_fprop': (c_int, [POINTER(ConvArgs), S]),
     'mvd_conv3d_dgrad': (c_int, [POINTER(ConvArgs), S]),
     'mvd_conv3d_wgrad': (c_int, [POINTER(ConvArgs), S]),
+    'mvd_conv3d_dgrad_fuses_norm_bwd': (c_int, [POINTER(ConvArgs)]),
     'mvd_inorm_stats': (c_int, [P, I, I, LL, I, P, S]),
     'mvd_inorm_lrelu_fwd': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, S]),
     'mvd_inorm_lrelu_bwd_stats': (c_int, [P, I, P, I, P, P, P, I, LL, I, F, F, P, S]),
@@ -125,7 +133,7 @@ _SIGNATURES = {
 
 _UNCHECKED = {'mvd_version', 'mvd_last_error', 'mvd_launch_count', 'mvd_reset_launch_count', 'mvd_fallback_count',
               'mvd_reset_fallback_count', 'mvd_get_deterministic', 'mvd_inorm_lrelu_head_supported',
-              'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks'}
+              'mvd_conv3d_workspace_bytes', 'mvd_pack_blocks', 'mvd_conv3d_dgrad_fuses_norm_bwd'}
 
 
 def _load():

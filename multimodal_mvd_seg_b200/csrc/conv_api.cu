@@ -68,13 +68,29 @@ int mvd_conv3d_dgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {
                       a->ph == 1 && a->pw == 1;
   const bool fuse = a->stats && tc && a->algo != 1 && k3s1p1 && !a->accumulate && (a->Cin == 32 || a->Cin == 64) &&
                     tc_splitk_workspace_bytes(a, 1) == 0;
+  // optional backward statistics of the InstanceNorm + LeakyReLU in front of x: halo-kernel epilogue, else a pass over x
+  const bool fuse_nb = a->norm_bwd && a->algo != 1 && tc && tc_dgrad_fuses_norm_bwd(a);
   mvd_conv3d_args b = *a;
   if (!fuse) b.stats = nullptr;
+  if (!fuse_nb) b.norm_bwd = nullptr;
   rc = (a->algo != 1 && tc) ? tc_dgrad(&b, st) : generic_dgrad(&b, st);
   if (rc) return rc;
-  if (a->stats && !fuse)
-    return mvd_inorm_stats(a->x, a->ldx, a->B, (long long)a->Di * a->Hi * a->Wi, a->Cin, a->stats, stream);
+  if (a->stats && !fuse) {
+    rc = mvd_inorm_stats(a->x, a->ldx, a->B, (long long)a->Di * a->Hi * a->Wi, a->Cin, a->stats, stream);
+    if (rc) return rc;
+  }
+  if (a->norm_bwd && !fuse_nb) {
+    const mvd_norm_bwd_stats_args* nb = a->norm_bwd;
+    MVD_REQUIRE(nb->y && nb->stats && nb->bstats, "conv3d_dgrad: incomplete norm_bwd description");
+    return mvd_inorm_lrelu_bwd_stats(a->x, a->ldx, nb->y, nb->ldy, nb->stats, nb->gamma, nb->beta, a->B,
+                                     (long long)a->Di * a->Hi * a->Wi, a->Cin, nb->eps, nb->slope, nb->bstats, stream);
+  }
   return MVD_OK;
+}
+
+int mvd_conv3d_dgrad_fuses_norm_bwd(const mvd_conv3d_args* a) {
+  if (!a || !a->norm_bwd || !a->x || !a->y || !a->w || a->algo == 1) return 0;
+  return tc_dgrad_fuses_norm_bwd(a) ? 1 : 0;
 }
 
 int mvd_conv3d_wgrad(const mvd_conv3d_args* a, mvd_stream_t stream) {

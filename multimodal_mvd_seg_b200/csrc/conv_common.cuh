@@ -13,6 +13,7 @@ bool tc_dgrad_supported(const mvd_conv3d_args* a);
 bool tc_wgrad_supported(const mvd_conv3d_args* a);
 int tc_fprop(const mvd_conv3d_args* a, cudaStream_t st);
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st);
+bool tc_dgrad_fuses_norm_bwd(const mvd_conv3d_args* a);   // a->norm_bwd goes into the dgrad epilogue (halo kernels)
 int tc_wgrad(const mvd_conv3d_args* a, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const mvd_conv3d_args* a);   // fp32 scratch [taps][Cin][Cout]
 size_t tc_splitk_workspace_bytes(const mvd_conv3d_args* a, int pass);   // fprop (0) / dgrad (1): split-K partials, 0 = not split

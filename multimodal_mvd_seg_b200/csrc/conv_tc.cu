@@ -669,6 +669,15 @@ bool tc_dgrad_supported(const mvd_conv3d_args* a) {
   return get_encode_tiled() != nullptr;
 }
 
+bool tc_dgrad_fuses_norm_bwd(const mvd_conv3d_args* a) {
+  const mvd_norm_bwd_stats_args* nb = a->norm_bwd;
+  if (!nb || !nb->y || !nb->stats || !nb->bstats || a->stats) return false;
+  if (!tc_dgrad_supported(a) || tc_subpixel_dgrad_supported(a)) return false;
+  if (!(is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 1))) return false;
+  // built into the depth-folded halo kernel's epilogue for 32 produced channels (the two full-resolution blocks)
+  return a->Cin == 32 && tc_halo_fold_eligible(a->Cin, a->Cout, a->Di) && nb->ldy % 8 == 0 && (((uintptr_t)nb->y) & 15) == 0;
+}
+
 int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
   if (tc_subpixel_dgrad_supported(a)) return tc_subpixel_dgrad(a, st);
   if (is_k3s1p1(a) && tc_halo_enabled() && !tc_splitk_wanted(a, 1)) {
@@ -677,7 +686,8 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
     // a->stats (conv_api passes it only for Cin = 32 / 64 without accumulate): per-(sample, channel) sums of the produced
     // gradient from the epilogue -- the bias gradient of the up-convolution that produced half of this tensor
     return tc_halo_conv((const bf16*)a->y, a->ldy, a->Cout, (bf16*)a->x, a->ldx, a->Cin, (const bf16*)a->w, wrow,
-                        a->bias, a->accumulate, a->stats, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)");
+                        a->bias, a->accumulate, a->stats, a->B, a->Di, a->Hi, a->Wi, st, "conv3d_dgrad(tcgen05 halo)",
+                        a->norm_bwd);
   }
   const int kc = (a->Cout % 64 == 0) ? 64 : 32;
   TcMaps maps;

@@ -22,6 +22,7 @@ namespace {
 using namespace tc;
 
 constexpr int kThreads = 224;
+constexpr size_t kFoldBudget = 215 * 1024;   // dynamic shared memory of the depth-folded kernel (weights + plane ring)
 constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2, PLANE_ROWS = HALO_W * HALO_H;
 constexpr int kMaxRing = 8, kMaxWStages = 16;
 constexpr int kMaxN = 1024;   // largest produced-channel count the tap-major kernel stages a bias vector for
@@ -44,6 +45,15 @@ struct HaloParams {
   int Ntot;
   long long* prof;   // optional [gridDim.x][8] cycle counters of the MMA issuer (debug / DESIGN.md evidence)
   int wrow[27];
+  int lane_own;      // epilogue stores each lane's own accumulator row (no shared-memory transpose), see tc_epilogue.cuh
+  // data gradient of the depth-folded kernel only: backward statistics of the InstanceNorm + LeakyReLU in front of the
+  // produced tensor (mvd_norm_bwd_stats_args); nb_out == nullptr switches it off
+  const bf16* nb_y;
+  int nb_ld;
+  const double* nb_stats;
+  const float *nb_gamma, *nb_beta;
+  float nb_eps, nb_slope;
+  double* nb_out;
 };
 
 // work item -> (N tile, sample, first output plane, brick origin)
@@ -96,12 +106,18 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
         uint32_t w2[16];
-        epilogue_chunk<SC>(v, sbias + n0 + c, hs, c, ok, w2);
-        store_rows_coalesced_packed(stage, lane, w2, [&](int R) -> bf16* {
-          const int r2 = q * 32 + R;
-          const int h = h0 + (r2 >> 3), w = w0 + (r2 & 7);
-          return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
-        }, P.accumulate != 0);
+        epilogue_chunk<SC>(v, P.bias ? sbias + n0 + c : nullptr, hs, c, ok, w2);
+        if (P.lane_own) {
+          if (ok)
+            store_row_lane_own(tile_base + (long long)(h0 + (rr >> 3)) * sh + (long long)(w0 + (rr & 7)) * sw + c, w2,
+                               P.accumulate != 0);
+        } else {
+          store_rows_coalesced_packed(stage, lane, w2, [&](int R) -> bf16* {
+            const int r2 = q * 32 + R;
+            const int h = h0 + (r2 >> 3), w = w0 + (r2 & 7);
+            return (h < H && w < W) ? tile_base + (long long)h * sh + (long long)w * sw + c : nullptr;
+          }, P.accumulate != 0);
+        }
       }
     }
     tcgen05_fence_before();
@@ -111,6 +127,145 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
     if (acc == 0) accphase ^= 1;
   }
   if (do_stats && hs.b >= 0) hs.flush(P.stats, P.Ntot, lane);
+}
+
+// ---- data-gradient epilogue (N = 32) that also leaves the backward statistics of the InstanceNorm + LeakyReLU in front
+// of the produced tensor (csrc/norm_act.cu: inorm_lrelu_bwd_stats_kernel), from the values it stores:
+//   g' = g * (gamma*xhat + beta > 0 ? 1 : slope),   S1 = sum g',   S2 = sum g' xhat,   xhat = (y - mean) * rstd.
+// Everything stays in the lane-own layout (lane = voxel, 32 channels in registers): the raw conv outputs y of the lane's
+// voxel are 64 contiguous bytes, the LeakyReLU mask is a comparison of y with a per-channel threshold (the sign of
+// gamma*rstd folded in by flipping the signs of y and of the threshold), and every lane keeps fp32 partial sums of g' and
+// g'*(+-y) for all 32 channels across the CTA's work items; cross-lane reduction, the affine map sum g'y -> sum g'xhat
+// and the fp64 atomics run once per (sample, CTA).  No shared memory in the item loop (see store_row_lane_own).
+struct NbTables {
+  float thr[32];       // threshold of (+-y) above which the pre-activation is positive (+-inf for a constant mask)
+  uint32_t neg;        // bit c: gamma*rstd < 0, i.e. the comparison runs on -y
+};
+
+template <int MT>
+__device__ __forceinline__ void halo_epilogue_nb(const HaloParams& P, uint32_t tmem_base, uint64_t* bar_tfull,
+                                                 uint64_t* bar_tempty, const float* sbias, NbTables* tab, int q,
+                                                 int lane) {
+  int acc = 0;
+  uint32_t accphase = 0;
+  int cur_b = -1;
+  const int H = P.H, W = P.W;
+  const long long ysw = P.nb_ld, ysh = ysw * W, ysd = ysh * H;
+  const double Vd = (double)P.D * (double)H * (double)W;
+  LaneStats<0> none;
+  float thr[32], s1[32], s2[32];
+  uint32_t neg = 0;
+  auto mean_rstd = [&](int b, int c, float& mean, float& rstd) {     // exactly as load_scale_shift (norm_act.cu)
+    const double a1 = P.nb_stats[((long long)b * 32 + c) * 2 + 0];
+    const double a2 = P.nb_stats[((long long)b * 32 + c) * 2 + 1];
+    const double m = a1 / Vd;
+    double var = a2 / Vd - m * m;
+    if (var < 0.0) var = 0.0;
+    rstd = (float)(1.0 / sqrt(var + (double)P.nb_eps));
+    mean = (float)m;
+  };
+  auto flush = [&](int b) {
+    // column sums over the warp's 32 lanes: afterwards lane l owns channel l
+    const float S1 = warp_column_sum32(s1, lane), A = warp_column_sum32(s2, lane);
+    float mean, rstd;
+    mean_rstd(b, lane, mean, rstd);
+    const double Ay = ((tab->neg >> lane) & 1u) ? -(double)A : (double)A;      // sum g' y
+    double* d = P.nb_out + ((long long)b * 32 + lane) * 2;
+    atomicAdd(d, (double)S1);
+    atomicAdd(d + 1, (double)rstd * (Ay - (double)mean * (double)S1));          // sum g' xhat
+  };
+  for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+    int n0, b, d0, h0, w0;
+    halo_decode(P, MT, item, n0, b, d0, h0, w0);
+    if (b != cur_b) {       // all four epilogue warps arrive here at the same items
+      if (cur_b >= 0) flush(cur_b);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0) {
+        float mean, rstd;
+        mean_rstd(b, lane, mean, rstd);
+        const float g = P.nb_gamma ? P.nb_gamma[lane] : 1.f;
+        const float be = P.nb_beta ? P.nb_beta[lane] : 0.f;
+        const float sc = g * rstd, shf = be - mean * g * rstd;      // pre-activation t = y * sc + shf;  mask = t > 0
+        float th;
+        if (sc > 0.f) th = -shf / sc;                 // y > th
+        else if (sc < 0.f) th = shf / sc;             // y < -shf/sc  <=>  -y > shf/sc
+        else th = __int_as_float(shf > 0.f ? 0xff800000 : 0x7f800000);   // constant mask: -inf (always) / +inf (never)
+        tab->thr[lane] = th;
+        const uint32_t negb = __ballot_sync(0xffffffffu, sc < 0.f);
+        if (lane == 0) tab->neg = negb;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      neg = tab->neg;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        thr[j] = tab->thr[j];
+        s1[j] = s2[j] = 0.f;
+      }
+      cur_b = b;
+    }
+    const float slope = P.nb_slope;
+    const int rr = q * 32 + lane;
+    const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+    const bool ok = h < H && w < W;
+    const int mt = min(MT, P.D - d0);
+    bf16* out_row = P.out + (long long)b * P.sb + (long long)d0 * P.sd + (long long)h * P.sh + (long long)w * P.sw;
+    const bf16* y_row = P.nb_y + ((long long)b * P.D + d0) * ysd + (long long)h * ysh + (long long)w * ysw;
+    // the lane's 64 bytes of y for plane t, two planes ahead of the one being reduced (MT is a compile-time constant:
+    // the loop below is fully unrolled and the three buffers keep static names)
+    uint4 yb[3][4];
+    auto load_y = [&](int t, uint4* dst) {
+      if (ok && t < mt) {
+        const bf16* src = y_row + (long long)t * ysd;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(dst[g].x), "=r"(dst[g].y), "=r"(dst[g].z), "=r"(dst[g].w) : "l"(src + 8 * g) : "memory");
+      }
+    };
+    load_y(0, yb[0]);
+    load_y(1, yb[1]);
+    mbar_wait(&bar_tfull[acc], accphase, 36);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+      if (t < mt) {      // uniform across the CTA
+        load_y(t + 2, yb[(t + 2) % 3]);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + t) * 32);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        uint32_t w2[16];
+        epilogue_chunk<0>(v, P.bias ? sbias : nullptr, none, 0, false, w2);
+        if (ok) {
+          store_row_lane_own(out_row + (long long)t * P.sd, w2, P.accumulate != 0);
+          const uint4* yv = yb[t % 3];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t yw[4] = {yv[g].x, yv[g].y, yv[g].z, yv[g].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = 8 * g + 2 * k;          // channels j, j + 1
+              const float g0 = __uint_as_float(w2[4 * g + k] << 16), g1 = __uint_as_float(w2[4 * g + k] & 0xffff0000u);
+              const float y0 = __uint_as_float((yw[k] << 16) ^ ((neg << (31 - j)) & 0x80000000u));
+              const float y1 = __uint_as_float((yw[k] & 0xffff0000u) ^ ((neg << (30 - j)) & 0x80000000u));
+              const float p0 = g0 * (y0 > thr[j] ? 1.f : slope);
+              const float p1 = g1 * (y1 > thr[j + 1] ? 1.f : slope);
+              s1[j] += p0;
+              s2[j] = fmaf(p0, y0, s2[j]);
+              s1[j + 1] += p1;
+              s2[j + 1] = fmaf(p1, y1, s2[j + 1]);
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+    acc ^= 1;
+    if (acc == 0) accphase ^= 1;
+  }
+  if (cur_b >= 0) flush(cur_b);
 }
 
 template <int MT>
@@ -311,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 // once per CTA) and lets the planes stream through a short ring across work items; MT is limited by TMEM only
 // (2 x MT x N <= 512 columns).  The first MMA that touches a new output plane is split off (accumulate = 0).
 // ------------------------------------------------------------------------------------------------------------------
-template <int KC, int MT>
+template <int KC, int MT, bool NB = false>   // NB: data gradient + norm-backward statistics (halo_epilogue_nb)
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __grid_constant__ HaloMaps maps,
                                                                      const __grid_constant__ HaloParams P) {
   constexpr int ROWB = KC * 2;
@@ -325,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[4][2048];
   __shared__ __align__(16) float s_bias[64];
+  __shared__ NbTables s_nbtab;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = P.n_tile;
   const int wtile_bytes = 3 * N * ROWB;                   // one (chunk, in-plane tap): rows [oz=2 | oz=1 | oz=0] x N
@@ -447,7 +603,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_fold_kernel(const __gri
       }
     }
   } else if (warp >= 2 && warp <= 5) {
-    halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], s_bias, warp & 3, lane);
+    if constexpr (NB) halo_epilogue_nb<MT>(P, tmem_base, bar_tfull, bar_tempty, s_bias, &s_nbtab, warp & 3, lane);
+    else halo_epilogue<MT>(P, tmem_base, bar_tfull, bar_tempty, s_stage[warp & 3], s_bias, warp & 3, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -647,9 +804,22 @@ bool tc_halo_enabled() {
   return v == 1;
 }
 
+// narrow layers whose 27 weight tiles fit in shared memory next to a short plane ring run the depth-folded kernel
+bool tc_halo_fold_eligible(int N, int K, int D) {
+  static int fold_enabled = -1;
+  if (fold_enabled < 0) {
+    const char* e = getenv("MVD_NO_HALO_FOLD");
+    fold_enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!fold_enabled || !(N == 32 || N == 64) || D < 2 || K % 32) return false;
+  const int kc = (K % 64 == 0) ? 64 : 32;
+  const size_t plane_bytes_f = (size_t)((PLANE_ROWS * kc * 2 + 1023) & ~1023);
+  return (size_t)27 * N * K * 2 + 3 * plane_bytes_f <= kFoldBudget;
+}
+
 int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
                  const float* bias, int accumulate, double* stats, int B, int D, int H, int W, cudaStream_t st,
-                 const char* who) {
+                 const char* who, const mvd_norm_bwd_stats_args* nb) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_error("%s: no cuTensorMapEncodeTiled", who); return MVD_ERR_CUDA; }
   const int kc = (K % 64 == 0) ? 64 : 32;
@@ -697,6 +867,10 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
     mt_cap = g_plan_mt > 0 ? g_plan_mt : 4;
   }
   if (stats && N != 32 && N != 64) { set_error("%s: fused InstanceNorm sums need N = 32 or 64", who); return MVD_ERR_UNSUPPORTED; }
+  if (nb && (stats || !tc_halo_fold_eligible(N, K, D) || N != 32 || nb->ldy % 8 || !nb->y || !nb->stats || !nb->bstats)) {
+    set_error("%s: the backward statistics of the norm in front are built for the depth-folded kernel with N = 32", who);
+    return MVD_ERR_UNSUPPORTED;
+  }
   {
     const long long ld = lds;
     cuuint64_t gdim[5] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
@@ -715,16 +889,11 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   }
   // narrow layers whose weights fit in shared memory: depth-folded kernel (see conv_halo_fold_kernel)
   {
-    static int fold_enabled = -1;
-    if (fold_enabled < 0) {
-      const char* e = getenv("MVD_NO_HALO_FOLD");
-      fold_enabled = (e && e[0] == '1') ? 0 : 1;
-    }
     const int rowb_f = kc * 2;
     const int plane_bytes_f = (PLANE_ROWS * rowb_f + 1023) & ~1023;
     const size_t w_res = (size_t)27 * N * K * 2;
-    const size_t budget_f = 216 * 1024;
-    if (fold_enabled && N == P.n_tile && (N == 32 || N == 64) && D >= 2 && w_res + 3 * (size_t)plane_bytes_f <= budget_f) {
+    const size_t budget_f = kFoldBudget;
+    if (tc_halo_fold_eligible(N, K, D)) {
       int MTf = 512 / (2 * N);                 // 8 (N = 32) or 4 (N = 64)
       while (MTf > D) MTf >>= 1;
       int ringf = (int)((budget_f - w_res) / plane_bytes_f);
@@ -744,6 +913,11 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
       P.bias = bias; P.accumulate = accumulate;
       P.prof = g_halo_prof;
       P.stats = stats; P.Ntot = N;
+      P.lane_own = (N == 32);      // narrow layers: the tensor pipe's operand reads own the shared-memory bandwidth
+      if (nb) {
+        P.nb_y = (const bf16*)nb->y; P.nb_ld = nb->ldy; P.nb_stats = nb->stats; P.nb_gamma = nb->gamma;
+        P.nb_beta = nb->beta; P.nb_eps = nb->eps; P.nb_slope = nb->slope; P.nb_out = nb->bstats;
+      }
       for (int i = 0; i < 27; ++i) P.wrow[i] = wrow[i];
       const size_t smemf = w_res + (size_t)ringf * plane_bytes_f + 1024;
       int gridf = num_sms();
@@ -757,10 +931,19 @@ int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, con
   }
       FOLD_PICK(64, 2, 0) FOLD_PICK(64, 4, 1) FOLD_PICK(64, 8, 2) FOLD_PICK(32, 2, 3) FOLD_PICK(32, 4, 4) FOLD_PICK(32, 8, 5)
 #undef FOLD_PICK
+#define FOLD_PICK_NB(KCV, MTV, IDX)                    \
+  if (nb && kc == KCV && MTf == MTV) {                 \
+    kf = conv_halo_fold_kernel<KCV, MTV, true>;        \
+    kif = IDX;                                         \
+  }
+      // N = 32 -> MT = 8 (4 / 2 for short volumes)
+      FOLD_PICK_NB(64, 2, 6) FOLD_PICK_NB(64, 4, 7) FOLD_PICK_NB(64, 8, 8) FOLD_PICK_NB(32, 2, 9) FOLD_PICK_NB(32, 4, 10)
+      FOLD_PICK_NB(32, 8, 11)
+#undef FOLD_PICK_NB
       if (kf) {
-        static bool fattr[6] = {false, false, false, false, false, false};
+        static bool fattr[12] = {};
         if (!fattr[kif]) {
-          cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+          cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);
           if (e != cudaSuccess) {
             (void)cudaGetLastError();
             set_error("%s: cudaFuncSetAttribute(fold): %s", who, cudaGetErrorString(e));

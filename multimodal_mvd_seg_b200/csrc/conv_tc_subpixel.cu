@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_subpixel_dgrad_kernel(const 
   __shared__ uint64_t bar_pfull[kRing], bar_pempty[kRing], bar_wres, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[8][2048];
-  __shared__ __align__(16) float s_zero[NCH];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
   uint8_t* smem_p = smem + W_BYTES;
@@ -81,7 +80,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_subpixel_dgrad_kernel(const 
     for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 8); }
     fence_barrier_init();
   }
-  if (threadIdx.x < NCH) s_zero[threadIdx.x] = 0.f;
   if (warp == 1) tmem_alloc(&s_tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
@@ -202,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_subpixel_dgrad_kernel(const 
           tmem_ld_32x32b_x32(taddr + (uint32_t)(c * NCH), v);
           tmem_ld_wait();
           uint32_t w2[16];
-          epilogue_chunk<0>(v, s_zero, nostats, 0, true, w2);
+          epilogue_chunk<0>(v, nullptr, nostats, 0, true, w2);
           if (accum) {
             bf16x8 cur[4];
             bool chas[4];

@@ -173,8 +173,9 @@ bool tc_encode_w_map(CUtensorMap* m, const bf16* w, long long rows, int K, int n
 // halo-plane kernel for 3x3x3 / stride 1 / pad 1 (conv_tc_halo.cu): dst[v][n] = sum_{o in {0,1,2}^3} sum_k
 // src[v + o - 1][k] * W[wrow[o] + n][k] (+ bias[n]); src/dst are pitched NDHWC lattices of the same extent B,D,H,W.
 bool tc_halo_enabled();
+bool tc_halo_fold_eligible(int N, int K, int D);   // would tc_halo_conv run the depth-folded kernel for this layer?
 int tc_halo_conv(const bf16* src, int lds, int K, bf16* dst, int ldd, int N, const bf16* w, const int wrow[27],
                  const float* bias, int accumulate, double* stats, int B, int D, int H, int W, cudaStream_t st,
-                 const char* who);
+                 const char* who, const mvd_norm_bwd_stats_args* norm_bwd = nullptr);
 
 }  // namespace mvd

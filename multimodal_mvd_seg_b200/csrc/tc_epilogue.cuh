@@ -85,6 +85,35 @@ __device__ __forceinline__ void store_rows_accumulate_packed(uint8_t* stage, int
   __syncwarp();
 }
 
+// Lane-own stores: every lane writes the 64 bytes of ITS accumulator row (32 channels of one voxel) with four 16-byte
+// stores -- no shared-memory transpose.  Each store instruction then touches 32 rows with half a sector each (L2 merges
+// them), which costs L1->L2 requests but no shared-memory bandwidth: the tensor pipe's operand reads take almost all of it
+// for narrow layers (N = 32: 7 KB per 56-cycle MMA = 125 B/clk of the 128 B/clk), and an epilogue that goes through shared
+// memory is then throttled to the leftover (measured, 32->32 at 128^3: forward 0.229 -> 0.212 ms with lane-own stores;
+// profiles/r2_epilogue_shared_memory.txt).  w[i] = bf16x2 of columns (2i, 2i+1); returns the values written (after the
+// optional accumulate) in w.
+__device__ __forceinline__ void store_row_lane_own(bf16* dst, uint32_t* w, bool accumulate) {
+  if (accumulate) {
+    uint4 old[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) old[g] = *reinterpret_cast<const uint4*>(dst + 8 * g);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t o[4] = {old[g].x, old[g].y, old[g].z, old[g].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = __uint_as_float(w[4 * g + k] << 16) + __uint_as_float(o[k] << 16);
+        const float hi = __uint_as_float(w[4 * g + k] & 0xffff0000u) + __uint_as_float(o[k] & 0xffff0000u);
+        __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+        w[4 * g + k] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+}
+
 // ---- InstanceNorm statistics fused into the conv epilogue ---------------------------------------------------------
 // Every lane holds one accumulator row (32 channels).  Column sums over the warp's 32 rows are formed with a
 // recursive-halving exchange (16+8+4+2+1 = 31 shuffles per quantity instead of 5 x 32): afterwards lane l owns channel l.
@@ -143,11 +172,19 @@ struct LaneStats {
 template <int SC>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t* v, const float* bias32, LaneStats<SC>& st, int c,
                                                bool ok, uint32_t* w2) {
+  if (bias32) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float2 bb = *reinterpret_cast<const float2*>(bias32 + j);
-    __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y);
-    w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    for (int j = 0; j < 32; j += 2) {
+      const float2 bb = *reinterpret_cast<const float2*>(bias32 + j);
+      __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y);
+      w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+  } else {     // no bias (data gradients): no shared-memory reads next to the tensor pipe's operand traffic
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    }
   }
   if (SC > 0 && ok) {
     if (SC == 1 || c == 0) {

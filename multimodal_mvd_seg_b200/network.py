@@ -60,18 +60,19 @@ class ConvDropoutNormReLU(nn.Module):
         self._geom = ConvGeom(k, s, [(i - 1) // 2 for i in k])
 
     def forward_cl(self, x_cl: torch.Tensor, out: Optional[torch.Tensor] = None,
-                   head: Optional[nn.Conv3d] = None) -> torch.Tensor:
+                   head: Optional[nn.Conv3d] = None, private_input: bool = False) -> torch.Tensor:
         """``head``: the 1x1x1 segmentation layer that is the only consumer of this block's output -- the call then
-        returns the head's logits (InstanceNorm + LeakyReLU folded into the head, ops.ConvNormActFn)."""
+        returns the head's logits (InstanceNorm + LeakyReLU folded into the head, ops.ConvNormActFn).
+        ``private_input``: x_cl is another block's output that nothing else reads (ops.ConvNormActFn)."""
         params = [p for p in (self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias) if p is not None]
         if head is not None:
             params = params + [p for p in (head.weight, head.bias) if p is not None]
             return ops.ConvNormActFn.apply(x_cl, self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias,
                                            self._geom, float(self.norm.eps), float(self.nonlin.negative_slope), None,
-                                           params, head.weight, head.bias)
+                                           params, head.weight, head.bias, private_input)
         return ops.ConvNormActFn.apply(x_cl, self.conv.weight, self.conv.bias, self.norm.weight, self.norm.bias,
                                        self._geom, float(self.norm.eps), float(self.nonlin.negative_slope),
-                                       Slot(out) if out is not None else None, params)
+                                       Slot(out) if out is not None else None, params, None, None, private_input)
 
     def forward(self, x):
         return ops.ncdhw_view(self.forward_cl(_to_cl(x)))
@@ -103,7 +104,7 @@ class StackedConvBlocks(nn.Module):
     def forward_cl(self, x_cl, out: Optional[torch.Tensor] = None, head: Optional[nn.Conv3d] = None):
         n = len(self.convs)
         for i, blk in enumerate(self.convs):
-            x_cl = blk.forward_cl(x_cl, out if i == n - 1 else None, head if i == n - 1 else None)
+            x_cl = blk.forward_cl(x_cl, out if i == n - 1 else None, head if i == n - 1 else None, private_input=i > 0)
         return x_cl
 
     def forward(self, x):

@@ -5,12 +5,14 @@ the hand-written sm_100a library.  Activations travel as bf16 tensors of logical
 possibly a channel slice of a wider buffer (voxel pitch ld > C), see include/mvdseg.h.
 """
 import ctypes
+import os
+import weakref
 import numpy as np
 from typing import Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import ConvArgs, DiceCESegment, MvdError, lib
+from ._lib import NormBwdStatsArgs, ConvArgs, DiceCESegment, MvdError, lib
 
 BF16 = torch.bfloat16
 
@@ -406,11 +408,39 @@ def conv_fprop(geom, x_cl, y_cl, wf, bias=None, stats=None, accumulate=False):
     del ws
 
 
-def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False, stats=None):
+def _norm_bwd_args(nb, bstats) -> NormBwdStatsArgs:
+    """nb = (y, stats, gamma, beta, eps, slope) of the ConvNormAct block whose output the conv consumed."""
+    y, stats, gamma, beta, eps, slope = nb
+    n = NormBwdStatsArgs()
+    n.y, n.ldy = y.data_ptr(), cl_pitch(y)
+    n.stats, n.gamma, n.beta = stats.data_ptr(), _ptr(gamma), _ptr(beta)
+    n.eps, n.slope = eps, slope
+    n.bstats = bstats.data_ptr()
+    return n
+
+
+def conv_dgrad_fuses_norm_bwd(geom, x_cl_out, y_cl, wd, nb) -> bool:
+    """Would conv_dgrad(..., norm_bwd=nb) form the statistics in its epilogue (no extra pass)?"""
+    a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd)
+    ws = _maybe_workspace(a, 1, y_cl.device)
+    n = _norm_bwd_args(nb, nb[1])      # the output pointer only has to be non-null for the query
+    a.norm_bwd = ctypes.addressof(n)
+    ok = bool(lib.conv3d_dgrad_fuses_norm_bwd(ctypes.byref(a)))
+    del ws
+    return ok
+
+
+def conv_dgrad(geom, x_cl_out, y_cl, wd, bias=None, accumulate=False, stats=None, norm_bwd=None, bstats=None):
+    """norm_bwd / bstats: also leave the backward statistics of the InstanceNorm + LeakyReLU in front of x_cl_out in
+    ``bstats`` ([B][Cin][2] fp64, zeroed by the caller) -- mvd_conv3d_args.norm_bwd."""
     a = _conv_args(geom, x_cl_out, y_cl, w_packed=wd, bias=bias, accumulate=accumulate, stats=stats)
     ws = _maybe_workspace(a, 1, y_cl.device)
+    n = None
+    if norm_bwd is not None:
+        n = _norm_bwd_args(norm_bwd, bstats)
+        a.norm_bwd = ctypes.addressof(n)
     _timed('dgrad', a, lib.conv3d_dgrad)
-    del ws
+    del ws, n
 
 
 def conv_wgrad(geom, x_cl, y_cl, dw, dbias=None):
@@ -529,6 +559,8 @@ def reset_skip_registry():
     _head_inputs.clear()
     _concat_bufs.clear()
     _dx_colsum.clear()
+    _norm_outputs.clear()
+    _dx_bstats.clear()
     _pair_pending.clear()      # entries whose head never ran backward (zero-weighted scale) must not pile up
 
 
@@ -544,6 +576,12 @@ _concat_bufs = set()   # data_ptr of the decoder's concat buffers (this forward)
                        # gradient of an up-convolution's output, whose bias gradient is its per-channel sum
 _dx_colsum = {}        # data_ptr of such a gradient tensor -> (statistics buffer its dgrad epilogue filled, channels)
 _colsum_fusion = True
+# A ConvNormAct block whose output feeds exactly one 3x3x3 / stride-1 conv (the first conv of every stage): that conv's
+# data-gradient epilogue already holds each gradient value it writes, so it also forms the block's InstanceNorm-backward
+# sums there (mvd_conv3d_args.norm_bwd) and the block skips its statistics pass over the gradient.
+_norm_outputs = {}     # data_ptr of a block's activation -> (weakref to it, y, stats, gamma, beta, eps, slope) of the block
+_dx_bstats = {}        # data_ptr of a produced gradient -> (bstats it comes with, data_ptr of the block's raw conv output)
+_norm_bwd_fusion = os.environ.get('MVD_NO_NORM_BWD_FUSION', '0') != '1'
 
 
 import os as _os
@@ -566,6 +604,12 @@ _head_fusion = _os.environ.get('MVD_HEAD_FUSION', '0') == '1'
 def head_fusion_ok(channels: int, head) -> bool:
     return (_head_fusion and head is not None and _default_algo != 1 and head.weight.is_cuda
             and bool(lib.inorm_lrelu_head_supported(int(channels), int(head.weight.shape[0]))))
+
+
+def set_norm_bwd_fusion(on: bool):
+    """InstanceNorm-backward sums out of the consumer conv's data-gradient epilogue (default on)."""
+    global _norm_bwd_fusion
+    _norm_bwd_fusion = bool(on)
 
 
 def set_colsum_fusion(on: bool):
@@ -666,10 +710,13 @@ def _defer_wgrad(dev, launch, keepalive, dw=None):
 class ConvNormActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_cl, weight, bias, gamma, beta, geom: ConvGeom, eps: float, slope: float,
-                out_slot: Optional['Slot'], params_for_hook, head_w=None, head_b=None):
+                out_slot: Optional['Slot'], params_for_hook, head_w=None, head_b=None, private_input=False):
         """head_w / head_b: the 1x1x1 segmentation head that is the ONLY consumer of this block's output (last decoder
         stage): the function then returns the head's logits and the normalised activation never exists in HBM
-        (csrc/norm_head.cu)."""
+        (csrc/norm_head.cu).
+        private_input: x_cl is the output of another ConvNormAct block and this conv is its ONLY consumer (conv i > 0 of a
+        StackedConvBlocks): the data gradient this conv produces is then that block's complete incoming gradient, and
+        its InstanceNorm-backward sums are formed in our data-gradient epilogue (see _norm_outputs)."""
         require_cuda(x_cl, 'ConvNormAct')
         out = out_slot.t if out_slot is not None else None
         x_cl = as_cl(x_cl)
@@ -713,6 +760,12 @@ class ConvNormActFn(torch.autograd.Function):
         else:
             wf, wd = _packed_for(weight, True, need_dx)
             conv_fprop(geom, x_cl, y, wf, bias=bias, stats=stats)   # InstanceNorm sums come out of the conv epilogue
+        ctx.prev_norm = None
+        if _norm_bwd_fusion and private_input and need_dx and not stem:
+            ent = _norm_outputs.pop(x_cl.data_ptr(), None)
+            if ent is not None and ent[0]() is not None and tuple(ent[1].shape) == tuple(x_cl.shape) and \
+                    conv_dgrad_fuses_norm_bwd(geom, x_cl, y, wd, ent[1:]):
+                ctx.prev_norm = ent[1:]
         ctx.geom, ctx.eps, ctx.slope = geom, eps, slope
         ctx.params_for_hook = params_for_hook
         ctx.has_head = head_w is not None
@@ -730,6 +783,8 @@ class ConvNormActFn(torch.autograd.Function):
         _timed_mem('inorm_lrelu_fwd', 4.0 * B * V * Cout, lib.inorm_lrelu_fwd, y.data_ptr(), cl_pitch(y), z.data_ptr(),
                    cl_pitch(z), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _stream())
         ctx.save_for_backward(x_cl, y, stats, wd if need_dx else None, weight, bias, gamma, beta, None, None)
+        if _norm_bwd_fusion and out is None:
+            _norm_outputs[z.data_ptr()] = (weakref.ref(z), y, stats, gamma, beta, eps, slope)
         return z
 
     @staticmethod
@@ -740,7 +795,12 @@ class ConvNormActFn(torch.autograd.Function):
         V = Do * Ho * Wo
         dev = y.device
         st = _stream()
-        bstats = zeros((B, Cout, 2), torch.float64, dev)
+        fused = None if ctx.has_head else _dx_bstats.pop(dz.data_ptr(), None)
+        if fused is not None and fused[1] == y.data_ptr() and tuple(dz.shape) == tuple(y.shape):
+            bstats = fused[0]          # left by the data-gradient epilogue of the conv that consumed our activation
+        else:
+            fused = None
+            bstats = zeros((B, Cout, 2), torch.float64, dev)
         dy = torch.empty_like(y)
         dgamma = _grad_like(gamma) if gamma is not None and ctx.needs_input_grad[3] else None
         dbeta = _grad_like(beta) if beta is not None and ctx.needs_input_grad[4] else None
@@ -765,9 +825,10 @@ class ConvNormActFn(torch.autograd.Function):
                        _ptr(dbeta), _ptr(db), st)
         else:
             dz = as_cl(dz)
-            _timed_mem('inorm_lrelu_bwd_stats', 4.0 * B * V * Cout, lib.inorm_lrelu_bwd_stats, dz.data_ptr(), cl_pitch(dz),
-                       y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope,
-                       bstats.data_ptr(), st)
+            if fused is None:
+                _timed_mem('inorm_lrelu_bwd_stats', 4.0 * B * V * Cout, lib.inorm_lrelu_bwd_stats, dz.data_ptr(),
+                           cl_pitch(dz), y.data_ptr(), cl_pitch(y), stats.data_ptr(), _ptr(gamma), _ptr(beta), B, V, Cout,
+                           eps, slope, bstats.data_ptr(), st)
             _timed_mem('inorm_lrelu_bwd_apply', 6.0 * B * V * Cout, lib.inorm_lrelu_bwd_apply, dz.data_ptr(), cl_pitch(dz),
                        y.data_ptr(), cl_pitch(y), dy.data_ptr(), cl_pitch(dy), stats.data_ptr(), bstats.data_ptr(),
                        _ptr(gamma), _ptr(beta), B, V, Cout, eps, slope, _ptr(dgamma), _ptr(dbeta), _ptr(db), st)
@@ -802,14 +863,19 @@ class ConvNormActFn(torch.autograd.Function):
                 if ctx.want_colsum:      # channel sums of dx out of the dgrad epilogue: the up-convolution's bias gradient
                     colsum = zeros((x_cl.shape[0], x_cl.shape[-1], 2), torch.float64, dev)
                     _dx_colsum[dx.data_ptr()] = (colsum, x_cl.shape[-1])
-                conv_dgrad(geom, dx, dy, wd, stats=colsum)
+                nb = ctx.prev_norm if colsum is None else None
+                nb_out = None
+                if nb is not None:
+                    nb_out = zeros((x_cl.shape[0], x_cl.shape[-1], 2), torch.float64, dev)
+                    _dx_bstats[dx.data_ptr()] = (nb_out, nb[0].data_ptr())
+                conv_dgrad(geom, dx, dy, wd, stats=colsum, norm_bwd=nb, bstats=nb_out)
         if plain_wgrad:   # after the dgrad: deferred onto the side stream (see "Backward overlap"), else right here
             if not _defer_wgrad(dev, lambda: conv_wgrad(geom, x_cl, dy, dw, None), (x_cl, dy, dw), dw):
                 conv_wgrad(geom, x_cl, dy, dw, None)
         if ctx.params_for_hook:
             _notify(ctx.params_for_hook)
         return (dx, _ret(dw, weight), _ret(db, bias), _ret(dgamma, gamma), _ret(dbeta, beta), None, None, None, None, None,
-                _ret(dhw, head_w), _ret(dhb, head_b))
+                _ret(dhw, head_w), _ret(dhb, head_b), None)
 
 
 # ---------------------------------------------------------------------------------------------------------------

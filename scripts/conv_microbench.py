@@ -23,11 +23,22 @@ bias = torch.zeros(cout, device=dev)
 wf, wd = ops.pack_weights(w)
 dw = torch.empty_like(w)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+nb = bstats = None
+if os.environ.get('NB') == '1' and which == 'dgrad':   # + backward sums of the norm in front (mvd_conv3d_args.norm_bwd)
+    y_prev = torch.randn((B, D, H, W, cin), device=dev).to(torch.bfloat16)
+    fstats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev)
+    m.lib.inorm_stats(y_prev.data_ptr(), cin, B, D * H * W, cin, fstats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    nb = (y_prev, fstats, torch.ones(cin, device=dev), torch.zeros(cin, device=dev), 1e-5, 0.01)
+    bstats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev)
 def run():
     if which == 'fprop':
         ops.conv_fprop(geom, x, y, wf, bias=bias)
     elif which == 'dgrad':
-        ops.conv_dgrad(geom, x, y, wd)
+        if nb is not None:
+            bstats.zero_()
+            ops.conv_dgrad(geom, x, y, wd, norm_bwd=nb, bstats=bstats)
+        else:
+            ops.conv_dgrad(geom, x, y, wd)
     else:
         ops.conv_wgrad(geom, x, y, dw)
 for _ in range(3):

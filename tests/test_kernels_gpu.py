@@ -336,6 +336,99 @@ def test_instance_norm_lrelu_fwd_bwd(m, C, shape):
     assert rel_err(db, br.grad) < 5e-3
 
 
+@pytest.mark.parametrize('cin,cout,shape,accumulate,fused', [
+    (32, 32, (2, 20, 24, 40), False, True),      # depth-folded kernel, two samples
+    (32, 64, (2, 9, 17, 21), False, True),       # ragged bricks in h and w, MT tail in d
+    (32, 32, (1, 16, 16, 24), True, True),       # accumulate into an existing gradient (6144 voxels: no split-K)
+    (32, 32, (2, 3, 48, 32), False, True),       # short volume: MT = 2
+    (64, 64, (1, 16, 32, 24), False, False),     # wider layers: the statistics pass runs inside the call
+    (128, 128, (2, 12, 16, 16), True, False),
+])
+def test_dgrad_epilogue_forms_norm_backward_statistics(m, cin, cout, shape, accumulate, fused):
+    """mvd_conv3d_args.norm_bwd: the data gradient call also leaves the InstanceNorm + LeakyReLU backward sums of the block
+    in front of the produced tensor -- for 32 produced channels out of the conv epilogue (one launch) -- equal to
+    mvd_inorm_lrelu_bwd_stats run over the gradient it wrote; the produced gradient is bit-identical to the plain call."""
+    lib, ops = m.lib, m.ops
+    g = torch.Generator().manual_seed(31)
+    B, D, H, W = shape
+    V = D * H * W
+    geom = ops.ConvGeom((3,) * 3, (1,) * 3, (1,) * 3)
+    dy = torch.randn((B, D, H, W, cout), generator=g).to(BF).to(dev())
+    w = (torch.randn((cout, cin, 3, 3, 3), generator=g) / np.sqrt(cout * 27)).to(dev())
+    _, wd = ops.pack_weights(w)
+    # the block in front: raw conv output y_prev, its forward sums, affine parameters
+    y_prev = (torch.randn((B, D, H, W, cin), generator=g) * 1.5 + 0.3).to(BF).to(dev())
+    gamma = (torch.rand(cin, generator=g) - 0.3)                     # both signs ...
+    gamma[3] = 0.0                                                   # ... and constant masks: beta > 0 / beta <= 0
+    gamma[5] = 0.0
+    beta = torch.randn(cin, generator=g) * 0.3
+    beta[3], beta[5] = 0.25, -0.25
+    gamma, beta = gamma.to(dev()), beta.to(dev())
+    st = torch.cuda.current_stream().cuda_stream
+    stats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev())
+    lib.inorm_stats(y_prev.data_ptr(), cin, B, V, cin, stats.data_ptr(), st)
+    nb = (y_prev, stats, gamma, beta, 1e-5, 0.01)
+    base = torch.randn((B, D, H, W, cin), generator=g).to(BF).to(dev()) if accumulate else None
+    plain = base.clone() if accumulate else torch.empty((B, D, H, W, cin), dtype=BF, device=dev())
+    ops.conv_dgrad(geom, plain, dy, wd, accumulate=accumulate)
+    assert ops.conv_dgrad_fuses_norm_bwd(geom, plain, dy, wd, nb) == fused
+    out = base.clone() if accumulate else torch.empty_like(plain)
+    bstats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev())
+    launches = lib.launch_count()
+    ops.conv_dgrad(geom, out, dy, wd, accumulate=accumulate, norm_bwd=nb, bstats=bstats)
+    assert lib.launch_count() - launches == (1 if fused else 2)
+    assert torch.equal(out, plain)
+    want = torch.zeros_like(bstats)
+    lib.inorm_lrelu_bwd_stats(plain.data_ptr(), cin, y_prev.data_ptr(), cin, stats.data_ptr(), gamma.data_ptr(),
+                              beta.data_ptr(), B, V, cin, 1e-5, 0.01, want.data_ptr(), st)
+    if not fused:
+        assert torch.equal(bstats, want)
+        return
+    # fp32 partial sums in a different order, and sum g'y - mean sum g' instead of sum g'(y - mean): judge both kernels
+    # against an fp64 evaluation, in units of the root-sum-of-squares of the summands (the sums themselves cancel heavily)
+    m_ = stats[..., 0] / V
+    var = (stats[..., 1] / V - m_ * m_).clamp_min(0)
+    rstd = (1.0 / torch.sqrt(var + 1e-5)).float()
+    mean = m_.float()
+    sc = gamma[None] * rstd
+    shf = beta[None] - mean * gamma[None] * rstd
+    yf = y_prev.float().reshape(B, V, cin)
+    t = yf * sc[:, None] + shf[:, None]
+    gp = plain.float().reshape(B, V, cin).double() * torch.where(t > 0, 1.0, 0.01).double()
+    xh = (yf - mean[:, None]).double() * rstd[:, None].double()
+    ref = torch.stack([gp.sum(1), (gp * xh).sum(1)], -1)
+    rss = torch.stack([gp.pow(2).sum(1).sqrt(), (gp * xh).pow(2).sum(1).sqrt()], -1) + 1e-12
+    err_fused = float(((bstats - ref).abs() / rss).max())
+    err_pass = float(((want - ref).abs() / rss).max())
+    print('norm-backward sums vs fp64: epilogue %.2e, streaming pass %.2e (units of rss)' % (err_fused, err_pass))
+    assert err_fused < 2e-6
+
+
+def test_dgrad_norm_backward_statistics_fallback_pass(m):
+    """shapes the halo epilogue does not cover (stride 2 here) still honour norm_bwd through a pass over the gradient"""
+    lib, ops = m.lib, m.ops
+    g = torch.Generator().manual_seed(32)
+    B, E, cin, cout = 2, 12, 32, 64
+    geom = ops.ConvGeom((3,) * 3, (2,) * 3, (1,) * 3)
+    dy = torch.randn((B, E // 2, E // 2, E // 2, cout), generator=g).to(BF).to(dev())
+    w = (torch.randn((cout, cin, 3, 3, 3), generator=g) / 30).to(dev())
+    _, wd = ops.pack_weights(w)
+    y_prev = torch.randn((B, E, E, E, cin), generator=g).to(BF).to(dev())
+    gamma, beta = torch.ones(cin, device=dev()), torch.zeros(cin, device=dev())
+    st = torch.cuda.current_stream().cuda_stream
+    stats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev())
+    lib.inorm_stats(y_prev.data_ptr(), cin, B, E ** 3, cin, stats.data_ptr(), st)
+    nb = (y_prev, stats, gamma, beta, 1e-5, 0.01)
+    dx = torch.empty_like(y_prev)
+    assert not ops.conv_dgrad_fuses_norm_bwd(geom, dx, dy, wd, nb)
+    bstats = torch.zeros((B, cin, 2), dtype=torch.float64, device=dev())
+    ops.conv_dgrad(geom, dx, dy, wd, norm_bwd=nb, bstats=bstats)
+    want = torch.zeros_like(bstats)
+    lib.inorm_lrelu_bwd_stats(dx.data_ptr(), cin, y_prev.data_ptr(), cin, stats.data_ptr(), gamma.data_ptr(),
+                              beta.data_ptr(), B, E ** 3, cin, 1e-5, 0.01, want.data_ptr(), st)
+    assert torch.equal(bstats, want)
+
+
 @pytest.mark.parametrize('C,K', [(32, 4), (320, 4), (64, 3), (128, 4), (256, 4), (64, 4)])
 @pytest.mark.parametrize('vol', [(2, 5, 6, 7), (2, 48, 64, 40)])   # tails only / several steps of the staged sweep
 def test_head(m, C, K, vol):
