@@ -91,7 +91,8 @@ __device__ __forceinline__ void store_rows_accumulate_packed(uint8_t* stage, int
 // for narrow layers (N = 32: 7 KB per 56-cycle MMA = 125 B/clk of the 128 B/clk), and an epilogue that goes through shared
 // memory is then throttled to the leftover (measured, 32->32 at 128^3: forward 0.229 -> 0.212 ms with lane-own stores;
 // profiles/r2_epilogue_shared_memory.txt).  w[i] = bf16x2 of columns (2i, 2i+1); returns the values written (after the
-// optional accumulate) in w.
+// optional accumulate) in w.  (Not for the stride-2 sub-pixel data gradient: there the accumulate path's old values arrive
+// better through the transposed, prefetched form -- 0.239 vs 0.206 ms for 32->64 at 64^3 when tried.)
 __device__ __forceinline__ void store_row_lane_own(bf16* dst, uint32_t* w, bool accumulate) {
   if (accumulate) {
     uint4 old[4];

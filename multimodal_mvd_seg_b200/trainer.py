@@ -467,12 +467,21 @@ class nnUNetTrainer(object):
             a.begin_step()
         return self._forward(data)
 
+    def _unit_gradient(self, loss: torch.Tensor) -> torch.Tensor:
+        """a persistent tensor of ones shaped like the loss (created once per device / dtype: CUDA-graph friendly)"""
+        key = (loss.device, loss.dtype, tuple(loss.shape))
+        cache = self.__dict__.setdefault('_unit_gradients', {})
+        one = cache.get(key)
+        if one is None:
+            one = cache[key] = torch.ones(loss.shape, dtype=loss.dtype, device=loss.device)
+        return one
+
     def _step_body(self, data, target) -> torch.Tensor:
         return self._step_backward(self._step_forward(data), target)
 
     def _step_backward(self, output, target) -> torch.Tensor:
         l, _ = self._loss(output, target)
-        l.backward()
+        l.backward(self._unit_gradient(l))      # explicit seed: autograd would launch a fill kernel for its implicit ones
         world = 1
         for a in self._arenas:
             a.finish()
@@ -764,7 +773,7 @@ class MVDTrainer(nnUNetTrainer):
         if not self.concurrent_networks or self._net2_stream is None:
             return super()._step_backward(output, target)
         l, _ = self._loss(output, target)
-        l.backward()
+        l.backward(self._unit_gradient(l))      # explicit seed: autograd would launch a fill kernel for its implicit ones
         # network 2's backward ran on its own stream (autograd keeps every node on its forward stream); parameter
         # gradients bypass AccumulateGrad here, so the engine has no leaf stream to join: do it explicitly
         torch.cuda.current_stream().wait_stream(self._net2_stream)
