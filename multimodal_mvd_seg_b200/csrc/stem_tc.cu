@@ -31,8 +31,16 @@ constexpr int kIssuerWarp = 8;
 constexpr int kThreadsFprop = 17 * 32, kThreadsWgrad = 13 * 32;
 constexpr int kProducers = 128;   // threads per producer group = rows of a tile
 constexpr int TILE_W = 8, TILE_H = 16, HALO_W = 10, HALO_H = 18, HALO_VOX = 3 * HALO_H * HALO_W;   // 540
+// Shared-memory pitch of a halo line, in voxels.  A warp's 32 rows read 4 h-lines x 8 consecutive voxels per tap; with
+// 32-bit voxels (CIN = 2) and the natural pitch of 10 the fourth line lands on the banks of the first (ncu: 6.4 M of 12 M
+// shared-load wavefronts were bank conflicts); a pitch of 24 words puts the four lines on banks 0 / 24 / 16 / 8.
+template <int CIN> struct HaloPitch {
+  static constexpr int value = (CIN == 2) ? 24 : HALO_W;
+  static constexpr int vox = 3 * HALO_H * value;      // voxels of one staged halo in shared memory
+};
 constexpr int NOUT = 32;          // output features of the stem
 constexpr int kStages = 4;
+constexpr bool kLaneOwnStores = true;
 
 struct StemParams {
   const bf16* x;                  // dense NDHWC input, CIN channels
@@ -98,8 +106,10 @@ __device__ __forceinline__ void halo_store(bf16* halo, int t, const HaloRegs<CIN
   for (int u = 0; u < kHaloPerThread; ++u) {
     const int i = t + u * kProducers;
     if (i < HALO_VOX) {
-      if (CIN == 2) reinterpret_cast<uint32_t*>(halo)[i] = r.v[u];
-      else reinterpret_cast<unsigned short*>(halo)[i] = (unsigned short)r.v[u];
+      const int line = i / HALO_W, pw = i - line * HALO_W;          // line = pd * HALO_H + ph
+      const int o = line * HaloPitch<CIN>::value + pw;
+      if (CIN == 2) reinterpret_cast<uint32_t*>(halo)[o] = r.v[u];
+      else reinterpret_cast<unsigned short*>(halo)[o] = (unsigned short)r.v[u];
     }
   }
 }
@@ -121,7 +131,7 @@ __device__ __forceinline__ void build_row(const bf16* halo, uint8_t* tile, int t
         uint32_t v = 0u;
         if (tap < 27) {
           const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-          v = reinterpret_cast<const uint32_t*>(halo)[(td * HALO_H + hh + th) * HALO_W + ww + tw];
+          v = reinterpret_cast<const uint32_t*>(halo)[(td * HALO_H + hh + th) * HaloPitch<CIN>::value + ww + tw];
         }
         wv[e] = v;
       } else {
@@ -131,7 +141,7 @@ __device__ __forceinline__ void build_row(const bf16* halo, uint8_t* tile, int t
           const int tap = 8 * j + 2 * e + s;
           if (tap < 27) {
             const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-            const uint32_t u = reinterpret_cast<const unsigned short*>(halo)[(td * HALO_H + hh + th) * HALO_W + ww + tw];
+            const uint32_t u = reinterpret_cast<const unsigned short*>(halo)[(td * HALO_H + hh + th) * HaloPitch<CIN>::value + ww + tw];
             v |= u << (16 * s);
           }
         }
@@ -146,10 +156,10 @@ __device__ __forceinline__ void build_row(const bf16* halo, uint8_t* tile, int t
 // the producer loop shared by fprop and wgrad: group g (warps 4g..4g+3) builds the bricks with local index = g mod 2
 // into ring stage (local index % kStages); one mbarrier arrival per warp
 template <int CIN>
-__device__ __forceinline__ void produce_tiles(const StemParams& P, bf16 (*s_halo)[HALO_VOX * CIN], uint8_t* smem_a,
+__device__ __forceinline__ void produce_tiles(const StemParams& P, bf16 (*s_halo)[HaloPitch<CIN>::vox * CIN], uint8_t* smem_a,
                                               int tile_bytes, uint64_t* bar_full, uint64_t* bar_empty) {
   const int group = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31;
-  bf16 (*halo2)[HALO_VOX * CIN] = s_halo + 2 * group;
+  bf16 (*halo2)[HaloPitch<CIN>::vox * CIN] = s_halo + 2 * group;
   HaloRegs<CIN> regs;
   const int first = blockIdx.x + group * gridDim.x, step = 2 * gridDim.x;
   if (first < P.total_tiles) halo_fetch<CIN>(P, first, t, regs);
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(kThreadsFprop, 1) stem_fprop_kernel(const __gr
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) uint8_t s_stage[8][2048];
   __shared__ __align__(16) float s_bias[NOUT];
-  __shared__ __align__(16) bf16 s_halo[4][HALO_VOX * CIN];
+  __shared__ __align__(16) bf16 s_halo[4][HaloPitch<CIN>::vox * CIN];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;                         // [32][KPAD]
   uint8_t* smem_a = smem + 4096;                  // kStages tiles
@@ -287,11 +297,15 @@ __global__ void __launch_bounds__(kThreadsFprop, 1) stem_fprop_kernel(const __gr
         ssq += warp_column_sum32(a, lane);
       }
       bf16* base = P.y + (long long)b * P.ysb + (long long)d * P.ysd;
-      store_rows_coalesced_packed(stage_buf, lane, w2, [&](int R) -> bf16* {
-        const int rr = q * 32 + R;
-        const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
-        return (h < P.H && w < P.W) ? base + (long long)h * P.ysh + (long long)w * P.ysw : nullptr;
-      }, false);
+      if (kLaneOwnStores) {   // no shared-memory transpose next to the tile producers' traffic (tc_epilogue.cuh)
+        if (ok) store_row_lane_own(base + (long long)(h0 + (rr0 >> 3)) * P.ysh + (long long)(w0 + (rr0 & 7)) * P.ysw, w2, false);
+      } else {
+        store_rows_coalesced_packed(stage_buf, lane, w2, [&](int R) -> bf16* {
+          const int rr = q * 32 + R;
+          const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+          return (h < P.H && w < P.W) ? base + (long long)h * P.ysh + (long long)w * P.ysw : nullptr;
+        }, false);
+      }
     }
     if (do_stats && sb >= 0) flush();
   }
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) stem_wgrad_kernel(const __gr
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_bfull[kBRing], bar_bempty[kBRing], bar_done;
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) bf16 s_halo[4][HALO_VOX * CIN];
+  __shared__ __align__(16) bf16 s_halo[4][HaloPitch<CIN>::vox * CIN];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem;                                   // kBRing dy bricks
   uint8_t* smem_a = smem + kBRing * BRICK_BYTES;            // kStages tiles (+ slack read by the junk M rows)
