@@ -115,6 +115,37 @@ int mvd_sw_accumulate(const void* pred, int ldp, const float* gaussian, float sc
                       int d, int h, int w, int D, int H, int W, int z0, int y0, int x0, int flip_mask,
                       mvd_stream_t stream);
 int mvd_sw_finalize(float* acc, const float* npred, int K, long long vol, mvd_stream_t stream);   /* acc /= npred */
+/* ---- training-batch augmentation on the GPU ------------------------------------------------------
+ * Replaces the batchgenerators transform chain of nnUNetTrainer.get_training_transforms (MVDTrainer.py:700-765; the
+ * transforms themselves live in the third-party package batchgenerators, absent from the reference tree).  Volumes are
+ * fp32 planes [N][D][H][W], N = B * C.  The random draws are explicit per-plane / per-sample parameter arrays in DEVICE
+ * memory; multimodal_mvd_seg_b200/augment.py samples them with the reference's distributions. */
+/* cubic B-spline coefficients in place (scipy.ndimage.spline_filter, order 3, mode 'mirror'); apply: [N] flags or NULL */
+int mvd_aug_spline_prefilter(float* vol, int N, int D, int H, int W, const unsigned char* apply, mvd_stream_t stream);
+/* SpatialTransform (MVDTrainer.py:700-711): dst[b][c] = src[b][c] sampled at  M_b * (idx - (out - 1) / 2) + in / 2 - 0.5
+ * (augment_spatial's zero-centred mesh, random_crop = False).  mat: [B][9] row-major; mode: [B], 0 = centre crop without
+ * interpolation (no rotation / scaling drawn), 1 = interpolate.  seg_labels == 0: images, order 3 (src holds the spline
+ * coefficients of mvd_aug_spline_prefilter for the samples with mode 1) or 1, constant border cval.  seg_labels > 0: the
+ * segmentation rule of interpolate_img(is_seg = True, order = 1): label = the largest c in [1, seg_labels) whose linearly
+ * interpolated mask is >= 0.5, else 0 (RemoveLabelTransform(-1, 0), MVDTrainer.py:738, folded in). */
+int mvd_aug_spatial(const float* src, int B, int C, int Di, int Hi, int Wi, float* dst, int D, int H, int W,
+                    const float* mat, const int* mode, int order, float cval, int seg_labels, mvd_stream_t stream);
+/* GaussianNoiseTransform (:716): x += N(0, sigma[plane]); sigma 0 skips the plane; counter-based generator */
+int mvd_aug_gaussian_noise(float* x, long long V, int N, const float* sigma, unsigned long long seed, mvd_stream_t stream);
+/* GaussianBlurTransform (:717-718): scipy.ndimage.gaussian_filter (truncate 4, 'reflect') with sigma[plane]; 0 skips */
+int mvd_aug_gaussian_blur(float* x, float* tmp, int N, int D, int H, int W, const float* sigma, mvd_stream_t stream);
+/* out[N][4] doubles (sum, sum of squares, min, max), accumulated: the caller initialises (0, 0, +inf, -inf) */
+int mvd_aug_plane_stats(const float* x, long long V, int N, double* out, mvd_stream_t stream);
+/* op 0: x *= a[p] (BrightnessMultiplicativeTransform, :719).  op 1: ContrastAugmentationTransform (:720, preserve_range):
+ * x = clip((x - mean) a[p] + mean, min, max) with stats0 of x; a = 0 skips.  op 2 / 3: GammaTransform (:726-727,
+ * retain_stats): op 2 maps s x (s = -1 when invert) through ((. - min) / (range + 1e-7)) ^ a[p] * range + min, op 3 restores
+ * mean / std (stats0 = before op 2, stats1 = after op 2) and undoes the inversion; a = 0 skips. */
+int mvd_aug_intensity(float* x, long long V, int N, int op, const float* a, const double* stats0, const double* stats1,
+                      int invert, mvd_stream_t stream);
+/* MirrorTransform (:729-730): flips[B][3] (d, h, w) per sample, out of place */
+int mvd_aug_mirror(const float* src, float* dst, int B, int C, int D, int H, int W, const unsigned char* flips,
+                   mvd_stream_t stream);
+
 /* Deep-supervision targets on the GPU.  Replaces DownsampleSegForDSTransform2.__call__
  * (training/data_augmentation/custom_transforms/deep_supervision_donwsampling.py:27-55; batchgenerators'
  * resize_segmentation with order 0): nearest-neighbour with pixel-centre alignment, src = floor((o + 0.5) * I / O) per

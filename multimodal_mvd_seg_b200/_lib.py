@@ -128,6 +128,13 @@ _SIGNATURES = {
     'mvd_channel_sum': (c_int, [P, I, LL, I, P, S]),
     'mvd_scalar_axpy': (c_int, [P, F, P, I, S]),
     'mvd_add_bf16': (c_int, [P, I, P, I, LL, I, S]),
+    'mvd_aug_spline_prefilter': (c_int, [P, I, I, I, I, P, S]),
+    'mvd_aug_spatial': (c_int, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, I, S]),
+    'mvd_aug_gaussian_noise': (c_int, [P, LL, I, P, c_ulonglong, S]),
+    'mvd_aug_gaussian_blur': (c_int, [P, P, I, I, I, I, P, S]),
+    'mvd_aug_plane_stats': (c_int, [P, LL, I, P, S]),
+    'mvd_aug_intensity': (c_int, [P, LL, I, I, P, P, P, I, S]),
+    'mvd_aug_mirror': (c_int, [P, P, I, I, I, I, I, P, S]),
     'mvd_im2col_small': (c_int, [P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, S]),
 }
 
