@@ -142,6 +142,12 @@ int mvd_aug_plane_stats(const float* x, long long V, int N, double* out, mvd_str
  * mean / std (stats0 = before op 2, stats1 = after op 2) and undoes the inversion; a = 0 skips. */
 int mvd_aug_intensity(float* x, long long V, int N, int op, const float* a, const double* stats0, const double* stats1,
                       int invert, mvd_stream_t stream);
+/* SimulateLowResolutionTransform (:721-725): per plane with tshape[p] != 0, nearest-neighbour down-sampling to tshape[p]
+ * (= round(shape * zoom)) and cubic up-sampling back (skimage resize(mode='edge', anti_aliasing=False) = scipy zoom(
+ * grid_mode=True, mode='nearest'), clipped to the range of the low-resolution volume).  buf: N x buf_stride floats of
+ * scratch, buf_stride >= (D+24)(H+24)(W+24); minmax: [N][2] doubles initialised (+inf, -inf). */
+int mvd_aug_simulate_lowres(float* x, int N, int D, int H, int W, const int* tshape, float* buf, long long buf_stride,
+                            double* minmax, mvd_stream_t stream);
 /* MirrorTransform (:729-730): flips[B][3] (d, h, w) per sample, out of place */
 int mvd_aug_mirror(const float* src, float* dst, int B, int C, int D, int H, int W, const unsigned char* flips,
                    mvd_stream_t stream);

@@ -134,6 +134,7 @@ _SIGNATURES = {
     'mvd_aug_gaussian_blur': (c_int, [P, P, I, I, I, I, P, S]),
     'mvd_aug_plane_stats': (c_int, [P, LL, I, P, S]),
     'mvd_aug_intensity': (c_int, [P, LL, I, I, P, P, P, I, S]),
+    'mvd_aug_simulate_lowres': (c_int, [P, I, I, I, I, P, P, LL, P, S]),
     'mvd_aug_mirror': (c_int, [P, P, I, I, I, I, I, P, S]),
     'mvd_im2col_small': (c_int, [P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, S]),
 }

@@ -8,14 +8,15 @@ chain runs as a handful of HBM-bound kernels (csrc/augment.cu) on the batch that
   SpatialTransform(rotation, isotropic scale; order 3 images / order 1 per-label segmentation; constant border)  :700-711
   GaussianNoiseTransform(p 0.1)   GaussianBlurTransform((0.5, 1), per channel, p 0.2 / 0.5)                       :716-718
   BrightnessMultiplicativeTransform((0.75, 1.25), p 0.15)   ContrastAugmentationTransform(p 0.15)                  :719-720
+  SimulateLowResolutionTransform(zoom (0.5, 1), per channel p 0.5, nearest down / cubic up, p 0.25)               :721-725
   GammaTransform((0.7, 1.5), invert, retain_stats, p 0.1)   GammaTransform((0.7, 1.5), retain_stats, p 0.3)        :726-727
   MirrorTransform(mirror_axes)   RemoveLabelTransform(-1, 0)   DownsampleSegForDSTransform2 (ds_targets.py)        :729-760
 
 The random draws are made on the host with the reference's distributions (``sample_parameters``) and handed to the kernels
 as small parameter arrays, so every transform is a deterministic function of (batch, parameters) -- which is what the
 tests compare with the numpy / scipy restatement in ``oracle/augment.py``.
-NOT built: SimulateLowResolutionTransform (:721-725, skimage cubic resize), elastic deformation (disabled in the reference
-call, p_el_per_sample = 0), the cascade / region / mask transforms (:732-752, not used by 3d_fullres without cascade).
+NOT built: elastic deformation (disabled in the reference call, p_el_per_sample = 0) and the cascade / region / mask
+transforms (:732-752, not used by 3d_fullres without cascade).
 No CPU path: the inputs must be CUDA tensors."""
 import ctypes
 from typing import Dict, List, Optional, Sequence
@@ -55,6 +56,7 @@ def sample_parameters(rng: np.random.Generator, B: int, C: int, rotation_for_DA:
     P = dict(mat=np.zeros((B, 3, 3), np.float32), mode=np.zeros((B,), np.int32),
              noise_sigma=np.zeros((B, C), np.float32), blur_sigma=np.zeros((B, C), np.float32),
              brightness=np.ones((B, C), np.float32), contrast=np.zeros((B, C), np.float32),
+             lowres_zoom=np.zeros((B, C), np.float32),
              gamma_inv=np.zeros((B, C), np.float32), gamma=np.zeros((B, C), np.float32),
              flips=np.zeros((B, 3), np.uint8))
     for b in range(B):
@@ -78,6 +80,10 @@ def sample_parameters(rng: np.random.Generator, B: int, C: int, rotation_for_DA:
         if rng.random() < 0.15:                                  # Contrast, per channel
             for c in range(C):
                 P['contrast'][b, c] = _range_draw(rng, 0.75, 1.25)
+        if rng.random() < 0.25:                                  # SimulateLowResolution: per channel with p 0.5
+            for c in range(C):
+                if rng.random() < 0.5:
+                    P['lowres_zoom'][b, c] = rng.uniform(0.5, 1.0)
         if rng.random() < 0.1:                                   # Gamma on the inverted image
             for c in range(C):
                 P['gamma_inv'][b, c] = _range_draw(rng, 0.7, 1.5)
@@ -178,6 +184,16 @@ class GpuAugmenter:
             s0 = stats()
             lib.aug_intensity(x.data_ptr(), V, N, 1, pd['contrast'].data_ptr(),
                               s0.data_ptr(), None, 0, st)
+        if 'lowres_zoom' in params and params['lowres_zoom'].any():
+            zf = params['lowres_zoom'].reshape(-1).astype(np.float64)
+            tshape = np.zeros((N, 3), np.int32)
+            sel = zf != 0
+            tshape[sel] = np.round(np.array([D, H, W])[None, :] * zf[sel, None]).astype(np.int32)   # np.round: half to even
+            stride = (D + 24) * (H + 24) * (W + 24)
+            scratch = torch.empty((N, stride), dtype=torch.float32, device=dev)
+            mm = torch.tensor([float('inf'), float('-inf')], dtype=torch.float64, device=dev).repeat(N, 1).contiguous()
+            ts = self._dev(tshape, dev)
+            lib.aug_simulate_lowres(x.data_ptr(), N, D, H, W, ts.data_ptr(), scratch.data_ptr(), stride, mm.data_ptr(), st)
         for key, invert in (('gamma_inv', 1), ('gamma', 0)):
             if params[key].any():
                 g = pd[key]

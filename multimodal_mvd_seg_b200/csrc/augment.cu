@@ -350,6 +350,132 @@ __global__ void __launch_bounds__(256) intensity_kernel(float* __restrict__ x, l
   }
 }
 
+// ---- SimulateLowResolutionTransform (MVDTrainer.py:721-725): per selected plane, nearest-neighbour down-sampling to
+// ---- round(shape * zoom) followed by cubic up-sampling back, both skimage.transform.resize(mode='edge',
+// ---- anti_aliasing=False) = scipy.ndimage.zoom(grid_mode=True, mode='nearest') + clipping to the input range.
+// The low-resolution volume is written edge-padded by 12 voxels per side (what scipy pre-pads before its spline filter for
+// mode 'nearest'; the prefilter's own boundary rule then only matters to z^12 = 1.4e-7), prefiltered in place, and sampled
+// at (o + 0.5) * t / n - 0.5 + 12.
+constexpr int kLowresPad = 12;
+struct LowresParams {
+  float* x;            // [N][D][H][W]
+  float* buf;          // [N][buf_stride]: the padded low-resolution volumes, compact strides (t + 24 per axis)
+  long long buf_stride;
+  int N, D, H, W;
+  const int* tshape;   // [N][3] target (low-resolution) shape, 0 = plane not selected
+  double* minmax;      // [N][2] minimum / maximum of the low-resolution volume (caller initialises +inf / -inf)
+};
+
+__global__ void __launch_bounds__(256) lowres_down_kernel(const LowresParams P) {
+  const int p = blockIdx.y;
+  const int td = P.tshape[3 * p], th = P.tshape[3 * p + 1], tw = P.tshape[3 * p + 2];
+  if (td <= 0) return;
+  const int pd = td + 2 * kLowresPad, ph = th + 2 * kLowresPad, pw = tw + 2 * kLowresPad;
+  const long long total = (long long)pd * ph * pw;
+  const float* src = P.x + (long long)p * P.D * P.H * P.W;
+  float* dst = P.buf + (long long)p * P.buf_stride;
+  const double rd = (double)P.D / td, rh = (double)P.H / th, rw = (double)P.W / tw;
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i;
+    const int k = (int)(j % pw); j /= pw;
+    const int e = (int)(j % ph);
+    const int a = (int)(j / ph);
+    const int ld = min(max(a - kLowresPad, 0), td - 1), lh = min(max(e - kLowresPad, 0), th - 1),
+              lw = min(max(k - kLowresPad, 0), tw - 1);
+    const int sd = min((int)floor((ld + 0.5) * rd), P.D - 1), sh = min((int)floor((lh + 0.5) * rh), P.H - 1),
+              sw = min((int)floor((lw + 0.5) * rw), P.W - 1);
+    const float v = __ldg(src + ((long long)sd * P.H + sh) * P.W + sw);
+    dst[i] = v;
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  __shared__ float smn[256], smx[256];
+  smn[threadIdx.x] = mn; smx[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      smn[threadIdx.x] = fminf(smn[threadIdx.x], smn[threadIdx.x + o]);
+      smx[threadIdx.x] = fmaxf(smx[threadIdx.x], smx[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomic_min_double(P.minmax + 2 * p, (double)smn[0]);
+    atomic_max_double(P.minmax + 2 * p + 1, (double)smx[0]);
+  }
+}
+
+// cubic prefilter of the padded low-resolution volumes, one axis per launch, one thread per line (per-plane extents)
+__global__ void __launch_bounds__(128) lowres_prefilter_kernel(const LowresParams P, int axis) {
+  const int p = blockIdx.y;
+  const int td = P.tshape[3 * p];
+  if (td <= 0) return;
+  const int dims[3] = {td + 2 * kLowresPad, P.tshape[3 * p + 1] + 2 * kLowresPad, P.tshape[3 * p + 2] + 2 * kLowresPad};
+  const int len = dims[axis];
+  const long long inner = axis == 0 ? (long long)dims[1] * dims[2] : (axis == 1 ? dims[2] : 1);
+  const long long n_lines = (long long)dims[0] * dims[1] * dims[2] / len;
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= n_lines) return;
+  const long long outer = line / inner, in = line - outer * inner;
+  float* c = P.buf + (long long)p * P.buf_stride + outer * (long long)len * inner + in;
+  const long long stride = inner;
+  const double z = (double)kPole;
+  const double lambda = (1.0 - z) * (1.0 - 1.0 / z);
+  double zi = z, sum = (double)c[0] * lambda;
+  for (int i = 1; i < len; ++i) { sum += zi * (double)c[(long long)i * stride] * lambda; zi *= z; }
+  for (int i = len - 2; i > 0; --i) { sum += zi * (double)c[(long long)i * stride] * lambda; zi *= z; }
+  double prev = sum / (1.0 - zi);
+  c[0] = (float)prev;
+  for (int i = 1; i < len; ++i) {
+    prev = (double)c[(long long)i * stride] * lambda + z * prev;
+    c[(long long)i * stride] = (float)prev;
+  }
+  double last = (z / (z * z - 1.0)) * (z * (double)c[(long long)(len - 2) * stride] + (double)c[(long long)(len - 1) * stride]);
+  c[(long long)(len - 1) * stride] = (float)last;
+  for (int i = len - 2; i >= 0; --i) {
+    last = z * (last - (double)c[(long long)i * stride]);
+    c[(long long)i * stride] = (float)last;
+  }
+}
+
+__global__ void __launch_bounds__(256) lowres_up_kernel(const LowresParams P) {
+  const int p = blockIdx.y;
+  const int td = P.tshape[3 * p], th = P.tshape[3 * p + 1], tw = P.tshape[3 * p + 2];
+  if (td <= 0) return;
+  const int ph = th + 2 * kLowresPad, pw = tw + 2 * kLowresPad;
+  const long long V = (long long)P.D * P.H * P.W;
+  const float* co = P.buf + (long long)p * P.buf_stride;
+  float* dst = P.x + (long long)p * V;
+  const float lo = (float)P.minmax[2 * p], hi = (float)P.minmax[2 * p + 1];
+  const float rd = (float)td / (float)P.D, rh = (float)th / (float)P.H, rw = (float)tw / (float)P.W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i;
+    const int w = (int)(j % P.W); j /= P.W;
+    const int h = (int)(j % P.H);
+    const int d = (int)(j / P.H);
+    const float cd = ((float)d + 0.5f) * rd - 0.5f + (float)kLowresPad, ch = ((float)h + 0.5f) * rh - 0.5f + (float)kLowresPad,
+                cw = ((float)w + 0.5f) * rw - 0.5f + (float)kLowresPad;
+    const int fd = (int)floorf(cd), fh = (int)floorf(ch), fw = (int)floorf(cw);
+    float wd[4], wh[4], ww[4];
+    cubic_weights(cd - (float)fd, wd);
+    cubic_weights(ch - (float)fh, wh);
+    cubic_weights(cw - (float)fw, ww);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float accd = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float* row = co + ((long long)(fd - 1 + a) * ph + (fh - 1 + e)) * pw + (fw - 1);
+        accd += wh[e] * (ww[0] * __ldg(row) + ww[1] * __ldg(row + 1) + ww[2] * __ldg(row + 2) + ww[3] * __ldg(row + 3));
+      }
+      acc += wd[a] * accd;
+    }
+    dst[i] = fminf(fmaxf(acc, lo), hi);      // skimage resize(clip=True)
+  }
+}
+
 // MirrorTransform: per sample, flip along d / h / w when flips[b][axis] != 0 (images and segmentation alike)
 __global__ void __launch_bounds__(256) mirror_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
                                                      int D, int H, int W, const unsigned char* __restrict__ flips) {
@@ -451,6 +577,28 @@ int mvd_aug_intensity(float* x, long long V, int N, int op, const float* a, cons
   intensity_kernel<<<grid_for((long long)N * V, 256 * 4, num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(x, V, N, op, a, stats0,
                                                                                                           stats1, invert);
   MVD_LAUNCH_CHECK("aug_intensity");
+  return MVD_OK;
+}
+
+int mvd_aug_simulate_lowres(float* x, int N, int D, int H, int W, const int* tshape, float* buf, long long buf_stride,
+                            double* minmax, mvd_stream_t stream) {
+  MVD_REQUIRE(x && tshape && buf && minmax && N > 0 && D > 0 && H > 0 && W > 0, "aug_simulate_lowres: bad arguments");
+  MVD_REQUIRE(buf_stride >= (long long)(D + 2 * kLowresPad) * (H + 2 * kLowresPad) * (W + 2 * kLowresPad),
+              "aug_simulate_lowres: the scratch needs (D + 24)(H + 24)(W + 24) floats per plane");
+  LowresParams P;
+  P.x = x; P.buf = buf; P.buf_stride = buf_stride; P.N = N; P.D = D; P.H = H; P.W = W; P.tshape = tshape; P.minmax = minmax;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per_plane = (num_sms() * 8 + N - 1) / N;
+  lowres_down_kernel<<<dim3(per_plane, N), 256, 0, st>>>(P);
+  MVD_LAUNCH_CHECK("aug_simulate_lowres(down)");
+  const long long max_lines = (long long)(D + 2 * kLowresPad) * (H + 2 * kLowresPad) * (W + 2 * kLowresPad) /
+                              (D < H ? (D < W ? D : W) : (H < W ? H : W));
+  for (int axis = 0; axis < 3; ++axis) {
+    lowres_prefilter_kernel<<<dim3((unsigned)((max_lines + 127) / 128), N), 128, 0, st>>>(P, axis);
+    MVD_LAUNCH_CHECK("aug_simulate_lowres(prefilter)");
+  }
+  lowres_up_kernel<<<dim3(per_plane, N), 256, 0, st>>>(P);
+  MVD_LAUNCH_CHECK("aug_simulate_lowres(up)");
   return MVD_OK;
 }
 

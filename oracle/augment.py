@@ -10,11 +10,13 @@ pin against.  What is restated here is the published algorithm of batchgenerator
   augment_gaussian_noise   .../noise_augmentations.py          augment_gaussian_blur   .../noise_augmentations.py
   augment_brightness_multiplicative / augment_contrast / augment_gamma   .../color_augmentations.py
   augment_mirroring        .../spatial_transformations.py
+  augment_linear_downsampling_scipy   .../resample_augmentations.py  (skimage.transform.resize, itself scipy.ndimage.zoom(
+                           grid_mode=True) + clipping in skimage >= 0.19; skimage is not in this image either)
 Every function takes the random draws as explicit arguments (the call sites in MVDTrainer.py fix the distributions, see
 ``multimodal_mvd_seg_b200.augment.sample_parameters``), which turns each transform into a deterministic function the CUDA
 kernels can be compared with."""
 import numpy as np
-from scipy.ndimage import gaussian_filter, map_coordinates
+from scipy.ndimage import gaussian_filter, map_coordinates, zoom as _zoom
 
 
 def rotation_scale_matrix(angle_x: float, angle_y: float, angle_z: float, scale: float) -> np.ndarray:
@@ -118,3 +120,22 @@ def mirror(x, flips):
             if flips[b][ax]:
                 y[b] = np.flip(y[b], axis=1 + ax)
     return np.ascontiguousarray(y)
+
+
+def simulate_lowres(x, zoom_factor):
+    """augment_linear_downsampling_scipy(order_downsample=0, order_upsample=3, per_channel=True): per plane with
+    zoom_factor != 0: resize to round(shape * zoom) with nearest neighbours, resize back with cubic splines; resize =
+    skimage.transform.resize(mode='edge', anti_aliasing=False, clip=True) = scipy zoom(grid_mode=True, mode='nearest')
+    clipped to the range of ITS input."""
+    y = x.astype(np.float32).copy()
+    for p in range(x.shape[0]):
+        if zoom_factor[p] == 0:
+            continue
+        shp = np.array(x[p].shape)
+        tgt = np.round(shp * float(zoom_factor[p])).astype(int)
+        vol = x[p].astype(np.float64)
+        down = _zoom(vol, tgt / shp, order=0, mode='nearest', grid_mode=True)
+        down = np.clip(down, vol.min(), vol.max())
+        up = _zoom(down, shp / tgt, order=3, mode='nearest', grid_mode=True)
+        y[p] = np.clip(up, down.min(), down.max()).astype(np.float32)
+    return y

@@ -43,6 +43,9 @@ def test_sample_parameters_follow_the_reference_probabilities():
     c = P['contrast'][P['contrast'] != 0]
     assert abs(rate(P['contrast'][:, 0] != 0) - 0.15) < 0.02 and c.min() >= 0.75 and c.max() <= 1.25
     assert abs(rate(c < 1) - 0.5) < 0.06                                      # below 1 with probability 1/2
+    assert abs(rate(P['lowres_zoom'] != 0) - 0.25 * 0.5) < 0.02
+    lz = P['lowres_zoom'][P['lowres_zoom'] != 0]
+    assert lz.min() >= 0.5 and lz.max() <= 1.0
     assert abs(rate(P['gamma_inv'][:, 0] != 0) - 0.1) < 0.02 and abs(rate(P['gamma'][:, 0] != 0) - 0.3) < 0.03
     g = P['gamma'][P['gamma'] != 0]
     assert g.min() >= 0.7 and g.max() <= 1.5
@@ -227,6 +230,33 @@ def test_intensity_transforms_match_oracle():
 
 
 @pytest.mark.gpu
+def test_simulate_lowres_matches_scipy_zoom():
+    import multimodal_mvd_seg_b200 as m
+    rng = _rng(14)
+    N, D, H, W = 4, 20, 26, 18
+    zz, yy, xx = np.meshgrid(*[np.linspace(-1, 1, s) for s in (D, H, W)], indexing='ij')
+    x = np.stack([np.sin(4 * zz + p) * np.cos(3 * yy) + xx * (p - 1) for p in range(N)]).astype(np.float32)
+    x += 0.1 * rng.normal(size=x.shape).astype(np.float32)
+    zoom = np.array([0.5, 0.0, 0.77, 1.0], np.float32)
+    want = oa.simulate_lowres(x, zoom)
+    tshape = np.zeros((N, 3), np.int32)
+    for p in range(N):
+        if zoom[p]:
+            tshape[p] = np.round(np.array([D, H, W]) * float(zoom[p])).astype(np.int32)
+    t = _cuda(x)
+    stride = (D + 24) * (H + 24) * (W + 24)
+    buf = torch.empty((N, stride), dtype=torch.float32, device='cuda:0')
+    mm = torch.tensor([float('inf'), float('-inf')], dtype=torch.float64, device='cuda:0').repeat(N, 1).contiguous()
+    ts = _cuda(tshape)
+    m.lib.aug_simulate_lowres(t.data_ptr(), N, D, H, W, ts.data_ptr(), buf.data_ptr(), stride, mm.data_ptr(), _st())
+    got = t.cpu().numpy()
+    np.testing.assert_array_equal(got[1], x[1])
+    assert np.abs(got - want).max() < 3e-4
+    np.testing.assert_allclose(got[3], x[3], atol=3e-4)          # zoom 1: cubic interpolation at the samples = identity
+    assert np.abs(want[0] - x[0]).max() > 0.05                   # ... and zoom 0.5 is not
+
+
+@pytest.mark.gpu
 def test_gpu_augmenter_pipeline_matches_the_chained_oracle():
     from multimodal_mvd_seg_b200.augment import GpuAugmenter, sample_parameters
     rng = _rng(13)
@@ -246,6 +276,7 @@ def test_gpu_augmenter_pipeline_matches_the_chained_oracle():
     P['blur_sigma'][:] = [[0.6, 0.0], [0.0, 0.9], [0.0, 0.0], [0.8, 0.7]]
     P['brightness'][1] = [0.8, 1.2]
     P['contrast'][:] = [[1.2, 0.8], [0, 0], [0.9, 1.1], [0, 0]]
+    P['lowres_zoom'][:] = [[0.0, 0.6], [0.83, 0.0], [0.0, 0.0], [0.5, 1.0]]
     P['gamma_inv'][:] = [[0, 0], [1.3, 0.8], [0, 0], [0, 0]]
     P['gamma'][:] = [[0.75, 1.4], [0, 0], [0, 0], [1.2, 0.9]]
     P['flips'][:] = [[1, 0, 0], [0, 1, 1], [0, 0, 0], [1, 1, 1]]
@@ -258,6 +289,7 @@ def test_gpu_augmenter_pipeline_matches_the_chained_oracle():
     x = oa.gaussian_blur(x, P['blur_sigma'].reshape(-1))
     x = oa.brightness_multiplicative(x, P['brightness'].reshape(-1))
     x = oa.contrast(x, P['contrast'].reshape(-1))
+    x = oa.simulate_lowres(x, P['lowres_zoom'].reshape(-1))
     x = oa.gamma(x, P['gamma_inv'].reshape(-1), invert=True)
     x = oa.gamma(x, P['gamma'].reshape(-1), invert=False)
     x = oa.mirror(x.reshape((B, C) + patch), P['flips'])
@@ -278,6 +310,7 @@ def test_gpu_augmenter_pipeline_matches_the_chained_oracle():
     bseg = (torch.rand((2, 1, 160, 160, 160), device='cuda:0') < 0.1).float()
     Pb = {k: v[:2].copy() for k, v in P.items()}
     Pb['noise_sigma'][:] = 0.05
+    Pb['lowres_zoom'][:] = [[0.7, 0.9], [0.55, 0.8]]
     augb = GpuAugmenter((128, 128, 128), 4, deep_supervision_scales=scales)
     augb(big, bseg, params=Pb)
     torch.cuda.synchronize()
