@@ -146,6 +146,45 @@ def cpu_port_step_times(patch, batch, dual, topo_iter, steps, warmup, threads=No
     return times, torch.get_num_threads()
 
 
+def gpu_augmentation_rate(patch, dev, batches=20):
+    """the batch-production side.  The transform chain of MVDTrainer.py:700-765 on the GPU
+    (multimodal_mvd_seg_b200/augment.py) over synthetic raw patches of the loader's initial patch size (1.25 x the patch),
+    once with the reference's own probabilities (what a training run sees on average) and once with every transform
+    switched on; includes the deep-supervision targets.  Device-resident inputs, CUDA events."""
+    import numpy as np
+    import torch
+    from multimodal_mvd_seg_b200.augment import GpuAugmenter, sample_parameters
+    raw = tuple(int(round(p * 1.25 / 8) * 8) for p in patch)
+    data = torch.randn((PER_GPU_BATCH, 2) + raw, device=dev)
+    seg = (torch.rand((PER_GPU_BATCH, 1) + raw, device=dev) * N_CLASSES).floor()
+    scales = [[1.0 / 2 ** i] * 3 for i in range(5)]
+    aug = GpuAugmenter(patch, N_CLASSES, deep_supervision_scales=scales, seed=0)
+    rng = np.random.default_rng(0)
+    drawn = [sample_parameters(rng, PER_GPU_BATCH, 2) for _ in range(batches)]
+    full = sample_parameters(rng, PER_GPU_BATCH, 2)
+    full['mode'][:] = 1
+    for b in range(PER_GPU_BATCH):
+        full['mat'][b] = np.eye(3) * 1.1
+    full['noise_sigma'][:] = 0.05; full['blur_sigma'][:] = 0.8; full['brightness'][:] = 1.1; full['contrast'][:] = 0.9
+    full['lowres_zoom'][:] = 0.7; full['gamma_inv'][:] = 1.2; full['gamma'][:] = 0.8; full['flips'][:] = 1
+    out = {}
+    for name, plist in (('reference_probabilities', drawn), ('all_transforms_on', [full] * 5)):
+        aug(data, seg, params=plist[0])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for prm in plist:
+            aug(data, seg, params=prm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / len(plist)
+        out[name] = {'ms_per_batch': ms, 'patches_per_s': PER_GPU_BATCH / (ms / 1e3), 'batches': len(plist)}
+    out['what'] = (f'GPU augmentation chain (SpatialTransform order 3 / per-label order 1, noise, blur, brightness, contrast, '
+                   f'SimulateLowResolution, 2 x gamma, mirror, DS targets) on {PER_GPU_BATCH} x 2 x {raw} raw patches -> {patch}; '
+                   'context for the batch-production row, not part of the timed step')
+    return out
+
+
 def gpu_torch_context(patch, dual, topo_iter, dev, steps=5, warmup=2):
     """CONTEXT ONLY (not an arm of the comparison): the oracle modules -- stock torch.nn Conv3d / InstanceNorm3d /
     ConvTranspose3d, i.e. ATen + cuDNN -- stepping the same workload on the same GPU under bf16 autocast with
@@ -537,6 +576,10 @@ def main():
         line['extra_workloads'] = ex
     if n_gpus == 1 and not args.no_extra:
         line['gpu_torch_context'] = gpu_torch_context(patch, dual, topo_iter, dev)
+        try:
+            line['gpu_augmentation'] = gpu_augmentation_rate(patch, dev)
+        except Exception as e:      # context only: never lose the bench line over it
+            line['gpu_augmentation'] = {'error': repr(e)}
     if n_gpus == 1 and not args.no_cpu_baseline:
         # (i) the survey's CPU case (BASELINE.md section 4 / SURVEY.md 8d): cfg-1 = 5-stage net, 1 x 2 x 64^3, best of 3
         # after one warm-up; (ii) ONE full step of the benchmark configuration itself so that the GPU/CPU comparison is

@@ -124,9 +124,29 @@ class GpuAugmenter:
     def sample(self, B: int, C: int) -> Dict[str, np.ndarray]:
         return sample_parameters(self.rng, B, C, self.rotation_for_DA, self.mirror_axes)
 
-    @staticmethod
-    def _dev(a: np.ndarray, dev) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    def _upload(self, pieces: Dict[str, np.ndarray], dev) -> Dict[str, torch.Tensor]:
+        """pack the arrays (16-byte aligned) into a pinned staging buffer, copy once, return typed device views"""
+        offs, total = {}, 0
+        for k, a in pieces.items():
+            offs[k] = total
+            total += (a.nbytes + 15) // 16 * 16
+        # two staging buffers in turn: the asynchronous copy of the previous call may still be reading the other one
+        ring = self.__dict__.setdefault('_staging', [None, None])
+        turn = self.__dict__.get('_staging_turn', 0)
+        self._staging_turn = turn ^ 1
+        if ring[turn] is None or ring[turn][0].numel() < total:
+            ring[turn] = (torch.empty((max(total, 4096),), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+        else:
+            ring[turn][1].synchronize()
+        host, ev = ring[turn]
+        hv = host.numpy()
+        for k, a in pieces.items():
+            hv[offs[k]:offs[k] + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        d = host[:total].to(dev, non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+               np.dtype(np.float64): torch.float64}
+        return {k: d[offs[k]:offs[k] + a.nbytes].view(tdt[a.dtype]) for k, a in pieces.items()}
 
     def __call__(self, data: torch.Tensor, seg: torch.Tensor, params: Optional[Dict[str, np.ndarray]] = None,
                  noise_seed: Optional[int] = None):
@@ -142,17 +162,28 @@ class GpuAugmenter:
         if params is None:
             params = self.sample(B, C)
         st = _stream(dev)
-        mode = self._dev(params['mode'].astype(np.int32), dev)
-        mat = self._dev(params['mat'].astype(np.float32).reshape(B, 9), dev)
-        # all per-plane parameter arrays go up front and stay referenced until the call returns
-        pd = {k: self._dev(params[k].astype(np.float32).reshape(-1), dev)
-              for k in ('noise_sigma', 'blur_sigma', 'brightness', 'contrast', 'gamma_inv', 'gamma')}
+        N, V = B * C, D * H * W
+        # every parameter array of the call travels in ONE pinned buffer / one asynchronous copy (the dozen tiny
+        # synchronous uploads this replaces cost more than the kernels of an average batch)
+        tshape = np.zeros((N, 3), np.int32)
+        if 'lowres_zoom' in params and params['lowres_zoom'].any():
+            zf = params['lowres_zoom'].reshape(-1).astype(np.float64)
+            sel = zf != 0
+            tshape[sel] = np.round(np.array([D, H, W])[None, :] * zf[sel, None]).astype(np.int32)   # np.round: half to even
+        pieces = {'mat': params['mat'].astype(np.float32).reshape(-1), 'mode': params['mode'].astype(np.int32),
+                  'tshape': tshape.reshape(-1), 'apply': np.repeat(params['mode'].astype(np.uint8), C),
+                  'flips': params['flips'].astype(np.uint8).reshape(-1),
+                  'stats_init': np.tile(np.array([0.0, 0.0, np.inf, -np.inf]), N),
+                  'mm_init': np.tile(np.array([np.inf, -np.inf]), N)}
+        for k in ('noise_sigma', 'blur_sigma', 'brightness', 'contrast', 'gamma_inv', 'gamma'):
+            pieces[k] = params[k].astype(np.float32).reshape(-1)
+        pd = self._upload(pieces, dev)
+        mode, mat = pd['mode'], pd['mat']
         # ---- SpatialTransform ---------------------------------------------------------------------------------------
         src = data
         if self.order_data == 3 and int(params['mode'].max(initial=0)) > 0:
             src = data.clone()        # spline coefficients of the samples that are interpolated (the input stays intact)
-            apply = self._dev(np.repeat(params['mode'].astype(np.uint8), C), dev)
-            lib.aug_spline_prefilter(src.data_ptr(), B * C, Di, Hi, Wi, apply.data_ptr(), st)
+            lib.aug_spline_prefilter(src.data_ptr(), B * C, Di, Hi, Wi, pd['apply'].data_ptr(), st)
         x = torch.empty((B, C, D, H, W), dtype=torch.float32, device=dev)
         lib.aug_spatial(src.data_ptr(), B, C, Di, Hi, Wi, x.data_ptr(), D, H, W, mat.data_ptr(), mode.data_ptr(),
                         self.order_data, 0.0, 0, st)
@@ -160,7 +191,6 @@ class GpuAugmenter:
         lib.aug_spatial(segf.data_ptr(), B, segf.shape[1], Di, Hi, Wi, s.data_ptr(), D, H, W, mat.data_ptr(),
                         mode.data_ptr(), 1, -1.0, self.n_seg_labels, st)
         # ---- intensity chain (in place, per-plane parameters) ------------------------------------------------------------
-        N, V = B * C, D * H * W
         if params['noise_sigma'].any():
             seed = noise_seed if noise_seed is not None else int(self.rng.integers(0, 2 ** 63 - 1))
             lib.aug_gaussian_noise(x.data_ptr(), V, N, pd['noise_sigma'].data_ptr(),
@@ -173,10 +203,8 @@ class GpuAugmenter:
         if (params['brightness'] != 1).any():
             lib.aug_intensity(x.data_ptr(), V, N, 0, pd['brightness'].data_ptr(), None, None,
                               0, st)
-        init = torch.tensor([0.0, 0.0, float('inf'), float('-inf')], dtype=torch.float64, device=dev)
-
         def stats():
-            out = init.repeat(N, 1).contiguous()
+            out = pd['stats_init'].clone()
             lib.aug_plane_stats(x.data_ptr(), V, N, out.data_ptr(), st)
             return out
 
@@ -184,16 +212,12 @@ class GpuAugmenter:
             s0 = stats()
             lib.aug_intensity(x.data_ptr(), V, N, 1, pd['contrast'].data_ptr(),
                               s0.data_ptr(), None, 0, st)
-        if 'lowres_zoom' in params and params['lowres_zoom'].any():
-            zf = params['lowres_zoom'].reshape(-1).astype(np.float64)
-            tshape = np.zeros((N, 3), np.int32)
-            sel = zf != 0
-            tshape[sel] = np.round(np.array([D, H, W])[None, :] * zf[sel, None]).astype(np.int32)   # np.round: half to even
+        if tshape.any():
             stride = (D + 24) * (H + 24) * (W + 24)
             scratch = torch.empty((N, stride), dtype=torch.float32, device=dev)
-            mm = torch.tensor([float('inf'), float('-inf')], dtype=torch.float64, device=dev).repeat(N, 1).contiguous()
-            ts = self._dev(tshape, dev)
-            lib.aug_simulate_lowres(x.data_ptr(), N, D, H, W, ts.data_ptr(), scratch.data_ptr(), stride, mm.data_ptr(), st)
+            mm = pd['mm_init'].clone()
+            lib.aug_simulate_lowres(x.data_ptr(), N, D, H, W, pd['tshape'].data_ptr(), scratch.data_ptr(), stride,
+                                    mm.data_ptr(), st)
         for key, invert in (('gamma_inv', 1), ('gamma', 0)):
             if params[key].any():
                 g = pd[key]
@@ -203,7 +227,7 @@ class GpuAugmenter:
                 lib.aug_intensity(x.data_ptr(), V, N, 3, g.data_ptr(), s0.data_ptr(), s1.data_ptr(), invert, st)
         # ---- MirrorTransform ---------------------------------------------------------------------------------------
         if params['flips'].any():
-            flips = self._dev(params['flips'].astype(np.uint8).reshape(-1), dev)
+            flips = pd['flips']
             x2 = tmp if tmp is not None else torch.empty_like(x)
             lib.aug_mirror(x.data_ptr(), x2.data_ptr(), B, C, D, H, W, flips.data_ptr(), st)
             s2 = torch.empty_like(s)
