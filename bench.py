@@ -312,7 +312,7 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
     m.ops.set_conv_timer(None)
     conv = timer.summary()
     mem = timer.mem_summary()
-    per_layer = timer.per_layer() if args.per_layer else None
+    per_layer = timer.per_layer()
     for d in list(conv.values()) + list(mem.values()):
         for k in d:
             d[k] /= n_instr
@@ -320,6 +320,7 @@ def measure_workload(name, args, rank, world, dev, steps, with_e2e=True, with_cl
         for d in per_layer.values():
             d['ms'] /= n_instr
             d['flops'] /= n_instr
+            d['launches'] /= n_instr
 
     if conc:
         tr.concurrent_networks = True
@@ -407,7 +408,25 @@ def conv_roofline(r, peaks, clocks):
             'per_pass': {k: {'tflops': d['flops'] / (d['ms'] / 1e3) / 1e12, 'ms_per_step': d['ms'],
                              'launches_per_step': d['launches']} for k, d in conv.items()},
             'algorithmic_conv_gflop_per_step': conv_flops_per_step(r['patch'], PER_GPU_BATCH, 1 if r['dual'] else 2,
-                                                                   r['dual']) / 1e9}
+                                                                   r['dual']) / 1e9,
+            'dominant_kernel': dominant_kernel(r, burst, sustained)}
+
+
+def dominant_kernel(r, burst, sustained):
+    """the single kernel with the largest share of the step: wgrad_halo_kernel = the weight gradients of all 3x3x3 /
+    stride-1 layers (profiles/r2_step_profile_cfg2.txt: 19 % of the in-step kernel time, 16 launches per network).
+    Algorithmic FLOPs of those launches / their event-timed duration in the instrumented pass."""
+    pl = r.get('per_layer') or {}
+    sel = [d for (kind, tag), d in pl.items() if kind == 'wgrad' and 'k333 s111' in tag and not tag.startswith('stem')]
+    ms = sum(d['ms'] for d in sel)
+    if not sel or ms <= 0:
+        return None
+    fl = sum(d['flops'] for d in sel)
+    tf = fl / (ms / 1e3) / 1e12
+    return {'name': 'wgrad_halo_kernel', 'achieved': tf, 'unit': 'TFLOP/s', 'frac_vs_burst': tf / burst,
+            'frac_vs_sustained': tf / sustained, 'ms_per_step': ms, 'launches_per_step': sum(d['launches'] for d in sel),
+            'gflop_per_step': fl / 1e9, 'share_of_step': ms / r['ms_per_step'],
+            'ncu': 'profiles/r2_ncu_wgrad_halo.txt (tensor pipe 65 %, DRAM 557 MB for 537 MB algorithmic at 32->32, 2 x 128^3)'}
 
 
 def hbm_roofline(r, peaks):
@@ -594,7 +613,7 @@ def main():
                                 'cfg1': {'what': 'BASELINE.json configs[0]: 5-stage PlainConvUNet, 1 x 2 x 64^3, DC+CE, '
                                                  'fwd+bwd+clip+SGD on CPU, best of 3 after 1 warm-up',
                                          'seconds_per_step': min(t1), 'patches_64cubed_per_s': 1.0 / min(t1)}}
-    if r['per_layer']:
+    if r['per_layer'] and args.per_layer:
         rows = sorted(r['per_layer'].items(), key=lambda kv: -kv[1]['ms'])
         for (kind, tag), d in rows:
             print(f'{kind:6s} {tag:44s} {d["ms"]:8.3f} ms/step '
