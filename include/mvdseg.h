@@ -278,9 +278,13 @@ int mvd_dice_ce_bwd(const void* logits, int ld, const float* target, int B, long
 /* The deep-supervision loss of a whole step in three launches (csrc/losses_multi.cu).  One segment per (network,
  * active scale); production shape only: C = 4, dense logits [B][V][4] (pitch 4), fp32 targets [B][V], V % 4 == 0,
  * 16-byte aligned pointers (anything else: the per-scale entry points above).  The table is a HOST array.
- *   fwd      : acc [n_seg][B*4*3 + 1] doubles (caller zeroes) <- per-(b,c) sums and the CE sum of every segment; when
- *              `counter` (device unsigned, zero before the first call; the kernel leaves it zero) is given, the last
- *              block to finish also writes coef [n_seg][B][4][2] and loss_out[0] = sum_seg weight * (w_ce CE + w_dice Dice)
+ *   fwd      : acc [n_seg][B*4*3 + 2] doubles (caller zeroes) <- per-(b,c) sums, the CE sum and the number of VALID voxels
+ *              of every segment; when `counter` (device unsigned, zero before the first call; the kernel leaves it zero) is
+ *              given, the last block to finish also writes coef [n_seg][B*4*2 + 1] ((A, E) per (b, c), then 1 / valid) and
+ *              loss_out[0] = sum_seg weight * (w_ce CE + w_dice Dice)
+ *   ignore label: a voxel whose target is outside [0, 4) is ignored -- it enters none of the Dice sums (loss_mask of
+ *              MemoryEfficientSoftDiceLoss), the cross entropy is the mean over the valid voxels (ignore_index; 0 when there
+ *              are none) and its dlogits are 0.  nnU-Net's ignore label is the id behind the last class, i.e. out of range.
  *   finalize : the same scalar algebra as its own launch (data-parallel batch_dice: the sums are all-reduced first)
  *   bwd      : dlogits of every segment = gout[0] * weight * d(w_ce CE + w_dice Dice)/dlogits; coef_scale multiplies
  *              the Dice coefficients (world size under AllGatherGrad, ddp_allgather.py:35-48; else 1) */

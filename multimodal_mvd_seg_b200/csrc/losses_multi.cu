@@ -79,8 +79,11 @@ __device__ __forceinline__ int find_segment(const SegTable& T, int block) {
   return si;
 }
 
-// acc layout per segment: [B][4][3] (intersect, sum_pred, sum_gt) + 1 (sum of -log p[target]); stride acc_stride doubles
-// coef layout per segment: [B][4][2] (A, E): d(w_dice * Dice)/dp_vc = A * y_vc - E
+// acc layout per segment: [B][4][3] (intersect, sum_pred, sum_gt) + 2 (sum of -log p[target], number of valid voxels);
+//   stride acc_stride doubles.  A voxel whose target is outside [0, 4) is IGNORED (the reference's ignore_label, which
+//   nnU-Net places behind the last class): it contributes to none of the sums (loss_mask of MemoryEfficientSoftDiceLoss,
+//   ignore_index of the cross entropy) and gets a zero gradient.
+// coef layout per segment: [B][4][2] (A, E): d(w_dice * Dice)/dp_vc = A * y_vc - E, + 1 (1 / number of valid voxels)
 __device__ void finalize_segment(const double* __restrict__ acc, int B, long long V, const FinalizeArgs& F,
                                  float* __restrict__ coef, double& loss) {
   const int C = C4, c0 = F.do_bg ? 0 : 1, nC = C - c0;
@@ -126,7 +129,12 @@ __device__ void finalize_segment(const double* __restrict__ acc, int B, long lon
       }
     dc_sum /= nterms;
   }
-  const double ce = __ldcg(&acc[B * C * 3]) / ((double)B * (double)V);
+  // cross entropy: mean over the VALID voxels (targets outside [0, C) are the reference's ignore label: F.cross_entropy(
+  // ignore_index) divides by the number of non-ignored targets; DC_and_CE_loss returns 0 for the term when there are none)
+  const double nvalid = __ldcg(&acc[B * C * 3 + 1]);
+  const double ce = nvalid > 0.0 ? __ldcg(&acc[B * C * 3]) / nvalid : 0.0;
+  coef[B * C * 2] = nvalid > 0.0 ? (float)(1.0 / nvalid) : 0.f;
+  (void)V;
   loss = (double)F.w_ce * ce + (double)F.w_dice * (-dc_sum);
 }
 
@@ -136,7 +144,7 @@ __device__ void finalize_all(const SegTable& T, const FinalizeArgs& F, const dou
   if ((int)threadIdx.x < T.n) {
     double l = 0.0;
     finalize_segment(acc + (long long)threadIdx.x * acc_stride, T.B, T.s[threadIdx.x].V, F,
-                     coef + (long long)threadIdx.x * T.B * C4 * 2, l);
+                     coef + (long long)threadIdx.x * (T.B * C4 * 2 + 1), l);
     sh_loss[threadIdx.x] = (double)T.s[threadIdx.x].weight * l;
   }
   __syncthreads();
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) dice_ce_multi_fwd_kernel(const __gri
                                                                      unsigned* __restrict__ counter) {
   constexpr int NS = 3;
   extern __shared__ __align__(16) uint4 ring4[];
-  __shared__ float red[kThreads / 32][3 * C4 + 1];
+  __shared__ float red[kThreads / 32][3 * C4 + 2];
   __shared__ double sh_loss[kMaxSeg];
   __shared__ bool is_last;
   const int si = find_segment(T, blockIdx.x);
@@ -169,9 +177,9 @@ __global__ void __launch_bounds__(kThreads) dice_ce_multi_fwd_kernel(const __gri
   const long long iters = q0 < Q ? (Q - q0 + step - 1) / step : 0;
   const uint4* mine = ring4 + threadIdx.x;
   const uint32_t mine_u = (uint32_t)__cvta_generic_to_shared(mine);
-  float vals[3 * C4 + 1];
+  float vals[3 * C4 + 2];
 #pragma unroll
-  for (int i = 0; i < 3 * C4 + 1; ++i) vals[i] = 0.f;
+  for (int i = 0; i < 3 * C4 + 2; ++i) vals[i] = 0.f;
   sweep(
       iters,
       [&](long long i, int st) {
@@ -195,29 +203,31 @@ __global__ void __launch_bounds__(kThreads) dice_ce_multi_fwd_kernel(const __gri
 #pragma unroll
           for (int c = 0; c < C4; ++c) zt = (c == t) ? z[c] : zt;
           const float lse = softmax4(z);
+          const bool valid = t >= 0 && t < C4;
 #pragma unroll
           for (int c = 0; c < C4; ++c) {
             const float y = (c == t) ? 1.f : 0.f;
             vals[3 * c + 0] += z[c] * y;
-            vals[3 * c + 1] += z[c];
+            vals[3 * c + 1] += valid ? z[c] : 0.f;
             vals[3 * c + 2] += y;
           }
-          vals[3 * C4] += (t >= 0 && t < C4) ? (lse - zt) : 0.f;
+          vals[3 * C4] += valid ? (lse - zt) : 0.f;
+          vals[3 * C4 + 1] += valid ? 1.f : 0.f;
         }
       });
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 3 * C4 + 1; ++i) {
+  for (int i = 0; i < 3 * C4 + 2; ++i) {
     const float sum = warp_sum(vals[i]);
     if (lane == 0) red[warp][i] = sum;
   }
   __syncthreads();
   double* a = acc + (long long)si * acc_stride;
-  if (threadIdx.x < 3 * C4 + 1) {
+  if (threadIdx.x < 3 * C4 + 2) {
     double v = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) v += (double)red[w][threadIdx.x];
     if (threadIdx.x < 3 * C4) atomicAdd(&a[(long long)b * C4 * 3 + threadIdx.x], v);
-    else atomicAdd(&a[(long long)T.B * C4 * 3], v);
+    else atomicAdd(&a[(long long)T.B * C4 * 3 + (threadIdx.x - 3 * C4)], v);
   }
   if (counter == nullptr) return;
   // ---- last block done: scalar algebra of all segments (threadfence reduction pattern)
@@ -255,11 +265,12 @@ __global__ void __launch_bounds__(kThreads) dice_ce_multi_bwd_kernel(const __gri
   const uint4* tq = reinterpret_cast<const uint4*>(S.target + (long long)b * S.V);
   uint4* dq = reinterpret_cast<uint4*>(S.dlogits + (long long)b * S.V * C4);
   float A[C4], E[C4];
-  const float* cf = coef + ((long long)si * T.B + b) * C4 * 2;
+  const float* cseg = coef + (long long)si * (T.B * C4 * 2 + 1);
+  const float* cf = cseg + (long long)b * C4 * 2;
 #pragma unroll
   for (int c = 0; c < C4; ++c) { A[c] = cf[2 * c] * coef_scale; E[c] = cf[2 * c + 1] * coef_scale; }
   const float g = (gout ? gout[0] : 1.f) * S.weight;
-  const float ce_scale = w_ce / ((float)T.B * (float)S.V);
+  const float ce_scale = w_ce * cseg[T.B * C4 * 2];        // 1 / number of valid voxels of the segment
   const long long Q = S.V >> 2, step = (long long)S.bps * kThreads;
   const long long q0 = (long long)blk * kThreads + threadIdx.x;
   const long long iters = q0 < Q ? (Q - q0 + step - 1) / step : 0;
@@ -293,10 +304,11 @@ __global__ void __launch_bounds__(kThreads) dice_ce_multi_bwd_kernel(const __gri
             dot = fmaf(p[c], qv[c], dot);
           }
           float o[C4];
+          const bool valid = t >= 0 && t < C4;      // ignored voxels: no gradient
 #pragma unroll
           for (int c = 0; c < C4; ++c) {
             const float dce = (p[c] - ((c == t) ? 1.f : 0.f)) * ce_scale;
-            o[c] = g * (dce + p[c] * (qv[c] - dot));
+            o[c] = valid ? g * (dce + p[c] * (qv[c] - dot)) : 0.f;
           }
           __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), bb = __floats2bfloat162_rn(o[2], o[3]);
           ow[2 * j] = *reinterpret_cast<uint32_t*>(&a);
@@ -484,7 +496,7 @@ int mvd_dice_ce_multi_fwd(const mvd_dice_ce_segment* segs, int n_seg, int B, int
   const int blocks = build_table(segs, n_seg, B, false, budget, T, "dice_ce_multi_fwd");
   if (blocks < 0) return blocks;
   FinalizeArgs F{smooth, w_ce, w_dice, do_bg, batch_dice};
-  dice_ce_multi_fwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(T, F, acc, B * C4 * 3 + 1, coef, loss_out,
+  dice_ce_multi_fwd_kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(T, F, acc, B * C4 * 3 + 2, coef, loss_out,
                                                                              counter);
   MVD_LAUNCH_CHECK("dice_ce_multi_fwd");
   return MVD_OK;
@@ -498,7 +510,7 @@ int mvd_dice_ce_multi_finalize(const mvd_dice_ce_segment* segs, int n_seg, int B
   const int blocks = build_table(segs, n_seg, B, false, 1, T, "dice_ce_multi_finalize");
   if (blocks < 0) return blocks;
   FinalizeArgs F{smooth, w_ce, w_dice, do_bg, batch_dice};
-  dice_ce_multi_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(T, F, acc, B * C4 * 3 + 1, coef, loss_out);
+  dice_ce_multi_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(T, F, acc, B * C4 * 3 + 2, coef, loss_out);
   MVD_LAUNCH_CHECK("dice_ce_multi_finalize");
   return MVD_OK;
 }

@@ -11,7 +11,8 @@
   soft_cldice(iter_, smooth)(y_true, y_pred)                            (clDice wrapper)
 Inputs are the network's bf16 logits of logical shape [B,C,D,H,W] (channels-last views are consumed in place) and
 the reference's float targets [B,1,D,H,W].  The unsupported corners of the reference API raise NotImplementedError
-instead of silently falling back to PyTorch: ignore_label, class weights, loss_mask, region (BCE) training.
+instead of silently falling back to PyTorch: class weights, a stand-alone loss_mask, region (BCE) training
+(ignore_label is built: DC_and_CE_loss(ignore_label=...) with the label behind the last class, as nnU-Net defines it).
 """
 from typing import Callable, List, Optional, Sequence
 
@@ -27,7 +28,8 @@ def softmax_helper_dim1(x: torch.Tensor) -> torch.Tensor:
     return torch.softmax(x, 1)
 
 
-def _dice_ce(logits, target, *, w_ce, w_dice, smooth, do_bg, batch_dice, ddp, weights=None, networks=None):
+def _dice_ce(logits, target, *, w_ce, w_dice, smooth, do_bg, batch_dice, ddp, weights=None, networks=None,
+             ignore_label=None):
     """logits / target: one tensor, or one list over the deep-supervision scales.  ``networks``: a list of such logits
     lists (several networks supervised by the same targets): everything goes through one autograd node."""
     if networks is None:
@@ -42,7 +44,7 @@ def _dice_ce(logits, target, *, w_ce, w_dice, smooth, do_bg, batch_dice, ddp, we
         weights = [1.0] * n
     cfg = dict(weights=[float(w) for w in weights], weight_ce=float(w_ce), weight_dice=float(w_dice),
                smooth=float(smooth), do_bg=bool(do_bg), batch_dice=bool(batch_dice), ddp=bool(ddp),
-               n_nets=len(networks))
+               n_nets=len(networks), ignore_label=ignore_label)
     return ops.DiceCEMultiScaleFn.apply(cfg, *[t for net in networks for t in net], *target)
 
 
@@ -79,15 +81,16 @@ class DC_and_CE_loss(nn.Module):
     def __init__(self, soft_dice_kwargs, ce_kwargs, weight_ce=1, weight_dice=1, ignore_label=None,
                  dice_class=MemoryEfficientSoftDiceLoss):
         super().__init__()
-        if ignore_label is not None:
-            raise NotImplementedError('ignore_label is outside the built hot path')
+        # ignore_label (nnUNetTrainer.py:353-361 passes label_manager.ignore_label): voxels carrying it are masked out of
+        # the Dice sums (loss_mask) and of the cross-entropy mean (ignore_index) inside the fused kernels, which treat
+        # every target outside [0, C) that way -- nnU-Net's ignore label is the id behind the last class
         self.weight_dice, self.weight_ce, self.ignore_label = weight_dice, weight_ce, ignore_label
         self.ce = RobustCrossEntropyLoss(**ce_kwargs)
         self.dc = dice_class(apply_nonlin=softmax_helper_dim1, **soft_dice_kwargs)
 
     def _kw(self):
         return dict(w_ce=self.weight_ce, w_dice=self.weight_dice, smooth=self.dc.smooth, do_bg=self.dc.do_bg,
-                    batch_dice=self.dc.batch_dice, ddp=self.dc.ddp)
+                    batch_dice=self.dc.batch_dice, ddp=self.dc.ddp, ignore_label=self.ignore_label)
 
     def forward(self, net_output: torch.Tensor, target: torch.Tensor):
         return _dice_ce(net_output, target, **self._kw())

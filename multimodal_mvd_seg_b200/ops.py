@@ -1078,6 +1078,14 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
         C = items[0][2].shape[-1]
         fused = (len(items) <= lib.DICE_CE_MAX_SEGMENTS and all(it[2].shape[0] == B and _quad_ok(it[2], it[3]) for it in items))
         ctx.cfg, ctx.items_meta, ctx.n_tensors, ctx.fused, ctx.gscale = cfg, [(it[0], it[1]) for it in items], len(tensors), fused, gscale
+        ign = cfg.get('ignore_label')
+        if ign is not None:
+            # the kernels ignore every voxel whose target is outside [0, C): nnU-Net's ignore label sits behind the last class
+            if 0 <= int(ign) < C:
+                raise NotImplementedError('ignore_label inside the class range [0, %d) is outside the built hot path' % C)
+            if not fused:
+                raise NotImplementedError('ignore_label is built for the production shape of the loss kernels only '
+                                          '(4 classes, dense logits, voxels % 4 == 0)')
         if fused:
             ns = len(items)
             segs = (DiceCESegment * ns)()
@@ -1085,12 +1093,12 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
                 V = lg.shape[1] * lg.shape[2] * lg.shape[3]
                 segs[j].logits, segs[j].target, segs[j].dlogits, segs[j].V, segs[j].weight = \
                     lg.data_ptr(), tg.data_ptr(), None, V, float(weights[i])
-            stride = B * C * 3 + 1
+            stride = B * C * 3 + 2          # per-(b,c) sums, CE sum, number of valid (not ignored) voxels
             # (the data-parallel batch_dice branch all-reduces and edits `acc` with in-place torch ops: those bump the
             # version counter of the whole tensor they alias, so it must not be a view of the shared zero pool, whose
             # other views are saved for backward elsewhere)
             acc = torch.zeros((ns, stride), dtype=torch.float64, device=dev) if ddp_bd else zeros((ns, stride), torch.float64, dev)
-            coef = torch.empty((ns, B, C, 2), dtype=torch.float32, device=dev)
+            coef = torch.empty((ns, B * C * 2 + 1), dtype=torch.float32, device=dev)   # (A, E) per (b, c) + 1 / valid
             loss = torch.empty((), dtype=torch.float32, device=dev)
             nbytes = sum(B * s.V * (2.0 * C + 4) for s in segs)
             args = (segs, ns, B, C, cfg['smooth'], int(cfg['do_bg']), int(cfg['batch_dice']), cfg['weight_ce'],
@@ -1099,9 +1107,9 @@ class DiceCEMultiScaleFn(torch.autograd.Function):
                 _timed_mem('dice_ce_fwd', nbytes, lib.dice_ce_multi_fwd, *args, _ticket_counter(dev).data_ptr(), st)
             else:
                 _timed_mem('dice_ce_fwd', nbytes, lib.dice_ce_multi_fwd, *args, None, st)
-                ce = acc[:, stride - 1].clone()          # the CE mean stays per rank; only the Dice sums are gathered
+                ce = acc[:, stride - 2:].clone()         # the CE mean stays per rank; only the Dice sums are gathered
                 torch.distributed.all_reduce(acc)        # AllGatherGrad(...).sum(0), ddp_allgather.py:35-48
-                acc[:, stride - 1] = ce
+                acc[:, stride - 2:] = ce
                 lib.dice_ce_multi_finalize(*args, st)
             ctx.save_for_backward(coef, *[it[2] for it in items], *[it[3] for it in items])
             return loss

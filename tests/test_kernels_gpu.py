@@ -558,6 +558,50 @@ def test_deep_supervision_two_networks_one_launch(m, batch_dice):
     assert abs(float(l_again) - float(l)) <= 1e-6 * max(1.0, abs(float(l)))
 
 
+@pytest.mark.parametrize('batch_dice', [False, True])
+def test_dc_and_ce_ignore_label_matches_oracle(m, batch_dice):
+    """DC_and_CE_loss(ignore_label = the id behind the last class, nnUNetTrainer.py:353-361): ignored voxels are masked out
+    of the Dice sums (loss_mask) and of the cross-entropy mean (ignore_index) and receive no gradient -- value and
+    gradients against the oracle, through the deep-supervision wrapper; plus the all-ignored corner (CE term = 0)."""
+    import oracle
+    outs, tgts = _logits_targets(2, 4, (16, 20, 12), 51, scales=3)
+    g = torch.Generator().manual_seed(52)
+    tgts = [t.clone() for t in tgts]
+    for t in tgts:                                   # ~20 % ignored voxels, in blobs and scattered
+        t[:, :, : t.shape[2] // 3] = 4.0
+        mask = torch.rand(t.shape, generator=g).to(t.device) < 0.05
+        t[mask] = 4.0
+    w = m.deep_supervision_weights(3)
+    mk = lambda mod: mod.DeepSupervisionWrapper(
+        mod.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, weight_ce=1,
+                           weight_dice=1, ignore_label=4, dice_class=mod.MemoryEfficientSoftDiceLoss), w)
+    x = [m.ops.ncdhw_view(o).requires_grad_(True) for o in outs]
+    r = [o.float().permute(0, 4, 1, 2, 3).requires_grad_(True) for o in outs]
+    l, lr = mk(m)(x, tgts), mk(oracle)(r, tgts)
+    assert abs(float(l) - float(lr)) <= 1e-5 * max(1.0, abs(float(lr))), (float(l), float(lr))
+    l.backward()
+    lr.backward()
+    for i in range(2):
+        assert rel_err(x[i].grad.float(), r[i].grad) < 6e-3
+        ign = (tgts[i] == 4).expand(-1, 4, -1, -1, -1)
+        assert float(x[i].grad.float()[ign].abs().max()) == 0.0          # no gradient on ignored voxels
+    # without ignored voxels nothing changes with respect to ignore_label=None
+    outs2, tg2 = _logits_targets(2, 4, (16, 20, 12), 53, scales=3)
+    plain = m.DeepSupervisionWrapper(
+        m.DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, weight_ce=1,
+                         weight_dice=1, ignore_label=None, dice_class=m.MemoryEfficientSoftDiceLoss), w)
+    xs = [m.ops.ncdhw_view(o) for o in outs2]
+    assert float(plain(xs, tg2)) == float(mk(m)(xs, tg2))
+    # every voxel ignored: the cross-entropy term is 0 (the reference's num_fg > 0 guard), Dice = -smooth/smooth
+    allign = [torch.full_like(t, 4.0) for t in tg2]
+    la, lo = mk(m)(xs, allign), mk(oracle)([o.float().permute(0, 4, 1, 2, 3) for o in outs2], allign)
+    assert abs(float(la) - float(lo)) <= 1e-5 * max(1.0, abs(float(lo))), (float(la), float(lo))
+    # an ignore label inside the class range is refused
+    bad = m.DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False, 'ddp': False}, {}, ignore_label=2)
+    with pytest.raises(NotImplementedError):
+        bad(xs[0], tg2[0])
+
+
 @pytest.mark.parametrize('T', [1.0, 2.0])
 def test_distill_kl_single_pass_with_upstream_factor(m, T):
     """distill_kl(..., upstream_grad=lambda1): loss and both gradients from ONE kernel; exact for the announced upstream
