@@ -169,7 +169,9 @@ class GpuAugmenter:
         if 'lowres_zoom' in params and params['lowres_zoom'].any():
             zf = params['lowres_zoom'].reshape(-1).astype(np.float64)
             sel = zf != 0
-            tshape[sel] = np.round(np.array([D, H, W])[None, :] * zf[sel, None]).astype(np.int32)   # np.round: half to even
+            if (zf[sel] > 1).any() or (zf[sel] <= 0).any():
+                raise ValueError('lowres_zoom must lie in (0, 1] (SimulateLowResolutionTransform zoom_range, MVDTrainer.py:721)')
+            tshape[sel] = np.maximum(np.round(np.array([D, H, W])[None, :] * zf[sel, None]), 1).astype(np.int32)   # np.round: half to even
         pieces = {'mat': params['mat'].astype(np.float32).reshape(-1), 'mode': params['mode'].astype(np.int32),
                   'tshape': tshape.reshape(-1), 'apply': np.repeat(params['mode'].astype(np.uint8), C),
                   'flips': params['flips'].astype(np.uint8).reshape(-1),
