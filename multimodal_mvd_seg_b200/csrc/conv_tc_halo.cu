@@ -83,6 +83,13 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
   constexpr bool do_stats = SC > 0;           // host guarantees n_tile == Ntot == 32 * SC when statistics are fused
   LaneStats<SC> hs;
   hs.reset(-1);
+  // 32-channel layers: the bias lives in registers (the shared-memory pipe belongs to the tensor core's operands)
+  const bool reg_bias = P.bias != nullptr && P.n_tile == 32 && P.Ntot == 32;
+  float2 breg[16];
+  if (reg_bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) breg[j] = *reinterpret_cast<const float2*>(sbias + 2 * j);
+  }
   for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
     int n0, b, d0, h0, w0;
     halo_decode(P, MT, item, n0, b, d0, h0, w0);
@@ -106,7 +113,7 @@ __device__ __forceinline__ void halo_epilogue_sc(const HaloParams& P, uint32_t t
         tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
         uint32_t w2[16];
-        epilogue_chunk<SC>(v, P.bias ? sbias + n0 + c : nullptr, hs, c, ok, w2);
+        epilogue_chunk<SC>(v, P.bias ? sbias + n0 + c : nullptr, hs, c, ok, w2, reg_bias ? breg : nullptr);
         if (P.lane_own) {
           if (ok)
             store_row_lane_own(tile_base + (long long)(h0 + (rr >> 3)) * sh + (long long)(w0 + (rr & 7)) * sw + c, w2,

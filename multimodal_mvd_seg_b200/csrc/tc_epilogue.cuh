@@ -172,8 +172,15 @@ struct LaneStats {
 // InstanceNorm sums of the rounded values (per-lane fp32 partials, see LaneStats).
 template <int SC>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t* v, const float* bias32, LaneStats<SC>& st, int c,
-                                               bool ok, uint32_t* w2) {
-  if (bias32) {
+                                               bool ok, uint32_t* w2, const float2* bias_reg = nullptr) {
+  if (bias_reg) {     // bias of a single-chunk layer kept in registers by the caller (no shared-memory reads per step)
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[j]) + bias_reg[j >> 1].x,
+                                                __uint_as_float(v[j + 1]) + bias_reg[j >> 1].y);
+      w2[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+  } else if (bias32) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const float2 bb = *reinterpret_cast<const float2*>(bias32 + j);
