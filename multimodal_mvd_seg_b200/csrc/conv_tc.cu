@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           int n = n0 + cc;          // bias index: channel within the parity in scatter mode
           if (P.scatter_c) n -= (n / P.scatter_c) * P.scatter_c;
           uint32_t w2[16];
-          epilogue_chunk<SC>(v, s_bias + n, st, cc, ok, w2);
+          epilogue_chunk<SC>(v, P.bias ? s_bias + n : nullptr, st, cc, ok, w2);   // no bias: no shared-memory reads
           if (accum) {
             bf16x8 cur[4];
             bool chas[4];
