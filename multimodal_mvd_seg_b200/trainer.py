@@ -458,7 +458,42 @@ class nnUNetTrainer(object):
 
     def train_step(self, batch: dict) -> dict:
         l = self.train_step_async(batch)
+        st = getattr(self, '_graph_state', None)
+        if self.use_cuda_graph and st is not None and st.get('graph2') is not None and l is st['loss'] and \
+                os.environ.get('MVD_LOOKAHEAD', '1') != '0':
+            # The reference reads the loss back every step (`l.detach().cpu().numpy()`, nnUNetTrainer.py:925), which leaves
+            # the GPU idle from the end of this step until the host has returned and launched the next one.  With
+            # `prefetching` the next batch is already staged: its FORWARD graph (weights of this step's update, no
+            # dependence on anything the host still has to do) is queued first, and the loss comes back over the copy
+            # stream behind this step's completion event -- the host wakes up when THIS step is done while the GPU is
+            # already in the next forward pass.
+            self._prelaunch_forward(st)
+            side = st['copy_stream']
+            if 'loss_host' not in st:
+                st['loss_host'] = torch.empty(st['loss'].shape, dtype=st['loss'].dtype).pin_memory()
+                st['ev_loss'] = torch.cuda.Event()
+            side.wait_event(st['ev_done'])
+            with torch.cuda.stream(side):
+                st['loss_host'].copy_(st['loss'], non_blocking=True)
+                st['ev_loss'].record(side)
+            st['ev_loss'].synchronize()
+            return {'loss': st['loss_host'].numpy().copy()}
         return {'loss': l.detach().cpu().numpy()}
+
+    def _prelaunch_forward(self, st) -> None:
+        """queue the forward graph of the batch `prefetching` has staged next (if it fits the captured shapes)"""
+        up = getattr(self, '_upload_state', None)
+        if up is None or len(up['staged']) != 1 or st.get('pre') is not None:
+            return
+        slot = next(iter(up['staged'].values()))
+        if tuple(slot['data'].shape) != tuple(st['data'].shape) or slot['data'].dtype != st['data'].dtype:
+            return
+        main = torch.cuda.current_stream()
+        main.wait_event(slot['ready'])
+        st['data'].copy_(slot['data'], non_blocking=True)
+        st['graph'].replay()
+        st['pre'] = slot
+        self._lookahead_launches = getattr(self, '_lookahead_launches', 0) + 1
 
     def _step_forward(self, data):
         self.optimizer.zero_grad(set_to_none=True)
@@ -641,7 +676,10 @@ class nnUNetTrainer(object):
             return st['loss']
         main = torch.cuda.current_stream()
         side = st['copy_stream']
-        st['data'].copy_(data, non_blocking=True)
+        pre = st.pop('pre', None)
+        launched = pre is not None and data is pre['data']      # train_step queued this batch's forward pass already
+        if not launched:
+            st['data'].copy_(data, non_blocking=True)
         side.wait_event(st['ev_done'])              # the previous step has finished reading the static targets
         if target and target[0].is_cuda:             # staged device batch: its upload is ordered before `main` only
             ev = st.setdefault('ev_start', torch.cuda.Event())
@@ -651,7 +689,8 @@ class nnUNetTrainer(object):
             for a, b in zip(st['target'], target):
                 a.copy_(b, non_blocking=True)
             st['ev_targets'].record(side)
-        st['graph'].replay()                         # forward: needs `data` only
+        if not launched:
+            st['graph'].replay()                     # forward: needs `data` only
         main.wait_event(st['ev_targets'])
         st['graph2'].replay()                        # losses, backward, exchange, optimiser
         st['ev_done'].record(main)

@@ -332,13 +332,31 @@ def test_prefetching_loop_matches_plain_loop():
             tr = m.nnUNetTrainer(plans, '3d_fullres', 0, dj, device=torch.device('cuda:0'))
             tr.initialize()
             tr.use_cuda_graph = graph
+            tr.split_graph = True          # forward | backward as two graphs: what the look-ahead launch needs
             tr.graph_warmup_steps = 1
             tr.on_train_epoch_start()
             it = tr.prefetching([dict(b) for b in batches]) if mode == 'prefetch' else batches
             res[(mode, graph)] = [float(tr.train_step(b)['loss']) for b in it]
+            if mode == 'prefetch' and graph:
+                # train_step queued the NEXT batch's forward graph before it blocked on this step's loss (graph replays
+                # start at step 3: one eager warm-up step, one capture step)
+                assert getattr(tr, '_lookahead_launches', 0) >= 3
     # the weight-gradient reductions use fp32 atomics, so two runs agree to rounding, not bit for bit
     for graph in (False, True):
         np.testing.assert_allclose(res[('prefetch', graph)], res[('plain', graph)], rtol=2e-3, atol=2e-4)
+    # the dual-network trainer through the same loop (forward on two streams inside the captured graph)
+    mres = {}
+    for mode in ('plain', 'prefetch'):
+        torch.manual_seed(0)
+        tr = m.MVDTrainer(plans, '3d_fullres', 0, dj, device=torch.device('cuda:0'), topo_iter=3)
+        tr.initialize()
+        tr.use_cuda_graph = True
+        tr.split_graph = True
+        tr.graph_warmup_steps = 1
+        tr.on_train_epoch_start()
+        it = tr.prefetching([dict(b) for b in batches]) if mode == 'prefetch' else batches
+        mres[mode] = [float(tr.train_step(b)['loss']) for b in it]
+    np.testing.assert_allclose(mres['prefetch'], mres['plain'], rtol=2e-3, atol=2e-4)
 
 
 def test_mvd_checkpoint_roundtrip_and_missing_second_network(tmp_path):
