@@ -246,12 +246,30 @@ __global__ void __launch_bounds__(kSkelThreads) skel_fused_kernel(const __grid_c
   // stage the box row by row (one warp per x row: no per-element index arithmetic)
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int row = warp; row < SY * SZ; row += nwarps) {
-      const int sy = row % SY, sz = row / SY;
-      const bool row_in = sy >= ly && sy < hy && sz >= lz && sz < hz;
-      const float* grow = src + ((long long)(z0 - R + sz) * H + (y0 - R + sy)) * W + (x0 - R);
-      float* arow = A + row * SX;
-      for (int sx = lane; sx < SX; sx += 32) arow[sx] = (row_in && sx >= lx && sx < hx) ? grow[sx] : INF;
+    // four rows per trip, all loads issued before the first store (one row per trip left a single load in flight per lane)
+    for (int row0 = warp; row0 < SY * SZ; row0 += 4 * nwarps) {
+      float v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = row0 + u * nwarps;
+        v[u][0] = v[u][1] = INF;
+        if (row < SY * SZ) {
+          const int sy = row % SY, sz = row / SY;
+          const bool row_in = sy >= ly && sy < hy && sz >= lz && sz < hz;
+          const float* grow = src + ((long long)(z0 - R + sz) * H + (y0 - R + sy)) * W + (x0 - R);
+          if (row_in && lane >= lx && lane < hx) v[u][0] = grow[lane];
+          if (row_in && lane + 32 < SX && lane + 32 >= lx && lane + 32 < hx) v[u][1] = grow[lane + 32];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = row0 + u * nwarps;
+        if (row < SY * SZ) {
+          float* arow = A + row * SX;
+          if (lane < SX) arow[lane] = v[u][0];
+          if (lane + 32 < SX) arow[lane + 32] = v[u][1];
+        }
+      }
     }
   }
   const int TN = kSkelTX * kSkelTY * P.TZ;
@@ -394,15 +412,54 @@ __global__ void __launch_bounds__(kBwdThreads) skel_bwd_fused_kernel(const __gri
   const int W = P.s.W, H = P.s.H, D = P.s.D;
   const long long vol = (long long)D * H * W;
   const long long boff = (long long)b * vol;
-  auto inside = [&](int x, int y, int z) { return x0 + x >= 0 && x0 + x < W && y0 + y >= 0 && y0 + y < H && z0 + z >= 0 && z0 + z < D; };
-  auto gidx = [&](int x, int y, int z) { return boff + ((long long)(z0 + z) * H + (y0 + y)) * W + (x0 + x); };
+  // (ncu: the first version spent most of its 627 M warp instructions on per-cell index arithmetic -- div / mod by the
+  // run-time box extents, 64-bit offsets, six-way bounds tests.  Now: multiply-high division, unsigned bounds tests,
+  // 32-bit offsets inside the sample.)
+  auto inside = [&](int x, int y, int z) {
+    return (unsigned)(x0 + x) < (unsigned)W && (unsigned)(y0 + y) < (unsigned)H && (unsigned)(z0 + z) < (unsigned)D;
+  };
+  auto gidx = [&](int x, int y, int z) { return boff + (long long)(((z0 + z) * H + (y0 + y)) * W + (x0 + x)); };
+  // c -> (x, y, z) of an ex x ey x ez box: exact for c < 2^16 and extents <= 64 (magic = ceil(2^32 / d))
+  struct Dec { unsigned ex, ey, mx, my; };
+  auto make_dec = [](int ex, int ey) {
+    Dec d;
+    d.ex = (unsigned)ex; d.ey = (unsigned)ey;
+    d.mx = (unsigned)((0x100000000ull + ex - 1) / (unsigned)ex);
+    d.my = (unsigned)((0x100000000ull + ey - 1) / (unsigned)ey);
+    return d;
+  };
+  auto decode = [](const Dec& d, int c, int h, int& x, int& y, int& z) {
+    const unsigned r = __umulhi((unsigned)c, d.mx);
+    x = (int)((unsigned)c - r * d.ex) - h;
+    const unsigned q = __umulhi(r, d.my);
+    y = (int)(r - q * d.ey) - h;
+    z = (int)q - h;
+  };
   // fill a box region (tile grown by `h`) from a global volume, `oob` outside the volume (src == nullptr: all `oob`)
+  // (four independent global loads per thread in flight: with one load per trip the 512-thread CTA -- the only one its
+  // 200 KB of boxes leave room for on the SM -- spent most of the kernel waiting for single loads: 1.04 ms per launch)
   auto load_box = [&](float* dst, const Box& bx, const float* src, int h, float oob) {
     const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
-    for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
-      const int x = c % ex - h, r = c / ex;
-      const int y = r % ey - h, z = r / ey - h;
-      dst[bx.idx(x, y, z)] = (src && inside(x, y, z)) ? __ldg(src + gidx(x, y, z)) : oob;
+    const int total = ex * ey * ez;
+    const Dec dd = make_dec(ex, ey);
+    for (int c0 = threadIdx.x; c0 < total; c0 += 4 * kBwdThreads) {
+      float v[4];
+      int di[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * kBwdThreads;
+        v[u] = oob;
+        di[u] = -1;
+        if (c < total) {
+          int x, y, z;
+          decode(dd, c, h, x, y, z);
+          di[u] = bx.idx(x, y, z);
+          if (src && inside(x, y, z)) v[u] = __ldg(src + gidx(x, y, z));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (di[u] >= 0) dst[di[u]] = v[u];
     }
   };
   load_box(G, gb, P.G_in, R, 0.f);
@@ -419,10 +476,15 @@ __global__ void __launch_bounds__(kBwdThreads) skel_bwd_fused_kernel(const __gri
       const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
       const float* Ej = P.E[l];
       const float* skp = P.skel_prev[l];
+      const Dec dd = make_dec(ex, ey);
       for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
-        const int x = c % ex - h, r = c / ex;
-        const int y = r % ey - h, z = r / ey - h;
+        int x, y, z;
+        decode(dd, c, h, x, y, z);
         if (!inside(x, y, z)) continue;
+        // the two global operands of the cell are requested first: they arrive while the 27-point scan runs
+        const long long g = gidx(x, y, z);
+        const float ej = __ldg(Ej + g);
+        const float sk = level0 ? 0.f : __ldg(skp + g);
         // opened = max27(E_{j+1}) with the FIRST maximum in (z, y, x) scan order; out-of-volume cells hold +inf: skipped
         float best = 0.f;
         int bo = -1;
@@ -436,14 +498,12 @@ __global__ void __launch_bounds__(kBwdThreads) skel_bwd_fused_kernel(const __gri
               const float v = Eb[o];
               if (v != INF && (bo < 0 || v > best)) { best = v; bo = ((dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1); }
             }
-        const long long g = gidx(x, y, z);
-        const float delta = fmaxf(__ldg(Ej + g) - best, 0.f);
+        const float delta = fmaxf(ej - best, 0.f);
         const int gi = gb.idx(x, y, z);
         float Gv = G[gi], gdel;
         if (level0) {
           gdel = Gv;
         } else {
-          const float sk = __ldg(skp + g);
           const bool m = __fsub_rn(delta, __fmul_rn(sk, delta)) > 0.f;
           gdel = m ? Gv * (1.f - sk) : 0.f;
           if (m) G[gi] = Gv * (1.f - delta);
@@ -463,9 +523,10 @@ __global__ void __launch_bounds__(kBwdThreads) skel_bwd_fused_kernel(const __gri
     {
       const int h = l + 1;
       const int ex = kBwdTX + 2 * h, ey = kBwdTY + 2 * h, ez = kBwdTZ + 2 * h;
+      const Dec dd = make_dec(ex, ey);
       for (int c = threadIdx.x; c < ex * ey * ez; c += kBwdThreads) {
-        const int x = c % ex - h, r = c / ex;
-        const int y = r % ey - h, z = r / ey - h;
+        int x, y, z;
+        decode(dd, c, h, x, y, z);
         const float g = gUp[gb.idx(x, y, z)];
         if (g == 0.f || !inside(x, y, z)) continue;
         // first minimum of each axis window (out-of-volume taps hold +inf and can never win: the centre is finite)
