@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) skel_level_bwd_kernel(const float* __rest
 // level in the level-by-level form (mvd_soft_erode + mvd_skel_update).  Arithmetic is identical (min / max / the same
 // rounded adds and multiplies), so results are bit-identical to the unfused kernels and to the reference.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kSkelMaxLevels = 4, kSkelTX = 32, kSkelTY = 16, kSkelThreads = 512;
+constexpr int kSkelMaxLevels = 4, kSkelTX = 32, kSkelTY = 16, kSkelThreads = 1024;
 
 struct SkelPass {
   const float* E_in;                  // E_j0
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kSkelThreads) skel_fused_kernel(const __grid_c
 // boxes (G, gE upper, gE lower) with halo n + 1 plus one E box with halo n + 2 live in shared memory; the E box is
 // refilled per phase (E_{j+1} for A, E_j for B).  Between launches only G and the upper gE travel through HBM.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kSkelBwdLevels = 2, kBwdTX = 32, kBwdTY = 16, kBwdTZ = 8, kBwdThreads = 512;
+constexpr int kSkelBwdLevels = 2, kBwdTX = 32, kBwdTY = 16, kBwdTZ = 8, kBwdThreads = 1024;
 
 struct SkelBwdPass {
   const float* E[kSkelBwdLevels + 1];        // E_a ... E_{a+n}
