@@ -87,6 +87,7 @@ struct TcParams {
   // n % scatter_c of the voxel displaced by par_off[n / scatter_c]
   int scatter_c;
   long long par_off[8];
+  int lane_own;                  // scatter mode without accumulate: each lane stores its own 64-byte row (tc_epilogue.cuh)
   // split-K (small produced lattices: 8^3 / 4^3 layers whose few tiles would leave most SMs idle while every tile
   // re-streams the whole weight set): a work unit is (tile, slice s of the tap x channel-chunk loop); the epilogue adds
   // its fp32 partial into `scratch` (same element offsets as `out`) with vector reductions, splitk_finish_kernel then
@@ -320,6 +321,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               prefetch_rows(lane, [&](int R) { return row_ptr_at(R, con); }, old, has);
             }
             store_rows_accumulate_packed(stage, lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, cur, chas);
+          } else if (P.lane_own) {
+            // up-sampling scatter: a row is its own 64-byte segment of the output either way (stride-2 positions), and
+            // with 256 columns per tile the eight epilogue warps, not the tensor pipe, set this kernel's pace
+            if (ok) store_row_lane_own(tile_base + own_off + col_off, w2, false);
           } else {
             store_rows_coalesced_packed(stage, lane, w2, [&](int R) { return row_ptr_at(R, col_off); }, false);
           }
@@ -733,6 +738,11 @@ int tc_dgrad(const mvd_conv3d_args* a, cudaStream_t st) {
     add_class(P, a->Do, a->Ho, a->Wo, 0, 1, 0);
     P.num_n_tiles = scatter_n / P.n_tile;
     P.scatter_c = a->Cin;
+    {
+      static int lo = -1;
+      if (lo < 0) { const char* e = getenv("MVD_TC_LANE_OWN"); lo = (e && e[0] == '0') ? 0 : 1; }
+      P.lane_own = (lo && !a->accumulate && a->Cin % 32 == 0) ? 1 : 0;
+    }
     for (int td = 0; td < a->kd; ++td)
       for (int th = 0; th < a->kh; ++th)
         for (int tw = 0; tw < a->kw; ++tw)
